@@ -1,0 +1,88 @@
+"""ctypes binding of libaread_sm100.so (the C ABI declared in include/aread_sm100.h).
+
+There is deliberately no fallback: if the library is missing or fails to load, every op raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
+ABI_VERSION = 1
+
+AREAD_OK = 0
+AREAD_ERR_INVALID = -1
+AREAD_ERR_INDEX = -2
+AREAD_ERR_CUDA = -3
+AREAD_ERR_WORKSPACE = -4
+
+
+class AreadError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libaread_sm100: {message} (status {code})")
+        self.code = code
+
+
+class EmbedPlan(Structure):
+    _fields_ = [("n_cols", c_int32), ("n_fields", c_int32), ("max_src", c_int32), ("embed_dim", c_int32),
+                ("n_rows", c_int64), ("col_offset", c_void_p), ("field_src", c_void_p),
+                ("field_nsrc", c_void_p), ("field_div", c_void_p)]
+
+
+class GatherArgs(Structure):
+    _fields_ = [("plan", EmbedPlan), ("batch", c_int64), ("x", c_void_p), ("table", c_void_p),
+                ("out", c_void_p), ("out_bf16", c_void_p), ("status", c_void_p)]
+
+
+class ScatterArgs(Structure):
+    _fields_ = [("plan", EmbedPlan), ("batch", c_int64), ("x", c_void_p), ("d_out", c_void_p),
+                ("d_table", c_void_p), ("zero_fill", c_int32), ("workspace", c_void_p),
+                ("workspace_bytes", c_size_t), ("sorted_rows", c_void_p), ("sorted_pos", c_void_p)]
+
+
+_SIGNATURES = {
+    "aread_last_error": (c_char_p, []),
+    "aread_abi_version": (c_int32, []),
+    "aread_launch_count": (c_uint64, []),
+    "aread_gather_fwd": (c_int32, [POINTER(GatherArgs), c_void_p]),
+    "aread_scatter_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "aread_scatter_bwd": (c_int32, [POINTER(ScatterArgs), c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise (never fall back) when it is unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AreadError(AREAD_ERR_INVALID,
+                         f"{LIB_PATH} not found -- build it with `python {os.path.join(PKG_DIR, 'build.py')}`; "
+                         "this package has no CPU or eager fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.aread_abi_version() != ABI_VERSION:
+        raise AreadError(AREAD_ERR_INVALID, f"ABI version {lib.aread_abi_version()} != binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != AREAD_OK:
+        msg = load().aread_last_error().decode(errors="replace")
+        if code == AREAD_ERR_INDEX:
+            raise IndexError(msg or "index out of range in self")
+        raise AreadError(code, msg)
+
+
+def launch_count():
+    return int(load().aread_launch_count())
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)

@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference `model/aread.py`: the AREAD nn.Module.
+
+The class keeps the reference's constructor / forward signature, attribute names, `state_dict`
+layout and HEMP mask API so that `run.py` drives it unchanged.  The forward runs
+on the C-ABI CUDA library through `dense_ops` / `embedding_ops`; the HEMP bookkeeping is host
+logic (`hemp.py`).  Reference lines are cited per method.
+"""
+import copy
+import re
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import dense_ops, hemp
+from .layer import BaseModel, CrossNetwork, MultiLayerPerceptron, _weights_without_bn
+
+
+class AREAD(BaseModel):
+    """Adaptive REcommendation for All Domains (reference: model/aread.py:15-680)."""
+
+    def __init__(self, one_hot_feature_dims, embed_dim, multi_hot_dict, n_tower, n_domain, base_model,
+                 expert_dims, tower_dims, domain_idx,
+                 domain2group=None, n_cross_layers=3, dropout=0.2, device=None,
+                 l2_reg_embedding=1e-5, l2_reg_linear=1e-5, l2_reg_dnn=1e-5, l2_reg_cross=1e-5, config=None):
+        super().__init__(one_hot_feature_dims, embed_dim, multi_hot_dict,
+                         l2_reg_embedding=l2_reg_embedding, l2_reg_linear=l2_reg_linear)
+        if base_model != 'mmoe':
+            # the 'ple' bottom cannot be built from the shipped config
+            raise NotImplementedError("aread_b200 implements the 'mmoe' bottom of AREAD only")
+        self.model_name = 'aread'
+        self.base_model = base_model
+        self.domain_idx = domain_idx
+        self.n_tower = n_tower
+        self.n_level = len(n_tower)
+        self.edge_num = n_tower[0] + np.sum([n_tower[l - 1] * n_tower[l] for l in range(1, self.n_level)]) \
+            + n_tower[-1]
+        self.n_domain = n_domain
+        self.tower_dims = tower_dims
+        self.bottom_level = len(expert_dims)
+        self.device = device
+        self.dropout_p = dropout
+        self.domain2group = None if domain2group is None else np.array([domain2group[d] for d in range(n_domain)])
+        self.domain_mask = [None] * n_domain
+        self.candidate_domain_mask = None
+        self.tower2cluster = [[None] * n_tower[l] for l in range(self.n_level)]
+        self.model_state = None
+        self.domain_tower_gate_values = None
+        self.tmp_tower_gate_values = [[None] * n_tower[l] for l in range(self.n_level)]
+        self.gate_value_threshold = None
+        self.eval_loss = None
+        self.group_embedding = nn.Embedding(n_tower[0], embed_dim)
+        self.final_gate = nn.Sequential(nn.Linear(2 * embed_dim, n_tower[-1], bias=False), nn.Softmax(dim=1))
+        self.domain_size = np.array(config.domain_size[config.dataset_name])
+        self.use_dcn = getattr(config, 'use_dcn', False)
+        self.use_atten = getattr(config, 'use_atten', False)
+        if not self.use_dcn:
+            # the reference forward reads cn_out unconditionally in every masked mode (aread.py:231, 242)
+            raise ValueError("AREAD needs config.use_dcn = True (the reference fails without it)")
+        self.cn = CrossNetwork(self.embed_output_dim, config.n_cross_layers)
+        if self.use_atten:
+            # parameters only: the reference computes this branch and never reads the result
+            # (aread.py:139-140), so it is kept for state_dict compatibility and never executed
+            self.build_atten(config, dropout)
+
+        n_expert = config.mmoe_n_expert
+        self.mmoe_experts = nn.ModuleList(
+            MultiLayerPerceptron(self.embed_output_dim, expert_dims, dropout, output_layer=False)
+            for _ in range(n_expert))
+        self.mmoe_gates = nn.ModuleList(
+            nn.Sequential(nn.Linear(self.embed_output_dim, n_expert), nn.Softmax(dim=1)) for _ in range(n_tower[0]))
+        self.add_regularization_weight(_weights_without_bn(self.mmoe_experts), l2=l2_reg_dnn)
+
+        towers, gates = [], []
+        width = expert_dims[-1]
+        for l in range(self.n_level):
+            towers.append(nn.ModuleList(MultiLayerPerceptron(width, tower_dims[l], dropout, output_layer=False)
+                                        for _ in range(n_tower[l])))
+            if l > 0:
+                gates.append(nn.ModuleList(nn.Sequential(nn.Linear(2 * embed_dim, n_tower[l - 1]))
+                                           for _ in range(n_tower[l])))
+            width = tower_dims[l][-1]
+        self.towers = nn.ModuleList(towers)
+        self.tower_gates = nn.ModuleList(gates)
+        self.towers_linear = nn.ModuleList(nn.Linear(self.embed_output_dim + width, 1, bias=False)
+                                           for _ in range(n_tower[-1]))
+        self.output_layers = nn.ModuleList(nn.Sigmoid() for _ in range(n_tower[-1]))
+        self.add_regularization_weight(_weights_without_bn(self.towers), l2=l2_reg_dnn)
+        self.add_regularization_weight(_weights_without_bn(self.cn), l2=l2_reg_cross)
+        self._mask_cache = {}
+
+    # ------------------------------------------------------------------------------------ forward
+    def forward(self, x, mode='wo_mask', targets=None, memory_gate_value=False,
+                domain_i=None, current_mask=None, tmp_memory_gate_value=False):
+        """Reference: aread.py:129-261.  Live modes: 'wo_mask', 'domain_with_mask',
+        'domain_mask_bagging'; 'domain_mask_final' is kept callable (full masks only, as in the
+        reference); 'with_mask' raises like the reference does (undefined name at aread.py:215)."""
+        if mode == 'with_mask':
+            raise NameError("name 'other_outs' is not defined")      # reference behaviour, aread.py:215
+        if mode == 'wo_mask':
+            out = dense_ops.aread_forward(self, x, None, want_gates=memory_gate_value)
+            y = out.probs.mean(dim=0).unsqueeze(-1)                                       # [B, 1]
+            if memory_gate_value:
+                self._record_unmasked_gates(x, out.gates, domain_i)
+            return y
+        if mode not in ('domain_with_mask', 'domain_mask_bagging', 'domain_mask_final'):
+            raise ValueError(f"unknown forward mode '{mode}'")
+        mask = self.domain_mask[domain_i] if current_mask is None else current_mask
+        info = self.mask_info(mask)
+        if mode == 'domain_mask_final':
+            with torch.no_grad():
+                out = dense_ops.aread_forward(self, x, info, want_gate_means=memory_gate_value)
+            self._store_gate_means(out, info, domain_i, memory_gate_value, False)
+            gate = self.final_gate(out.gate_inputs.detach()) * mask[-1].squeeze(1)
+            gate = gate / (gate.sum(dim=1, keepdim=True) + 1e-8)
+            return torch.sum(out.probs.transpose(0, 1) * gate, dim=1)
+        out = dense_ops.aread_forward(self, x, info, want_gate_means=memory_gate_value or tmp_memory_gate_value)
+        self._store_gate_means(out, info, domain_i, memory_gate_value, tmp_memory_gate_value)
+        return out.probs if mode == 'domain_mask_bagging' else out.probs.mean(dim=0)
+
+    def hier_tower_mask_forward(self, d, tower_inputs, gate_inputs, domain_cn_out, domain_linear_out,
+                                single_domain_mask, memory_gate_value=False, tmp_memory_gate_value=False):
+        """Reference: aread.py:263-322.  Kept for API completeness; `forward` does not go through it."""
+        info = self.mask_info(single_domain_mask)
+        out = dense_ops.hei_forward(self, tower_inputs, gate_inputs, domain_cn_out, domain_linear_out, info,
+                                    want_gate_means=memory_gate_value or tmp_memory_gate_value)
+        self._store_gate_means(out, info, d, memory_gate_value, tmp_memory_gate_value)
+        return out.probs
+
+    def mask_info(self, mask):
+        """Host copy of a mask (active towers per level, edge matrices) cached per mask content
+        so that the forward never synchronises on `bool(device_tensor)` like aread.py:272/297/309."""
+        key = tuple((m.data_ptr(), m._version) if isinstance(m, torch.Tensor) else id(m) for m in mask)
+        info = self._mask_cache.get(key)
+        if info is None:
+            if len(self._mask_cache) > 4096:
+                self._mask_cache.clear()
+            info = dense_ops.MaskInfo(hemp.to_numpy(mask), self.n_tower)
+            self._mask_cache[key] = info
+        return info
+
+    def _store_gate_means(self, out, info, d, memory_gate_value, tmp_memory_gate_value):
+        """aread.py:275-295: `tmp_tower_gate_values[l][t]` / `domain_tower_gate_values[d][l][t]` receive
+        mean_b(softmax * mask column) for active towers and zeros for inactive ones."""
+        if not (memory_gate_value or tmp_memory_gate_value):
+            return
+        for l in range(1, self.n_level):
+            means = out.gate_means[l]                      # [n_tower[l-1], n_tower[l]], detached
+            for t in range(self.n_tower[l]):
+                v = means[:, t]
+                if tmp_memory_gate_value:
+                    self.tmp_tower_gate_values[l][t] = v.clone()
+                if memory_gate_value:
+                    self.domain_tower_gate_values[d][l][t].append(v.clone())
+
+    def _record_unmasked_gates(self, x, gates, domain_i):
+        """aread.py:187-200: per-domain batch means of the raw gate softmax."""
+        if domain_i is not None:
+            for l in range(1, self.n_level):
+                means = gates[l].mean(dim=0)                # gates[l]: [B, n_tower[l-1], n_tower[l]]
+                for t in range(self.n_tower[l]):
+                    self.domain_tower_gate_values[domain_i][l][t].append(means[:, t].clone())
+            return
+        domain_ids = x[:, self.domain_idx]
+        for d in range(self.n_domain):
+            sel = (domain_ids == d)
+            for l in range(1, self.n_level):
+                means = gates[l][sel].mean(dim=0)
+                for t in range(self.n_tower[l]):
+                    self.domain_tower_gate_values[d][l][t].append(means[:, t].clone())
+
+    # --------------------------------------------------------------------------- HEMP bookkeeping
+    def add_eval_loss(self, loss_mean, d, mask_z):                                   # aread.py:324-328
+        if len(self.eval_loss[d]) <= mask_z:
+            self.eval_loss[d].append([loss_mean])
+        else:
+            self.eval_loss[d][mask_z].append(loss_mean)
+
+    def update_all_mask(self, regroup_times=None, update_mode='best4single_domain'):   # aread.py:330-355
+        print('\n============Update Mask============')
+        if update_mode != 'best4single_domain':
+            return
+        n_cand = len(self.candidate_domain_mask[0])
+        means, stds = [], []
+        for d in range(self.n_domain):
+            per_mask = [np.mean(self.eval_loss[d][z]) for z in range(n_cand)]
+            self.domain_mask[d] = self.candidate_domain_mask[d][int(np.argmin(per_mask))]
+            means.append(np.mean(per_mask))
+            stds.append(np.std(per_mask))
+        print('regroup_times: ', regroup_times,
+              'current domain mask active ratio: ', self.count_current_active_ratio())
+        print(f'loss_mean of different domain masks: {means}')
+        print(f'loss_std of different domain masks: {stds}')
+        users = [[] for _ in range(self.n_tower[1])]
+        for d in range(self.n_domain):
+            for t in np.nonzero(self.mask_info(self.domain_mask[d]).active[1])[0]:
+                users[t].append(d)
+        print(f'active domain num of each tower in the middle layer: {[len(u) for u in users]}')
+        print('sample size training each tower in the middle layer: '
+              f'{[sum(self.domain_size[u]) for u in users]}')
+        print('============Finish Update Mask============')
+
+    def prun_single_mask(self, d, current_mask, prun_ratio=0.05):                      # aread.py:357-381
+        gate_values = [torch.stack(self.tmp_tower_gate_values[l], dim=1) for l in range(1, self.n_level)]
+        threshold = 1
+        for g in gate_values:
+            live = g > 1e-8
+            if live.any():
+                threshold = min(threshold, torch.quantile(g[live].flatten(), prun_ratio))
+        if threshold == 1:
+            self.print_domain_mask(current_mask, all_edges=True)
+            for i in range(self.n_level):
+                print(f'level {i} gate_values: {self.tmp_tower_gate_values[i]}')
+            raise ValueError('no valid tmp_tower_gate_values in candidate mask')
+        before = copy.deepcopy(current_mask)
+        for l in range(1, self.n_level):
+            current_mask[l] = current_mask[l] & (gate_values[l - 1] >= threshold)
+        valid = self.validate_mask(current_mask)
+        self.tmp_tower_gate_values = [[None] * self.n_tower[l] for l in range(self.n_level)]
+        return valid if valid[-1].any().item() else before
+
+    def _empty_gate_log(self):
+        return [[[] for _ in range(self.n_tower[l])] for l in range(self.n_level)] + \
+               [[[] for _ in range(self.n_tower[-1])]]
+
+    def reset_for_mask_update(self, d=None):                                          # aread.py:383-401
+        if d is None:
+            self.domain_tower_gate_values = [self._empty_gate_log() for _ in range(self.n_domain)]
+            self.gate_value_threshold = [None] * self.n_domain
+            self.candidate_domain_mask = [[] for _ in range(self.n_domain)]
+            self.eval_loss = [[] for _ in range(self.n_domain)]
+        else:
+            self.domain_tower_gate_values[d] = self._empty_gate_log()
+            self.gate_value_threshold[d] = None
+            self.candidate_domain_mask[d] = []
+            self.eval_loss[d] = []
+
+    def mean_domain_tower_gate_values(self, d, get_threshold=None):                    # aread.py:403-430
+        log = self.domain_tower_gate_values[d]
+        if not isinstance(log[0], list):
+            return
+        dev = self.device
+        mean_values = [torch.zeros(1, self.n_tower[0], dtype=torch.float32, device=dev)]
+        for l in range(1, self.n_level):
+            cols = []
+            for t in range(self.n_tower[l]):
+                if len(log[l][t]) == 0:
+                    cols.append(torch.zeros(self.n_tower[l - 1], dtype=torch.float32, device=dev))
+                else:
+                    cols.append(torch.mean(torch.stack(log[l][t], dim=0), dim=0))
+            mean_values.append(torch.stack(cols, dim=1))
+        mean_values.append(torch.zeros(self.n_tower[-1], 1, dtype=torch.float32, device=dev))
+        self.domain_tower_gate_values[d] = mean_values
+        if get_threshold is not None:
+            threshold = 1
+            for ts in mean_values[1:-1]:
+                live = ts > 1e-8
+                if live.any():
+                    threshold = min(threshold, torch.quantile(ts[live].flatten(), 1 - get_threshold))
+            self.gate_value_threshold[d] = None if threshold == 1 else threshold
+
+    def generate_mask(self, generate_mode='rand', d=None, init_active_percent=0.7, random_modify_sigma=0.2):
+        """Candidate mask for one domain (aread.py:432-532).  Random draws are made in the
+        reference's order so that a seeded schedule reproduces the same masks."""
+        n_mat = self.n_level + 1
+        if generate_mode == 'rand':
+            while True:
+                valid = hemp.validate_arrays(hemp.full_mask(self.n_tower, init_active_percent), tuple(self.n_tower))
+                if valid[-1].any():
+                    return hemp.as_device_mask(valid, self.device)
+        if generate_mode == 'mask_norm_rand':
+            original = hemp.to_numpy(self.domain_mask[d])
+            n_active = sum(int(m.sum()) for m in original)
+            while True:
+                p = min(1, np.abs(np.random.normal(0, random_modify_sigma)))
+                grow = n_active < self.edge_num * p
+                cand = []
+                for l in range(n_mat):
+                    flip = np.random.rand(*original[l].shape) < p
+                    cand.append(original[l] | flip if grow else original[l] ^ flip)
+                valid = hemp.validate_arrays(cand, tuple(self.n_tower))
+                changed = any(not np.array_equal(valid[l], original[l]) for l in range(n_mat))
+                if changed and valid[-1].any():
+                    return hemp.as_device_mask(valid, self.device)
+        if generate_mode in ('max_gate', 'max_gate_norm_rand'):
+            if not any(self.domain_tower_gate_values):
+                raise ValueError('tower_gate_values is None')
+            self.mean_domain_tower_gate_values(d, get_threshold=init_active_percent)
+            if self.gate_value_threshold[d] is None:
+                return self.generate_mask('rand', d, init_active_percent, random_modify_sigma)
+            top = [t >= self.gate_value_threshold[d] for t in self.domain_tower_gate_values[d]]
+            if generate_mode == 'max_gate':
+                valid = self.validate_mask(top)
+                if not valid[-1].any().item():
+                    raise ValueError(f"mask generated for domain {d} in the 'max_gate' mode has no output")
+                return valid
+            p = min(1, np.abs(np.random.normal(0, random_modify_sigma)))
+            while True:
+                cand = [top[l] ^ (torch.rand(top[l].shape, device=self.device) < p) for l in range(n_mat)]
+                valid = self.validate_mask(cand)
+                if valid[-1].any().item():
+                    return valid
+        if generate_mode == 'mask_max_gate':
+            if not any(self.domain_tower_gate_values):
+                raise ValueError('tower_gate_values is None')
+            self.mean_domain_tower_gate_values(d, get_threshold=init_active_percent)
+            if self.gate_value_threshold[d] is None:
+                top = self.generate_mask('rand', d, init_active_percent, random_modify_sigma)
+            else:
+                top = [t >= self.gate_value_threshold[d] for t in self.domain_tower_gate_values[d]]
+            p = min(1, np.abs(np.random.normal(0, random_modify_sigma)))
+            origin = self.domain_mask[d] if self.domain_mask[d] is not None else top
+            shrink = (self.count_active_edge(d_mask=origin) * 1. / self.edge_num) > init_active_percent
+            while True:
+                cand = []
+                for l in range(n_mat):
+                    flip = torch.rand(top[l].shape, device=self.device) < p
+                    merged = origin[l] | top[l]
+                    cand.append(merged ^ flip if shrink else merged | flip)
+                valid = self.validate_mask(cand)
+                changed = any(not torch.all(valid[l] == origin[l]) for l in range(n_mat))
+                if changed and valid[-1].any().item():
+                    return valid
+        raise ValueError(f"unknown generate_mode '{generate_mode}'")
+
+    _ROLLBACK_PREFIXES = ('cn', 'cgc_layers', 'towers', 'tower_gates', 'towers_linear', 'output_layers',
+                          'embedding', 'linear', 'reg_loss', 'regularization_weight')
+
+    def save_model_state(self):                                                      # aread.py:534-543
+        pattern = re.compile('^(' + '|'.join(self._ROLLBACK_PREFIXES) + ')')
+        self.model_state = {k: v.detach().clone() for k, v in self.state_dict().items() if pattern.match(k)}
+
+    def load_model_state(self):                                                      # aread.py:545-546
+        self.load_state_dict(self.model_state, strict=False)
+
+    def create_single_full_mask(self, fill_value=0):                                 # aread.py:548-568
+        return hemp.full_mask(self.n_tower, fill_value)
+
+    def validate_mask(self, mask, add_input=True, add_output=True, remove_hidden=True):   # aread.py:570-605
+        return hemp.validate(mask, self.n_tower, add_input, add_output, remove_hidden)
+
+    def create_domain_mask(self, cluster_z):                                         # aread.py:607-638
+        """Initial masks from a hierarchical-clustering linkage matrix (unused by run.py, kept)."""
+        masks = [hemp.full_mask(self.n_tower, 0) for _ in range(self.n_domain)]
+        members = [[i] for i in range(self.n_domain)]
+        alive = list(range(self.n_domain))
+        level_clusters = [None] * self.n_level
+        for i in range(self.n_domain - self.n_tower[0]):
+            a, b = int(cluster_z[i][0]), int(cluster_z[i][1])
+            members.append(members[a] + members[b])
+            alive.append(i + self.n_domain)
+            alive.remove(a)
+            alive.remove(b)
+            if len(alive) in self.n_tower:
+                level_clusters[self.n_tower.index(len(alive))] = list(alive)
+        for l in range(self.n_level):
+            for t in range(self.n_tower[l]):
+                cluster = members[level_clusters[l][t]]
+                self.tower2cluster[l][t] = cluster
+                for d in cluster:
+                    masks[d][l + 1][t, :] = True
+        self.domain_mask = [hemp.as_device_mask(hemp.validate_arrays(m, tuple(self.n_tower)), self.device)
+                            for m in masks]
+
+    def print_domain_mask(self, d_mask=None, d=None, all_edges=False):                 # aread.py:640-662
+        mask = hemp.to_numpy(d_mask if d_mask is not None else self.domain_mask[d])
+        print('level 0 towers:', np.nonzero(mask[0])[1])
+        if all_edges:
+            for l in range(1, self.n_level):
+                print(f'========= level {l} =========')
+                for t in range(self.n_tower[l]):
+                    feeders = np.nonzero(mask[l][:, t])[0]
+                    print(f'last level input towers of tower {t}:', feeders if len(feeders) else None)
+            print('========= level finish =========')
+        else:
+            for l in range(1, self.n_level):
+                print(f'level {l} used last level towers:', np.nonzero(np.any(mask[l], axis=1))[0])
+        print('the last level output towers:', np.nonzero(mask[-1])[0])
+
+    def count_current_active_ratio(self):                                            # aread.py:664-669
+        return sum(self.count_active_edge(d=d) * 1. / self.edge_num for d in range(self.n_domain)) / self.n_domain
+
+    def count_active_edge(self, d=None, d_mask=None):                                  # aread.py:671-680
+        return hemp.count_edges(d_mask if d_mask is not None else self.domain_mask[d])

@@ -1,0 +1,133 @@
+"""Host orchestration of the dense part of the AREAD step (trunk, HEI levels, heads, regulariser).
+
+Reference: model/aread.py:131-153 (trunk), :263-322 (HEI under a HEMP mask), :156-202 (unmasked
+walk), model/layer.py:96-112 (regulariser).
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+class MaskInfo:
+    """Host view of one HEMP mask: which towers run, which edges are open.  Built once per distinct
+    mask; the forward consults it instead of synchronising on device booleans."""
+
+    def __init__(self, arrays, n_tower):
+        self.arrays = [np.asarray(a, dtype=bool) for a in arrays]
+        self.n_tower = tuple(n_tower)
+        n_level = len(self.n_tower)
+        # a tower runs when any edge enters it (aread.py:268: any(mask[l], dim=0))
+        self.active = [self.arrays[l].any(axis=0) for l in range(n_level)]
+        self.active_last = np.nonzero(self.active[-1])[0]
+        self.group_idx = np.nonzero(self.arrays[0])[1]            # aread.py:226 / 237
+        self._edges = {}
+
+    def edges(self, l, device):
+        key = (l, device)
+        e = self._edges.get(key)
+        if e is None:
+            e = torch.from_numpy(self.arrays[l].astype(np.float32)).to(device)
+            self._edges[key] = e
+        return e
+
+    def group_index(self, device):
+        key = ("grp", device)
+        e = self._edges.get(key)
+        if e is None:
+            e = torch.from_numpy(self.group_idx.astype(np.int64)).to(device)
+            self._edges[key] = e
+        return e
+
+
+@dataclass
+class ForwardOut:
+    probs: torch.Tensor                                  # [n_active_last, B]
+    gate_inputs: Optional[torch.Tensor] = None           # [B, 2 * D]
+    gate_means: Dict[int, torch.Tensor] = field(default_factory=dict)   # l -> [n_{l-1}, n_l]
+    gates: Dict[int, torch.Tensor] = field(default_factory=dict)        # l -> [B, n_{l-1}, n_l]
+
+
+def _require_cuda(model, x):
+    if not x.is_cuda:
+        raise RuntimeError("aread_b200: inputs must be CUDA tensors -- this implementation is sm_100a-only and "
+                           "has no CPU fallback")
+
+
+def aread_forward(model, x, info: Optional[MaskInfo], want_gate_means=False, want_gates=False) -> ForwardOut:
+    """Embedding lookup -> trunk -> HEI levels -> per-tower probabilities."""
+    _require_cuda(model, x)
+    embed_x = model.embedding(x, squeeze_dim=False)
+    domain_embed = embed_x[:, model.domain_idx, :]
+    X = embed_x.flatten(start_dim=1)
+    lin = model.linear(X)
+    cn = model.cn(X)
+    experts = torch.stack([e(X) for e in model.mmoe_experts], dim=1)                # [B, n_expert, h]
+    t0 = [torch.sum(g(X).unsqueeze(-1) * experts, dim=1) for g in model.mmoe_gates]
+    if info is None:
+        group_embed = torch.zeros_like(domain_embed)                                 # aread.py:157
+    else:
+        group_embed = model.group_embedding(info.group_index(x.device))
+        if group_embed.shape[0] > 1:
+            group_embed = group_embed.mean(dim=0, keepdim=True)
+        group_embed = group_embed.expand(x.shape[0], -1)
+    q = torch.cat([domain_embed, group_embed], dim=1)
+    out = hei_forward(model, t0, q, cn, lin, info, want_gate_means, want_gates)
+    out.gate_inputs = q
+    return out
+
+
+def hei_forward(model, tower_inputs, q, cn, lin, info: Optional[MaskInfo], want_gate_means=False,
+                want_gates=False) -> ForwardOut:
+    B = lin.shape[0]
+    n_level, n_tower = model.n_level, model.n_tower
+    out = ForwardOut(probs=None)
+    prev = None
+    for l in range(n_level):
+        active = np.ones(n_tower[l], dtype=bool) if info is None else info.active[l]
+        width = model.tower_dims[l][-1]
+        if l > 0:
+            logits = torch.stack([model.tower_gates[l - 1][t][0](q) for t in range(n_tower[l])], dim=2)
+            s = torch.softmax(logits, dim=1)                                        # [B, n_{l-1}, n_l]
+            if want_gates:
+                out.gates[l] = s.detach()
+            if info is None:
+                r = s
+            else:
+                sm = s * info.edges(l, q.device)
+                r = sm / (sm.sum(dim=1, keepdim=True) + 1e-8)
+                if want_gate_means:
+                    out.gate_means[l] = sm.mean(dim=0).detach()
+            inputs = torch.einsum('bjt,bjw->btw', r, prev)                          # [B, n_l, w_{l-1}]
+        level_out = []
+        for t in range(n_tower[l]):
+            if not active[t]:
+                level_out.append(torch.zeros(B, width, dtype=torch.float32, device=q.device))
+                continue
+            h = tower_inputs[t] if l == 0 else inputs[:, t, :]
+            level_out.append(model.towers[l][t](h))
+        if l < n_level - 1:
+            prev = torch.stack(level_out, dim=1)
+        else:
+            probs = []
+            for t in range(n_tower[l]):
+                if active[t]:
+                    z = model.towers_linear[t](torch.cat([cn, level_out[t]], dim=1)) + lin
+                    probs.append(torch.sigmoid(z).squeeze(-1))
+            out.probs = torch.stack(probs, dim=0)
+    return out
+
+
+def regularization_loss(regularization_weight, device):
+    """sum_groups sum_w l1*|w| + l2*w^2 as a [1] tensor (layer.py:96-112)."""
+    total = torch.zeros((1,), device=device)
+    for weights, l1, l2 in regularization_weight:
+        for w in weights:
+            p = w[1] if isinstance(w, tuple) else w
+            if l1 > 0:
+                total = total + torch.sum(l1 * torch.abs(p))
+            if l2 > 0:
+                total = total + l2 * torch.sum(torch.square(p))
+    return total

@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""AREAD train throughput on synthetic data of the BASELINE.json shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload amazon|aliccp|cloudtheme] [--batch B]
+
+One step = forward(mode='domain_mask_bagging') + mean-over-towers BCE + L2 regulariser +
+zero_grad + backward + Adam.step on one single-domain batch (run.py:663-682).  Prints ONE JSON
+line (rank 0): samples/s with inputs resident in HBM (`value`), through the module API from
+pinned host buffers (`e2e`), the gather kernel's roofline, and the CPU baseline.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_TOWER = (3, 6, 12)
+EXPERT_DIMS = (256, 128, 64)
+TOWER_DIMS = ((64, 32), (32, 16), (16, 8))
+LR, WD = 1e-3, 1e-8
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="amazon", choices=["amazon", "aliccp", "cloudtheme"])
+    ap.add_argument("--batch", type=int, default=65536, help="samples per step per GPU")
+    ap.add_argument("--cpu-batch", type=int, default=2048, help="rows per step of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--active", type=float, default=0.7, help="HEMP init_active_percent of the per-domain masks")
+    ap.add_argument("--dropout", type=float, default=0.2)
+    ap.add_argument("--seed", type=int, default=2000)
+    return ap.parse_args()
+
+
+def make_config(wl):
+    return types.SimpleNamespace(domain_size={wl.name: list(wl.domain_size)}, dataset_name=wl.name, use_dcn=True,
+                                 use_atten=True, n_cross_layers=3, mmoe_n_expert=4, atten_embed_dim=64,
+                                 att_head_num=2, att_layer_num=3, att_res=True)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_rate(wl, batch, steps, warmup, active, seed, dropout=0.2, threads=None):
+    """The oracle port (oracle/aread_torch.py: the reference's torch ops restated functionally) timed on
+    the host cores: same step definition, fp32, all threads."""
+    from oracle import aread_torch as O
+    from oracle import synth
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    mh = wl.multi_hot_dict
+    spec = O.Spec(one_hot_field_dims=list(wl.one_hot_field_dims), embed_dim=wl.embed_dim,
+                  multi_hot_flag=mh["multi_hot_flag"], itemid_idx=wl.itemid_idx, seq_maxlen=wl.seq_maxlen,
+                  method=wl.method, n_tower=N_TOWER, n_domain=wl.n_domain, expert_dims=EXPERT_DIMS,
+                  tower_dims=TOWER_DIMS, domain_idx=wl.domain_idx, dropout=dropout)
+    sd = O.make_leaf_params(synth.deterministic_state(spec))
+    opt = O.make_adam(sd, lr=LR, wd=WD)
+    np.random.seed(seed)
+    hemp = importlib.import_module("aread-multi-domain-recommendation_b200.hemp")
+    masks = {}
+    times = []
+    for step in range(warmup + steps):
+        x, y, d = wl.batch(batch, seed=seed + step)
+        if d not in masks:
+            while True:
+                m = hemp.validate_arrays(hemp.full_mask(N_TOWER, active), N_TOWER)
+                if m[-1].any():
+                    break
+            masks[d] = [torch.from_numpy(a) for a in m]
+        xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+        t0 = time.perf_counter()
+        O.train_step(sd, spec, xt, yt, masks[d], opt, masks="rng")
+        dt = time.perf_counter() - t0
+        if step >= warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    return {"value": batch * len(times) / total, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{len(times)} train steps of {batch} rows ({wl.name}, fp32, dropout {dropout}, {warmup} "
+                      f"warm-up; the reference's dead attention branch is not executed), {total:.1f} s"}, total / len(times)
+
+
+def run_reference(args, wl, rank):
+    if rank != 0:
+        return
+    res, sec_per_step = cpu_reference_rate(wl, args.cpu_batch, max(1, args.steps), max(1, args.warmup), args.active,
+                                           args.seed, args.dropout)
+    line = {"impl": "reference", "metric": "aread_train_samples_per_sec", "value": res["value"],
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, args.warmup),
+            "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl.name}_singledomain_B{args.cpu_batch}", "batch_per_step": args.cpu_batch,
+                       "n_tower": list(N_TOWER), "embed_dim": wl.embed_dim, "mask_active_percent": args.active,
+                       "note": "reference path = torch CPU ops restated in oracle/aread_torch.py (the Python "
+                               "reference itself cannot travel to the GPU box); bounded sample of the workload"},
+            "cpu_baseline": res,
+            "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, wl, rank, world, local_rank):
+    import torch.distributed as dist
+    pkg = importlib.import_module("aread-multi-domain-recommendation_b200")
+    lib = importlib.import_module("aread-multi-domain-recommendation_b200._lib")
+    ops = importlib.import_module("aread-multi-domain-recommendation_b200.embedding_ops")
+    lib.load()                                     # fail loudly when the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(args.seed + rank)
+    np.random.seed(args.seed)                      # same masks on every rank
+
+    model = pkg.AREAD(np.asarray(wl.one_hot_field_dims), wl.embed_dim, wl.multi_hot_dict, n_tower=N_TOWER,
+                      n_domain=wl.n_domain, base_model="mmoe", expert_dims=EXPERT_DIMS, tower_dims=TOWER_DIMS,
+                      domain_idx=wl.domain_idx, device=dev, dropout=args.dropout, config=make_config(wl)).to(dev)
+    model.reset_for_mask_update()
+    for d in range(wl.n_domain):
+        model.domain_mask[d] = model.generate_mask("rand", d, init_active_percent=args.active)
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, src=0)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=LR, betas=(0.9, 0.99), eps=1e-8, weight_decay=WD)
+    crit = torch.nn.BCELoss()
+    dense_params = [p for p in model.parameters()]
+
+    B = args.batch
+    n_batches = args.warmup + args.steps
+    host = [wl.batch(B, seed=args.seed + 1000 * rank + i) for i in range(n_batches)]
+    host_x = [torch.from_numpy(x).pin_memory() for x, _, _ in host]
+    host_y = [torch.from_numpy(y).pin_memory() for _, y, _ in host]
+    domains = [d for _, _, d in host]
+
+    def step(x, y, d):
+        preds = model(x, mode="domain_mask_bagging", domain_i=d)
+        tgt = y.squeeze().float()
+        loss = sum(crit(p, tgt) for p in preds.unbind(dim=0)) / preds.shape[0]
+        loss = loss + model.get_regularization_loss(device=dev)
+        model.zero_grad()
+        loss.backward()
+        if world > 1:
+            for p in dense_params:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(run_one, first, count):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(first, first + count):
+            run_one(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- device-resident pass
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+    for i in range(args.warmup):
+        step(dev_x[i], dev_y[i], domains[i])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.launch_count()
+    ms_dev = timed(lambda i: step(dev_x[i], dev_y[i], domains[i]), args.warmup, args.steps)
+    launches = lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the module API from pinned host memory (H2D of ids+labels, D2H of the loss)
+    def e2e_step(i):
+        x = host_x[i].to(dev, non_blocking=True)
+        y = host_y[i].to(dev, non_blocking=True)
+        return float(step(x, y, domains[i]).item())
+    for i in range(min(2, args.warmup)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.warmup, args.steps)
+
+    # ---- gather kernel alone, on its launch stream, over the same batches (roofline numerator)
+    plan = model.embedding.plan(dev)
+    table = model.embedding.embedding_dict.weight.detach()
+    for i in range(args.warmup):
+        ops.gather(plan, table, dev_x[i])
+    stream = torch.cuda.current_stream(dev)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    g0.record(stream)
+    for i in range(args.warmup, args.warmup + args.steps):
+        ops.gather(plan, table, dev_x[i])
+    g1.record(stream)
+    torch.cuda.synchronize(dev)
+    gather_ms = g0.elapsed_time(g1) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, peak_src = load_peaks()
+    gather_bytes = wl.gather_bytes_per_sample() * B
+    achieved = gather_bytes / (gather_ms * 1e-3) / 1e9
+    total_samples = B * args.steps * world
+    line = {
+        "metric": "aread_train_samples_per_sec", "value": total_samples / (ms_dev * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{wl.name}_singledomain_B{B}", "batch_per_gpu": B, "n_tower": list(N_TOWER),
+                   "embed_dim": wl.embed_dim, "table_rows": wl.n_rows, "n_cols": wl.n_cols,
+                   "mask_active_percent": args.active, "dropout": args.dropout, "optimizer": "torch.optim.Adam",
+                   "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2: table %d MB + per-step activations" % (wl.n_rows * wl.embed_dim * 4 >> 20)},
+        "e2e": {"value": total_samples / (ms_e2e * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": int(host_x[0].numel() * 4 + host_y[0].numel() * 2), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "gather_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": gather_bytes, "launch_ms": gather_ms},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"], _ = cpu_reference_rate(wl, args.cpu_batch, args.cpu_steps, 1, args.active, args.seed,
+                                                       args.dropout)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    wl = importlib.import_module("aread-multi-domain-recommendation_b200.workloads").WORKLOADS[args.workload]()
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+    else:
+        run_ours(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

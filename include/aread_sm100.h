@@ -1,0 +1,128 @@
+/*
+ * aread_sm100.h -- C ABI of libaread_sm100.so: the AREAD hot path as hand-written sm_100a CUDA.
+ *
+ * The reference (Chrissie-Law/AREAD-Multi-Domain-Recommendation) is pure PyTorch and has no FFI of
+ * its own; each entry point below names the reference function (file:line under the reference
+ * tree) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller unless a
+ *     field says "host".  The library never allocates device memory and keeps no global state
+ *     besides a thread-local error string.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     and is safe to capture in a CUDA graph unless stated otherwise.
+ *   - return value: AREAD_OK or a negative aread_status; aread_last_error() describes the failure.
+ *   - workspaces: `aread_<op>_workspace_bytes()` gives the scratch size; pass a buffer at least
+ *     that large, 256-byte aligned.
+ *   - fp32 tensors are row-major and contiguous; "rows" are samples, never padded.
+ */
+#ifndef AREAD_SM100_H
+#define AREAD_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AREAD_API __attribute__((visibility("default")))
+#else
+#define AREAD_API
+#endif
+
+typedef void* aread_stream_t; /* cudaStream_t */
+
+typedef enum aread_status {
+  AREAD_OK = 0,
+  AREAD_ERR_INVALID = -1, /* bad argument (null pointer, unsupported size, misalignment)            */
+  AREAD_ERR_INDEX = -2,   /* an id + field offset fell outside [0, n_rows): torch raises IndexError */
+  AREAD_ERR_CUDA = -3,    /* a CUDA runtime call failed                                            */
+  AREAD_ERR_WORKSPACE = -4 /* workspace too small                                                   */
+} aread_status;
+
+/* Human-readable description of the last failure on the calling thread ("" if none). */
+AREAD_API const char* aread_last_error(void);
+/* ABI version of the loaded library (bumped whenever a struct below changes). */
+AREAD_API int aread_abi_version(void);
+/* Number of kernel launches issued through this library by the calling process so far. */
+AREAD_API uint64_t aread_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-field embedding lookup.
+ * Replaces FeaturesEmbedding.forward (model/layer.py:160-183): idx = x + offsets (:165), table
+ * gather (:166), mean/sum pooling of multi-hot columns over seq_maxlen positions, padding positions
+ * included (:168-176), concat [one-hot fields | pooled fields] (:178).
+ *
+ * The layout of the lookup is described once by a "plan" living in device memory:
+ *   col_offset[c]            row offset added to column c of x              (layer.py:151-157)
+ *   field_src[f * max_src+k] k-th input column feeding output field f (k < field_nsrc[f])
+ *   field_nsrc[f]            1 for a one-hot field, seq_maxlen for a pooled field
+ *   field_div[f]             divisor applied after the in-order sum (1 or seq_maxlen for 'mean')
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_embed_plan {
+  int32_t n_cols;            /* columns of x                                   */
+  int32_t n_fields;          /* output fields (output_dim0, layer.py:141-143)  */
+  int32_t max_src;           /* stride of field_src                            */
+  int32_t embed_dim;         /* D; must be a multiple of 4                     */
+  int64_t n_rows;            /* rows of the table (sum of the one-hot dims)    */
+  const int32_t* col_offset; /* [n_cols]                                       */
+  const int32_t* field_src;  /* [n_fields * max_src]                           */
+  const int32_t* field_nsrc; /* [n_fields]                                     */
+  const float* field_div;    /* [n_fields]                                     */
+} aread_embed_plan;
+
+typedef struct aread_gather_args {
+  aread_embed_plan plan;
+  int64_t batch;       /* B                                                                       */
+  const int32_t* x;    /* [B, n_cols] ids (run.py:274 stores them as int32)                        */
+  const float* table;  /* [n_rows, D] fp32                                                         */
+  float* out;          /* [B, n_fields, D] fp32, bit-exact copy / in-order pooled sum              */
+  uint16_t* out_bf16;  /* optional [B, n_fields * D] bf16 (round-to-nearest-even) copy, or NULL    */
+  int32_t* status;     /* [2] device ints: status[0] != 0 after an out-of-range id, status[1] = the
+                          offending row index.  Zero it before the first call.  Rows that are out
+                          of range produce zeros.                                                 */
+} aread_gather_args;
+
+AREAD_API int aread_gather_fwd(const aread_gather_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gradient of the lookup: deterministic sort-by-row segmented scatter-add.
+ * Replaces the autograd of model/layer.py:166 (aten::embedding_dense_backward, dense because
+ * sparse=False at layer.py:150) including the 1/seq_maxlen factor of the mean pooling.
+ *
+ * Order of summation (documented so that it can be reproduced bit for bit, oracle/embedding_np.py
+ * scatter_bwd_tiled): lookups are stably sorted by table row; the sorted list is cut into tiles of
+ * AREAD_SCATTER_TILE consecutive entries; inside a tile a row's entries are summed left to right.
+ * A row spanning 1 + K tiles takes the partial of its first tile, cuts the K following per-tile
+ * partials into AREAD_SCATTER_SPAN_BLOCKS contiguous blocks of ceil(K / blocks), sums every block
+ * left to right and then adds the block sums left to right onto the first partial (for K <= 32
+ * that is simply left to right).  A row whose entries all fall in one tile therefore reproduces
+ * the reference (sequential) order exactly.
+ * ---------------------------------------------------------------------------------------------- */
+#define AREAD_SCATTER_TILE 32
+#define AREAD_SCATTER_SPAN_BLOCKS 32
+
+typedef struct aread_scatter_args {
+  aread_embed_plan plan;
+  int64_t batch;
+  const int32_t* x;     /* [B, n_cols]                                                          */
+  const float* d_out;   /* [B, n_fields, D] gradient w.r.t. the gather output                   */
+  float* d_table;       /* [n_rows, D]; rows that were looked up are OVERWRITTEN with their sum,
+                           other rows are left untouched (zero-fill it first for the dense
+                           gradient of the reference, see zero_fill)                            */
+  int32_t zero_fill;    /* != 0: clear d_table on `stream` before scattering                    */
+  void* workspace;      /* aread_scatter_workspace_bytes(B * n_cols, D) bytes                   */
+  size_t workspace_bytes;
+  int32_t* sorted_rows; /* optional out [B * n_cols]: table rows in sorted order, or NULL       */
+  int32_t* sorted_pos;  /* optional out [B * n_cols]: flattened (b, c) position of each, or NULL */
+} aread_scatter_args;
+
+AREAD_API size_t aread_scatter_workspace_bytes(int64_t n_lookups, int32_t embed_dim);
+AREAD_API int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AREAD_SM100_H */

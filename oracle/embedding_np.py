@@ -106,20 +106,36 @@ def sort_segments(idx_flat):
     return sorted_rows, perm, sorted_rows[starts], np.concatenate([starts, [len(sorted_rows)]]).astype(np.int64)
 
 
-def scatter_bwd_chunked(d_cols, idx_flat, n_rows, chunk):
-    """The summation order of the CUDA segmented reduce: each row's segment (in stable
-    sorted order) is cut into runs of `chunk` lookups, every run is summed left to right,
-    and the run partials are then summed left to right.  For segments no longer than
-    `chunk` this is exactly the reference order."""
-    d_cols = np.asarray(d_cols, dtype=np.float32).reshape(len(np.asarray(idx_flat).reshape(-1)), -1)
+def scatter_bwd_tiled(d_cols, idx_flat, n_rows, tile=32, span_blocks=32):
+    """The summation order of the CUDA segmented reduce (include/aread_sm100.h): the stably
+    sorted lookups are cut into tiles of `tile` consecutive entries (aligned to the sorted list,
+    not to the segments); inside a tile a row's entries are summed left to right.  A row
+    spanning 1 + K tiles keeps the partial of its first tile, cuts the K following partials into
+    `span_blocks` contiguous blocks of ceil(K / span_blocks), sums each block left to right and
+    adds the block sums left to right onto the first partial.  A row whose entries all fall
+    inside one tile reproduces the reference (sequential) order exactly."""
+    idx_flat = np.asarray(idx_flat).reshape(-1)
+    d_cols = np.asarray(d_cols, dtype=np.float32).reshape(len(idx_flat), -1)
     _, perm, uniq, seg = sort_segments(idx_flat)
     dw = np.zeros((n_rows, d_cols.shape[1]), dtype=np.float32)
     for r, s, e in zip(uniq, seg[:-1], seg[1:]):
-        total = None
-        for c0 in range(s, e, chunk):
+        parts = []
+        c0 = s
+        while c0 < e:
+            c1 = min(e, (c0 // tile + 1) * tile)
             part = d_cols[perm[c0]].copy()
-            for p in perm[c0 + 1:min(c0 + chunk, e)]:
+            for p in perm[c0 + 1:c1]:
                 part = part + d_cols[p]
-            total = part if total is None else total + part
+            parts.append(part)
+            c0 = c1
+        total = parts[0]
+        K = len(parts) - 1
+        if K > 0:
+            m = -(-K // span_blocks)
+            for j0 in range(1, K + 1, m):
+                blk = parts[j0]
+                for q in parts[j0 + 1:min(K + 1, j0 + m)]:
+                    blk = blk + q
+                total = total + blk
         dw[r] = total
     return dw

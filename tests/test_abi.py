@@ -1,0 +1,66 @@
+"""The C-ABI library loads and exports every symbol include/*.h declares; the ctypes structs match
+the header field for field.  No compute calls (runs without a GPU)."""
+import ctypes
+import glob
+import importlib
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = importlib.import_module("aread-multi-domain-recommendation_b200._lib")
+build = importlib.import_module("aread-multi-domain-recommendation_b200.build")
+
+
+def declared_functions():
+    names = []
+    for header in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+        names += re.findall(r"AREAD_API\s+[\w\s\*]+?\b(aread_\w+)\s*\(", text)
+    return sorted(set(names))
+
+
+def struct_fields(name):
+    text = "".join(open(h).read() for h in glob.glob(os.path.join(ROOT, "include", "*.h")))
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    return [re.search(r"(\w+)\s*$", decl.strip()).group(1) for decl in body.split(";") if decl.strip()]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_functions()
+    assert len(names) >= 6
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert set(_lib.exported_symbols()) == set(names), "ctypes binding and header disagree"
+    assert lib.aread_abi_version() == _lib.ABI_VERSION
+    assert lib.aread_last_error() == b""
+
+
+@pytest.mark.parametrize("cname,ctype", [("aread_embed_plan", "EmbedPlan"), ("aread_gather_args", "GatherArgs"),
+                                         ("aread_scatter_args", "ScatterArgs")])
+def test_struct_fields_match_header(cname, ctype):
+    fields = [f for f, _ in getattr(_lib, ctype)._fields_]
+    assert fields == struct_fields(cname)
+
+
+def test_struct_sizes_are_native(lib):
+    assert ctypes.sizeof(_lib.EmbedPlan) == 56
+    assert ctypes.sizeof(_lib.GatherArgs) == 56 + 8 * 6
+    assert ctypes.sizeof(_lib.ScatterArgs) == 56 + 8 * 9
+
+
+def test_argument_validation_without_gpu(lib):
+    """Bad arguments are rejected before any CUDA call is made."""
+    args = _lib.GatherArgs()
+    assert lib.aread_gather_fwd(ctypes.byref(args), None) == _lib.AREAD_ERR_INVALID
+    assert b"plan" in lib.aread_last_error()
+    with pytest.raises(_lib.AreadError):
+        _lib.check(lib.aread_scatter_bwd(None, None))

@@ -53,12 +53,12 @@ def test_scatter_matches_reference_table_grad(name):
     (out * G).sum().backward()
     got = E.scatter_bwd_dense(G.numpy(), x.numpy(), spec.offsets, spec.n_rows, spec.flag, spec.seq_maxlen, spec.method)
     assert np.array_equal(got.view(np.uint32), W.grad.numpy().view(np.uint32))
-    # chunked order == sequential order when no segment is longer than the chunk
+    # tiled order == sequential order when every segment sits inside one tile
     idx = E.lookup_rows(x.numpy(), spec.offsets, spec.n_rows).reshape(-1)
     g_cols = E.expand_pooled_grad(G.numpy(), x.shape[1], spec.flag, spec.seq_maxlen, spec.method)
-    big = E.scatter_bwd_chunked(g_cols, idx, spec.n_rows, chunk=1 << 20)
+    big = E.scatter_bwd_tiled(g_cols, idx, spec.n_rows, tile=1 << 20)
     assert np.array_equal(big.view(np.uint32), got.view(np.uint32))
-    small = E.scatter_bwd_chunked(g_cols, idx, spec.n_rows, chunk=8)
+    small = E.scatter_bwd_tiled(g_cols, idx, spec.n_rows, tile=8)
     np.testing.assert_allclose(small, got, rtol=1e-5, atol=1e-6)
 
 

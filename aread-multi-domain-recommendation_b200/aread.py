@@ -136,6 +136,7 @@ class AREAD(BaseModel):
             if len(self._mask_cache) > 4096:
                 self._mask_cache.clear()
             info = dense_ops.MaskInfo(hemp.to_numpy(mask), self.n_tower)
+            info.keepalive = list(mask)     # pins the storage so a recycled data_ptr cannot alias the key
             self._mask_cache[key] = info
         return info
 

@@ -13,7 +13,6 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kTile = AREAD_SCATTER_TILE;
-constexpr int kSpanBlocks = AREAD_SCATTER_SPAN_BLOCKS;  // fixed: part of the documented summation order
 
 // ---------------------------------------------------------------------------------------------
 // plan staging: the per-column / per-field tables are tiny, every CTA copies them to smem once
@@ -60,8 +59,9 @@ __device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// gather: one "slot" = one (sample, output field); LPR lanes move one slot's D floats.
-// Each lane group keeps UNROLL independent slots in flight to cover the HBM latency.
+// gather: LPR lanes (one float4 each) own one sample and walk its output fields, UNROLL fields at
+// a time so that every lane group keeps UNROLL independent 128-byte row reads in flight.  All lane
+// groups of a warp are in the same field at the same time, so pooled fields do not diverge.
 // ---------------------------------------------------------------------------------------------
 template <int LPR, int UNROLL>
 __global__ void __launch_bounds__(kThreads) gather_kernel(const aread_gather_args a) {
@@ -69,68 +69,66 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const aread_gather_arg
   const aread_embed_plan& p = a.plan;
   const PlanView pv = stage_plan(p, smem);
 
-  const int D = p.embed_dim;
-  const int F = p.n_fields;
-  const int C = p.n_cols;
+  const int D = p.embed_dim, F = p.n_fields, C = p.n_cols, MS = p.max_src;
   const int lane = threadIdx.x % LPR;
   const bool lane_on = lane * 4 < D;
-  const int64_t groups_per_cta = blockDim.x / LPR;
+  const int groups_per_cta = blockDim.x / LPR;
   const int64_t n_groups = static_cast<int64_t>(gridDim.x) * groups_per_cta;
-  const int64_t group = static_cast<int64_t>(blockIdx.x) * groups_per_cta + threadIdx.x / LPR;
-  const int64_t n_slots = a.batch * F;
   const int64_t n_rows = p.n_rows;
+  const float* __restrict__ table = a.table + lane * 4;
+  int* __restrict__ status = a.status;
 
-  for (int64_t s0 = group; s0 < n_slots; s0 += n_groups * UNROLL) {
-    float4 acc[UNROLL];
-    int64_t b[UNROLL];
-    int f[UNROLL];
-    int nsrc[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int64_t s = s0 + u * n_groups;
-      acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      nsrc[u] = 0;
-      b[u] = 0;
-      f[u] = 0;
-      if (s < n_slots) {
-        b[u] = s / F;
-        f[u] = static_cast<int>(s - b[u] * F);
-        nsrc[u] = pv.field_nsrc[f[u]];
-        const int c = pv.field_src[f[u] * p.max_src];
-        const int row = row_of(__ldg(a.x + b[u] * C + c), pv.col_offset[c]);
-        if (row < 0 || row >= n_rows) {
-          if (lane == 0 && atomicExch(a.status, 1) == 0) a.status[1] = row;
-        } else if (lane_on) {
-          acc[u] = ldg4(a.table + static_cast<int64_t>(row) * D + lane * 4);
-        }
-      }
+  auto fetch = [&](const int* __restrict__ xr, int c, float4& v) {
+    const int row = row_of(__ldg(xr + c), pv.col_offset[c]);
+    if (row < 0 || row >= n_rows) {
+      if (lane == 0 && atomicExch(status, 1) == 0) status[1] = row;
+    } else if (lane_on) {
+      v = ldg4(table + static_cast<int64_t>(row) * D);
     }
+  };
+
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * groups_per_cta + threadIdx.x / LPR; b < a.batch;
+       b += n_groups) {
+    const int* __restrict__ xr = a.x + b * C;
+    float* __restrict__ orow = a.out + b * F * D + lane * 4;
+    uint16_t* __restrict__ hrow = a.out_bf16 ? a.out_bf16 + b * F * D + lane * 4 : nullptr;
+    for (int f0 = 0; f0 < F; f0 += UNROLL) {
+      float4 acc[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      if (nsrc[u] > 1) {  // pooled multi-hot field: in-order sum over the sequence positions
-        for (int k = 1; k < nsrc[u]; ++k) {
-          const int c = pv.field_src[f[u] * p.max_src + k];
-          const int row = row_of(__ldg(a.x + b[u] * C + c), pv.col_offset[c]);
-          if (row < 0 || row >= n_rows) {
-            if (lane == 0 && atomicExch(a.status, 1) == 0) a.status[1] = row;
-          } else if (lane_on) {
-            add4(acc[u], ldg4(a.table + static_cast<int64_t>(row) * D + lane * 4));
+      for (int u = 0; u < UNROLL; ++u) {
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f0 + u < F) fetch(xr, pv.field_src[(f0 + u) * MS], acc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int f = f0 + u;
+        if (f < F && pv.field_nsrc[f] > 1) {  // pooled multi-hot field: in-order sum over the positions
+          const int nsrc = pv.field_nsrc[f];
+          for (int k = 1; k < nsrc; k += 4) {
+            float4 r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (k + j < nsrc) fetch(xr, pv.field_src[f * MS + k + j], r[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (k + j < nsrc) add4(acc[u], r[j]);
+          }
+          const float dv = pv.field_div[f];
+          if (dv != 1.f) {
+            acc[u].x = acc[u].x / dv; acc[u].y = acc[u].y / dv;
+            acc[u].z = acc[u].z / dv; acc[u].w = acc[u].w / dv;
           }
         }
-        const float dv = pv.field_div[f[u]];
-        if (dv != 1.f) {
-          acc[u].x = acc[u].x / dv; acc[u].y = acc[u].y / dv;
-          acc[u].z = acc[u].z / dv; acc[u].w = acc[u].w / dv;
-        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int64_t s = s0 + u * n_groups;
-      if (s < n_slots && lane_on) {
-        *reinterpret_cast<float4*>(a.out + s * D + lane * 4) = acc[u];
-        if (a.out_bf16 != nullptr)
-          *reinterpret_cast<uint2*>(a.out_bf16 + s * D + lane * 4) = pack_bf16x4(acc[u]);
+      for (int u = 0; u < UNROLL; ++u) {
+        const int f = f0 + u;
+        if (f < F && lane_on) {
+          *reinterpret_cast<float4*>(orow + f * D) = acc[u];
+          if (hrow != nullptr) *reinterpret_cast<uint2*>(hrow + f * D) = pack_bf16x4(acc[u]);
+        }
       }
     }
   }
@@ -153,123 +151,191 @@ __global__ void __launch_bounds__(kThreads) scatter_keys_kernel(const aread_embe
 }
 
 // ---------------------------------------------------------------------------------------------
-// scatter step 3: one lane group per tile of kTile sorted lookups, in-order run sums
+// scatter step 3: one lane group per tile of kTile sorted lookups, in-order run sums.  The tile's
+// keys / positions are loaded once (kTile / LPR per lane) and handed round by shuffles; gradient
+// rows are fetched eight at a time so the reads overlap, then consumed strictly in order.
 // ---------------------------------------------------------------------------------------------
 template <int LPR>
 __global__ void __launch_bounds__(kThreads) scatter_tile_kernel(
     const aread_embed_plan p, const unsigned* __restrict__ keys, const int* __restrict__ pos, int64_t n,
     int64_t n_tiles, const float* __restrict__ d_out, float* __restrict__ d_table, float* __restrict__ carry_in,
-    float* __restrict__ carry_out, int* __restrict__ span_count, int* __restrict__ span_tiles) {
+    float* __restrict__ carry_out) {
   extern __shared__ int smem[];
   int* s_field = smem;                                        // column -> output field
-  float* s_div = reinterpret_cast<float*>(smem + p.n_cols);   // column -> pooling divisor
+  float* s_div = reinterpret_cast<float*>(smem + p.n_cols);   // column -> fl32(1 / pooling divisor)
   for (int i = threadIdx.x; i < p.n_fields * p.max_src; i += blockDim.x) {
     const int f = i / p.max_src, k = i - f * p.max_src;
     if (k < p.field_nsrc[f]) {
       const int c = p.field_src[i];
       s_field[c] = f;
-      s_div[c] = p.field_div[f];
+      s_div[c] = 1.f / p.field_div[f];
     }
   }
   __syncthreads();
 
+  constexpr int PER = kTile / LPR;  // tile entries held per lane
+  constexpr int BATCH = 8;
   const int D = p.embed_dim, F = p.n_fields, C = p.n_cols;
   const int lane = threadIdx.x % LPR;
   const bool lane_on = lane * 4 < D;
+  const unsigned gmask =
+      LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (((threadIdx.x % 32) / LPR) * LPR));
   const int64_t t = static_cast<int64_t>(blockIdx.x) * (blockDim.x / LPR) + threadIdx.x / LPR;
   if (t >= n_tiles) return;
   const int64_t start = t * kTile;
-  const int64_t end = min(n, start + static_cast<int64_t>(kTile));
+  const int cnt = static_cast<int>(min(n - start, static_cast<int64_t>(kTile)));
   const unsigned n_rows = static_cast<unsigned>(p.n_rows);
 
-  auto grad = [&](int64_t i) -> float4 {
-    const int q = __ldg(pos + i);
-    const int b = q / C, c = q - b * C;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane_on) v = ldg4(d_out + (static_cast<int64_t>(b) * F + s_field[c]) * D + lane * 4);
-    const float dv = s_div[c];
-    if (dv != 1.f) { v.x = v.x / dv; v.y = v.y / dv; v.z = v.z / dv; v.w = v.w / dv; }
-    return v;
-  };
+  unsigned k_reg[PER];
+  int q_reg[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int e = j * LPR + lane;
+    k_reg[j] = e < cnt ? __ldg(keys + start + e) : 0xffffffffu;
+    q_reg[j] = e < cnt ? __ldg(pos + start + e) : 0;
+  }
+  const float* __restrict__ g_base = d_out + lane * 4;
+
   auto flush = [&](unsigned key, const float4& acc, bool leading, bool trailing) {
     if (key >= n_rows) return;
     if (leading) {
       if (lane_on) *reinterpret_cast<float4*>(carry_in + t * D + lane * 4) = acc;
     } else if (trailing) {
       if (lane_on) *reinterpret_cast<float4*>(carry_out + t * D + lane * 4) = acc;
-      if (lane == 0) span_tiles[atomicAdd(span_count, 1)] = static_cast<int>(t);
     } else if (lane_on) {
       *reinterpret_cast<float4*>(d_table + static_cast<int64_t>(key) * D + lane * 4) = acc;
     }
   };
 
-  unsigned cur = __ldg(keys + start);
-  bool leading = start > 0 && __ldg(keys + start - 1) == cur;
-  float4 acc = grad(start);
-#pragma unroll 4
-  for (int64_t i = start + 1; i < end; ++i) {
-    const unsigned k = __ldg(keys + i);
-    const float4 g = grad(i);
-    if (k == cur) {
-      add4(acc, g);
-    } else {
-      flush(cur, acc, leading, false);
-      leading = false;
-      cur = k;
-      acc = g;
+  unsigned cur = 0;
+  bool leading = false;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int e0 = 0; e0 < kTile; e0 += BATCH) {
+    float4 g[BATCH];
+    unsigned kk[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const int e = e0 + j;
+      kk[j] = __shfl_sync(gmask, k_reg[e / LPR], e % LPR, LPR);
+      const int q = __shfl_sync(gmask, q_reg[e / LPR], e % LPR, LPR);
+      g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < cnt) {
+        const int b = q / C, c = q - b * C;
+        if (lane_on) g[j] = ldg4(g_base + (static_cast<int64_t>(b) * F + s_field[c]) * D);
+        const float sc = s_div[c];
+        if (sc != 1.f) { g[j].x *= sc; g[j].y *= sc; g[j].z *= sc; g[j].w *= sc; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const int e = e0 + j;
+      if (e >= cnt) continue;
+      if (e == 0) {
+        cur = kk[j];
+        acc = g[j];
+        leading = start > 0 && __ldg(keys + start - 1) == cur;
+      } else if (kk[j] == cur) {
+        add4(acc, g[j]);
+      } else {
+        flush(cur, acc, leading, false);
+        leading = false;
+        cur = kk[j];
+        acc = g[j];
+      }
     }
   }
-  flush(cur, acc, leading, end < n && __ldg(keys + end) == cur);
+  flush(cur, acc, leading, start + cnt < n && __ldg(keys + start + cnt) == cur);
 }
 
 // ---------------------------------------------------------------------------------------------
-// scatter step 4: rows spanning several tiles.  One CTA per such row: its K carry-in partials are
-// cut into kSpanBlocks contiguous blocks of ceil(K / kSpanBlocks), one lane group sums each block
-// left to right, then the block sums are added left to right onto the first tile's carry-out.
+// scatter step 4: rows spanning several tiles.  Blocks of 32^l sorted entries form an aligned
+// 32-ary tree over the sorted list.  A level-l block leaves at most two open partial sums behind:
+// `in` (its leading run, when that run continues from the previous block) and `out` (its trailing
+// run, when that run continues into the next block and is not the leading run).  One lane group
+// per parent block walks its 32 children's open partials in order, adds runs of equal rows left to
+// right, writes rows that are now complete and passes the still-open ones up.  Serial chains are
+// at most 64 adds per level whatever the skew (a row hit by every sample needs log32(n) levels).
 // ---------------------------------------------------------------------------------------------
 template <int LPR>
-__global__ void __launch_bounds__(kSpanBlocks* LPR) scatter_span_kernel(
-    int D, const unsigned* __restrict__ keys, int64_t n, const float* __restrict__ carry_in,
-    const float* __restrict__ carry_out, const int* __restrict__ span_count, const int* __restrict__ span_tiles,
-    float* __restrict__ d_table) {
-  extern __shared__ float s_part[];  // [kSpanBlocks][D]
-  __shared__ int64_t s_last_tile;
+__global__ void __launch_bounds__(kThreads) scatter_level_kernel(
+    int D, unsigned n_rows, const unsigned* __restrict__ keys, int64_t n, int64_t child_size, int64_t n_children,
+    int64_t n_blocks, const float* __restrict__ in_c, const float* __restrict__ out_c, float* __restrict__ in_p,
+    float* __restrict__ out_p, float* __restrict__ d_table) {
+  constexpr int PER = 32 / LPR;  // children held per lane
+  constexpr int BATCH = 4;       // children whose partials are fetched together
   const int lane = threadIdx.x % LPR;
-  const int blk = threadIdx.x / LPR;
   const bool lane_on = lane * 4 < D;
-  const int n_span = *span_count;
-  for (int w = blockIdx.x; w < n_span; w += gridDim.x) {
-    const int64_t t = span_tiles[w];
-    const int64_t t_end = min(n, (t + 1) * kTile);
-    const unsigned key = keys[t_end - 1];
-    if (threadIdx.x == 0) {  // last entry of this row: upper bound in the sorted key list
-      int64_t lo = t_end, hi = n;
-      while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (keys[mid] <= key) lo = mid + 1; else hi = mid;
-      }
-      s_last_tile = (lo - 1) / kTile;
+  const unsigned gmask =
+      LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (((threadIdx.x % 32) / LPR) * LPR));
+  const int64_t J = static_cast<int64_t>(blockIdx.x) * (blockDim.x / LPR) + threadIdx.x / LPR;
+  if (J >= n_blocks) return;
+  const int64_t c0 = J * 32;
+
+  unsigned kf[PER], kl[PER], fl[PER];  // first key, last key, flags (1: has in, 2: has out)
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int64_t c = c0 + j * LPR + lane;
+    const int64_t s = c * child_size;
+    kf[j] = kl[j] = 0xffffffffu;
+    fl[j] = 0;
+    if (c < n_children) {
+      const int64_t e = min(n, s + child_size);
+      kf[j] = __ldg(keys + s);
+      kl[j] = __ldg(keys + e - 1);
+      const bool lead = s > 0 && __ldg(keys + s - 1) == kf[j];
+      const bool trail = e < n && __ldg(keys + e) == kl[j];
+      fl[j] = (lead ? 1u : 0u) | ((trail && !(lead && kf[j] == kl[j])) ? 2u : 0u);
     }
-    __syncthreads();
-    const int64_t K = s_last_tile - t;  // carry-in partials: tiles t+1 .. t+K
-    const int64_t m = (K + kSpanBlocks - 1) / kSpanBlocks;
-    const int64_t u0 = t + 1 + blk * m;
-    const int64_t u1 = min(t + 1 + K, u0 + m);
-    if (u0 < u1 && lane_on) {
-      float4 acc = ldg4(carry_in + u0 * D + lane * 4);
-#pragma unroll 8
-      for (int64_t u = u0 + 1; u < u1; ++u) add4(acc, ldg4(carry_in + u * D + lane * 4));
-      *reinterpret_cast<float4*>(s_part + blk * D + lane * 4) = acc;
-    }
-    __syncthreads();
-    if (blk == 0 && lane_on) {
-      float4 acc = ldg4(carry_out + t * D + lane * 4);
-      const int n_blk = static_cast<int>((K + m - 1) / m);
-      for (int j = 0; j < n_blk; ++j) add4(acc, *reinterpret_cast<const float4*>(s_part + j * D + lane * 4));
-      *reinterpret_cast<float4*>(d_table + static_cast<int64_t>(key) * D + lane * 4) = acc;
-    }
-    __syncthreads();
   }
+  const int64_t end_J = min(n, (c0 + 32) * child_size);
+  const bool trailing_J = end_J < n && __ldg(keys + end_J) == __ldg(keys + end_J - 1);
+
+  unsigned cur = 0;
+  bool started = false, leading = false;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto flush = [&](bool trailing) {
+    if (cur >= n_rows) return;
+    float* dst = leading ? in_p + J * D : (trailing ? out_p + J * D : d_table + static_cast<int64_t>(cur) * D);
+    if (lane_on) *reinterpret_cast<float4*>(dst + lane * 4) = acc;
+  };
+  auto element = [&](unsigned key, const float4& v, bool first_of_block) {
+    if (!started) {
+      started = true;
+      cur = key;
+      acc = v;
+      leading = first_of_block;
+    } else if (key == cur) {
+      add4(acc, v);
+    } else {
+      flush(false);
+      leading = false;
+      cur = key;
+      acc = v;
+    }
+  };
+
+#pragma unroll
+  for (int i0 = 0; i0 < 32; i0 += BATCH) {
+    unsigned a_kf[BATCH], a_kl[BATCH], a_fl[BATCH];
+    float4 v_in[BATCH], v_out[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const int i = i0 + j;
+      a_kf[j] = __shfl_sync(gmask, kf[i / LPR], i % LPR, LPR);
+      a_kl[j] = __shfl_sync(gmask, kl[i / LPR], i % LPR, LPR);
+      a_fl[j] = __shfl_sync(gmask, fl[i / LPR], i % LPR, LPR);
+      v_in[j] = v_out[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((a_fl[j] & 1u) && lane_on) v_in[j] = ldg4(in_c + (c0 + i) * D + lane * 4);
+      if ((a_fl[j] & 2u) && lane_on) v_out[j] = ldg4(out_c + (c0 + i) * D + lane * 4);
+    }
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      if (a_fl[j] & 1u) element(a_kf[j], v_in[j], i0 + j == 0);
+      if (a_fl[j] & 2u) element(a_kl[j], v_out[j], false);
+    }
+  }
+  if (started) flush(trailing_J);
 }
 
 int lanes_per_row(int D) {
@@ -289,10 +355,10 @@ struct ScatterWorkspace {
   unsigned* keys_out;
   int* pos_in;
   int* pos_out;
-  float* carry_in;
-  float* carry_out;
-  int* span_count;
-  int* span_tiles;
+  float* in_a;   // open partials of the odd levels (sized for the tiles)
+  float* out_a;
+  float* in_b;   // open partials of the even levels (sized for tiles / 32)
+  float* out_b;
   void* cub_temp;
   size_t cub_bytes;
   size_t total;
@@ -300,6 +366,7 @@ struct ScatterWorkspace {
 
 int carve_scatter_workspace(void* base, int64_t n, int D, ScatterWorkspace* w) {
   const int64_t n_tiles = (n + kTile - 1) / kTile;
+  const int64_t n_l2 = (n_tiles + 31) / 32;
   size_t cub_bytes = 0;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<unsigned*>(nullptr),
                                                   static_cast<unsigned*>(nullptr), static_cast<int*>(nullptr),
@@ -318,10 +385,10 @@ int carve_scatter_workspace(void* base, int64_t n, int D, ScatterWorkspace* w) {
   w->keys_out = reinterpret_cast<unsigned*>(take(nn * 4));
   w->pos_in = reinterpret_cast<int*>(take(nn * 4));
   w->pos_out = reinterpret_cast<int*>(take(nn * 4));
-  w->carry_in = reinterpret_cast<float*>(take(static_cast<size_t>(n_tiles + 1) * D * 4));
-  w->carry_out = reinterpret_cast<float*>(take(static_cast<size_t>(n_tiles + 1) * D * 4));
-  w->span_count = reinterpret_cast<int*>(take(256));
-  w->span_tiles = reinterpret_cast<int*>(take(static_cast<size_t>(n_tiles + 1) * 4));
+  w->in_a = reinterpret_cast<float*>(take(static_cast<size_t>(n_tiles + 1) * D * 4));
+  w->out_a = reinterpret_cast<float*>(take(static_cast<size_t>(n_tiles + 1) * D * 4));
+  w->in_b = reinterpret_cast<float*>(take(static_cast<size_t>(n_l2 + 1) * D * 4));
+  w->out_b = reinterpret_cast<float*>(take(static_cast<size_t>(n_l2 + 1) * D * 4));
   w->cub_temp = take(cub_bytes);
   w->cub_bytes = cub_bytes;
   w->total = off;
@@ -341,9 +408,7 @@ int check_plan(const aread_embed_plan& p) {
 template <int LPR>
 int launch_gather(const aread_gather_args& a, cudaStream_t stream) {
   constexpr int kUnroll = 4;
-  const int64_t n_slots = a.batch * a.plan.n_fields;
-  const int64_t groups = (n_slots + kUnroll - 1) / kUnroll;
-  int64_t grid = (groups * LPR + kThreads - 1) / kThreads;
+  int64_t grid = (a.batch * LPR + kThreads - 1) / kThreads;
   const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;  // 8 CTAs of 256 threads fill an SM
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
@@ -359,10 +424,25 @@ int launch_scatter(const aread_scatter_args& a, const ScatterWorkspace& w, int64
   const int groups_per_cta = kThreads / LPR;
   const size_t smem = sizeof(int) * 2 * static_cast<size_t>(a.plan.n_cols);
   AREAD_LAUNCH((scatter_tile_kernel<LPR>), static_cast<unsigned>((n_tiles + groups_per_cta - 1) / groups_per_cta),
-               kThreads, smem, stream, a.plan, w.keys_out, w.pos_out, n, n_tiles, a.d_out, a.d_table, w.carry_in,
-               w.carry_out, w.span_count, w.span_tiles);
-  AREAD_LAUNCH((scatter_span_kernel<LPR>), kNumSMs * 2, kSpanBlocks * LPR, sizeof(float) * kSpanBlocks * D, stream, D,
-               w.keys_out, n, w.carry_in, w.carry_out, w.span_count, w.span_tiles, a.d_table);
+               kThreads, smem, stream, a.plan, w.keys_out, w.pos_out, n, n_tiles, a.d_out, a.d_table, w.in_a,
+               w.out_a);
+  const float *in_c = w.in_a, *out_c = w.out_a;
+  float *in_p = w.in_b, *out_p = w.out_b;
+  int64_t child_size = kTile, n_children = n_tiles;
+  while (n_children > 1) {
+    const int64_t n_blocks = (n_children + 31) / 32;
+    AREAD_LAUNCH((scatter_level_kernel<LPR>), static_cast<unsigned>((n_blocks + groups_per_cta - 1) / groups_per_cta),
+                 kThreads, 0, stream, D, static_cast<unsigned>(a.plan.n_rows), w.keys_out, n, child_size, n_children,
+                 n_blocks, in_c, out_c, in_p, out_p, a.d_table);
+    const float* t_in = in_c;
+    const float* t_out = out_c;
+    in_c = in_p;
+    out_c = out_p;
+    in_p = const_cast<float*>(t_in);
+    out_p = const_cast<float*>(t_out);
+    child_size *= 32;
+    n_children = n_blocks;
+  }
   return AREAD_OK;
 }
 
@@ -423,7 +503,6 @@ int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream_) {
   if (w.total > a.workspace_bytes)
     return fail(AREAD_ERR_WORKSPACE, "scatter: workspace %zu < %zu bytes", a.workspace_bytes, w.total);
 
-  AREAD_CUDA(cudaMemsetAsync(w.span_count, 0, sizeof(int), stream));
   {
     int64_t grid = (n + kThreads - 1) / kThreads;
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;

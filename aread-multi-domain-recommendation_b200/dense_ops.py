@@ -89,7 +89,10 @@ def hei_forward(model, tower_inputs, q, cn, lin, info: Optional[MaskInfo], want_
         active = np.ones(n_tower[l], dtype=bool) if info is None else info.active[l]
         width = model.tower_dims[l][-1]
         if l > 0:
-            logits = torch.stack([model.tower_gates[l - 1][t][0](q) for t in range(n_tower[l])], dim=2)
+            # gates of towers that do not run are never evaluated (their parameters keep grad None)
+            zeros = torch.zeros(B, n_tower[l - 1], dtype=torch.float32, device=q.device)
+            logits = torch.stack([model.tower_gates[l - 1][t][0](q) if active[t] else zeros
+                                  for t in range(n_tower[l])], dim=2)
             s = torch.softmax(logits, dim=1)                                        # [B, n_{l-1}, n_l]
             if want_gates:
                 out.gates[l] = s.detach()

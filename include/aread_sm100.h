@@ -93,16 +93,14 @@ AREAD_API int aread_gather_fwd(const aread_gather_args* args, aread_stream_t str
  * sparse=False at layer.py:150) including the 1/seq_maxlen factor of the mean pooling.
  *
  * Order of summation (documented so that it can be reproduced bit for bit, oracle/embedding_np.py
- * scatter_bwd_tiled): lookups are stably sorted by table row; the sorted list is cut into tiles of
- * AREAD_SCATTER_TILE consecutive entries; inside a tile a row's entries are summed left to right.
- * A row spanning 1 + K tiles takes the partial of its first tile, cuts the K following per-tile
- * partials into AREAD_SCATTER_SPAN_BLOCKS contiguous blocks of ceil(K / blocks), sums every block
- * left to right and then adds the block sums left to right onto the first partial (for K <= 32
- * that is simply left to right).  A row whose entries all fall in one tile therefore reproduces
- * the reference (sequential) order exactly.
+ * scatter_bwd_tiled): lookups are stably sorted by table row; gradient rows of mean-pooled columns
+ * are scaled by fl32(1 / seq_maxlen); the sorted list is covered by an aligned 32-ary tree whose
+ * level-l blocks hold AREAD_SCATTER_TILE^l consecutive entries.  A row's entries inside one
+ * level-1 block (tile) are summed left to right; its sum inside a level-l block is the left to
+ * right sum of its sums inside that block's children.  A row whose entries all fall in one tile
+ * therefore reproduces the reference (sequential) order exactly.
  * ---------------------------------------------------------------------------------------------- */
 #define AREAD_SCATTER_TILE 32
-#define AREAD_SCATTER_SPAN_BLOCKS 32
 
 typedef struct aread_scatter_args {
   aread_embed_plan plan;

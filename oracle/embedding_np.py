@@ -53,7 +53,7 @@ def gather_fwd(weight, x, offsets, multi_hot_flag=None, seq_maxlen=1, method=Non
         return e
     B, _, D = e.shape
     one_hot = e[:, ~flag, :]
-    mh = e[:, flag, :].reshape(B, -1, seq_maxlen, D)
+    mh = e[:, flag, :].reshape(B, int(flag.sum()) // seq_maxlen, seq_maxlen, D)
     acc = mh[:, :, 0, :].copy()
     for l in range(1, seq_maxlen):
         acc = acc + mh[:, :, l, :]
@@ -62,8 +62,10 @@ def gather_fwd(weight, x, offsets, multi_hot_flag=None, seq_maxlen=1, method=Non
     return np.concatenate([one_hot, acc.astype(np.float32)], axis=1)
 
 
-def expand_pooled_grad(d_out, n_cols, multi_hot_flag=None, seq_maxlen=1, method=None):
-    """Gradient of the pooling/concat: [B, output_dim0, D] -> per-column [B, n_cols, D]."""
+def expand_pooled_grad(d_out, n_cols, multi_hot_flag=None, seq_maxlen=1, method=None, reciprocal=False):
+    """Gradient of the pooling/concat: [B, output_dim0, D] -> per-column [B, n_cols, D].  The
+    reference divides by seq_maxlen; the CUDA scatter multiplies by fl32(1/seq_maxlen)
+    (`reciprocal=True`), which can differ in the last bit."""
     d_out = np.asarray(d_out, dtype=np.float32)
     flag = None if multi_hot_flag is None else np.asarray(multi_hot_flag, dtype=bool)
     if flag is None or not flag.any() or method not in ("mean", "sum"):
@@ -74,7 +76,7 @@ def expand_pooled_grad(d_out, n_cols, multi_hot_flag=None, seq_maxlen=1, method=
     g[:, ~flag, :] = d_out[:, :n_oh, :]
     gp = d_out[:, n_oh:, :]
     if method == "mean":
-        gp = gp / np.float32(seq_maxlen)
+        gp = gp * (np.float32(1.0) / np.float32(seq_maxlen)) if reciprocal else gp / np.float32(seq_maxlen)
     g[:, flag, :] = np.repeat(gp, seq_maxlen, axis=1)
     return g
 
@@ -106,36 +108,36 @@ def sort_segments(idx_flat):
     return sorted_rows, perm, sorted_rows[starts], np.concatenate([starts, [len(sorted_rows)]]).astype(np.int64)
 
 
-def scatter_bwd_tiled(d_cols, idx_flat, n_rows, tile=32, span_blocks=32):
-    """The summation order of the CUDA segmented reduce (include/aread_sm100.h): the stably
-    sorted lookups are cut into tiles of `tile` consecutive entries (aligned to the sorted list,
-    not to the segments); inside a tile a row's entries are summed left to right.  A row
-    spanning 1 + K tiles keeps the partial of its first tile, cuts the K following partials into
-    `span_blocks` contiguous blocks of ceil(K / span_blocks), sums each block left to right and
-    adds the block sums left to right onto the first partial.  A row whose entries all fall
-    inside one tile reproduces the reference (sequential) order exactly."""
+def scatter_bwd_tiled(d_cols, idx_flat, n_rows, tile=32):
+    """The summation order of the CUDA segmented reduce (include/aread_sm100.h): the stably sorted
+    lookups are covered by an aligned `tile`-ary tree whose level-l blocks hold tile**l consecutive
+    entries.  A row's entries inside one level-1 block are summed left to right; its sum inside a
+    level-l block is the left to right sum of its sums inside the block's children.  A row whose
+    entries all fall inside one level-1 block reproduces the reference (sequential) order."""
     idx_flat = np.asarray(idx_flat).reshape(-1)
     d_cols = np.asarray(d_cols, dtype=np.float32).reshape(len(idx_flat), -1)
     _, perm, uniq, seg = sort_segments(idx_flat)
-    dw = np.zeros((n_rows, d_cols.shape[1]), dtype=np.float32)
-    for r, s, e in zip(uniq, seg[:-1], seg[1:]):
-        parts = []
+    top = 1
+    while tile ** top < max(len(idx_flat), 1):
+        top += 1
+
+    def part(s, e, level):
+        if level == 1:
+            acc = d_cols[perm[s]].copy()
+            for p in perm[s + 1:e]:
+                acc = acc + d_cols[p]
+            return acc
+        child = tile ** (level - 1)
+        acc = None
         c0 = s
         while c0 < e:
-            c1 = min(e, (c0 // tile + 1) * tile)
-            part = d_cols[perm[c0]].copy()
-            for p in perm[c0 + 1:c1]:
-                part = part + d_cols[p]
-            parts.append(part)
+            c1 = min(e, (c0 // child + 1) * child)
+            sub = part(c0, c1, level - 1)
+            acc = sub if acc is None else acc + sub
             c0 = c1
-        total = parts[0]
-        K = len(parts) - 1
-        if K > 0:
-            m = -(-K // span_blocks)
-            for j0 in range(1, K + 1, m):
-                blk = parts[j0]
-                for q in parts[j0 + 1:min(K + 1, j0 + m)]:
-                    blk = blk + q
-                total = total + blk
-        dw[r] = total
+        return acc
+
+    dw = np.zeros((n_rows, d_cols.shape[1]), dtype=np.float32)
+    for r, s, e in zip(uniq, seg[:-1], seg[1:]):
+        dw[r] = part(int(s), int(e), top)
     return dw

@@ -132,12 +132,23 @@ def test_scatter_documented_order_bit_exact(D, method, L):
     s_rows, perm, _, _ = E.sort_segments(idx)
     assert np.array_equal(rows.cpu().numpy(), s_rows.astype(np.int32))       # sorted rows
     assert np.array_equal(pos.cpu().numpy(), perm.astype(np.int32))          # stable permutation
-    g_cols = E.expand_pooled_grad(g.numpy(), x.shape[1], np.array(flag), L, method)
+    g_cols = E.expand_pooled_grad(g.numpy(), x.shape[1], np.array(flag), L, method, reciprocal=True)
     ref = E.scatter_bwd_tiled(g_cols, idx, plan.n_rows)
     assert np.array_equal(bits(dw.cpu().numpy()), bits(ref))
     # and it is the reference gradient up to summation order
     seq = E.scatter_bwd_dense(g.numpy(), x, emb.offsets, plan.n_rows, np.array(flag), L, method)
     np.testing.assert_allclose(dw.cpu().numpy(), seq, rtol=2e-5, atol=2e-5)
+
+
+def test_scatter_documented_order_four_levels():
+    """1.3e5 lookups -> a 4-level tree; one row is hit by every sample, others by thousands"""
+    dims = [3, 40, 70000]
+    B = 44000
+    emb, plan, x, g = _scatter_case(dims, 32, [False] * 3, 0, 1, None, B, seed=9, skew=True)
+    dw = ops.scatter(plan, torch.from_numpy(x).to(DEV), g.to(DEV))
+    idx = E.lookup_rows(x, emb.offsets, plan.n_rows).reshape(-1)
+    ref = E.scatter_bwd_tiled(g.numpy().reshape(-1, 32), idx, plan.n_rows)
+    assert np.array_equal(bits(dw.cpu().numpy()), bits(ref))
 
 
 def test_scatter_equals_reference_order_without_long_segments():
@@ -176,7 +187,7 @@ def test_scatter_is_deterministic_and_autograd_wired():
     assert torch.equal(grads[0], grads[1]) and torch.equal(grads[1], grads[2])
     W = emb.embedding_dict.weight.detach().cpu().clone().requires_grad_(True)
     (O.embed({"embedding.embedding_dict.weight": W}, spec, x) * G.cpu()).sum().backward()
-    torch.testing.assert_close(grads[0].cpu(), W.grad, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(grads[0].cpu(), W.grad, rtol=1e-4, atol=1e-3)   # row 500 sums ~10^4 terms
 
 
 def test_full_size_properties():

@@ -40,6 +40,12 @@ class ScatterArgs(Structure):
                 ("workspace_bytes", c_size_t), ("sorted_rows", c_void_p), ("sorted_pos", c_void_p)]
 
 
+class GroupedLinearArgs(Structure):
+    _fields_ = [("m", c_int64), ("n", c_int32), ("k", c_int32), ("groups", c_int32), ("a_group_cols", c_int32),
+                ("group_mask", c_uint64), ("a", c_void_p), ("lda", c_int64), ("b", c_void_p), ("ldb", c_int64),
+                ("bias", c_void_p), ("c_f32", c_void_p), ("c_bf16", c_void_p), ("ldc", c_int64)]
+
+
 _SIGNATURES = {
     "aread_last_error": (c_char_p, []),
     "aread_abi_version": (c_int32, []),
@@ -47,6 +53,7 @@ _SIGNATURES = {
     "aread_gather_fwd": (c_int32, [POINTER(GatherArgs), c_void_p]),
     "aread_scatter_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "aread_scatter_bwd": (c_int32, [POINTER(ScatterArgs), c_void_p]),
+    "aread_grouped_linear_bf16": (c_int32, [POINTER(GroupedLinearArgs), c_void_p]),
 }
 
 _lib = None

@@ -138,15 +138,26 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const aread_gather_arg
 // scatter step 1: (row key, flattened position) pairs
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) scatter_keys_kernel(const aread_embed_plan p, const int* __restrict__ x,
-                                                                int64_t n, unsigned* __restrict__ keys,
-                                                                int* __restrict__ pos) {
+                                                                int64_t n, int col_shift,
+                                                                unsigned* __restrict__ keys, int* __restrict__ pos) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int c = static_cast<int>(i % p.n_cols);
+    const int b = static_cast<int>(i / p.n_cols);
+    const int c = static_cast<int>(i - static_cast<int64_t>(b) * p.n_cols);
     const int row = row_of(x[i], __ldg(p.col_offset + c));
     // out-of-range ids (already reported by the forward) sort behind every real row and are skipped
     keys[i] = (row < 0 || row >= p.n_rows) ? static_cast<unsigned>(p.n_rows) : static_cast<unsigned>(row);
-    pos[i] = static_cast<int>(i);
+    pos[i] = (b << col_shift) | c;  // (sample, column) packed so that the reduce needs no division
+  }
+}
+
+// sorted payloads back to flattened positions b * n_cols + c (only for callers that ask for them)
+__global__ void __launch_bounds__(kThreads) scatter_unpack_kernel(const int* __restrict__ packed, int64_t n,
+                                                                  int col_shift, int n_cols, int* __restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int q = packed[i];
+    out[i] = (q >> col_shift) * n_cols + (q & ((1 << col_shift) - 1));
   }
 }
 
@@ -158,8 +169,8 @@ __global__ void __launch_bounds__(kThreads) scatter_keys_kernel(const aread_embe
 template <int LPR>
 __global__ void __launch_bounds__(kThreads) scatter_tile_kernel(
     const aread_embed_plan p, const unsigned* __restrict__ keys, const int* __restrict__ pos, int64_t n,
-    int64_t n_tiles, const float* __restrict__ d_out, float* __restrict__ d_table, float* __restrict__ carry_in,
-    float* __restrict__ carry_out) {
+    int64_t n_tiles, int col_shift, const float* __restrict__ d_out, float* __restrict__ d_table,
+    float* __restrict__ carry_in, float* __restrict__ carry_out) {
   extern __shared__ int smem[];
   int* s_field = smem;                                        // column -> output field
   float* s_div = reinterpret_cast<float*>(smem + p.n_cols);   // column -> fl32(1 / pooling divisor)
@@ -175,7 +186,8 @@ __global__ void __launch_bounds__(kThreads) scatter_tile_kernel(
 
   constexpr int PER = kTile / LPR;  // tile entries held per lane
   constexpr int BATCH = 8;
-  const int D = p.embed_dim, F = p.n_fields, C = p.n_cols;
+  const int D = p.embed_dim, F = p.n_fields;
+  const int col_mask = (1 << col_shift) - 1;
   const int lane = threadIdx.x % LPR;
   const bool lane_on = lane * 4 < D;
   const unsigned gmask =
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(kThreads) scatter_tile_kernel(
       const int q = __shfl_sync(gmask, q_reg[e / LPR], e % LPR, LPR);
       g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (e < cnt) {
-        const int b = q / C, c = q - b * C;
+        const int b = q >> col_shift, c = q & col_mask;
         if (lane_on) g[j] = ldg4(g_base + (static_cast<int64_t>(b) * F + s_field[c]) * D);
         const float sc = s_div[c];
         if (sc != 1.f) { g[j].x *= sc; g[j].y *= sc; g[j].z *= sc; g[j].w *= sc; }
@@ -418,14 +430,15 @@ int launch_gather(const aread_gather_args& a, cudaStream_t stream) {
 }
 
 template <int LPR>
-int launch_scatter(const aread_scatter_args& a, const ScatterWorkspace& w, int64_t n, cudaStream_t stream) {
+int launch_scatter(const aread_scatter_args& a, const ScatterWorkspace& w, int64_t n, int col_shift,
+                   cudaStream_t stream) {
   const int D = a.plan.embed_dim;
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   const int groups_per_cta = kThreads / LPR;
   const size_t smem = sizeof(int) * 2 * static_cast<size_t>(a.plan.n_cols);
   AREAD_LAUNCH((scatter_tile_kernel<LPR>), static_cast<unsigned>((n_tiles + groups_per_cta - 1) / groups_per_cta),
-               kThreads, smem, stream, a.plan, w.keys_out, w.pos_out, n, n_tiles, a.d_out, a.d_table, w.in_a,
-               w.out_a);
+               kThreads, smem, stream, a.plan, w.keys_out, w.pos_out, n, n_tiles, col_shift, a.d_out, a.d_table,
+               w.in_a, w.out_a);
   const float *in_c = w.in_a, *out_c = w.out_a;
   float *in_p = w.in_b, *out_p = w.out_b;
   int64_t child_size = kTile, n_children = n_tiles;
@@ -493,7 +506,10 @@ int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream_) {
     AREAD_CUDA(cudaMemsetAsync(a.d_table, 0, static_cast<size_t>(a.plan.n_rows) * D * sizeof(float), stream));
   const int64_t n = a.batch * a.plan.n_cols;
   if (n == 0) return AREAD_OK;
-  AREAD_REQUIRE(n < (int64_t{1} << 31), "scatter: %lld lookups exceed int32 positions", static_cast<long long>(n));
+  int col_shift = 0;
+  while ((1 << col_shift) < a.plan.n_cols) ++col_shift;
+  AREAD_REQUIRE((a.batch << col_shift) < (int64_t{1} << 31), "scatter: batch %lld x %d columns exceeds int32 positions",
+                static_cast<long long>(a.batch), a.plan.n_cols);
   AREAD_REQUIRE(a.x && a.d_out && a.workspace, "scatter: null pointer");
   AREAD_REQUIRE((reinterpret_cast<uintptr_t>(a.d_table) | reinterpret_cast<uintptr_t>(a.d_out) |
                  reinterpret_cast<uintptr_t>(a.workspace)) % 16 == 0,
@@ -506,8 +522,8 @@ int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream_) {
   {
     int64_t grid = (n + kThreads - 1) / kThreads;
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    AREAD_LAUNCH(scatter_keys_kernel, static_cast<unsigned>(grid), kThreads, 0, stream, a.plan, a.x, n, w.keys_in,
-                 w.pos_in);
+    AREAD_LAUNCH(scatter_keys_kernel, static_cast<unsigned>(grid), kThreads, 0, stream, a.plan, a.x, n, col_shift,
+                 w.keys_in, w.pos_in);
   }
   // Stable LSD radix sort by table row (CUB, the CUDA toolkit's header library); the payload is the
   // flattened (sample, column) position, so equal rows keep the reference's accumulation order.
@@ -517,18 +533,22 @@ int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream_) {
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   int rc;
   switch (lanes_per_row(D)) {
-    case 1: rc = launch_scatter<1>(a, w, n, stream); break;
-    case 2: rc = launch_scatter<2>(a, w, n, stream); break;
-    case 4: rc = launch_scatter<4>(a, w, n, stream); break;
-    case 8: rc = launch_scatter<8>(a, w, n, stream); break;
-    case 16: rc = launch_scatter<16>(a, w, n, stream); break;
-    default: rc = launch_scatter<32>(a, w, n, stream); break;
+    case 1: rc = launch_scatter<1>(a, w, n, col_shift, stream); break;
+    case 2: rc = launch_scatter<2>(a, w, n, col_shift, stream); break;
+    case 4: rc = launch_scatter<4>(a, w, n, col_shift, stream); break;
+    case 8: rc = launch_scatter<8>(a, w, n, col_shift, stream); break;
+    case 16: rc = launch_scatter<16>(a, w, n, col_shift, stream); break;
+    default: rc = launch_scatter<32>(a, w, n, col_shift, stream); break;
   }
   if (rc) return rc;
   if (a.sorted_rows)
     AREAD_CUDA(cudaMemcpyAsync(a.sorted_rows, w.keys_out, n * 4, cudaMemcpyDeviceToDevice, stream));
-  if (a.sorted_pos)
-    AREAD_CUDA(cudaMemcpyAsync(a.sorted_pos, w.pos_out, n * 4, cudaMemcpyDeviceToDevice, stream));
+  if (a.sorted_pos) {
+    int64_t grid = (n + kThreads - 1) / kThreads;
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    AREAD_LAUNCH(scatter_unpack_kernel, static_cast<unsigned>(grid), kThreads, 0, stream, w.pos_out, n, col_shift,
+                 a.plan.n_cols, a.sorted_pos);
+  }
   return AREAD_OK;
 }
 

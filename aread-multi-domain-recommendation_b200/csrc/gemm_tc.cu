@@ -1,0 +1,308 @@
+// Grouped Linear layers of the MMoE experts / HEI towers on the 5th-generation tensor cores.
+//
+//   C[:, g*n : (g+1)*n] = A[:, g*a_group_cols : +k] . W_g^T (+ bias_g)      for every ACTIVE group g
+//
+// bf16 operands, fp32 accumulation in TMEM.  One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 4-stage ring)
+//   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M=128 x N=BN x K=16)
+//   warps 2..5  epilogue       (tcgen05.ld -> registers -> bias -> global store), double-buffered
+//                              accumulators so the epilogue of tile i overlaps the MMAs of tile i+1
+// Groups whose bit is clear in `group_mask` (towers pruned by the HEMP mask) produce no tiles at
+// all: the work is skipped, not multiplied by zero.
+//
+// Reference arithmetic: nn.Linear inside MultiLayerPerceptron (model/layer.py:210, 221-229) as used
+// for the experts (model/aread.py:93-95, 150) and towers (aread.py:108-110, 307, 319).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace aread {
+namespace {
+
+constexpr int BM = 128;       // UMMA M (cta_group::1)
+constexpr int BK = 64;        // one 128-byte swizzle row of bf16
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxGroups = 64;
+
+struct GemmParams {
+  int64_t m;
+  int n, k, n_active;
+  int a_group_cols;
+  int64_t ldc;
+  float* c_f32;
+  __nv_bfloat16* c_bf16;
+  const float* bias;
+  int n_m_tiles, n_n_tiles, n_k_blocks;
+  int64_t total_tiles;
+  unsigned char group_ids[kMaxGroups];
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarrierOffset + 256 + 1024;  // barriers + slack for 1024-byte alignment
+};
+
+struct TileCoord {
+  int m_t, g, n_t;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int64_t tile) {
+  TileCoord c;
+  c.n_t = static_cast<int>(tile % p.n_n_tiles);
+  const int64_t r = tile / p.n_n_tiles;
+  c.g = p.group_ids[r % p.n_active];
+  c.m_t = static_cast<int>(r / p.n_active);
+  return c;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const GemmParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* acc_full = empty_bar + kStages;
+  uint64_t* acc_empty = acc_full + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  constexpr uint32_t kTmemCols = kAccStages * BN;  // 128 or 256: a power of two >= 32
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_b);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      ptx::mbar_init(&acc_full[s], 1);
+      ptx::mbar_init(&acc_empty[s], 4);  // one arrival per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(p, tile);
+        const int a_col0 = c.g * p.a_group_cols;
+        const int b_row0 = c.g * p.n + c.n_t * BN;
+        for (int kb = 0; kb < p.n_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          ptx::tma_load_2d(sa, &map_a, &full_bar[stage], a_col0 + kb * BK, c.m_t * BM);
+          ptx::tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, b_row0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.n_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint64_t da = ptx::umma_desc_k_sw128(sa + kk * UMMA_K * 2, 8 * 128);
+            const uint64_t db = ptx::umma_desc_k_sw128(sb + kk * UMMA_K * 2, 8 * 128);
+            ptx::umma_bf16(d_tmem, da, db, idesc, (kb | kk) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {  // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+    const int quad = warp % 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord c = decode_tile(p, tile);
+      ptx::mbar_wait(&acc_full[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      const int64_t row = static_cast<int64_t>(c.m_t) * BM + quad * 32 + lane;
+      const int n0 = c.n_t * BN;  // column inside the group
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        float v[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cc * 32, v);
+        const int col_in_group = n0 + cc * 32;
+        if (col_in_group >= p.n) continue;
+        const int64_t col = static_cast<int64_t>(c.g) * p.n + col_in_group;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col_in_group + j < p.n) v[j] += __ldg(p.bias + col + j);
+        }
+        if (row < p.m) {
+          const bool full = col_in_group + 32 <= p.n;
+          if (p.c_f32 != nullptr) {
+            float* dst = p.c_f32 + row * p.ldc + col;
+            if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < 32 && col_in_group + j < p.n; ++j) dst[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* dst = p.c_bf16 + row * p.ldc + col;
+            if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<unsigned*>(&h0);
+                pk.y = *reinterpret_cast<unsigned*>(&h1);
+                pk.z = *reinterpret_cast<unsigned*>(&h2);
+                pk.w = *reinterpret_cast<unsigned*>(&h3);
+                *reinterpret_cast<uint4*>(dst + j) = pk;
+              }
+            } else {
+              for (int j = 0; j < 32 && col_in_group + j < p.n; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ----------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      sym = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(sym);
+  }();
+  return fn;
+}
+
+// bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t elem[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return AREAD_OK;
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  static bool configured = false;
+  if (!configured) {
+    AREAD_CUDA(cudaFuncSetAttribute(grouped_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kTotal));
+    configured = true;
+  }
+  const unsigned grid = static_cast<unsigned>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+  AREAD_LAUNCH((grouped_linear_kernel<BN>), grid, kGemmThreads, L::kTotal, stream, ma, mb, p);
+  return AREAD_OK;
+}
+
+}  // namespace
+}  // namespace aread
+
+extern "C" int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "grouped_linear: null args");
+  const aread_grouped_linear_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.n > 0 && a.k > 0, "grouped_linear: bad shape m=%lld n=%d k=%d", (long long)a.m, a.n, a.k);
+  AREAD_REQUIRE(a.groups > 0 && a.groups <= kMaxGroups, "grouped_linear: groups %d not in [1, %d]", a.groups,
+                kMaxGroups);
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.a && a.b, "grouped_linear: null operand");
+  AREAD_REQUIRE((a.c_f32 != nullptr) != (a.c_bf16 != nullptr), "grouped_linear: exactly one of c_f32 / c_bf16");
+  AREAD_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, "grouped_linear: lda/ldb must be multiples of 8 bf16 (16 bytes)");
+  AREAD_REQUIRE(reinterpret_cast<uintptr_t>(a.a) % 16 == 0 && reinterpret_cast<uintptr_t>(a.b) % 16 == 0,
+                "grouped_linear: operands must be 16-byte aligned");
+  AREAD_REQUIRE(a.a_group_cols == 0 || a.a_group_cols >= a.k, "grouped_linear: a_group_cols %d < k %d",
+                a.a_group_cols, a.k);
+
+  GemmParams p{};
+  p.m = a.m;
+  p.n = a.n;
+  p.k = a.k;
+  p.a_group_cols = a.a_group_cols;
+  p.ldc = a.ldc;
+  p.c_f32 = a.c_f32;
+  p.c_bf16 = reinterpret_cast<__nv_bfloat16*>(a.c_bf16);
+  p.bias = a.bias;
+  p.n_active = 0;
+  for (int g = 0; g < a.groups; ++g)
+    if (a.group_mask & (uint64_t{1} << g)) p.group_ids[p.n_active++] = static_cast<unsigned char>(g);
+  if (p.n_active == 0) return AREAD_OK;
+  const int bn = a.n > 64 ? 128 : 64;
+  p.n_m_tiles = ceil_div(a.m, BM);
+  p.n_n_tiles = ceil_div(a.n, bn);
+  p.n_k_blocks = ceil_div(a.k, BK);
+  p.total_tiles = static_cast<int64_t>(p.n_m_tiles) * p.n_active * p.n_n_tiles;
+
+  CUtensorMap ma, mb;
+  const int64_t a_cols = a.a_group_cols == 0 ? a.k : static_cast<int64_t>(a.a_group_cols) * (a.groups - 1) + a.k;
+  if (int rc = make_map(&ma, a.a, a.m, a_cols, a.lda, BM)) return rc;
+  if (int rc = make_map(&mb, a.b, static_cast<int64_t>(a.groups) * a.n, a.k, a.ldb, bn)) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return bn == 128 ? launch_gemm<128>(ma, mb, p, stream) : launch_gemm<64>(ma, mb, p, stream);
+}

@@ -120,6 +120,37 @@ typedef struct aread_scatter_args {
 AREAD_API size_t aread_scatter_workspace_bytes(int64_t n_lookups, int32_t embed_dim);
 AREAD_API int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Grouped Linear on the tensor cores (tcgen05 / TMEM, operands staged by TMA).
+ * Replaces the nn.Linear calls inside MultiLayerPerceptron.forward (model/layer.py:210, 221-229)
+ * for the four MMoE experts (model/aread.py:93-95, 150) -- group = expert -- and their gradients.
+ *
+ *   C[:, g*n : (g+1)*n] = A[:, g*a_group_cols : g*a_group_cols + k] . B[g*n : (g+1)*n, :]^T (+ bias)
+ *
+ * for every group g whose bit is set in group_mask; groups that are masked out are skipped entirely
+ * (no tiles are scheduled for them and their output columns are left untouched).  bf16 operands,
+ * fp32 accumulation; the result is stored as fp32 or as bf16 (round to nearest even).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_grouped_linear_args {
+  int64_t m;            /* rows (samples)                                                          */
+  int32_t n;            /* output width per group                                                  */
+  int32_t k;            /* reduction length per group                                              */
+  int32_t groups;       /* number of groups, <= 64                                                 */
+  int32_t a_group_cols; /* group g reads A columns starting at g * a_group_cols; 0 = all groups
+                           share the same A columns [0, k)                                         */
+  uint64_t group_mask;  /* bit g set = compute group g                                             */
+  const uint16_t* a;    /* bf16 [m, lda], 16-byte aligned, lda % 8 == 0                            */
+  int64_t lda;
+  const uint16_t* b;    /* bf16 [groups * n, ldb] (nn.Linear weight layout, groups stacked by rows) */
+  int64_t ldb;
+  const float* bias;    /* optional fp32 [groups * n]                                              */
+  float* c_f32;         /* exactly one of c_f32 / c_bf16: [m, ldc]                                 */
+  uint16_t* c_bf16;
+  int64_t ldc;
+} aread_grouped_linear_args;
+
+AREAD_API int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, aread_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,99 @@
+"""tcgen05 grouped Linear (C ABI: aread_grouped_linear_bf16) against a plain torch fp32 reference of
+the same op on the same bf16-rounded operands.  Tolerance: fp32 accumulation-order noise only
+(|d| <= 2e-5 * sum_k |a||w| + 1e-6); the bf16 output adds one rounding (rel 2^-8)."""
+import importlib
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+dk = importlib.import_module("aread-multi-domain-recommendation_b200.dense_kernels")
+DEV = "cuda:0"
+
+SHAPES = [
+    # m,    n,    k,   groups, a_group_cols
+    (300, 1024, 288, 1, 0),       # expert layer 1, Amazon-shaped E (K tail: 288 = 4.5 x 64)
+    (257, 1024, 736, 1, 0),       # expert layer 1, AliCCP-shaped E
+    (1000, 128, 256, 4, 256),     # expert layer 2: block diagonal
+    (129, 64, 128, 4, 128),       # expert layer 3
+    (37, 32, 40, 3, 0),           # tiny: n < tile, k < tile, shared A
+    (5, 16, 32, 3, 32),           # tiny grouped
+    (1, 8, 16, 2, 16),            # single row
+    (4096, 256, 1024, 1, 0),      # many k blocks (pipeline wrap-around), many m tiles
+]
+
+
+def reference(a, w, bias, n, k, groups, a_group_cols, mask):
+    m = a.shape[0]
+    out = torch.zeros(m, groups * n, dtype=torch.float32, device=a.device)
+    for g in range(groups):
+        if not (mask >> g) & 1:
+            continue
+        ag = a[:, g * a_group_cols:g * a_group_cols + k].float()
+        wg = w[g * n:(g + 1) * n, :k].float()
+        out[:, g * n:(g + 1) * n] = ag @ wg.t() + (bias[g * n:(g + 1) * n] if bias is not None else 0)
+    return out
+
+
+def bound(a, w, n, k, groups, a_group_cols):
+    m = a.shape[0]
+    out = torch.zeros(m, groups * n, dtype=torch.float32, device=a.device)
+    for g in range(groups):
+        ag = a[:, g * a_group_cols:g * a_group_cols + k].float().abs()
+        out[:, g * n:(g + 1) * n] = ag @ w[g * n:(g + 1) * n, :k].float().abs().t()
+    return out
+
+
+@pytest.mark.parametrize("m,n,k,groups,agc", SHAPES)
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_grouped_linear_fp32_out(m, n, k, groups, agc, use_bias):
+    gen = torch.Generator(device=DEV).manual_seed(m * 7 + n)
+    a_cols = k if agc == 0 else agc * groups
+    a = torch.randn(m, a_cols, device=DEV, generator=gen).to(torch.bfloat16)
+    w = (torch.randn(groups * n, k, device=DEV, generator=gen) / k ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(groups * n, device=DEV, generator=gen) if use_bias else None
+    full = (1 << groups) - 1
+    got = dk.grouped_linear(a, w, bias, n, k, groups, agc)
+    torch.cuda.synchronize()
+    ref = reference(a, w, bias, n, k, groups, agc, full)
+    tol = 2e-5 * bound(a, w, n, k, groups, agc) + 1e-6
+    assert bool(((got - ref).abs() <= tol).all()), float(((got - ref).abs() - tol).max())
+
+
+def test_group_mask_skips_groups():
+    m, n, k, groups = 500, 128, 256, 4
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    a = torch.randn(m, k * groups, device=DEV, generator=gen).to(torch.bfloat16)
+    w = (torch.randn(groups * n, k, device=DEV, generator=gen) / 16).to(torch.bfloat16)
+    for mask in (0b0101, 0b1000, 0b0000):
+        out = torch.full((m, groups * n), 7.0, device=DEV)
+        dk.grouped_linear(a, w, None, n, k, groups, k, group_mask=mask, out=out)
+        ref = reference(a, w, None, n, k, groups, k, mask)
+        for g in range(groups):
+            cols = slice(g * n, (g + 1) * n)
+            if (mask >> g) & 1:
+                torch.testing.assert_close(out[:, cols], ref[:, cols], rtol=1e-4, atol=1e-4)
+            else:
+                assert bool((out[:, cols] == 7.0).all())          # untouched
+
+
+def test_bf16_output_and_strided_operands():
+    m, n, k = 777, 128, 256
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    big = torch.randn(m, 1024 + 8, device=DEV, generator=gen).to(torch.bfloat16)
+    a = big[:, 8:8 + 1024]                                          # lda = 1032, 16-byte aligned start
+    w = (torch.randn(4 * n, k, device=DEV, generator=gen) / 16).to(torch.bfloat16)
+    got = dk.grouped_linear(a, w, None, n, k, 4, 256, out_dtype=torch.bfloat16)
+    ref = reference(a, w, None, n, k, 4, 256, 0b1111)
+    torch.testing.assert_close(got.float(), ref, rtol=2 ** -7, atol=1e-3)
+    assert got.dtype == torch.bfloat16
+
+
+def test_repeated_launches_are_bit_identical():
+    m, n, k = 2048, 1024, 736
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    a = torch.randn(m, k, device=DEV, generator=gen).to(torch.bfloat16)
+    w = (torch.randn(n, k, device=DEV, generator=gen) / 27).to(torch.bfloat16)
+    first = dk.grouped_linear(a, w, None, n, k, 1)
+    for _ in range(3):
+        assert torch.equal(first, dk.grouped_linear(a, w, None, n, k, 1))

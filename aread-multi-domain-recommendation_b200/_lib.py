@@ -46,6 +46,12 @@ class GroupedLinearArgs(Structure):
                 ("bias", c_void_p), ("c_f32", c_void_p), ("c_bf16", c_void_p), ("ldc", c_int64)]
 
 
+class GroupedWgradArgs(Structure):
+    _fields_ = [("m", c_int64), ("n", c_int32), ("k", c_int32), ("groups", c_int32), ("a_group_cols", c_int32),
+                ("group_mask", c_uint64), ("dz", c_void_p), ("ldz", c_int64), ("a", c_void_p), ("lda", c_int64),
+                ("dw", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
+
+
 _SIGNATURES = {
     "aread_last_error": (c_char_p, []),
     "aread_abi_version": (c_int32, []),
@@ -54,6 +60,8 @@ _SIGNATURES = {
     "aread_scatter_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "aread_scatter_bwd": (c_int32, [POINTER(ScatterArgs), c_void_p]),
     "aread_grouped_linear_bf16": (c_int32, [POINTER(GroupedLinearArgs), c_void_p]),
+    "aread_grouped_wgrad_workspace_bytes": (c_size_t, [POINTER(GroupedWgradArgs)]),
+    "aread_grouped_wgrad_bf16": (c_int32, [POINTER(GroupedWgradArgs), c_void_p]),
 }
 
 _lib = None

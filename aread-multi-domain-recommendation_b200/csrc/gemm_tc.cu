@@ -213,6 +213,190 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Weight gradient: dW_g[n, k] = sum_m dZ[m, g*n_out + n] * A[m, g*a_group_cols + k].
+// The reduction runs over the samples, so both operands are consumed in their natural row-major
+// layout as MN-major UMMA operands (no transposed copies).  The sample range is split over
+// `n_split` CTAs per output tile; fp32 partials are summed in split order by wgrad_reduce_kernel
+// (deterministic).  Output tile: 128 output features x BN input features.
+// ----------------------------------------------------------------------------------------------
+struct WgradParams {
+  int64_t m;
+  int n, k, n_active, n_split;
+  int a_group_cols;
+  float* partial;            // [n_split][groups_active][n][k]
+  int n_n_tiles, n_k_tiles;  // tiles over output features / input features
+  int kb_per_split, n_kb;    // 64-sample blocks
+  int64_t total_tiles;
+  unsigned char group_ids[kMaxGroups];
+};
+
+struct WgradCoord {
+  int split, gi, g, n_t, k_t;
+};
+
+__device__ __forceinline__ WgradCoord decode_wgrad(const WgradParams& p, int64_t tile) {
+  WgradCoord c;
+  c.k_t = static_cast<int>(tile % p.n_k_tiles);
+  int64_t r = tile / p.n_k_tiles;
+  c.n_t = static_cast<int>(r % p.n_n_tiles);
+  r /= p.n_n_tiles;
+  c.gi = static_cast<int>(r % p.n_active);
+  c.g = p.group_ids[c.gi];
+  c.split = static_cast<int>(r / p.n_active);
+  return c;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+grouped_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_a,
+                     const WgradParams p) {
+  constexpr int kBoxBytes = BK * 64 * 2;                 // [64 samples][64 features] bf16 = 8 KB
+  constexpr int kABytes = 2 * kBoxBytes;                 // 128 output features
+  constexpr int kBBytes = (BN / 64) * kBoxBytes;         // BN input features
+  constexpr int kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* acc_full = empty_bar + kStages;
+  uint64_t* acc_empty = acc_full + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  constexpr uint32_t kTmemCols = kAccStages * BN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_dz);
+    ptx::prefetch_tensormap(&map_a);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      ptx::mbar_init(&acc_full[s], 1);
+      ptx::mbar_init(&acc_empty[s], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const WgradCoord c = decode_wgrad(p, tile);
+        const int kb0 = c.split * p.kb_per_split;
+        const int kb1 = min(p.n_kb, kb0 + p.kb_per_split);
+        const int dz_col0 = c.g * p.n + c.n_t * BM;
+        const int a_col0 = c.g * p.a_group_cols + c.k_t * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          ptx::tma_load_2d(sa, &map_dz, &full_bar[stage], dz_col0, kb * BK);
+          ptx::tma_load_2d(sa + kBoxBytes, &map_dz, &full_bar[stage], dz_col0 + 64, kb * BK);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            ptx::tma_load_2d(sb + j * kBoxBytes, &map_a, &full_bar[stage], a_col0 + j * 64, kb * BK);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, /*mn_major=*/true);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const WgradCoord c = decode_wgrad(p, tile);
+        const int kb0 = c.split * p.kb_per_split;
+        const int kb1 = min(p.n_kb, kb0 + p.kb_per_split);
+        ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {  // 16 samples = two 8-row swizzle atoms
+            const uint64_t da = ptx::umma_desc_mn_sw128(sa + kk * 2048, kBoxBytes, 1024);
+            const uint64_t db = ptx::umma_desc_mn_sw128(sb + kk * 2048, kBoxBytes, 1024);
+            ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0) || (kk != 0));
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&acc_full[acc]);
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {  // ===== epilogue: fp32 partial tile =====
+    const int quad = warp % 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const WgradCoord c = decode_wgrad(p, tile);
+      ptx::mbar_wait(&acc_full[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      const int row = c.n_t * BM + quad * 32 + lane;  // output feature inside the group
+      float* base = p.partial + ((static_cast<int64_t>(c.split) * p.n_active + c.gi) * p.n + row) * p.k;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        float v[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cc * 32, v);
+        const int col = c.k_t * BN + cc * 32;
+        if (row < p.n && col < p.k) {
+          float* dst = base + col;
+          if (col + 32 <= p.k && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32 && col + j < p.k; ++j) dst[j] = v[j];
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// dw[g][n][k] = sum_s partial[s][gi][n][k] in split order; inactive groups are left untouched
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                           int n_split, int n_active, int64_t group_elems,
+                                                           const WgradParams p) {
+  const int64_t total = static_cast<int64_t>(n_active) * group_elems;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int gi = static_cast<int>(i / group_elems);
+    const int64_t e = i - gi * group_elems;
+    float acc = partial[i];
+    for (int s = 1; s < n_split; ++s) acc += partial[static_cast<int64_t>(s) * total + i];
+    dw[static_cast<int64_t>(p.group_ids[gi]) * group_elems + e] = acc;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ----------------------------------------------------------------------------------------------
@@ -233,12 +417,13 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+             int box_cols = BK) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t elem[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -258,6 +443,43 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
   }
   const unsigned grid = static_cast<unsigned>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
   AREAD_LAUNCH((grouped_linear_kernel<BN>), grid, kGemmThreads, L::kTotal, stream, ma, mb, p);
+  return AREAD_OK;
+}
+
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& mdz, const CUtensorMap& ma, const WgradParams& p, cudaStream_t stream) {
+  constexpr int kSmem = kStages * (2 + BN / 64) * (BK * 64 * 2) + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    AREAD_CUDA(cudaFuncSetAttribute(grouped_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  const unsigned grid = static_cast<unsigned>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+  AREAD_LAUNCH((grouped_wgrad_kernel<BN>), grid, kGemmThreads, kSmem, stream, mdz, ma, p);
+  return AREAD_OK;
+}
+
+int wgrad_plan(const aread_grouped_wgrad_args& a, WgradParams* p, int* bn_out) {
+  p->m = a.m;
+  p->n = a.n;
+  p->k = a.k;
+  p->a_group_cols = a.a_group_cols;
+  p->n_active = 0;
+  for (int g = 0; g < a.groups; ++g)
+    if (a.group_mask & (uint64_t{1} << g)) p->group_ids[p->n_active++] = static_cast<unsigned char>(g);
+  const int bn = a.k > 64 ? 128 : 64;
+  *bn_out = bn;
+  p->n_n_tiles = ceil_div(a.n, BM);
+  p->n_k_tiles = ceil_div(a.k, bn);
+  p->n_kb = ceil_div(a.m, BK);
+  const int64_t out_tiles = static_cast<int64_t>(p->n_active > 0 ? p->n_active : 1) * p->n_n_tiles * p->n_k_tiles;
+  int split = static_cast<int>((2 * kNumSMs + out_tiles - 1) / out_tiles);  // about two waves of CTAs
+  if (split > p->n_kb) split = p->n_kb;
+  if (split < 1) split = 1;
+  p->kb_per_split = ceil_div(p->n_kb, split);
+  p->n_split = ceil_div(p->n_kb, p->kb_per_split);
+  p->total_tiles = out_tiles * p->n_split;
   return AREAD_OK;
 }
 
@@ -305,4 +527,53 @@ extern "C" int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, 
   if (int rc = make_map(&mb, a.b, static_cast<int64_t>(a.groups) * a.n, a.k, a.ldb, bn)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   return bn == 128 ? launch_gemm<128>(ma, mb, p, stream) : launch_gemm<64>(ma, mb, p, stream);
+}
+
+extern "C" size_t aread_grouped_wgrad_workspace_bytes(const aread_grouped_wgrad_args* args) {
+  using namespace aread;
+  if (args == nullptr || args->m <= 0) return 256;
+  WgradParams p{};
+  int bn;
+  wgrad_plan(*args, &p, &bn);
+  return align_up(static_cast<size_t>(p.n_split) * (p.n_active > 0 ? p.n_active : 1) * args->n * args->k * 4, 256);
+}
+
+extern "C" int aread_grouped_wgrad_bf16(const aread_grouped_wgrad_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "grouped_wgrad: null args");
+  const aread_grouped_wgrad_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.n > 0 && a.k > 0, "grouped_wgrad: bad shape m=%lld n=%d k=%d", (long long)a.m, a.n, a.k);
+  AREAD_REQUIRE(a.groups > 0 && a.groups <= kMaxGroups, "grouped_wgrad: groups %d not in [1, %d]", a.groups,
+                kMaxGroups);
+  AREAD_REQUIRE(a.dz && a.a && a.dw && a.workspace, "grouped_wgrad: null pointer");
+  AREAD_REQUIRE(a.ldz % 8 == 0 && a.lda % 8 == 0, "grouped_wgrad: ldz/lda must be multiples of 8 bf16 (16 bytes)");
+  AREAD_REQUIRE(reinterpret_cast<uintptr_t>(a.dz) % 16 == 0 && reinterpret_cast<uintptr_t>(a.a) % 16 == 0,
+                "grouped_wgrad: operands must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  WgradParams p{};
+  int bn;
+  wgrad_plan(a, &p, &bn);
+  if (p.n_active == 0) return AREAD_OK;
+  const int64_t group_elems = static_cast<int64_t>(a.n) * a.k;
+  if (a.m == 0) {  // empty batch: the gradient of the active groups is zero
+    for (int gi = 0; gi < p.n_active; ++gi)
+      AREAD_CUDA(cudaMemsetAsync(a.dw + p.group_ids[gi] * group_elems, 0, group_elems * 4, stream));
+    return AREAD_OK;
+  }
+  const size_t need = static_cast<size_t>(p.n_split) * p.n_active * group_elems * 4;
+  if (need > a.workspace_bytes)
+    return fail(AREAD_ERR_WORKSPACE, "grouped_wgrad: workspace %zu < %zu bytes", a.workspace_bytes, need);
+  p.partial = static_cast<float*>(a.workspace);
+
+  CUtensorMap mdz, ma;
+  const int64_t a_cols = a.a_group_cols == 0 ? a.k : static_cast<int64_t>(a.a_group_cols) * (a.groups - 1) + a.k;
+  if (int rc = make_map(&mdz, a.dz, a.m, static_cast<int64_t>(a.groups) * a.n, a.ldz, BK, 64)) return rc;
+  if (int rc = make_map(&ma, a.a, a.m, a_cols, a.lda, BK, 64)) return rc;
+  if (int rc = (bn == 128 ? launch_wgrad<128>(mdz, ma, p, stream) : launch_wgrad<64>(mdz, ma, p, stream))) return rc;
+  const int64_t total = static_cast<int64_t>(p.n_active) * group_elems;
+  int64_t grid = (total + 255) / 256;
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  AREAD_LAUNCH(wgrad_reduce_kernel, static_cast<unsigned>(grid), 256, 0, stream, p.partial, a.dw, p.n_split,
+               p.n_active, group_elems, p);
+  return AREAD_OK;
 }

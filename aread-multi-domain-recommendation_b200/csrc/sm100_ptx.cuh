@@ -125,13 +125,30 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32
   d |= static_cast<uint64_t>(2) << 61;                            // [61,64) SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 A/B (both K-major) and fp32 D.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4)                               // [4,6)   D format: f32
-         | (1u << 7)                             // [7,10)  A format: bf16
-         | (1u << 10)                            // [10,13) B format: bf16
-         | (static_cast<uint32_t>(n >> 3) << 17) // [17,23) N >> 3
-         | (static_cast<uint32_t>(m >> 4) << 24);  // [24,29) M >> 4
+// Descriptor of an MN-major bf16 operand held as row-major [k rows][64 mn elements] tiles written
+// by TMA with 128B swizzle (the natural layout of an activation / gradient matrix whose rows are
+// the reduction dimension): 64 contiguous MN elements per 128-byte row, 8 k-rows per 1024-byte
+// swizzle atom (`sbo_bytes` between atoms), 64-wide MN blocks `lbo_bytes` apart.  A K step of 16
+// rows advances the start address by 2 * sbo_bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D; `mn_major` selects MN-major
+// (transposed) operands for both A and B instead of K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool mn_major = false) {
+  return (1u << 4)                                  // [4,6)   D format: f32
+         | (1u << 7)                                // [7,10)  A format: bf16
+         | (1u << 10)                               // [10,13) B format: bf16
+         | ((mn_major ? 1u : 0u) << 15)             // [15]    A major
+         | ((mn_major ? 1u : 0u) << 16)             // [16]    B major
+         | (static_cast<uint32_t>(n >> 3) << 17)    // [17,23) N >> 3
+         | (static_cast<uint32_t>(m >> 4) << 24);   // [24,29) M >> 4
 }
 
 }  // namespace ptx

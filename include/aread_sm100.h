@@ -151,6 +151,32 @@ typedef struct aread_grouped_linear_args {
 
 AREAD_API int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, aread_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Weight gradient of the grouped Linear: dW_g[j, i] = sum_b dZ[b, g*n + j] * A[b, g*a_group_cols + i].
+ * Replaces the autograd of the nn.Linear weights (model/layer.py:210) of the experts.  Both operands
+ * are read in their natural [samples, features] layout (MN-major tcgen05 operands); the sample
+ * range is split over CTAs and the fp32 partials are summed in a fixed order (deterministic).
+ * Rows of dw that belong to masked-out groups are left untouched.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_grouped_wgrad_args {
+  int64_t m;            /* samples                                                  */
+  int32_t n;            /* output features per group                                */
+  int32_t k;            /* input features per group                                 */
+  int32_t groups;
+  int32_t a_group_cols; /* as in aread_grouped_linear_args                          */
+  uint64_t group_mask;
+  const uint16_t* dz;   /* bf16 [m, ldz]: gradient w.r.t. the Linear output         */
+  int64_t ldz;
+  const uint16_t* a;    /* bf16 [m, lda]: the Linear input                          */
+  int64_t lda;
+  float* dw;            /* fp32 [groups * n, k] contiguous                          */
+  void* workspace;      /* aread_grouped_wgrad_workspace_bytes(args) bytes          */
+  size_t workspace_bytes;
+} aread_grouped_wgrad_args;
+
+AREAD_API size_t aread_grouped_wgrad_workspace_bytes(const aread_grouped_wgrad_args* args);
+AREAD_API int aread_grouped_wgrad_bf16(const aread_grouped_wgrad_args* args, aread_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

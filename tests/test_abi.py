@@ -46,7 +46,8 @@ def test_every_declared_symbol_is_exported(lib):
 
 @pytest.mark.parametrize("cname,ctype", [("aread_embed_plan", "EmbedPlan"), ("aread_gather_args", "GatherArgs"),
                                          ("aread_scatter_args", "ScatterArgs"),
-                                         ("aread_grouped_linear_args", "GroupedLinearArgs")])
+                                         ("aread_grouped_linear_args", "GroupedLinearArgs"),
+                                         ("aread_grouped_wgrad_args", "GroupedWgradArgs")])
 def test_struct_fields_match_header(cname, ctype):
     fields = [f for f, _ in getattr(_lib, ctype)._fields_]
     assert fields == struct_fields(cname)

@@ -4,11 +4,12 @@ There is deliberately no fallback: if the library is missing or fails to load, e
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint32, c_uint64,
+                    c_void_p)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -31,7 +32,7 @@ class EmbedPlan(Structure):
 
 class GatherArgs(Structure):
     _fields_ = [("plan", EmbedPlan), ("batch", c_int64), ("x", c_void_p), ("table", c_void_p),
-                ("out", c_void_p), ("out_bf16", c_void_p), ("status", c_void_p)]
+                ("out", c_void_p), ("out_bf16", c_void_p), ("out_bf16_lo", c_void_p), ("status", c_void_p)]
 
 
 class ScatterArgs(Structure):
@@ -43,13 +44,40 @@ class ScatterArgs(Structure):
 class GroupedLinearArgs(Structure):
     _fields_ = [("m", c_int64), ("n", c_int32), ("k", c_int32), ("groups", c_int32), ("a_group_cols", c_int32),
                 ("group_mask", c_uint64), ("a", c_void_p), ("lda", c_int64), ("b", c_void_p), ("ldb", c_int64),
-                ("bias", c_void_p), ("c_f32", c_void_p), ("c_bf16", c_void_p), ("ldc", c_int64)]
+                ("bias", c_void_p), ("c_f32", c_void_p), ("c_bf16", c_void_p), ("ldc", c_int64),
+                ("a_lo", c_void_p), ("b_lo", c_void_p)]
 
 
 class GroupedWgradArgs(Structure):
     _fields_ = [("m", c_int64), ("n", c_int32), ("k", c_int32), ("groups", c_int32), ("a_group_cols", c_int32),
                 ("group_mask", c_uint64), ("dz", c_void_p), ("ldz", c_int64), ("a", c_void_p), ("lda", c_int64),
-                ("dw", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
+                ("dw", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+                ("dz_lo", c_void_p), ("a_lo", c_void_p)]
+
+
+class BnActArgs(Structure):
+    _fields_ = [("m", c_int64), ("width", c_int32), ("training", c_int32), ("bn_skip", c_int32),
+                ("momentum", c_float), ("eps", c_float), ("dropout_p", c_float), ("seed", c_uint64),
+                ("salt", c_uint32), ("z", c_void_p), ("ldz", c_int64), ("gamma", c_void_p), ("beta", c_void_p),
+                ("running_mean", c_void_p), ("running_var", c_void_p), ("mean", c_void_p), ("rstd", c_void_p),
+                ("scale", c_void_p), ("shift", c_void_p), ("out_f32", c_void_p), ("out_bf16", c_void_p),
+                ("ldo", c_int64), ("workspace", c_void_p), ("workspace_bytes", c_size_t), ("out_bf16_lo", c_void_p)]
+
+
+class BnActBwdArgs(Structure):
+    _fields_ = [("m", c_int64), ("width", c_int32), ("bn_skip", c_int32), ("dropout_p", c_float),
+                ("salt", c_uint32), ("seed", c_uint64), ("z", c_void_p), ("ldz", c_int64), ("d_out", c_void_p),
+                ("ldd", c_int64), ("mean", c_void_p), ("rstd", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+                ("d_gamma", c_void_p), ("d_beta", c_void_p), ("d_bias", c_void_p), ("dz_f32", c_void_p),
+                ("dz_bf16", c_void_p), ("ldo", c_int64), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+                ("dz_bf16_lo", c_void_p)]
+
+
+class MmoeMixArgs(Structure):
+    _fields_ = [("m", c_int64), ("width", c_int32), ("n_expert", c_int32), ("n_gate", c_int32),
+                ("dropout_p", c_float), ("seed", c_uint64), ("salt", c_uint32), ("z", c_void_p), ("ldz", c_int64),
+                ("scale", c_void_p), ("shift", c_void_p), ("gate", c_void_p), ("out", c_void_p),
+                ("d_out", c_void_p), ("d_h", c_void_p), ("d_gate", c_void_p)]
 
 
 _SIGNATURES = {
@@ -62,6 +90,11 @@ _SIGNATURES = {
     "aread_grouped_linear_bf16": (c_int32, [POINTER(GroupedLinearArgs), c_void_p]),
     "aread_grouped_wgrad_workspace_bytes": (c_size_t, [POINTER(GroupedWgradArgs)]),
     "aread_grouped_wgrad_bf16": (c_int32, [POINTER(GroupedWgradArgs), c_void_p]),
+    "aread_bn_workspace_bytes": (c_size_t, [c_int32]),
+    "aread_bn_act_fwd": (c_int32, [POINTER(BnActArgs), c_void_p]),
+    "aread_bn_act_bwd": (c_int32, [POINTER(BnActBwdArgs), c_void_p]),
+    "aread_dropout_mask": (c_int32, [c_uint64, c_uint32, c_int64, c_float, c_void_p, c_void_p]),
+    "aread_mmoe_mix": (c_int32, [POINTER(MmoeMixArgs), c_void_p]),
 }
 
 _lib = None

@@ -6,6 +6,7 @@ on the C-ABI CUDA library through `dense_ops` / `embedding_ops`; the HEMP bookke
 logic (`hemp.py`).  Reference lines are cited per method.
 """
 import copy
+import os
 import re
 
 import numpy as np
@@ -13,7 +14,9 @@ import torch
 from torch import nn
 
 from . import dense_ops, hemp
+from .expert_ops import ExpertLayer
 from .layer import BaseModel, CrossNetwork, MultiLayerPerceptron, _weights_without_bn
+from .packing import PackSet
 
 
 class AREAD(BaseModel):
@@ -40,6 +43,11 @@ class AREAD(BaseModel):
         self.bottom_level = len(expert_dims)
         self.device = device
         self.dropout_p = dropout
+        # operand precision of the expert GEMMs: 'bf16' (one tensor-core pass, BASELINE "bf16 experts") or
+        # 'bf16x3' (split hi/lo operands, three passes, fp32-grade results)
+        self.expert_precision = os.environ.get("AREAD_EXPERT_PRECISION", "bf16")
+        if self.expert_precision not in ("bf16", "bf16x3"):
+            raise ValueError(f"AREAD_EXPERT_PRECISION must be 'bf16' or 'bf16x3', got {self.expert_precision!r}")
         self.domain2group = None if domain2group is None else np.array([domain2group[d] for d in range(n_domain)])
         self.domain_mask = [None] * n_domain
         self.candidate_domain_mask = None
@@ -88,6 +96,36 @@ class AREAD(BaseModel):
         self.add_regularization_weight(_weights_without_bn(self.towers), l2=l2_reg_dnn)
         self.add_regularization_weight(_weights_without_bn(self.cn), l2=l2_reg_cross)
         self._mask_cache = {}
+        self._build_packs()
+
+    # ----------------------------------------------------------------------------- packed storage
+    def _build_packs(self):
+        """Re-point the per-expert parameters at packed storage (packing.py) so that the grouped
+        kernels see all experts of a layer side by side."""
+        packs = PackSet()
+        layers = []
+        for i in range(self.bottom_level):
+            layers.append(ExpertLayer(packs, [e.layers[4 * i] for e in self.mmoe_experts],
+                                      [e.layers[4 * i + 1] for e in self.mmoe_experts], salt=0x1000 + i))
+        object.__setattr__(self, "_packs", packs)
+        object.__setattr__(self, "_expert_layers", layers)
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if getattr(self, "_packs", None) is not None:
+            for pack in self._packs.packs:          # .to() / .cuda() replaced every .data: pack again
+                pack.repack()
+        return out
+
+    def __deepcopy__(self, memo):
+        cls = self.__class__
+        clone = cls.__new__(cls)
+        memo[id(self)] = clone
+        for k, v in self.__dict__.items():
+            if k not in ("_packs", "_expert_layers"):
+                setattr(clone, k, copy.deepcopy(v, memo))
+        clone._build_packs()
+        return clone
 
     # ------------------------------------------------------------------------------------ forward
     def forward(self, x, mode='wo_mask', targets=None, memory_gate_value=False,

@@ -1,0 +1,513 @@
+// BatchNorm1d + ReLU + Dropout around the grouped Linear layers, forward and backward, and the
+// MMoE gate mixture.  All of it is HBM-bound elementwise / column-reduction work in fp32.
+//
+// Reference arithmetic: MultiLayerPerceptron.forward (model/layer.py:221-229): Linear ->
+// BatchNorm1d (training: batch mean / biased variance, eps 1e-5, running stats with momentum 0.1
+// and the unbiased variance; eval: running stats; skipped for a batch of one, layer.py:226) ->
+// ReLU -> Dropout(p); MMoE mixture: model/aread.py:150-153.
+//
+// Column reductions are deterministic: every CTA reduces a fixed row range into a partial, and the
+// partials are summed in CTA order.
+#include "common.cuh"
+
+namespace aread {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxColsPerThread = 8;  // width <= 2048
+constexpr int kStatCtas = kNumSMs * 2;
+
+// counter-based dropout stream: keep(element) is a pure function of (seed, salt, element index)
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t salt, uint64_t idx, uint32_t threshold) {
+  const uint32_t h = mix32(static_cast<uint32_t>(idx) ^ mix32(static_cast<uint32_t>(idx >> 32) ^ salt ^
+                                                               static_cast<uint32_t>(seed)) ^
+                           static_cast<uint32_t>(seed >> 32));
+  return h >= threshold;
+}
+inline uint32_t dropout_threshold(float p) {
+  if (p <= 0.f) return 0u;
+  const double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+}
+
+struct Geometry {  // how 256 threads cover [rows, width]
+  int tw, ty, nc;
+};
+inline Geometry geometry(int width) {
+  Geometry g;
+  g.tw = 1;
+  while (g.tw < width && g.tw < kThreads) g.tw <<= 1;
+  g.ty = kThreads / g.tw;
+  g.nc = (width + g.tw - 1) / g.tw;
+  return g;
+}
+
+// per-CTA partial column sums of f0(row, col) and f1(row, col) over the CTA's row range
+template <typename F>
+__device__ __forceinline__ void column_partials(int64_t m, int width, int tw, int ty_n, int nc, float* partial, F f) {
+  extern __shared__ float s_red[];  // [ty_n][2][nc * tw]
+  const int tx = threadIdx.x % tw, ty = threadIdx.x / tw;
+  const int64_t rows_per_cta = (m + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(m, r0 + rows_per_cta);
+  float s[kMaxColsPerThread], q[kMaxColsPerThread];
+#pragma unroll
+  for (int c = 0; c < kMaxColsPerThread; ++c) s[c] = q[c] = 0.f;
+  for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+#pragma unroll
+    for (int c = 0; c < kMaxColsPerThread; ++c) {
+      const int col = tx + c * tw;
+      if (c < nc && col < width) {
+        float a, b;
+        f(r, col, a, b);
+        s[c] += a;
+        q[c] += b;
+      }
+    }
+  }
+  const int stride = nc * tw;
+#pragma unroll
+  for (int c = 0; c < kMaxColsPerThread; ++c) {
+    if (c < nc) {
+      s_red[(ty * 2 + 0) * stride + c * tw + tx] = s[c];
+      s_red[(ty * 2 + 1) * stride + c * tw + tx] = q[c];
+    }
+  }
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int c = 0; c < kMaxColsPerThread; ++c) {
+      const int col = tx + c * tw;
+      if (c < nc && col < width) {
+        float a = 0.f, b = 0.f;
+        for (int y = 0; y < ty_n; ++y) {
+          a += s_red[(y * 2 + 0) * stride + c * tw + tx];
+          b += s_red[(y * 2 + 1) * stride + c * tw + tx];
+        }
+        partial[(static_cast<int64_t>(blockIdx.x) * 2 + 0) * width + col] = a;
+        partial[(static_cast<int64_t>(blockIdx.x) * 2 + 1) * width + col] = b;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(int64_t m, int width, int tw, int ty, int nc,
+                                                            const float* __restrict__ z, int64_t ldz,
+                                                            const float* __restrict__ pivot,
+                                                            float* __restrict__ partial) {
+  // sums are taken about the column's first row (a sample of the same distribution), which keeps
+  // E[v^2] - E[v]^2 well conditioned whatever the column mean is
+  column_partials(m, width, tw, ty, nc, partial, [&](int64_t r, int col, float& a, float& b) {
+    const float v = __ldg(z + r * ldz + col) - __ldg(pivot + col);
+    a = v;
+    b = v * v;
+  });
+}
+
+__global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const aread_bn_act_args a, const float* partial,
+                                                               int n_partial) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.width) return;
+  float scale, shift;
+  if (a.bn_skip) {
+    scale = 1.f;
+    shift = 0.f;
+    a.mean[col] = 0.f;
+    a.rstd[col] = 1.f;
+  } else if (a.training) {
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < n_partial; ++i) {
+      s += partial[(static_cast<int64_t>(i) * 2 + 0) * a.width + col];
+      q += partial[(static_cast<int64_t>(i) * 2 + 1) * a.width + col];
+    }
+    const float inv_m = 1.f / static_cast<float>(a.m);
+    const float d = s * inv_m;                       // mean - pivot
+    const float mean = a.z[col] + d;                 // the pivot is the column's first row
+    const float var = fmaxf(q * inv_m - d * d, 0.f);
+    const float rstd = 1.f / sqrtf(var + a.eps);
+    a.mean[col] = mean;
+    a.rstd[col] = rstd;
+    scale = a.gamma[col] * rstd;
+    shift = a.beta[col] - mean * scale;
+    const float unbiased = a.m > 1 ? var * (static_cast<float>(a.m) / static_cast<float>(a.m - 1)) : var;
+    a.running_mean[col] = (1.f - a.momentum) * a.running_mean[col] + a.momentum * mean;
+    a.running_var[col] = (1.f - a.momentum) * a.running_var[col] + a.momentum * unbiased;
+  } else {
+    const float rstd = 1.f / sqrtf(a.running_var[col] + a.eps);
+    a.mean[col] = a.running_mean[col];
+    a.rstd[col] = rstd;
+    scale = a.gamma[col] * rstd;
+    shift = a.beta[col] - a.running_mean[col] * scale;
+  }
+  a.scale[col] = scale;
+  a.shift[col] = shift;
+}
+
+__device__ __forceinline__ float act_value(float z, float scale, float shift, bool keep, float keep_scale) {
+  const float y = fmaf(z, scale, shift);
+  return (y > 0.f && keep) ? y * keep_scale : 0.f;
+}
+
+// rows by (blockIdx.x, ty), columns by tx, VEC consecutive columns per thread: no index divisions
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) bn_act_kernel(const aread_bn_act_args a, int tw, uint32_t threshold,
+                                                          float keep_scale) {
+  const int tx = threadIdx.x % tw, ty = threadIdx.x / tw, ty_n = kThreads / tw;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * ty_n + ty; r < a.m; r += static_cast<int64_t>(gridDim.x) * ty_n) {
+    for (int col = tx * VEC; col < a.width; col += tw * VEC) {
+      float z[VEC], v[VEC];
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.ldz + col));
+        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+      } else {
+        z[0] = __ldg(a.z + r * a.ldz + col);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const bool keep = threshold == 0u ||
+                          dropout_keep(a.seed, a.salt, static_cast<uint64_t>(r) * a.width + col + j, threshold);
+        v[j] = act_value(z[j], __ldg(a.scale + col + j), __ldg(a.shift + col + j), keep, keep_scale);
+      }
+      if (VEC == 4) {
+        if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + r * a.ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+        if (a.out_bf16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<unsigned*>(&lo);
+          pk.y = *reinterpret_cast<unsigned*>(&hi);
+          *reinterpret_cast<uint2*>(a.out_bf16 + r * a.ldo + col) = pk;
+          if (a.out_bf16_lo) {
+            const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
+            __nv_bfloat162 rl = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y);
+            __nv_bfloat162 rh = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
+            pk.x = *reinterpret_cast<unsigned*>(&rl);
+            pk.y = *reinterpret_cast<unsigned*>(&rh);
+            *reinterpret_cast<uint2*>(a.out_bf16_lo + r * a.ldo + col) = pk;
+          }
+        }
+      } else {
+        if (a.out_f32) a.out_f32[r * a.ldo + col] = v[0];
+        if (a.out_bf16) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v[0]);
+          reinterpret_cast<__nv_bfloat16*>(a.out_bf16)[r * a.ldo + col] = h;
+          if (a.out_bf16_lo)
+            reinterpret_cast<__nv_bfloat16*>(a.out_bf16_lo)[r * a.ldo + col] =
+                __float2bfloat16_rn(v[0] - __bfloat162float(h));
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- backward
+// dy = d_out * [y > 0] * keep / (1 - p);  xhat = (z - mean) * rstd
+__global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const aread_bn_act_bwd_args a, int tw, int ty, int nc,
+                                                                uint32_t threshold, float keep_scale,
+                                                                float* __restrict__ partial) {
+  column_partials(a.m, a.width, tw, ty, nc, partial, [&](int64_t r, int col, float& s1, float& s2) {
+    const float z = __ldg(a.z + r * a.ldz + col);
+    const float y = fmaf(z, __ldg(a.scale + col), __ldg(a.shift + col));
+    const bool keep = threshold == 0u ||
+                      dropout_keep(a.seed, a.salt, static_cast<uint64_t>(r) * a.width + col, threshold);
+    const float dy = (y > 0.f && keep) ? __ldg(a.d_out + r * a.ldd + col) * keep_scale : 0.f;
+    s1 = dy;
+    s2 = dy * (z - __ldg(a.mean + col)) * __ldg(a.rstd + col);
+  });
+}
+
+__global__ void __launch_bounds__(kThreads) bn_bwd_finalize_kernel(const aread_bn_act_bwd_args a, const float* partial,
+                                                                   int n_partial, float* coef) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.width) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < n_partial; ++i) {
+    s1 += partial[(static_cast<int64_t>(i) * 2 + 0) * a.width + col];
+    s2 += partial[(static_cast<int64_t>(i) * 2 + 1) * a.width + col];
+  }
+  if (a.bn_skip) {  // identity instead of BatchNorm: gamma / beta see no gradient, the bias sees sum(dy)
+    if (a.d_gamma) a.d_gamma[col] = 0.f;
+    if (a.d_beta) a.d_beta[col] = 0.f;
+    if (a.d_bias) a.d_bias[col] = s1;
+    coef[col] = 0.f;
+    coef[a.width + col] = 0.f;
+  } else {
+    if (a.d_gamma) a.d_gamma[col] = s2;
+    if (a.d_beta) a.d_beta[col] = s1;
+    if (a.d_bias) a.d_bias[col] = 0.f;  // BatchNorm removes the column mean: the exact gradient is zero
+    const float inv_m = 1.f / static_cast<float>(a.m);
+    coef[col] = s1 * inv_m;
+    coef[a.width + col] = s2 * inv_m;
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const aread_bn_act_bwd_args a, int tw,
+                                                                uint32_t threshold, float keep_scale,
+                                                                const float* __restrict__ coef) {
+  const int tx = threadIdx.x % tw, ty = threadIdx.x / tw, ty_n = kThreads / tw;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * ty_n + ty; r < a.m; r += static_cast<int64_t>(gridDim.x) * ty_n) {
+    for (int col = tx * VEC; col < a.width; col += tw * VEC) {
+      float z[VEC], d[VEC], dz[VEC];
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.ldz + col));
+        const float4 u = __ldg(reinterpret_cast<const float4*>(a.d_out + r * a.ldd + col));
+        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+        d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+      } else {
+        z[0] = __ldg(a.z + r * a.ldz + col);
+        d[0] = __ldg(a.d_out + r * a.ldd + col);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int c = col + j;
+        const float scale = __ldg(a.scale + c);
+        const float y = fmaf(z[j], scale, __ldg(a.shift + c));
+        const bool keep = threshold == 0u ||
+                          dropout_keep(a.seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
+        const float dy = (y > 0.f && keep) ? d[j] * keep_scale : 0.f;
+        const float xhat = (z[j] - __ldg(a.mean + c)) * __ldg(a.rstd + c);
+        dz[j] = a.bn_skip ? dy : scale * (dy - coef[c] - xhat * coef[a.width + c]);
+      }
+      if (VEC == 4) {
+        if (a.dz_f32) *reinterpret_cast<float4*>(a.dz_f32 + r * a.ldo + col) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+        if (a.dz_bf16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(dz[0], dz[1]), hi = __floats2bfloat162_rn(dz[2], dz[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<unsigned*>(&lo);
+          pk.y = *reinterpret_cast<unsigned*>(&hi);
+          *reinterpret_cast<uint2*>(a.dz_bf16 + r * a.ldo + col) = pk;
+          if (a.dz_bf16_lo) {
+            const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
+            __nv_bfloat162 rl = __floats2bfloat162_rn(dz[0] - f0.x, dz[1] - f0.y);
+            __nv_bfloat162 rh = __floats2bfloat162_rn(dz[2] - f1.x, dz[3] - f1.y);
+            pk.x = *reinterpret_cast<unsigned*>(&rl);
+            pk.y = *reinterpret_cast<unsigned*>(&rh);
+            *reinterpret_cast<uint2*>(a.dz_bf16_lo + r * a.ldo + col) = pk;
+          }
+        }
+      } else {
+        if (a.dz_f32) a.dz_f32[r * a.ldo + col] = dz[0];
+        if (a.dz_bf16) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(dz[0]);
+          reinterpret_cast<__nv_bfloat16*>(a.dz_bf16)[r * a.ldo + col] = h;
+          if (a.dz_bf16_lo)
+            reinterpret_cast<__nv_bfloat16*>(a.dz_bf16_lo)[r * a.ldo + col] =
+                __float2bfloat16_rn(dz[0] - __bfloat162float(h));
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- MMoE mixture
+// h[b, e, :] = dropout(relu(bn(z[b, e, :]))) ;  out[b, g, :] = sum_e gate[b, g, e] * h[b, e, :]
+__global__ void __launch_bounds__(kThreads) mmoe_mix_fwd_kernel(const aread_mmoe_mix_args a, uint32_t threshold,
+                                                                float keep_scale) {
+  const int H = a.width, NE = a.n_expert, G = a.n_gate;
+  const int64_t total = a.m * H;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t b = i / H;
+    const int c = static_cast<int>(i - b * H);
+    float h[16];
+    for (int e = 0; e < NE; ++e) {
+      const int col = e * H + c;
+      const bool keep = threshold == 0u ||
+                        dropout_keep(a.seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
+      h[e] = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep, keep_scale);
+    }
+    for (int g = 0; g < G; ++g) {
+      float acc = 0.f;
+      for (int e = 0; e < NE; ++e) acc = fmaf(__ldg(a.gate + b * (G * NE) + g * NE + e), h[e], acc);
+      a.out[b * (G * H) + g * H + c] = acc;
+    }
+  }
+}
+
+// d_h[b, e, :] = sum_g gate[b, g, e] * d_out[b, g, :] ;  d_gate[b, g, e] = <d_out[b, g, :], h[b, e, :]>
+// one warp per sample
+__global__ void __launch_bounds__(kThreads) mmoe_mix_bwd_kernel(const aread_mmoe_mix_args a, uint32_t threshold,
+                                                                float keep_scale) {
+  const int H = a.width, NE = a.n_expert, G = a.n_gate;
+  const int lane = threadIdx.x % 32;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x / 32);
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32; b < a.m; b += warps) {
+    float dg[64];  // [G][NE] partial dot products of this lane
+    for (int j = 0; j < G * NE; ++j) dg[j] = 0.f;
+    for (int c = lane; c < H; c += 32) {
+      float h[16], dout[8];
+      for (int g = 0; g < G; ++g) dout[g] = __ldg(a.d_out + b * (G * H) + g * H + c);
+      for (int e = 0; e < NE; ++e) {
+        const int col = e * H + c;
+        const bool keep = threshold == 0u ||
+                          dropout_keep(a.seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
+        h[e] = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep, keep_scale);
+        float acc = 0.f;
+        for (int g = 0; g < G; ++g) acc = fmaf(__ldg(a.gate + b * (G * NE) + g * NE + e), dout[g], acc);
+        a.d_h[b * (NE * H) + col] = acc;
+      }
+      for (int g = 0; g < G; ++g)
+        for (int e = 0; e < NE; ++e) dg[g * NE + e] = fmaf(dout[g], h[e], dg[g * NE + e]);
+    }
+    for (int j = 0; j < G * NE; ++j) {
+      const float v = warp_sum(dg[j]);
+      if (lane == 0) a.d_gate[b * (G * NE) + j] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) dropout_mask_kernel(uint64_t seed, uint32_t salt, int64_t n,
+                                                                uint32_t threshold, uint8_t* out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (threshold == 0u || dropout_keep(seed, salt, static_cast<uint64_t>(i), threshold)) ? 1 : 0;
+}
+
+struct RowGrid {
+  int tw, vec;
+  unsigned grid;
+};
+// thread layout of the row-major elementwise kernels: vec = 4 when every row start is 16-byte aligned
+RowGrid row_grid(int64_t m, int width, bool aligned) {
+  RowGrid g;
+  g.vec = (aligned && width % 4 == 0) ? 4 : 1;
+  g.tw = 1;
+  while (g.tw * g.vec < width && g.tw < kThreads) g.tw <<= 1;
+  const int rows_per_cta = kThreads / g.tw;
+  int64_t n = (m + rows_per_cta - 1) / rows_per_cta;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+  g.grid = static_cast<unsigned>(n < 1 ? 1 : (n > cap ? cap : n));
+  return g;
+}
+
+unsigned elementwise_grid(int64_t total) {
+  int64_t g = (total + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+  return static_cast<unsigned>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int stat_ctas(int64_t m) {
+  int64_t c = (m + 63) / 64;  // at least 64 rows per CTA
+  return static_cast<int>(c < 1 ? 1 : (c > kStatCtas ? kStatCtas : c));
+}
+
+}  // namespace
+}  // namespace aread
+
+extern "C" {
+
+size_t aread_bn_workspace_bytes(int32_t width) {
+  return aread::align_up(static_cast<size_t>(aread::kStatCtas) * 2 * width * 4 + 2 * static_cast<size_t>(width) * 4,
+                         256);
+}
+
+int aread_bn_act_fwd(const aread_bn_act_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "bn_act_fwd: null args");
+  const aread_bn_act_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width <= kThreads * kMaxColsPerThread, "bn_act_fwd: width %d unsupported",
+                a.width);
+  AREAD_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, "bn_act_fwd: dropout %f not in [0, 1)", a.dropout_p);
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.z && a.mean && a.rstd && a.scale && a.shift, "bn_act_fwd: null pointer");
+  AREAD_REQUIRE(a.bn_skip || (a.gamma && a.beta && a.running_mean && a.running_var), "bn_act_fwd: null BN tensor");
+  AREAD_REQUIRE(a.workspace_bytes >= aread_bn_workspace_bytes(a.width), "bn_act_fwd: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* partial = static_cast<float*>(a.workspace);
+  const int n_partial = stat_ctas(a.m);
+  if (a.training && !a.bn_skip) {
+    const Geometry g = geometry(a.width);
+    AREAD_LAUNCH(bn_stats_kernel, n_partial, kThreads, sizeof(float) * 2 * g.ty * g.nc * g.tw, stream, a.m, a.width,
+                 g.tw, g.ty, g.nc, a.z, a.ldz, a.z, partial);
+  }
+  AREAD_LAUNCH(bn_finalize_kernel, ceil_div(a.width, kThreads), kThreads, 0, stream, a, partial, n_partial);
+  if (a.out_f32 || a.out_bf16) {
+    const bool drop = a.training && a.dropout_p > 0.f;
+    const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;
+    const float keep_scale = drop ? 1.f / (1.f - a.dropout_p) : 1.f;
+    const bool aligned = a.ldz % 4 == 0 && a.ldo % 4 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0 &&
+                         reinterpret_cast<uintptr_t>(a.out_f32) % 16 == 0 &&
+                         reinterpret_cast<uintptr_t>(a.out_bf16) % 8 == 0 &&
+                         reinterpret_cast<uintptr_t>(a.out_bf16_lo) % 8 == 0;
+    const RowGrid rg = row_grid(a.m, a.width, aligned);
+    if (rg.vec == 4)
+      AREAD_LAUNCH(bn_act_kernel<4>, rg.grid, kThreads, 0, stream, a, rg.tw, threshold, keep_scale);
+    else
+      AREAD_LAUNCH(bn_act_kernel<1>, rg.grid, kThreads, 0, stream, a, rg.tw, threshold, keep_scale);
+  }
+  return AREAD_OK;
+}
+
+int aread_bn_act_bwd(const aread_bn_act_bwd_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "bn_act_bwd: null args");
+  const aread_bn_act_bwd_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width <= kThreads * kMaxColsPerThread, "bn_act_bwd: width %d unsupported",
+                a.width);
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.z && a.d_out && a.mean && a.rstd && a.scale && a.shift, "bn_act_bwd: null pointer");
+  AREAD_REQUIRE(a.workspace_bytes >= aread_bn_workspace_bytes(a.width), "bn_act_bwd: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* partial = static_cast<float*>(a.workspace);
+  float* coef = partial + static_cast<size_t>(kStatCtas) * 2 * a.width;
+  const int n_partial = stat_ctas(a.m);
+  const bool drop = a.dropout_p > 0.f;
+  const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;
+  const float keep_scale = drop ? 1.f / (1.f - a.dropout_p) : 1.f;
+  const Geometry g = geometry(a.width);
+  AREAD_LAUNCH(bn_bwd_stats_kernel, n_partial, kThreads, sizeof(float) * 2 * g.ty * g.nc * g.tw, stream, a, g.tw, g.ty,
+               g.nc, threshold, keep_scale, partial);
+  AREAD_LAUNCH(bn_bwd_finalize_kernel, ceil_div(a.width, kThreads), kThreads, 0, stream, a, partial, n_partial, coef);
+  if (a.dz_f32 || a.dz_bf16) {
+    const bool aligned = a.ldz % 4 == 0 && a.ldo % 4 == 0 && a.ldd % 4 == 0 &&
+                         reinterpret_cast<uintptr_t>(a.z) % 16 == 0 && reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0 &&
+                         reinterpret_cast<uintptr_t>(a.dz_f32) % 16 == 0 &&
+                         reinterpret_cast<uintptr_t>(a.dz_bf16) % 8 == 0 &&
+                         reinterpret_cast<uintptr_t>(a.dz_bf16_lo) % 8 == 0;
+    const RowGrid rg = row_grid(a.m, a.width, aligned);
+    if (rg.vec == 4)
+      AREAD_LAUNCH(bn_bwd_apply_kernel<4>, rg.grid, kThreads, 0, stream, a, rg.tw, threshold, keep_scale, coef);
+    else
+      AREAD_LAUNCH(bn_bwd_apply_kernel<1>, rg.grid, kThreads, 0, stream, a, rg.tw, threshold, keep_scale, coef);
+  }
+  return AREAD_OK;
+}
+
+int aread_mmoe_mix(const aread_mmoe_mix_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "mmoe_mix: null args");
+  const aread_mmoe_mix_args& a = *args;
+  AREAD_REQUIRE(a.n_expert > 0 && a.n_expert <= 16 && a.n_gate > 0 && a.n_gate <= 8 && a.n_expert * a.n_gate <= 64,
+                "mmoe_mix: %d experts x %d gates unsupported", a.n_expert, a.n_gate);
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.z && a.scale && a.shift && a.gate, "mmoe_mix: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool drop = a.dropout_p > 0.f;
+  const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;
+  const float keep_scale = drop ? 1.f / (1.f - a.dropout_p) : 1.f;
+  if (a.d_out == nullptr) {
+    AREAD_REQUIRE(a.out != nullptr, "mmoe_mix: null out");
+    AREAD_LAUNCH(mmoe_mix_fwd_kernel, elementwise_grid(a.m * a.width), kThreads, 0, stream, a, threshold, keep_scale);
+  } else {
+    AREAD_REQUIRE(a.d_h && a.d_gate, "mmoe_mix: null gradient output");
+    AREAD_LAUNCH(mmoe_mix_bwd_kernel, elementwise_grid(a.m * 32), kThreads, 0, stream, a, threshold, keep_scale);
+  }
+  return AREAD_OK;
+}
+
+int aread_dropout_mask(uint64_t seed, uint32_t salt, int64_t n, float p, uint8_t* out, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(n >= 0 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
+  if (n == 0) return AREAD_OK;
+  AREAD_REQUIRE(out != nullptr, "dropout_mask: null out");
+  AREAD_LAUNCH(dropout_mask_kernel, elementwise_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream_), seed, salt, n,
+               dropout_threshold(p), out);
+  return AREAD_OK;
+}
+
+}  // extern "C"

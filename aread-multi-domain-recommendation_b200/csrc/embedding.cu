@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const aread_gather_arg
     const int* __restrict__ xr = a.x + b * C;
     float* __restrict__ orow = a.out + b * F * D + lane * 4;
     uint16_t* __restrict__ hrow = a.out_bf16 ? a.out_bf16 + b * F * D + lane * 4 : nullptr;
+    uint16_t* __restrict__ lrow = a.out_bf16_lo ? a.out_bf16_lo + b * F * D + lane * 4 : nullptr;
     for (int f0 = 0; f0 < F; f0 += UNROLL) {
       float4 acc[UNROLL];
 #pragma unroll
@@ -127,7 +128,16 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const aread_gather_arg
         const int f = f0 + u;
         if (f < F && lane_on) {
           *reinterpret_cast<float4*>(orow + f * D) = acc[u];
-          if (hrow != nullptr) *reinterpret_cast<uint2*>(hrow + f * D) = pack_bf16x4(acc[u]);
+          if (hrow != nullptr) {
+            const uint2 hi = pack_bf16x4(acc[u]);
+            *reinterpret_cast<uint2*>(hrow + f * D) = hi;
+            if (lrow != nullptr) {  // split residual: bf16(x - bf16(x))
+              const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi.x));
+              const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi.y));
+              *reinterpret_cast<uint2*>(lrow + f * D) =
+                  pack_bf16x4(make_float4(acc[u].x - h0.x, acc[u].y - h0.y, acc[u].z - h1.x, acc[u].w - h1.y));
+            }
+          }
         }
       }
     }
@@ -476,6 +486,8 @@ int aread_gather_fwd(const aread_gather_args* args, aread_stream_t stream_) {
                 "gather: table/out must be 16-byte aligned");
   AREAD_REQUIRE(a.out_bf16 == nullptr || reinterpret_cast<uintptr_t>(a.out_bf16) % 8 == 0,
                 "gather: out_bf16 must be 8-byte aligned");
+  AREAD_REQUIRE(a.out_bf16_lo == nullptr || (a.out_bf16 != nullptr && reinterpret_cast<uintptr_t>(a.out_bf16_lo) % 8 == 0),
+                "gather: out_bf16_lo needs out_bf16 and 8-byte alignment");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   switch (lanes_per_row(a.plan.embed_dim)) {
     case 1: return launch_gather<1>(a, stream);

@@ -35,6 +35,7 @@ struct GemmParams {
   __nv_bfloat16* c_bf16;
   const float* bias;
   int n_m_tiles, n_n_tiles, n_k_blocks;
+  int n_seg;  // 1: bf16 operands; 3: split operands, A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
   int64_t total_tiles;
   unsigned char group_ids[kMaxGroups];
 };
@@ -64,6 +65,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int64_t ti
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo,
                       const GemmParams p) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -105,14 +107,18 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const TileCoord c = decode_tile(p, tile);
         const int a_col0 = c.g * p.a_group_cols;
         const int b_row0 = c.g * p.n + c.n_t * BN;
-        for (int kb = 0; kb < p.n_k_blocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          ptx::tma_load_2d(sa, &map_a, &full_bar[stage], a_col0 + kb * BK, c.m_t * BM);
-          ptx::tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, b_row0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        for (int seg = 0; seg < p.n_seg; ++seg) {
+          const CUtensorMap* ma = seg < 2 ? &map_a : &map_a_lo;
+          const CUtensorMap* mb = seg == 1 ? &map_b_lo : &map_b;
+          for (int kb = 0; kb < p.n_k_blocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            ptx::tma_load_2d(sa, ma, &full_bar[stage], a_col0 + kb * BK, c.m_t * BM);
+            ptx::tma_load_2d(sb, mb, &full_bar[stage], kb * BK, b_row0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -125,7 +131,8 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.n_k_blocks; ++kb) {
+        const int n_kb = p.n_k_blocks * p.n_seg;
+        for (int kb = 0; kb < n_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
@@ -228,6 +235,7 @@ struct WgradParams {
   float* partial;            // [n_split][groups_active][n][k]
   int n_n_tiles, n_k_tiles;  // tiles over output features / input features
   int kb_per_split, n_kb;    // 64-sample blocks
+  int n_seg;                 // 1: bf16; 3: dZ_hi.A_hi + dZ_hi.A_lo + dZ_lo.A_hi
   int64_t total_tiles;
   unsigned char group_ids[kMaxGroups];
 };
@@ -251,6 +259,7 @@ __device__ __forceinline__ WgradCoord decode_wgrad(const WgradParams& p, int64_t
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 grouped_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_a,
+                     const __grid_constant__ CUtensorMap map_dz_lo, const __grid_constant__ CUtensorMap map_a_lo,
                      const WgradParams p) {
   constexpr int kBoxBytes = BK * 64 * 2;                 // [64 samples][64 features] bf16 = 8 KB
   constexpr int kABytes = 2 * kBoxBytes;                 // 128 output features
@@ -297,17 +306,21 @@ grouped_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_co
         const int kb1 = min(p.n_kb, kb0 + p.kb_per_split);
         const int dz_col0 = c.g * p.n + c.n_t * BM;
         const int a_col0 = c.g * p.a_group_cols + c.k_t * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          ptx::tma_load_2d(sa, &map_dz, &full_bar[stage], dz_col0, kb * BK);
-          ptx::tma_load_2d(sa + kBoxBytes, &map_dz, &full_bar[stage], dz_col0 + 64, kb * BK);
+        for (int seg = 0; seg < p.n_seg; ++seg) {
+          const CUtensorMap* mz = seg < 2 ? &map_dz : &map_dz_lo;
+          const CUtensorMap* ma = seg == 1 ? &map_a_lo : &map_a;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            ptx::tma_load_2d(sa, mz, &full_bar[stage], dz_col0, kb * BK);
+            ptx::tma_load_2d(sa + kBoxBytes, mz, &full_bar[stage], dz_col0 + 64, kb * BK);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            ptx::tma_load_2d(sb + j * kBoxBytes, &map_a, &full_bar[stage], a_col0 + j * 64, kb * BK);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+            for (int j = 0; j < BN / 64; ++j)
+              ptx::tma_load_2d(sb + j * kBoxBytes, ma, &full_bar[stage], a_col0 + j * 64, kb * BK);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -323,7 +336,8 @@ grouped_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_co
         ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const int n_iter = (kb1 - kb0) * p.n_seg;
+        for (int it = 0; it < n_iter; ++it) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
@@ -332,7 +346,7 @@ grouped_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_co
           for (int kk = 0; kk < BK / UMMA_K; ++kk) {  // 16 samples = two 8-row swizzle atoms
             const uint64_t da = ptx::umma_desc_mn_sw128(sa + kk * 2048, kBoxBytes, 1024);
             const uint64_t db = ptx::umma_desc_mn_sw128(sb + kk * 2048, kBoxBytes, 1024);
-            ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0) || (kk != 0));
+            ptx::umma_bf16(d_tmem, da, db, idesc, (it > 0) || (kk != 0));
           }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -433,7 +447,8 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
 }
 
 template <int BN>
-int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma_lo, const CUtensorMap& mb_lo,
+                const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool configured = false;
   if (!configured) {
@@ -442,13 +457,14 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
     configured = true;
   }
   const unsigned grid = static_cast<unsigned>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
-  AREAD_LAUNCH((grouped_linear_kernel<BN>), grid, kGemmThreads, L::kTotal, stream, ma, mb, p);
+  AREAD_LAUNCH((grouped_linear_kernel<BN>), grid, kGemmThreads, L::kTotal, stream, ma, mb, ma_lo, mb_lo, p);
   return AREAD_OK;
 }
 
 
 template <int BN>
-int launch_wgrad(const CUtensorMap& mdz, const CUtensorMap& ma, const WgradParams& p, cudaStream_t stream) {
+int launch_wgrad(const CUtensorMap& mdz, const CUtensorMap& ma, const CUtensorMap& mdz_lo, const CUtensorMap& ma_lo,
+                 const WgradParams& p, cudaStream_t stream) {
   constexpr int kSmem = kStages * (2 + BN / 64) * (BK * 64 * 2) + 256 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -456,7 +472,7 @@ int launch_wgrad(const CUtensorMap& mdz, const CUtensorMap& ma, const WgradParam
     configured = true;
   }
   const unsigned grid = static_cast<unsigned>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
-  AREAD_LAUNCH((grouped_wgrad_kernel<BN>), grid, kGemmThreads, kSmem, stream, mdz, ma, p);
+  AREAD_LAUNCH((grouped_wgrad_kernel<BN>), grid, kGemmThreads, kSmem, stream, mdz, ma, mdz_lo, ma_lo, p);
   return AREAD_OK;
 }
 
@@ -521,12 +537,22 @@ extern "C" int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, 
   p.n_k_blocks = ceil_div(a.k, BK);
   p.total_tiles = static_cast<int64_t>(p.n_m_tiles) * p.n_active * p.n_n_tiles;
 
-  CUtensorMap ma, mb;
+  AREAD_REQUIRE((a.a_lo != nullptr) == (a.b_lo != nullptr), "grouped_linear: a_lo and b_lo go together");
+  p.n_seg = a.a_lo != nullptr ? 3 : 1;
+  CUtensorMap ma, mb, ma_lo, mb_lo;
   const int64_t a_cols = a.a_group_cols == 0 ? a.k : static_cast<int64_t>(a.a_group_cols) * (a.groups - 1) + a.k;
   if (int rc = make_map(&ma, a.a, a.m, a_cols, a.lda, BM)) return rc;
   if (int rc = make_map(&mb, a.b, static_cast<int64_t>(a.groups) * a.n, a.k, a.ldb, bn)) return rc;
+  ma_lo = ma;
+  mb_lo = mb;
+  if (p.n_seg == 3) {
+    AREAD_REQUIRE(reinterpret_cast<uintptr_t>(a.a_lo) % 16 == 0 && reinterpret_cast<uintptr_t>(a.b_lo) % 16 == 0,
+                  "grouped_linear: lo operands must be 16-byte aligned");
+    if (int rc = make_map(&ma_lo, a.a_lo, a.m, a_cols, a.lda, BM)) return rc;
+    if (int rc = make_map(&mb_lo, a.b_lo, static_cast<int64_t>(a.groups) * a.n, a.k, a.ldb, bn)) return rc;
+  }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  return bn == 128 ? launch_gemm<128>(ma, mb, p, stream) : launch_gemm<64>(ma, mb, p, stream);
+  return bn == 128 ? launch_gemm<128>(ma, mb, ma_lo, mb_lo, p, stream) : launch_gemm<64>(ma, mb, ma_lo, mb_lo, p, stream);
 }
 
 extern "C" size_t aread_grouped_wgrad_workspace_bytes(const aread_grouped_wgrad_args* args) {
@@ -565,11 +591,23 @@ extern "C" int aread_grouped_wgrad_bf16(const aread_grouped_wgrad_args* args, ar
     return fail(AREAD_ERR_WORKSPACE, "grouped_wgrad: workspace %zu < %zu bytes", a.workspace_bytes, need);
   p.partial = static_cast<float*>(a.workspace);
 
-  CUtensorMap mdz, ma;
+  AREAD_REQUIRE((a.dz_lo != nullptr) == (a.a_lo != nullptr), "grouped_wgrad: dz_lo and a_lo go together");
+  p.n_seg = a.dz_lo != nullptr ? 3 : 1;
+  CUtensorMap mdz, ma, mdz_lo, ma_lo;
   const int64_t a_cols = a.a_group_cols == 0 ? a.k : static_cast<int64_t>(a.a_group_cols) * (a.groups - 1) + a.k;
   if (int rc = make_map(&mdz, a.dz, a.m, static_cast<int64_t>(a.groups) * a.n, a.ldz, BK, 64)) return rc;
   if (int rc = make_map(&ma, a.a, a.m, a_cols, a.lda, BK, 64)) return rc;
-  if (int rc = (bn == 128 ? launch_wgrad<128>(mdz, ma, p, stream) : launch_wgrad<64>(mdz, ma, p, stream))) return rc;
+  mdz_lo = mdz;
+  ma_lo = ma;
+  if (p.n_seg == 3) {
+    AREAD_REQUIRE(reinterpret_cast<uintptr_t>(a.dz_lo) % 16 == 0 && reinterpret_cast<uintptr_t>(a.a_lo) % 16 == 0,
+                  "grouped_wgrad: lo operands must be 16-byte aligned");
+    if (int rc = make_map(&mdz_lo, a.dz_lo, a.m, static_cast<int64_t>(a.groups) * a.n, a.ldz, BK, 64)) return rc;
+    if (int rc = make_map(&ma_lo, a.a_lo, a.m, a_cols, a.lda, BK, 64)) return rc;
+  }
+  if (int rc = (bn == 128 ? launch_wgrad<128>(mdz, ma, mdz_lo, ma_lo, p, stream)
+                          : launch_wgrad<64>(mdz, ma, mdz_lo, ma_lo, p, stream)))
+    return rc;
   const int64_t total = static_cast<int64_t>(p.n_active) * group_elems;
   int64_t grid = (total + 255) / 256;
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;

@@ -10,7 +10,14 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def grouped_linear(a, w, bias, n, k, groups, a_group_cols=0, group_mask=None, out=None, out_dtype=torch.float32):
+def split_bf16(x):
+    """x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the operands of the split-precision GEMMs."""
+    hi = x.to(torch.bfloat16)
+    return hi, (x - hi.float()).to(torch.bfloat16)
+
+
+def grouped_linear(a, w, bias, n, k, groups, a_group_cols=0, group_mask=None, out=None, out_dtype=torch.float32,
+                   a_lo=None, w_lo=None):
     """C[:, g*n:(g+1)*n] = A[:, g*a_group_cols : +k] @ W[g*n:(g+1)*n, :k]^T (+ bias) for active groups.
 
     a: bf16 [m, lda]; w: bf16 [groups*n, ldb]; bias: fp32 [groups*n] or None.  Columns of masked-out
@@ -28,7 +35,10 @@ def grouped_linear(a, w, bias, n, k, groups, a_group_cols=0, group_mask=None, ou
         m, n, k, groups, a_group_cols, mask, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
         bias.data_ptr() if bias is not None else None,
         out.data_ptr() if out.dtype == torch.float32 else None,
-        out.data_ptr() if out.dtype == torch.bfloat16 else None, out.stride(0))
+        out.data_ptr() if out.dtype == torch.bfloat16 else None, out.stride(0),
+        a_lo.data_ptr() if a_lo is not None else None, w_lo.data_ptr() if w_lo is not None else None)
+    if a_lo is not None:
+        assert a_lo.stride() == a.stride() and w_lo.stride() == w.stride()
     _lib.check(_lib.load().aread_grouped_linear_bf16(ctypes.byref(args), _stream(a.device)))
     return out
 
@@ -36,7 +46,7 @@ def grouped_linear(a, w, bias, n, k, groups, a_group_cols=0, group_mask=None, ou
 _WGRAD_WS = {}
 
 
-def grouped_wgrad(dz, a, n, k, groups, a_group_cols=0, group_mask=None, out=None):
+def grouped_wgrad(dz, a, n, k, groups, a_group_cols=0, group_mask=None, out=None, dz_lo=None, a_lo=None):
     """dW[g*n + j, i] = sum_b dz[b, g*n + j] * a[b, g*a_group_cols + i] (fp32 [groups*n, k]).
     Rows of masked-out groups are left untouched (zero when `out` is None)."""
     assert dz.dtype == torch.bfloat16 and a.dtype == torch.bfloat16 and dz.is_cuda and a.is_cuda
@@ -49,7 +59,9 @@ def grouped_wgrad(dz, a, n, k, groups, a_group_cols=0, group_mask=None, out=None
         out = alloc((groups * n, k), dtype=torch.float32, device=dz.device)
     assert out.is_contiguous() and out.dtype == torch.float32
     args = _lib.GroupedWgradArgs(m, n, k, groups, a_group_cols, mask, dz.data_ptr(), dz.stride(0), a.data_ptr(),
-                                 a.stride(0), out.data_ptr(), None, 0)
+                                 a.stride(0), out.data_ptr(), None, 0,
+                                 dz_lo.data_ptr() if dz_lo is not None else None,
+                                 a_lo.data_ptr() if a_lo is not None else None)
     need = int(_lib.load().aread_grouped_wgrad_workspace_bytes(ctypes.byref(args)))
     ws = _WGRAD_WS.get(dz.device)
     if ws is None or ws.numel() < need:
@@ -58,3 +70,90 @@ def grouped_wgrad(dz, a, n, k, groups, a_group_cols=0, group_mask=None, out=None
     args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
     _lib.check(_lib.load().aread_grouped_wgrad_bf16(ctypes.byref(args), _stream(dz.device)))
     return out
+
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+_BN_WS = {}
+
+
+def _bn_workspace(device, width):
+    need = int(_lib.load().aread_bn_workspace_bytes(width))
+    ws = _BN_WS.get(device)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _BN_WS[device] = ws
+    return ws
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def bn_act_fwd(z, gamma, beta, running_mean, running_var, training, bn_skip, p, seed, salt, out_dtype,
+               want_lo=False):
+    """(out, saved) or (out, out_lo, saved) with want_lo: out = dropout(relu(bn(z))) as `out_dtype`
+    (None: statistics only); saved = [4, width] fp32 rows (mean, rstd, scale, shift)."""
+    m, width = z.shape
+    saved = torch.empty((4, width), dtype=torch.float32, device=z.device)
+    out = torch.empty((m, width), dtype=out_dtype, device=z.device) if out_dtype is not None else None
+    out_lo = torch.empty((m, width), dtype=torch.bfloat16, device=z.device) if want_lo else None
+    ws = _bn_workspace(z.device, width)
+    args = _lib.BnActArgs(m, width, 1 if training else 0, 1 if bn_skip else 0, BN_MOMENTUM, BN_EPS,
+                          float(p) if training else 0.0, seed, salt, z.data_ptr(), z.stride(0), _ptr(gamma),
+                          _ptr(beta), _ptr(running_mean), _ptr(running_var), saved[0].data_ptr(),
+                          saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(),
+                          _ptr(out) if out_dtype == torch.float32 else None,
+                          _ptr(out) if out_dtype == torch.bfloat16 else None, width, ws.data_ptr(), ws.numel(),
+                          _ptr(out_lo))
+    _lib.check(_lib.load().aread_bn_act_fwd(ctypes.byref(args), _stream(z.device)))
+    return (out, out_lo, saved) if want_lo else (out, saved)
+
+
+def bn_act_bwd(z, d_out, saved, bn_skip, p, seed, salt, dz_dtype=torch.bfloat16, want_lo=False):
+    """(dz, d_gamma, d_beta, d_bias) for out = dropout(relu(bn(z))); with want_lo dz is (hi, lo)."""
+    m, width = z.shape
+    grads = torch.empty((3, width), dtype=torch.float32, device=z.device)
+    dz = torch.empty((m, width), dtype=dz_dtype, device=z.device)
+    dz_lo = torch.empty((m, width), dtype=torch.bfloat16, device=z.device) if want_lo else None
+    ws = _bn_workspace(z.device, width)
+    args = _lib.BnActBwdArgs(m, width, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), z.stride(0),
+                             d_out.data_ptr(), d_out.stride(0), saved[0].data_ptr(), saved[1].data_ptr(),
+                             saved[2].data_ptr(), saved[3].data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(),
+                             grads[2].data_ptr(), _ptr(dz) if dz_dtype == torch.float32 else None,
+                             _ptr(dz) if dz_dtype == torch.bfloat16 else None, width, ws.data_ptr(), ws.numel(),
+                             _ptr(dz_lo))
+    _lib.check(_lib.load().aread_bn_act_bwd(ctypes.byref(args), _stream(z.device)))
+    return ((dz, dz_lo) if want_lo else dz), grads[0], grads[1], grads[2]
+
+
+def mmoe_mix_fwd(z, saved, gate, n_expert, n_gate, p, seed, salt):
+    m = z.shape[0]
+    width = z.shape[1] // n_expert
+    out = torch.empty((m, n_gate, width), dtype=torch.float32, device=z.device)
+    args = _lib.MmoeMixArgs(m, width, n_expert, n_gate, float(p), seed, salt, z.data_ptr(), z.stride(0),
+                            saved[2].data_ptr(), saved[3].data_ptr(), gate.data_ptr(), out.data_ptr(), None, None,
+                            None)
+    _lib.check(_lib.load().aread_mmoe_mix(ctypes.byref(args), _stream(z.device)))
+    return out
+
+
+def mmoe_mix_bwd(z, saved, gate, d_out, n_expert, n_gate, p, seed, salt):
+    m = z.shape[0]
+    width = z.shape[1] // n_expert
+    d_h = torch.empty((m, n_expert * width), dtype=torch.float32, device=z.device)
+    d_gate = torch.empty((m, n_gate, n_expert), dtype=torch.float32, device=z.device)
+    args = _lib.MmoeMixArgs(m, width, n_expert, n_gate, float(p), seed, salt, z.data_ptr(), z.stride(0),
+                            saved[2].data_ptr(), saved[3].data_ptr(), gate.data_ptr(), None, d_out.data_ptr(),
+                            d_h.data_ptr(), d_gate.data_ptr())
+    _lib.check(_lib.load().aread_mmoe_mix(ctypes.byref(args), _stream(z.device)))
+    return d_h, d_gate
+
+
+def dropout_mask(seed, salt, shape, p, device):
+    n = 1
+    for s in shape:
+        n *= s
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    _lib.check(_lib.load().aread_dropout_mask(seed, salt, n, float(p), out.data_ptr(), _stream(device)))
+    return out.view(*shape).bool()

@@ -10,6 +10,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import embedding_ops, expert_ops
+
 
 class MaskInfo:
     """Host view of one HEMP mask: which towers run, which edges are open.  Built once per distinct
@@ -59,13 +61,22 @@ def _require_cuda(model, x):
 def aread_forward(model, x, info: Optional[MaskInfo], want_gate_means=False, want_gates=False) -> ForwardOut:
     """Embedding lookup -> trunk -> HEI levels -> per-tower probabilities."""
     _require_cuda(model, x)
-    embed_x = model.embedding(x, squeeze_dim=False)
+    precise = model.expert_precision == "bf16x3"
+    embed_x, x_bf16 = model.embedding.lookup(x, want_bf16=True, want_lo=precise)
     domain_embed = embed_x[:, model.domain_idx, :]
     X = embed_x.flatten(start_dim=1)
+    B = X.shape[0]
     lin = model.linear(X)
     cn = model.cn(X)
-    experts = torch.stack([e(X) for e in model.mmoe_experts], dim=1)                # [B, n_expert, h]
-    t0 = [torch.sum(g(X).unsqueeze(-1) * experts, dim=1) for g in model.mmoe_gates]
+    # MMoE gates of level-0 towers that do not run are never evaluated (their parameters keep grad None)
+    active0 = np.ones(model.n_tower[0], dtype=bool) if info is None else info.active[0]
+    n_expert = len(model.mmoe_experts)
+    zeros = torch.zeros(B, n_expert, dtype=torch.float32, device=X.device)
+    gate = torch.stack([g(X) if active0[t] else zeros for t, g in enumerate(model.mmoe_gates)], dim=1)
+    training = model.training
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and model.dropout_p > 0) else 0
+    t0 = expert_ops.expert_stack(X, x_bf16, gate, model._expert_layers, training, model.dropout_p, seed,
+                                 precise).unbind(dim=1)
     if info is None:
         group_embed = torch.zeros_like(domain_embed)                                 # aread.py:157
     else:

@@ -99,16 +99,19 @@ class LookupPlan:
             self._status_event.record(torch.cuda.current_stream(self.device))
 
 
-def gather(plan, table, x, want_bf16=False):
-    """[B, n_cols] int32 ids -> [B, n_fields, D] fp32 (and optionally the bf16 copy)."""
+def gather(plan, table, x, want_bf16=False, want_lo=False):
+    """[B, n_cols] int32 ids -> [B, n_fields, D] fp32 (and optionally the bf16 copy; with want_lo the
+    bf16 result is the (hi, lo) split pair)."""
     B = x.shape[0]
     out = torch.empty((B, plan.n_fields, plan.embed_dim), dtype=torch.float32, device=x.device)
-    out_bf16 = torch.empty((B, plan.n_fields * plan.embed_dim), dtype=torch.bfloat16, device=x.device) \
-        if want_bf16 else None
+    shape16 = (B, plan.n_fields * plan.embed_dim)
+    out_bf16 = torch.empty(shape16, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    out_lo = torch.empty(shape16, dtype=torch.bfloat16, device=x.device) if (want_bf16 and want_lo) else None
     args = _lib.GatherArgs(plan.c_plan(), B, x.data_ptr(), table.data_ptr(), out.data_ptr(),
-                           out_bf16.data_ptr() if want_bf16 else None, plan.status.data_ptr())
+                           out_bf16.data_ptr() if want_bf16 else None,
+                           out_lo.data_ptr() if out_lo is not None else None, plan.status.data_ptr())
     _lib.check(_lib.load().aread_gather_fwd(ctypes.byref(args), _stream_ptr(x.device)))
-    return out, out_bf16
+    return out, ((out_bf16, out_lo) if want_lo else out_bf16)
 
 
 def scatter(plan, x, d_out, d_table=None, zero_fill=True, want_sorted=False):
@@ -131,19 +134,27 @@ def scatter(plan, x, d_out, d_table=None, zero_fill=True, want_sorted=False):
 
 
 class EmbeddingLookup(torch.autograd.Function):
-    """FeaturesEmbedding.forward / backward (model/layer.py:160-183) on the C ABI."""
+    """FeaturesEmbedding.forward / backward (model/layer.py:160-183) on the C ABI.  Optionally also
+    returns the bf16 copy of the flattened output (the experts' GEMM operand), written by the same
+    kernel; it carries no gradient."""
 
     @staticmethod
-    def forward(ctx, table, x, plan):
-        out, _ = gather(plan, table, x)
+    def forward(ctx, table, x, plan, want_bf16=False, want_lo=False):
+        out, out_bf16 = gather(plan, table, x, want_bf16, want_lo)
         ctx.plan = plan
         ctx.save_for_backward(x)
+        if want_bf16 and want_lo:
+            ctx.mark_non_differentiable(*out_bf16)
+            return (out, *out_bf16)
+        if want_bf16:
+            ctx.mark_non_differentiable(out_bf16)
+            return out, out_bf16
         return out
 
     @staticmethod
-    def backward(ctx, d_out):
+    def backward(ctx, d_out, *unused):
         (x,) = ctx.saved_tensors
-        return scatter(ctx.plan, x, d_out.contiguous()), None, None
+        return scatter(ctx.plan, x, d_out.contiguous()), None, None, None, None
 
 
 def prepare_ids(x, table):

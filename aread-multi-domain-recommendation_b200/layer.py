@@ -61,13 +61,21 @@ class FeaturesEmbedding(nn.Module):
             self._plans[key] = plan
         return plan
 
-    def forward(self, x, squeeze_dim=False):
-        """x: integer tensor (batch, n_cols) -> (batch, output_dim0, embed_dim) fp32."""
+    def lookup(self, x, want_bf16=False, want_lo=False):
+        """(fp32 [batch, output_dim0, embed_dim], bf16 [batch, output_dim0 * embed_dim] or None); with
+        want_lo the second element is the split pair (hi, lo)."""
         table = self.embedding_dict.weight
         x = embedding_ops.prepare_ids(x, table)
         plan = self.plan(x.device)
-        out = embedding_ops.EmbeddingLookup.apply(table, x, plan)
+        res = embedding_ops.EmbeddingLookup.apply(table, x, plan, want_bf16, want_lo)
         plan.post_lookup(BOUNDS_MODE)
+        if want_bf16 and want_lo:
+            return res[0], (res[1], res[2])
+        return res if want_bf16 else (res, None)
+
+    def forward(self, x, squeeze_dim=False):
+        """x: integer tensor (batch, n_cols) -> (batch, output_dim0, embed_dim) fp32."""
+        out, _ = self.lookup(x)
         return out.flatten(start_dim=1) if squeeze_dim else out
 
 

@@ -80,6 +80,7 @@ typedef struct aread_gather_args {
   const float* table;  /* [n_rows, D] fp32                                                         */
   float* out;          /* [B, n_fields, D] fp32, bit-exact copy / in-order pooled sum              */
   uint16_t* out_bf16;  /* optional [B, n_fields * D] bf16 (round-to-nearest-even) copy, or NULL    */
+  uint16_t* out_bf16_lo; /* optional [B, n_fields * D]: bf16(out - bf16(out)), the split residual  */
   int32_t* status;     /* [2] device ints: status[0] != 0 after an out-of-range id, status[1] = the
                           offending row index.  Zero it before the first call.  Rows that are out
                           of range produce zeros.                                                 */
@@ -147,6 +148,10 @@ typedef struct aread_grouped_linear_args {
   float* c_f32;         /* exactly one of c_f32 / c_bf16: [m, ldc]                                 */
   uint16_t* c_bf16;
   int64_t ldc;
+  const uint16_t* a_lo; /* optional split-precision residuals (same shapes / strides as a and b):  */
+  const uint16_t* b_lo; /* x = hi + lo with hi = bf16(x), lo = bf16(x - hi).  When given, the product
+                           is a.b + a.b_lo + a_lo.b (three tensor-core passes into one accumulator):
+                           fp32-grade results (~2^-16 relative) instead of bf16 operand rounding   */
 } aread_grouped_linear_args;
 
 AREAD_API int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, aread_stream_t stream);
@@ -172,10 +177,106 @@ typedef struct aread_grouped_wgrad_args {
   float* dw;            /* fp32 [groups * n, k] contiguous                          */
   void* workspace;      /* aread_grouped_wgrad_workspace_bytes(args) bytes          */
   size_t workspace_bytes;
+  const uint16_t* dz_lo; /* optional split-precision residuals, see aread_grouped_linear_args */
+  const uint16_t* a_lo;
 } aread_grouped_wgrad_args;
 
 AREAD_API size_t aread_grouped_wgrad_workspace_bytes(const aread_grouped_wgrad_args* args);
 AREAD_API int aread_grouped_wgrad_bf16(const aread_grouped_wgrad_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm1d + ReLU + Dropout after a Linear, forward and backward.
+ * Replaces the BatchNorm1d / ReLU / Dropout slots of MultiLayerPerceptron.forward
+ * (model/layer.py:211-215, 225-228): training uses batch mean / biased variance (eps 1e-5) and
+ * updates running_mean / running_var with momentum 0.1 and the unbiased variance; eval uses the
+ * running statistics; bn_skip = 1 is the batch-of-one rule (layer.py:226, BatchNorm not applied).
+ * Dropout keeps element (row, col) iff hash(seed, salt, row * width + col) >= p * 2^32 and scales by
+ * 1 / (1 - p); aread_dropout_mask exposes the same stream so tests can feed it to the oracle.
+ * Column sums are reduced per CTA over fixed row ranges and added in CTA order (deterministic).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_bn_act_args {
+  int64_t m;              /* rows                                                                  */
+  int32_t width;          /* columns (all groups of the layer side by side), <= 2048               */
+  int32_t training;       /* 1: batch statistics + running update + dropout, 0: running statistics */
+  int32_t bn_skip;        /* 1: BatchNorm is the identity (batch of one)                           */
+  float momentum, eps, dropout_p;
+  uint64_t seed;          /* dropout stream                                                        */
+  uint32_t salt;          /* per-layer constant mixed into the stream                              */
+  const float* z;         /* fp32 [m, ldz]: Linear output                                          */
+  int64_t ldz;
+  const float* gamma;     /* [width] BatchNorm weight                                              */
+  const float* beta;      /* [width] BatchNorm bias                                                */
+  float* running_mean;    /* [width], updated in place when training                               */
+  float* running_var;
+  float* mean;            /* out [width]: statistics used (saved for the backward)                 */
+  float* rstd;
+  float* scale;           /* out [width]: gamma * rstd                                             */
+  float* shift;           /* out [width]: beta - mean * scale                                      */
+  float* out_f32;         /* optional out [m, ldo]: dropout(relu(bn(z)))                           */
+  uint16_t* out_bf16;     /* optional out [m, ldo] as bf16                                         */
+  int64_t ldo;
+  void* workspace;        /* aread_bn_workspace_bytes(width)                                       */
+  size_t workspace_bytes;
+  uint16_t* out_bf16_lo;  /* optional out [m, ldo]: bf16(value - bf16(value)), the split residual  */
+} aread_bn_act_args;
+
+typedef struct aread_bn_act_bwd_args {
+  int64_t m;
+  int32_t width;
+  int32_t bn_skip;
+  float dropout_p;        /* 0 when the forward ran without dropout                                */
+  uint32_t salt;
+  uint64_t seed;
+  const float* z;         /* fp32 [m, ldz]: the forward's Linear output                            */
+  int64_t ldz;
+  const float* d_out;     /* fp32 [m, ldd]: gradient w.r.t. dropout(relu(bn(z)))                   */
+  int64_t ldd;
+  const float* mean;      /* saved by the forward                                                  */
+  const float* rstd;
+  const float* scale;
+  const float* shift;
+  float* d_gamma;         /* optional out [width]                                                  */
+  float* d_beta;          /* optional out [width]                                                  */
+  float* d_bias;          /* optional out [width]: gradient of the Linear bias (exactly 0 under BatchNorm) */
+  float* dz_f32;          /* optional out [m, ldo]: gradient w.r.t. z                              */
+  uint16_t* dz_bf16;      /* optional out [m, ldo] as bf16                                         */
+  int64_t ldo;
+  void* workspace;
+  size_t workspace_bytes;
+  uint16_t* dz_bf16_lo;   /* optional out [m, ldo]: the split residual of dz                       */
+} aread_bn_act_bwd_args;
+
+AREAD_API size_t aread_bn_workspace_bytes(int32_t width);
+AREAD_API int aread_bn_act_fwd(const aread_bn_act_args* args, aread_stream_t stream);
+AREAD_API int aread_bn_act_bwd(const aread_bn_act_bwd_args* args, aread_stream_t stream);
+AREAD_API int aread_dropout_mask(uint64_t seed, uint32_t salt, int64_t n, float p, uint8_t* out, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MMoE mixture fused with the last expert layer's BatchNorm/ReLU/Dropout.
+ * Replaces model/aread.py:150-153: h_e = expert_e(x) (here: dropout(relu(z_e * scale + shift))),
+ * out[b, g, :] = sum_e gate[b, g, e] * h[b, e, :].  Forward when d_out == NULL, else backward:
+ * d_h[b, e, :] = sum_g gate[b, g, e] * d_out[b, g, :], d_gate[b, g, e] = <d_out[b, g, :], h[b, e, :]>.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_mmoe_mix_args {
+  int64_t m;
+  int32_t width;          /* expert output width (expert_dims[-1])                                 */
+  int32_t n_expert;       /* <= 16                                                                 */
+  int32_t n_gate;         /* gates = level-0 towers, <= 8                                          */
+  float dropout_p;
+  uint64_t seed;
+  uint32_t salt;
+  const float* z;         /* fp32 [m, ldz]: last expert Linear output, experts side by side        */
+  int64_t ldz;
+  const float* scale;     /* [n_expert * width] folded BatchNorm                                   */
+  const float* shift;
+  const float* gate;      /* fp32 [m, n_gate, n_expert] softmax gates                              */
+  float* out;             /* forward out [m, n_gate, width]                                        */
+  const float* d_out;     /* backward in [m, n_gate, width]                                        */
+  float* d_h;             /* backward out [m, n_expert * width]                                    */
+  float* d_gate;          /* backward out [m, n_gate, n_expert]                                    */
+} aread_mmoe_mix_args;
+
+AREAD_API int aread_mmoe_mix(const aread_mmoe_mix_args* args, aread_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,9 @@ class Spec:
     l2_linear: float = 1e-5
     l2_dnn: float = 1e-5
     l2_cross: float = 1e-5
+    # "bf16 experts" (BASELINE.json configs[1]): inputs and weights of the expert Linear layers are
+    # rounded to bf16 (round to nearest even), products and sums stay fp32.  None = the reference's fp32.
+    expert_operand_dtype: Optional[torch.dtype] = None
     flag: np.ndarray = field(init=False)
 
     def __post_init__(self):
@@ -90,12 +93,16 @@ def _drop(h, p, training, masks, key):
     return h * keep / (1.0 - p)
 
 
-def mlp(sd, prefix, h, n_layers, training, p=0.0, masks=None, update_stats=True):
+def mlp(sd, prefix, h, n_layers, training, p=0.0, masks=None, update_stats=True, operand_dtype=None):
     """(Linear -> BatchNorm1d -> ReLU -> Dropout) x n; BN skipped when the batch is one row
     (layer.py:209-215, 225-228).  Running statistics in `sd` are updated in place in training."""
     for i in range(n_layers):
         li = 4 * i
-        h = F.linear(h, sd[f"{prefix}.layers.{li}.weight"], sd[f"{prefix}.layers.{li}.bias"])
+        w = sd[f"{prefix}.layers.{li}.weight"]
+        if operand_dtype is not None:      # rounding is not differentiated through (straight-through)
+            h = h + (h.to(operand_dtype).to(h.dtype) - h).detach()
+            w = w + (w.to(operand_dtype).to(w.dtype) - w).detach()
+        h = F.linear(h, w, sd[f"{prefix}.layers.{li}.bias"])
         if h.shape[0] != 1:
             bn = f"{prefix}.layers.{li + 1}"
             track = training and update_stats
@@ -128,7 +135,8 @@ def trunk(sd, spec, x, training, masks=None, update_stats=True):
     X = e.flatten(start_dim=1)
     lin = X @ sd["linear.fc.weight"].t() + sd["linear.fc.bias"]
     cn = cross(sd, spec, X)
-    hs = [mlp(sd, f"mmoe_experts.{k}", X, len(spec.expert_dims), training, spec.dropout, masks, update_stats)
+    hs = [mlp(sd, f"mmoe_experts.{k}", X, len(spec.expert_dims), training, spec.dropout, masks, update_stats,
+              spec.expert_operand_dtype)
           for k in range(spec.n_expert)]
     H = torch.stack(hs, dim=1)                                        # [B, n_expert, h]
     t0 = []

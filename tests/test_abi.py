@@ -25,7 +25,15 @@ def struct_fields(name):
     text = "".join(open(h).read() for h in glob.glob(os.path.join(ROOT, "include", "*.h")))
     body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    return [re.search(r"(\w+)\s*$", decl.strip()).group(1) for decl in body.split(";") if decl.strip()]
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        # "float momentum, eps, dropout_p" declares several fields
+        names = [re.search(r"(\w+)\s*$", part.strip()).group(1) for part in decl.split(",")]
+        fields.extend(names)
+    return fields
 
 
 @pytest.fixture(scope="module")
@@ -47,7 +55,9 @@ def test_every_declared_symbol_is_exported(lib):
 @pytest.mark.parametrize("cname,ctype", [("aread_embed_plan", "EmbedPlan"), ("aread_gather_args", "GatherArgs"),
                                          ("aread_scatter_args", "ScatterArgs"),
                                          ("aread_grouped_linear_args", "GroupedLinearArgs"),
-                                         ("aread_grouped_wgrad_args", "GroupedWgradArgs")])
+                                         ("aread_grouped_wgrad_args", "GroupedWgradArgs"),
+                                         ("aread_bn_act_args", "BnActArgs"), ("aread_bn_act_bwd_args", "BnActBwdArgs"),
+                                         ("aread_mmoe_mix_args", "MmoeMixArgs")])
 def test_struct_fields_match_header(cname, ctype):
     fields = [f for f, _ in getattr(_lib, ctype)._fields_]
     assert fields == struct_fields(cname)
@@ -55,7 +65,7 @@ def test_struct_fields_match_header(cname, ctype):
 
 def test_struct_sizes_are_native(lib):
     assert ctypes.sizeof(_lib.EmbedPlan) == 56
-    assert ctypes.sizeof(_lib.GatherArgs) == 56 + 8 * 6
+    assert ctypes.sizeof(_lib.GatherArgs) == 56 + 8 * 7
     assert ctypes.sizeof(_lib.ScatterArgs) == 56 + 8 * 9
 
 

@@ -143,3 +143,40 @@ def test_grouped_wgrad_mask_and_determinism():
     again = torch.full((groups * n, k), 3.0, device=DEV)
     dk.grouped_wgrad(dz, a, n, k, groups, k, group_mask=0b0110, out=again)
     assert torch.equal(out, again)
+
+
+@pytest.mark.parametrize("m,n,k,groups,agc", [(300, 1024, 288, 1, 0), (1000, 128, 256, 4, 256), (37, 32, 40, 3, 0)])
+def test_split_precision_linear_is_fp32_grade(m, n, k, groups, agc):
+    """hi/lo split operands, three passes: error ~2^-16 of sum |a||w| instead of bf16's 2^-8."""
+    gen = torch.Generator(device=DEV).manual_seed(m + k)
+    a_cols = k if agc == 0 else agc * groups
+    a32 = torch.randn(m, a_cols, device=DEV, generator=gen)
+    w32 = torch.randn(groups * n, k, device=DEV, generator=gen) / k ** 0.5
+    (a_hi, a_lo), (w_hi, w_lo) = dk.split_bf16(a32), dk.split_bf16(w32)
+    got = dk.grouped_linear(a_hi, w_hi, None, n, k, groups, agc, a_lo=a_lo, w_lo=w_lo)
+    one_pass = dk.grouped_linear(a_hi, w_hi, None, n, k, groups, agc)
+    for g in range(groups):
+        ag = a32[:, g * agc:g * agc + k].double()
+        wg = w32[g * n:(g + 1) * n].double()
+        ref = ag @ wg.t()
+        bound = ag.abs() @ wg.abs().t()
+        err3 = (got[:, g * n:(g + 1) * n].double() - ref).abs()
+        err1 = (one_pass[:, g * n:(g + 1) * n].double() - ref).abs()
+        assert bool((err3 <= 4e-5 * bound + 1e-6).all()), float((err3 / (bound + 1e-9)).max())
+        assert float(err3.mean()) < 0.02 * float(err1.mean())          # two orders of magnitude better than one pass
+
+
+def test_split_precision_wgrad_is_fp32_grade():
+    m, n, k, groups = 5000, 128, 256, 4
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    a32 = torch.randn(m, k * groups, device=DEV, generator=gen)
+    dz32 = torch.randn(m, groups * n, device=DEV, generator=gen) / m ** 0.5
+    (a_hi, a_lo), (z_hi, z_lo) = dk.split_bf16(a32), dk.split_bf16(dz32)
+    got = dk.grouped_wgrad(z_hi, a_hi, n, k, groups, k, dz_lo=z_lo, a_lo=a_lo)
+    for g in range(groups):
+        ag = a32[:, g * k:(g + 1) * k].double()
+        zg = dz32[:, g * n:(g + 1) * n].double()
+        ref = zg.t() @ ag
+        bound = zg.abs().t() @ ag.abs()
+        err = (got[g * n:(g + 1) * n].double() - ref).abs()
+        assert bool((err <= 4e-5 * bound + 1e-6).all()), float((err / (bound + 1e-9)).max())

@@ -80,6 +80,33 @@ class MmoeMixArgs(Structure):
                 ("d_out", c_void_p), ("d_h", c_void_p), ("d_gate", c_void_p)]
 
 
+class RowpassArgs(Structure):
+    _fields_ = [("m", c_int64), ("e", c_int32), ("n_gate", c_int32), ("n_expert", c_int32), ("n_cross", c_int32),
+                ("n_head", c_int32), ("ldp", c_int32), ("x", c_void_p), ("w", c_void_p), ("offset", c_void_p),
+                ("p", c_void_p), ("lin", c_void_p), ("gate", c_void_p), ("alpha", c_void_p), ("head", c_void_p),
+                ("d_lin", c_void_p), ("d_gate", c_void_p), ("d_head", c_void_p), ("d_p", c_void_p),
+                ("d_c", c_void_p), ("d_x", c_void_p), ("d_w", c_void_p), ("workspace", c_void_p),
+                ("workspace_bytes", c_size_t)]
+
+
+class L2RegArgs(Structure):
+    _fields_ = [("n_tensors", c_int32), ("n_chunks", c_int64), ("tensors", c_void_p), ("grads", c_void_p),
+                ("sizes", c_void_p), ("l2", c_void_p), ("chunk_start", c_void_p), ("out", c_void_p),
+                ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
+
+
+class TowerLinearArgs(Structure):
+    _fields_ = [("m", c_int64), ("groups", c_int32), ("in_width", c_int32), ("out_width", c_int32),
+                ("weight_is_out_by_in", c_int32), ("in_", c_void_p), ("ld_in", c_int64), ("weight", c_void_p),
+                ("bias", c_void_p), ("out", c_void_p), ("ld_out", c_int64)]
+
+
+class TowerWgradArgs(Structure):
+    _fields_ = [("m", c_int64), ("groups", c_int32), ("n", c_int32), ("k", c_int32), ("dz", c_void_p),
+                ("ld_dz", c_int64), ("in_", c_void_p), ("ld_in", c_int64), ("d_w", c_void_p),
+                ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
+
+
 _SIGNATURES = {
     "aread_last_error": (c_char_p, []),
     "aread_abi_version": (c_int32, []),
@@ -95,6 +122,15 @@ _SIGNATURES = {
     "aread_bn_act_bwd": (c_int32, [POINTER(BnActBwdArgs), c_void_p]),
     "aread_dropout_mask": (c_int32, [c_uint64, c_uint32, c_int64, c_float, c_void_p, c_void_p]),
     "aread_mmoe_mix": (c_int32, [POINTER(MmoeMixArgs), c_void_p]),
+    "aread_rowpass_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "aread_rowpass_fwd": (c_int32, [POINTER(RowpassArgs), c_void_p]),
+    "aread_rowpass_bwd": (c_int32, [POINTER(RowpassArgs), c_void_p]),
+    "aread_tower_linear": (c_int32, [POINTER(TowerLinearArgs), c_void_p]),
+    "aread_tower_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
+    "aread_tower_wgrad": (c_int32, [POINTER(TowerWgradArgs), c_void_p]),
+    "aread_l2_reg_chunk": (c_int64, []),
+    "aread_l2_reg_fwd": (c_int32, [POINTER(L2RegArgs), c_void_p]),
+    "aread_l2_reg_bwd": (c_int32, [POINTER(L2RegArgs), c_void_p, c_void_p]),
 }
 
 _lib = None

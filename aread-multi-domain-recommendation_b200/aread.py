@@ -107,8 +107,17 @@ class AREAD(BaseModel):
         for i in range(self.bottom_level):
             layers.append(ExpertLayer(packs, [e.layers[4 * i] for e in self.mmoe_experts],
                                       [e.layers[4 * i + 1] for e in self.mmoe_experts], salt=0x1000 + i))
+        tower_layers = []
+        for l in range(self.n_level):
+            per_level = []
+            for j in range(len(self.tower_dims[l])):
+                per_level.append(ExpertLayer(packs, [t.layers[4 * j] for t in self.towers[l]],
+                                             [t.layers[4 * j + 1] for t in self.towers[l]],
+                                             salt=0x2000 + 16 * l + j))
+            tower_layers.append(per_level)
         object.__setattr__(self, "_packs", packs)
         object.__setattr__(self, "_expert_layers", layers)
+        object.__setattr__(self, "_tower_layers", tower_layers)
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -122,7 +131,7 @@ class AREAD(BaseModel):
         clone = cls.__new__(cls)
         memo[id(self)] = clone
         for k, v in self.__dict__.items():
-            if k not in ("_packs", "_expert_layers"):
+            if k not in ("_packs", "_expert_layers", "_tower_layers"):
                 setattr(clone, k, copy.deepcopy(v, memo))
         clone._build_packs()
         return clone

@@ -1,0 +1,247 @@
+// Grouped small Linear layers of the HEI towers in fp32 on the CUDA cores: forward, data gradient
+// and weight gradient.  A tower layer is 16..64 wide (model/aread.py:106-117, tower_dims
+// ((64,32),(32,16),(16,8))), far below a tensor-core tile, and the towers are ~3 % of the FLOPs; what
+// matters is that ALL towers of a level run in one launch and that each activation row is read once.
+//
+//   out[b, g, j] = sum_i in[b, g, i] * M_g[i, j] (+ bias[g, j])
+//
+// forward:        in = tower input [m, G, K],  M_g = W_g^T (W_g is nn.Linear's [N, K]),  out = z [m, G, N]
+// data gradient:  in = dz [m, G, N],           M_g = W_g,                                out = d_in [m, G, K]
+// Towers pruned by the HEMP mask are simply absent: the caller passes the compact list of active towers.
+#include "common.cuh"
+
+namespace aread {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------- forward / dgrad
+// CTA = (row tile, group).  sM[i][j] holds the group's matrix, sIn the row tile; every thread owns a
+// 4 x 4 (rows x columns) block of the output tile.
+__global__ void __launch_bounds__(kThreads) tower_linear_kernel(const aread_tower_linear_args a, int tx_n, int ty_n) {
+  extern __shared__ float smem[];
+  const int I = a.in_width, J = a.out_width;
+  const int Jp = (J + 3) & ~3;
+  float* sM = smem;                    // [I][Jp]
+  float* sIn = smem + I * Jp;          // [tile_rows][I + 1]
+  const int tile_rows = ty_n * 4;
+  const int g = blockIdx.y;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * tile_rows;
+  const float* __restrict__ w = a.weight + static_cast<int64_t>(g) * I * J;
+
+  for (int idx = threadIdx.x; idx < I * Jp; idx += kThreads) {
+    const int i = idx / Jp, j = idx - i * Jp;
+    float v = 0.f;
+    if (j < J) v = a.weight_is_out_by_in ? __ldg(w + static_cast<int64_t>(j) * I + i) : __ldg(w + static_cast<int64_t>(i) * J + j);
+    sM[idx] = v;
+  }
+  for (int idx = threadIdx.x; idx < tile_rows * I; idx += kThreads) {
+    const int r = idx / I, i = idx - r * I;
+    sIn[r * (I + 1) + i] = b0 + r < a.m ? __ldg(a.in + (b0 + r) * a.ld_in + static_cast<int64_t>(g) * I + i) : 0.f;
+  }
+  __syncthreads();
+
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+  if (tx * 4 >= J || ty >= ty_n) return;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  const float* in_rows = sIn + (ty * 4) * (I + 1);
+  for (int i = 0; i < I; ++i) {
+    const float4 m4 = *reinterpret_cast<const float4*>(sM + i * Jp + tx * 4);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float v = in_rows[r * (I + 1) + i];
+      acc[r][0] = fmaf(v, m4.x, acc[r][0]);
+      acc[r][1] = fmaf(v, m4.y, acc[r][1]);
+      acc[r][2] = fmaf(v, m4.z, acc[r][2]);
+      acc[r][3] = fmaf(v, m4.w, acc[r][3]);
+    }
+  }
+  const int j0 = tx * 4;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t b = b0 + ty * 4 + r;
+    if (b >= a.m) continue;
+    float* dst = a.out + b * a.ld_out + static_cast<int64_t>(g) * J + j0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (j0 + c < J) dst[c] = acc[r][c] + (a.bias ? __ldg(a.bias + g * J + j0 + c) : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------- weight gradient
+// d_w[g][n][k] = sum_b dz[b, g, n] * in[b, g, k].  CTA = (row chunk, group); thread = one 4 x 4 block of
+// the [N, K] gradient for one of `rs_n` interleaved row subsets; subsets are summed in order at the end
+// and the per-chunk partials are added in chunk order by tower_wgrad_reduce_kernel (deterministic).
+constexpr int kWgradTile = 64;
+
+__global__ void __launch_bounds__(kThreads) tower_wgrad_kernel(const aread_tower_wgrad_args a, int mt_n, int rs_n,
+                                                               int64_t rows_per_chunk, float* __restrict__ partial) {
+  extern __shared__ float smem[];
+  const int N = a.n, K = a.k;
+  const int Np = (N + 3) & ~3, Kp = (K + 3) & ~3;
+  const int n4 = Np / 4, k4 = Kp / 4;
+  float* sDz = smem;                       // [kWgradTile][Np]
+  float* sIn = smem + kWgradTile * Np;     // [kWgradTile][Kp]
+  const int g = blockIdx.y;
+  const int mt = threadIdx.x % mt_n, rs = threadIdx.x / mt_n;
+  const bool live = mt < n4 * k4 && rs < rs_n;
+  const int nq = live ? mt / k4 : 0, kq = live ? mt - (mt / k4) * k4 : 0;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * rows_per_chunk;
+  const int64_t c1 = min(a.m, c0 + rows_per_chunk);
+  for (int64_t b0 = c0; b0 < c1; b0 += kWgradTile) {
+    const int rows = c1 - b0 < kWgradTile ? static_cast<int>(c1 - b0) : kWgradTile;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kWgradTile * Np; idx += kThreads) {
+      const int r = idx / Np, n = idx - r * Np;
+      sDz[idx] = (r < rows && n < N) ? __ldg(a.dz + (b0 + r) * a.ld_dz + static_cast<int64_t>(g) * N + n) : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < kWgradTile * Kp; idx += kThreads) {
+      const int r = idx / Kp, k = idx - r * Kp;
+      sIn[idx] = (r < rows && k < K) ? __ldg(a.in + (b0 + r) * a.ld_in + static_cast<int64_t>(g) * K + k) : 0.f;
+    }
+    __syncthreads();
+    if (live) {
+      for (int r = rs; r < rows; r += rs_n) {
+        const float4 d = *reinterpret_cast<const float4*>(sDz + r * Np + nq * 4);
+        const float4 x = *reinterpret_cast<const float4*>(sIn + r * Kp + kq * 4);
+        acc[0][0] = fmaf(d.x, x.x, acc[0][0]); acc[0][1] = fmaf(d.x, x.y, acc[0][1]);
+        acc[0][2] = fmaf(d.x, x.z, acc[0][2]); acc[0][3] = fmaf(d.x, x.w, acc[0][3]);
+        acc[1][0] = fmaf(d.y, x.x, acc[1][0]); acc[1][1] = fmaf(d.y, x.y, acc[1][1]);
+        acc[1][2] = fmaf(d.y, x.z, acc[1][2]); acc[1][3] = fmaf(d.y, x.w, acc[1][3]);
+        acc[2][0] = fmaf(d.z, x.x, acc[2][0]); acc[2][1] = fmaf(d.z, x.y, acc[2][1]);
+        acc[2][2] = fmaf(d.z, x.z, acc[2][2]); acc[2][3] = fmaf(d.z, x.w, acc[2][3]);
+        acc[3][0] = fmaf(d.w, x.x, acc[3][0]); acc[3][1] = fmaf(d.w, x.y, acc[3][1]);
+        acc[3][2] = fmaf(d.w, x.z, acc[3][2]); acc[3][3] = fmaf(d.w, x.w, acc[3][3]);
+      }
+    }
+  }
+  // combine the row subsets in order through shared memory (re-using the tile buffers)
+  __syncthreads();
+  float* sRed = smem;  // [rs_n][mt_n][16]
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sRed[(rs * mt_n + mt) * 16 + r * 4 + c] = acc[r][c];
+  }
+  __syncthreads();
+  if (live && rs == 0) {
+    float* dst = partial + (static_cast<int64_t>(blockIdx.x) * gridDim.y + g) * N * K;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v = 0.f;
+        for (int s = 0; s < rs_n; ++s) v += sRed[(s * mt_n + mt) * 16 + r * 4 + c];
+        const int n = nq * 4 + r, k = kq * 4 + c;
+        if (n < N && k < K) dst[n * K + k] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) tower_wgrad_reduce_kernel(int n_chunks, int64_t elems,
+                                                                      const float* __restrict__ partial,
+                                                                      float* __restrict__ d_w) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < elems;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < n_chunks; ++c) acc += partial[static_cast<int64_t>(c) * elems + i];
+    d_w[i] = acc;
+  }
+}
+
+int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+int wgrad_chunks(int64_t m, int groups) {
+  int64_t c = (m + 4 * kWgradTile - 1) / (4 * kWgradTile);  // at least 256 rows per chunk
+  const int64_t cap = (2 * kNumSMs + groups - 1) / groups;
+  if (c > cap) c = cap;
+  return static_cast<int>(c < 1 ? 1 : c);
+}
+
+}  // namespace
+}  // namespace aread
+
+extern "C" {
+
+int aread_tower_linear(const aread_tower_linear_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "tower_linear: null args");
+  const aread_tower_linear_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.groups > 0 && a.in_width > 0 && a.out_width > 0, "tower_linear: bad shape");
+  AREAD_REQUIRE(a.out_width <= 128 && a.in_width <= 256, "tower_linear: layer %d -> %d is too wide for this kernel",
+                a.in_width, a.out_width);
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.in && a.out && a.weight, "tower_linear: null pointer");
+  const int j4 = (a.out_width + 3) / 4;
+  const int tx_n = pow2_ceil(j4);
+  int ty_n = kThreads / tx_n;
+  if (ty_n > 32) ty_n = 32;  // at most 128 rows per tile
+  const int tile_rows = ty_n * 4;
+  const int jp = (a.out_width + 3) & ~3;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(a.in_width) * jp + static_cast<size_t>(tile_rows) * (a.in_width + 1));
+  AREAD_REQUIRE(smem <= 200 * 1024, "tower_linear: tile does not fit shared memory");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (smem > 48 * 1024)
+    AREAD_CUDA(cudaFuncSetAttribute(tower_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const dim3 grid(static_cast<unsigned>((a.m + tile_rows - 1) / tile_rows), static_cast<unsigned>(a.groups));
+  AREAD_LAUNCH(tower_linear_kernel, grid, kThreads, smem, stream, a, tx_n, ty_n);
+  return AREAD_OK;
+}
+
+size_t aread_tower_wgrad_workspace_bytes(int64_t m, int32_t groups, int32_t n, int32_t k) {
+  return aread::align_up(static_cast<size_t>(aread::wgrad_chunks(m, groups)) * groups * n * k * 4, 256);
+}
+
+int aread_tower_wgrad(const aread_tower_wgrad_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "tower_wgrad: null args");
+  const aread_tower_wgrad_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.groups > 0 && a.n > 0 && a.k > 0, "tower_wgrad: bad shape");
+  AREAD_REQUIRE(a.n <= 128 && a.k <= 256, "tower_wgrad: layer %d -> %d is too wide for this kernel", a.k, a.n);
+  AREAD_REQUIRE(a.d_w && a.workspace, "tower_wgrad: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t elems = static_cast<int64_t>(a.groups) * a.n * a.k;
+  if (a.m == 0) {
+    AREAD_CUDA(cudaMemsetAsync(a.d_w, 0, elems * 4, stream));
+    return AREAD_OK;
+  }
+  AREAD_REQUIRE(a.dz && a.in, "tower_wgrad: null pointer");
+  const int chunks = wgrad_chunks(a.m, a.groups);
+  AREAD_REQUIRE(a.workspace_bytes >= static_cast<size_t>(chunks) * elems * 4, "tower_wgrad: workspace too small");
+  const int np = (a.n + 3) & ~3, kp = (a.k + 3) & ~3;
+  const int blocks = (np / 4) * (kp / 4);
+  AREAD_REQUIRE(blocks <= kThreads, "tower_wgrad: %d x %d gradient is too large for this kernel (n * k <= 4096)", a.n,
+                a.k);
+  const int mt_n = pow2_ceil(blocks);
+  const int rs_n = kThreads / mt_n;
+  size_t smem = sizeof(float) * kWgradTile * (np + kp);
+  const size_t red = sizeof(float) * static_cast<size_t>(rs_n) * mt_n * 16;
+  if (red > smem) smem = red;
+  if (smem > 48 * 1024)
+    AREAD_CUDA(cudaFuncSetAttribute(tower_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int64_t rows_per_chunk = (a.m + chunks - 1) / chunks;
+  float* partial = static_cast<float*>(a.workspace);
+  const dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(a.groups));
+  AREAD_LAUNCH(tower_wgrad_kernel, grid, kThreads, smem, stream, a, mt_n, rs_n, rows_per_chunk, partial);
+  AREAD_LAUNCH(tower_wgrad_reduce_kernel, static_cast<unsigned>((elems + kThreads - 1) / kThreads), kThreads, 0, stream,
+               chunks, elems, partial, a.d_w);
+  return AREAD_OK;
+}
+
+}  // extern "C"

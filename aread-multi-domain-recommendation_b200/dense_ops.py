@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import embedding_ops, expert_ops
+from . import embedding_ops, expert_ops, rowpass_ops, tower_ops
 
 
 class MaskInfo:
@@ -24,6 +24,7 @@ class MaskInfo:
         # a tower runs when any edge enters it (aread.py:268: any(mask[l], dim=0))
         self.active = [self.arrays[l].any(axis=0) for l in range(n_level)]
         self.active_last = np.nonzero(self.active[-1])[0]
+        self.active_idx = [[int(t) for t in np.nonzero(a)[0]] for a in self.active]
         self.group_idx = np.nonzero(self.arrays[0])[1]            # aread.py:226 / 237
         self._edges = {}
 
@@ -32,6 +33,15 @@ class MaskInfo:
         e = self._edges.get(key)
         if e is None:
             e = torch.from_numpy(self.arrays[l].astype(np.float32)).to(device)
+            self._edges[key] = e
+        return e
+
+    def index(self, l, device):
+        """int64 device tensor of the towers of level l that run."""
+        key = ("idx", l, device)
+        e = self._edges.get(key)
+        if e is None:
+            e = torch.tensor(self.active_idx[l], dtype=torch.int64, device=device)
             self._edges[key] = e
         return e
 
@@ -65,18 +75,13 @@ def aread_forward(model, x, info: Optional[MaskInfo], want_gate_means=False, wan
     embed_x, x_bf16 = model.embedding.lookup(x, want_bf16=True, want_lo=precise)
     domain_embed = embed_x[:, model.domain_idx, :]
     X = embed_x.flatten(start_dim=1)
-    B = X.shape[0]
-    lin = model.linear(X)
-    cn = model.cn(X)
-    # MMoE gates of level-0 towers that do not run are never evaluated (their parameters keep grad None)
-    active0 = np.ones(model.n_tower[0], dtype=bool) if info is None else info.active[0]
-    n_expert = len(model.mmoe_experts)
-    zeros = torch.zeros(B, n_expert, dtype=torch.float32, device=X.device)
-    gate = torch.stack([g(X) if active0[t] else zeros for t, g in enumerate(model.mmoe_gates)], dim=1)
+    # towers that do not run: their MMoE gate / output head is never evaluated (parameters keep grad None)
+    active0 = list(range(model.n_tower[0])) if info is None else [int(t) for t in np.nonzero(info.active[0])[0]]
+    active_last = list(range(model.n_tower[-1])) if info is None else [int(t) for t in info.active_last]
+    lin, gate, head_cross = rowpass_ops.rowpass(model, X, active0, active_last)
     training = model.training
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and model.dropout_p > 0) else 0
-    t0 = expert_ops.expert_stack(X, x_bf16, gate, model._expert_layers, training, model.dropout_p, seed,
-                                 precise).unbind(dim=1)
+    mixed = expert_ops.expert_stack(X, x_bf16, gate, model._expert_layers, training, model.dropout_p, seed, precise)
     if info is None:
         group_embed = torch.zeros_like(domain_embed)                                 # aread.py:157
     else:
@@ -85,13 +90,62 @@ def aread_forward(model, x, info: Optional[MaskInfo], want_gate_means=False, wan
             group_embed = group_embed.mean(dim=0, keepdim=True)
         group_embed = group_embed.expand(x.shape[0], -1)
     q = torch.cat([domain_embed, group_embed], dim=1)
-    out = hei_forward(model, t0, q, cn, lin, info, want_gate_means, want_gates)
+    out = hei_levels(model, mixed, q, head_cross, lin, info, seed, want_gate_means, want_gates)
     out.gate_inputs = q
     return out
 
 
+def hei_levels(model, level0_in, q, head_cross, lin, info: Optional[MaskInfo], seed, want_gate_means=False,
+               want_gates=False) -> ForwardOut:
+    """The HEI levels on compact activations ([B, n_active, width]: only towers that run).
+
+    level0_in [B, n_active0, h]: MMoE mixtures of the active level-0 towers; head_cross [B, n_active_last]:
+    the cross-network part of the active heads; lin [B]."""
+    n_level, n_tower = model.n_level, model.n_tower
+    dev = q.device
+    training, p = model.training, model.dropout_p
+    out = ForwardOut(probs=None)
+    h = level0_in
+    prev_active = None
+    for l in range(n_level):
+        active = list(range(n_tower[l])) if info is None else info.active_idx[l]
+        index = None if (info is None or len(active) == n_tower[l]) else info.index(l, dev)
+        if l > 0:
+            # gates over ALL towers of the previous level (aread.py:282-285), evaluated only for towers that run
+            w_g = torch.stack([model.tower_gates[l - 1][t][0].weight for t in active], dim=0)   # [na, n_prev, 2D]
+            b_g = torch.stack([model.tower_gates[l - 1][t][0].bias for t in active], dim=0)     # [na, n_prev]
+            s = torch.softmax(torch.einsum('bd,tjd->btj', q, w_g) + b_g, dim=2)                 # [B, na, n_prev]
+            if want_gates:
+                out.gates[l] = s.detach().transpose(1, 2)                                       # [B, n_prev, n_l]
+            if info is None:
+                r = s
+            else:
+                edges = info.edges(l, dev).t()                                                  # [n_l, n_prev]
+                sm = s * (edges if index is None else edges.index_select(0, index))
+                r = sm / (sm.sum(dim=2, keepdim=True) + 1e-8)
+                if want_gate_means:
+                    means = sm.detach().mean(dim=0).t()                                         # [n_prev, na]
+                    if index is not None:       # towers that do not run report zeros (aread.py:278-280)
+                        means = torch.zeros(n_tower[l - 1], n_tower[l], dtype=torch.float32,
+                                            device=dev).index_copy_(1, index, means)
+                    out.gate_means[l] = means
+            if len(prev_active) != n_tower[l - 1]:
+                r = r.index_select(2, info.index(l - 1, dev))
+            h = torch.einsum('btj,bjw->btw', r, h)                                              # [B, na, w_prev]
+        for layer in model._tower_layers[l]:
+            h = tower_ops.tower_layer(h, layer, active, index, training, p, seed)
+        prev_active = active
+    E = model.embed_output_dim
+    w_tail = torch.stack([model.towers_linear[t].weight[0, E:] for t in prev_active], dim=0)     # [na, w_last]
+    z = head_cross + (h * w_tail).sum(dim=2) + lin.unsqueeze(1)                                  # [B, na]
+    out.probs = torch.sigmoid(z).t()
+    return out
+
+
 def hei_forward(model, tower_inputs, q, cn, lin, info: Optional[MaskInfo], want_gate_means=False,
-                want_gates=False) -> ForwardOut:
+                want_gates=False, head_cross=None) -> ForwardOut:
+    """`head_cross[t]` ([B, 1]) is the cross-network part of head t (w_out_t[:E] . cn_out) from the row
+    pass; without it the heads are evaluated from an explicit `cn` tensor like the reference does."""
     B = lin.shape[0]
     n_level, n_tower = model.n_level, model.n_tower
     out = ForwardOut(probs=None)
@@ -128,7 +182,11 @@ def hei_forward(model, tower_inputs, q, cn, lin, info: Optional[MaskInfo], want_
             probs = []
             for t in range(n_tower[l]):
                 if active[t]:
-                    z = model.towers_linear[t](torch.cat([cn, level_out[t]], dim=1)) + lin
+                    if head_cross is not None:
+                        E = model.embed_output_dim
+                        z = head_cross[t] + level_out[t] @ model.towers_linear[t].weight[:, E:].t() + lin
+                    else:
+                        z = model.towers_linear[t](torch.cat([cn, level_out[t]], dim=1)) + lin
                     probs.append(torch.sigmoid(z).squeeze(-1))
             out.probs = torch.stack(probs, dim=0)
     return out

@@ -197,8 +197,8 @@ class BaseModel(nn.Module):
         self.regularization_weight.append((weights, l1, l2))
 
     def get_regularization_loss(self, device):
-        from . import dense_ops
-        return dense_ops.regularization_loss(self.regularization_weight, device)
+        from . import reg_ops
+        return reg_ops.regularization_loss(self.regularization_weight, device)
 
 
 def _weights_without_bn(module):

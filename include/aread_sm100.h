@@ -278,6 +278,123 @@ typedef struct aread_mmoe_mix_args {
 
 AREAD_API int aread_mmoe_mix(const aread_mmoe_mix_args* args, aread_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row pass: every dot product of the flattened embedding row with a parameter vector, in fp32.
+ * Replaces FeaturesLinear.forward (model/layer.py:122-126), CrossNetwork.forward (layer.py:529-537),
+ * the MMoE gates Linear + Softmax (model/aread.py:96-99, 152) and the cross-network part of the
+ * towers_linear heads (aread.py:119-120, 307), forward and backward.
+ *
+ * P = X . W^T with the rows of W ordered [linear | gate g, expert e | cross layer k | head t]; then
+ *   lin[b]        = P[b, 0] + offset[0]
+ *   gate[b, g, :] = softmax_e(P[b, 1 + g*n_expert + e] + offset[..])
+ *   alpha_0 = 1, s_k = alpha_k * P[b, cross k] + offset[cross k], alpha_{k+1} = alpha_k + s_k
+ *   head[b, t]    = alpha_n * P[b, head t] + offset[head t]
+ * where offset holds the row-independent constants (biases, w_k . beta_k, w_out_t[:E] . beta_n with
+ * beta_k = b_0 + .. + b_{k-1}); the cross-network output itself is never materialised.
+ * The backward returns d_x, d_w ([columns, e], reduced over rows in a fixed CTA order) and d_c
+ * ([m, ldp]; its column sums are the gradients of `offset`).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_rowpass_args {
+  int64_t m;
+  int32_t e;             /* embed_output_dim                                                       */
+  int32_t n_gate;        /* MMoE gates that are evaluated (active level-0 towers)                  */
+  int32_t n_expert;
+  int32_t n_cross;       /* cross layers                                                           */
+  int32_t n_head;        /* output heads that are evaluated (active last-level towers)             */
+  int32_t ldp;           /* row stride of p / d_p / d_c, >= 1 + n_gate*n_expert + n_cross + n_head  */
+  const float* x;        /* fp32 [m, e]                                                            */
+  const float* w;        /* fp32 [columns, e]                                                      */
+  const float* offset;   /* fp32 [columns]                                                         */
+  float* p;              /* [m, ldp]: forward out, backward in                                     */
+  float* lin;            /* [m]                                                                    */
+  float* gate;           /* [m, n_gate, n_expert]                                                  */
+  float* alpha;          /* [m, n_cross + 1]                                                       */
+  float* head;           /* [m, n_head]                                                            */
+  const float* d_lin;    /* backward inputs (NULL = zero)                                          */
+  const float* d_gate;
+  const float* d_head;
+  float* d_p;            /* backward scratch/out [m, ldp]                                          */
+  float* d_c;            /* backward out [m, ldp]                                                  */
+  float* d_x;            /* backward out [m, e] or NULL                                            */
+  float* d_w;            /* backward out [columns, e]                                              */
+  void* workspace;       /* aread_rowpass_workspace_bytes(m, e, columns)                           */
+  size_t workspace_bytes;
+} aread_rowpass_args;
+
+AREAD_API size_t aread_rowpass_workspace_bytes(int64_t m, int32_t e, int32_t n_cols);
+AREAD_API int aread_rowpass_fwd(const aread_rowpass_args* args, aread_stream_t stream);
+AREAD_API int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * L2 regulariser over a list of fp32 tensors in one pass: out[0] = sum_i l2[i] * sum(w_i^2), and its
+ * gradient grads[i] = 2 * l2[i] * g * w_i.  Replaces BaseModel.get_regularization_loss
+ * (model/layer.py:96-112).  The concatenation of the tensors is cut into chunks of
+ * aread_l2_reg_chunk() elements (a chunk never straddles two tensors); chunk_start[i] is the index
+ * of tensor i's first chunk.  Partials are added in a fixed order (bit-reproducible).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_l2_reg_args {
+  int32_t n_tensors;
+  int64_t n_chunks;              /* sum_i ceil(sizes[i] / chunk)                    */
+  const float* const* tensors;   /* device array [n_tensors] of device pointers     */
+  float* const* grads;           /* device array [n_tensors] (backward only)        */
+  const int64_t* sizes;          /* device array [n_tensors]: elements per tensor   */
+  const float* l2;               /* device array [n_tensors]                        */
+  const int64_t* chunk_start;    /* device array [n_tensors]                        */
+  float* out;                    /* device scalar (forward)                         */
+  void* workspace;               /* n_chunks * 4 bytes (forward)                    */
+  size_t workspace_bytes;
+} aread_l2_reg_args;
+
+AREAD_API int64_t aread_l2_reg_chunk(void);
+AREAD_API int aread_l2_reg_fwd(const aread_l2_reg_args* args, aread_stream_t stream);
+/* g_out: device scalar with the incoming gradient (NULL = 1) */
+AREAD_API int aread_l2_reg_bwd(const aread_l2_reg_args* args, const float* g_out, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grouped small Linear of the HEI towers, fp32 on the CUDA cores (16..64 wide layers).
+ * Replaces the nn.Linear calls of the tower MLPs (model/layer.py:210 via model/aread.py:108-110,
+ * 307, 319) and their gradients.  The caller passes only the towers that run under the HEMP mask
+ * (compact group index g = 0 .. groups-1); pruned towers cost nothing.
+ *
+ *   out[b, g, j] = sum_i in[b, g, i] * M_g[i, j] (+ bias[g, j])
+ * forward:       in = tower inputs, weight = nn.Linear weights [groups, out, in], weight_is_out_by_in = 1
+ * data gradient: in = dz,           weight = the same tensor read as [groups, in = N, out = K],
+ *                weight_is_out_by_in = 0 (so that out = dz . W)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_tower_linear_args {
+  int64_t m;
+  int32_t groups;
+  int32_t in_width;             /* <= 256                                                   */
+  int32_t out_width;            /* <= 128                                                   */
+  int32_t weight_is_out_by_in;  /* 1: weight[g] is [out_width, in_width]; 0: [in_width, out_width] */
+  const float* in;              /* fp32 [m, ld_in], group g at columns g * in_width         */
+  int64_t ld_in;
+  const float* weight;          /* fp32 [groups, ...] contiguous                            */
+  const float* bias;            /* optional fp32 [groups * out_width]                       */
+  float* out;                   /* fp32 [m, ld_out], group g at columns g * out_width       */
+  int64_t ld_out;
+} aread_tower_linear_args;
+
+AREAD_API int aread_tower_linear(const aread_tower_linear_args* args, aread_stream_t stream);
+
+/* d_w[g, n, k] = sum_b dz[b, g, n] * in[b, g, k]; row chunks are reduced in a fixed order. */
+typedef struct aread_tower_wgrad_args {
+  int64_t m;
+  int32_t groups;
+  int32_t n;                    /* output width of the layer, n * k <= 4096                 */
+  int32_t k;                    /* input width                                              */
+  const float* dz;              /* fp32 [m, ld_dz]                                          */
+  int64_t ld_dz;
+  const float* in;              /* fp32 [m, ld_in]                                          */
+  int64_t ld_in;
+  float* d_w;                   /* fp32 [groups, n, k] contiguous                           */
+  void* workspace;              /* aread_tower_wgrad_workspace_bytes(m, groups, n, k)       */
+  size_t workspace_bytes;
+} aread_tower_wgrad_args;
+
+AREAD_API size_t aread_tower_wgrad_workspace_bytes(int64_t m, int32_t groups, int32_t n, int32_t k);
+AREAD_API int aread_tower_wgrad(const aread_tower_wgrad_args* args, aread_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

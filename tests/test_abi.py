@@ -57,9 +57,11 @@ def test_every_declared_symbol_is_exported(lib):
                                          ("aread_grouped_linear_args", "GroupedLinearArgs"),
                                          ("aread_grouped_wgrad_args", "GroupedWgradArgs"),
                                          ("aread_bn_act_args", "BnActArgs"), ("aread_bn_act_bwd_args", "BnActBwdArgs"),
-                                         ("aread_mmoe_mix_args", "MmoeMixArgs")])
+                                         ("aread_mmoe_mix_args", "MmoeMixArgs"), ("aread_rowpass_args", "RowpassArgs"),
+                                         ("aread_l2_reg_args", "L2RegArgs"), ("aread_tower_linear_args", "TowerLinearArgs"),
+                                         ("aread_tower_wgrad_args", "TowerWgradArgs")])
 def test_struct_fields_match_header(cname, ctype):
-    fields = [f for f, _ in getattr(_lib, ctype)._fields_]
+    fields = [f.rstrip("_") for f, _ in getattr(_lib, ctype)._fields_]      # `in` is a Python keyword
     assert fields == struct_fields(cname)
 
 

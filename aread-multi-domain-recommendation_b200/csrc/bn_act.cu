@@ -14,8 +14,7 @@ namespace aread {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxColsPerThread = 8;  // width <= 2048
-constexpr int kStatCtas = kNumSMs * 2;
+constexpr int kStatCtas = kNumSMs * 4;
 
 // counter-based dropout stream: keep(element) is a pure function of (seed, salt, element index)
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -34,85 +33,121 @@ inline uint32_t dropout_threshold(float p) {
   return t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
 }
 
-struct Geometry {  // how 256 threads cover [rows, width]
-  int tw, ty, nc;
+struct Geometry {  // how 256 threads cover [rows, width] in the column-sum kernels
+  int tw, vec;
 };
-inline Geometry geometry(int width) {
+inline Geometry geometry(int width, bool aligned) {
   Geometry g;
+  g.vec = (aligned && width % 4 == 0) ? 4 : 1;
   g.tw = 1;
-  while (g.tw < width && g.tw < kThreads) g.tw <<= 1;
-  g.ty = kThreads / g.tw;
-  g.nc = (width + g.tw - 1) / g.tw;
+  while (g.tw * g.vec < width && g.tw < kThreads) g.tw <<= 1;
   return g;
 }
 
-// per-CTA partial column sums of f0(row, col) and f1(row, col) over the CTA's row range
-template <typename F>
-__device__ __forceinline__ void column_partials(int64_t m, int width, int tw, int ty_n, int nc, float* partial, F f) {
-  extern __shared__ float s_red[];  // [ty_n][2][nc * tw]
+// Per-CTA partial column sums of the two quantities f produces, over the CTA's contiguous row range.
+// Threads: tx over column groups of VEC, ty over rows; four independent row loads are in flight per
+// thread.  The ty partials are added in ty order, the CTA partials later in CTA order.
+template <int VEC, typename F>
+__device__ __forceinline__ void column_partials(int64_t m, int width, int tw, float* partial, F f) {
+  extern __shared__ float s_red[];  // [ty_n][2][tw * VEC]
+  const int ty_n = kThreads / tw;
   const int tx = threadIdx.x % tw, ty = threadIdx.x / tw;
   const int64_t rows_per_cta = (m + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = blockIdx.x * rows_per_cta;
   const int64_t r1 = min(m, r0 + rows_per_cta);
-  float s[kMaxColsPerThread], q[kMaxColsPerThread];
+  const int span = tw * VEC;
+  for (int c0 = 0; c0 < width; c0 += span) {
+    const int col = c0 + tx * VEC;
+    float s[VEC], q[VEC];
 #pragma unroll
-  for (int c = 0; c < kMaxColsPerThread; ++c) s[c] = q[c] = 0.f;
-  for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+    for (int v = 0; v < VEC; ++v) s[v] = q[v] = 0.f;
+    if (col < width) {
+      int64_t r = r0 + ty;
+      for (; r + 3 * ty_n < r1; r += 4 * ty_n) {
+        float a[4][VEC], b[4][VEC];
 #pragma unroll
-    for (int c = 0; c < kMaxColsPerThread; ++c) {
-      const int col = tx + c * tw;
-      if (c < nc && col < width) {
-        float a, b;
+        for (int u = 0; u < 4; ++u) f(r + u * ty_n, col, a[u], b[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) { s[v] += a[u][v]; q[v] += b[u][v]; }
+      }
+      for (; r < r1; r += ty_n) {
+        float a[VEC], b[VEC];
         f(r, col, a, b);
-        s[c] += a;
-        q[c] += b;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { s[v] += a[v]; q[v] += b[v]; }
       }
     }
-  }
-  const int stride = nc * tw;
+    __syncthreads();
 #pragma unroll
-  for (int c = 0; c < kMaxColsPerThread; ++c) {
-    if (c < nc) {
-      s_red[(ty * 2 + 0) * stride + c * tw + tx] = s[c];
-      s_red[(ty * 2 + 1) * stride + c * tw + tx] = q[c];
+    for (int v = 0; v < VEC; ++v) {
+      s_red[(ty * 2 + 0) * span + tx * VEC + v] = s[v];
+      s_red[(ty * 2 + 1) * span + tx * VEC + v] = q[v];
     }
-  }
-  __syncthreads();
-  if (ty == 0) {
+    __syncthreads();
+    if (ty == 0 && col < width) {
 #pragma unroll
-    for (int c = 0; c < kMaxColsPerThread; ++c) {
-      const int col = tx + c * tw;
-      if (c < nc && col < width) {
+      for (int v = 0; v < VEC; ++v) {
         float a = 0.f, b = 0.f;
         for (int y = 0; y < ty_n; ++y) {
-          a += s_red[(y * 2 + 0) * stride + c * tw + tx];
-          b += s_red[(y * 2 + 1) * stride + c * tw + tx];
+          a += s_red[(y * 2 + 0) * span + tx * VEC + v];
+          b += s_red[(y * 2 + 1) * span + tx * VEC + v];
         }
-        partial[(static_cast<int64_t>(blockIdx.x) * 2 + 0) * width + col] = a;
-        partial[(static_cast<int64_t>(blockIdx.x) * 2 + 1) * width + col] = b;
+        partial[(static_cast<int64_t>(blockIdx.x) * 2 + 0) * width + col + v] = a;
+        partial[(static_cast<int64_t>(blockIdx.x) * 2 + 1) * width + col + v] = b;
       }
     }
   }
 }
 
+// Sum of the CTA partials of one column pair, by 8 threads in interleaved order then in thread order.
+// Block = 32 columns x 8; returns the totals to the threads with threadIdx.x < 32.
+__device__ __forceinline__ void combine_partials(const float* __restrict__ partial, int n_partial, int width, int col,
+                                                 float& s, float& q) {
+  __shared__ float s_c[2][8][32];
+  const int cx = threadIdx.x % 32, py = threadIdx.x / 32;
+  float a = 0.f, b = 0.f;
+  if (col < width) {
+    for (int i = py; i < n_partial; i += 8) {
+      a += partial[(static_cast<int64_t>(i) * 2 + 0) * width + col];
+      b += partial[(static_cast<int64_t>(i) * 2 + 1) * width + col];
+    }
+  }
+  s_c[0][py][cx] = a;
+  s_c[1][py][cx] = b;
+  __syncthreads();
+  s = q = 0.f;
+  if (py == 0) {
+    for (int y = 0; y < 8; ++y) { s += s_c[0][y][cx]; q += s_c[1][y][cx]; }
+  }
+}
+
 // ---------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(kThreads) bn_stats_kernel(int64_t m, int width, int tw, int ty, int nc,
-                                                            const float* __restrict__ z, int64_t ldz,
-                                                            const float* __restrict__ pivot,
-                                                            float* __restrict__ partial) {
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(int64_t m, int width, int tw, const float* __restrict__ z,
+                                                            int64_t ldz, float* __restrict__ partial) {
   // sums are taken about the column's first row (a sample of the same distribution), which keeps
   // E[v^2] - E[v]^2 well conditioned whatever the column mean is
-  column_partials(m, width, tw, ty, nc, partial, [&](int64_t r, int col, float& a, float& b) {
-    const float v = __ldg(z + r * ldz + col) - __ldg(pivot + col);
-    a = v;
-    b = v * v;
+  column_partials<VEC>(m, width, tw, partial, [&](int64_t r, int col, float (&a)[VEC], float (&b)[VEC]) {
+    if (VEC == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(z + r * ldz + col));
+      const float4 p = __ldg(reinterpret_cast<const float4*>(z + col));
+      a[0] = v.x - p.x; a[1] = v.y - p.y; a[2] = v.z - p.z; a[3] = v.w - p.w;
+    } else {
+      a[0] = __ldg(z + r * ldz + col) - __ldg(z + col);
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) b[v] = a[v] * a[v];
   });
 }
 
 __global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const aread_bn_act_args a, const float* partial,
                                                                int n_partial) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= a.width) return;
+  const int col = blockIdx.x * 32 + threadIdx.x % 32;
+  float s = 0.f, q = 0.f;
+  if (a.training && !a.bn_skip) combine_partials(partial, n_partial, a.width, col, s, q);
+  if (col >= a.width || threadIdx.x >= 32) return;
   float scale, shift;
   if (a.bn_skip) {
     scale = 1.f;
@@ -120,11 +155,6 @@ __global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const aread_bn_ac
     a.mean[col] = 0.f;
     a.rstd[col] = 1.f;
   } else if (a.training) {
-    float s = 0.f, q = 0.f;
-    for (int i = 0; i < n_partial; ++i) {
-      s += partial[(static_cast<int64_t>(i) * 2 + 0) * a.width + col];
-      q += partial[(static_cast<int64_t>(i) * 2 + 1) * a.width + col];
-    }
     const float inv_m = 1.f / static_cast<float>(a.m);
     const float d = s * inv_m;                       // mean - pivot
     const float mean = a.z[col] + d;                 // the pivot is the column's first row
@@ -206,29 +236,40 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const aread_bn_act_arg
 
 // ---------------------------------------------------------------------------------- backward
 // dy = d_out * [y > 0] * keep / (1 - p);  xhat = (z - mean) * rstd
-__global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const aread_bn_act_bwd_args a, int tw, int ty, int nc,
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const aread_bn_act_bwd_args a, int tw,
                                                                 uint32_t threshold, float keep_scale,
                                                                 float* __restrict__ partial) {
-  column_partials(a.m, a.width, tw, ty, nc, partial, [&](int64_t r, int col, float& s1, float& s2) {
-    const float z = __ldg(a.z + r * a.ldz + col);
-    const float y = fmaf(z, __ldg(a.scale + col), __ldg(a.shift + col));
-    const bool keep = threshold == 0u ||
-                      dropout_keep(a.seed, a.salt, static_cast<uint64_t>(r) * a.width + col, threshold);
-    const float dy = (y > 0.f && keep) ? __ldg(a.d_out + r * a.ldd + col) * keep_scale : 0.f;
-    s1 = dy;
-    s2 = dy * (z - __ldg(a.mean + col)) * __ldg(a.rstd + col);
+  column_partials<VEC>(a.m, a.width, tw, partial, [&](int64_t r, int col, float (&s1)[VEC], float (&s2)[VEC]) {
+    float z[VEC], d[VEC];
+    if (VEC == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.ldz + col));
+      const float4 u = __ldg(reinterpret_cast<const float4*>(a.d_out + r * a.ldd + col));
+      z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+      d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+    } else {
+      z[0] = __ldg(a.z + r * a.ldz + col);
+      d[0] = __ldg(a.d_out + r * a.ldd + col);
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int c = col + v;
+      const float y = fmaf(z[v], __ldg(a.scale + c), __ldg(a.shift + c));
+      const bool keep = threshold == 0u ||
+                        dropout_keep(a.seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
+      const float dy = (y > 0.f && keep) ? d[v] * keep_scale : 0.f;
+      s1[v] = dy;
+      s2[v] = dy * (z[v] - __ldg(a.mean + c)) * __ldg(a.rstd + c);
+    }
   });
 }
 
 __global__ void __launch_bounds__(kThreads) bn_bwd_finalize_kernel(const aread_bn_act_bwd_args a, const float* partial,
                                                                    int n_partial, float* coef) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= a.width) return;
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = 0; i < n_partial; ++i) {
-    s1 += partial[(static_cast<int64_t>(i) * 2 + 0) * a.width + col];
-    s2 += partial[(static_cast<int64_t>(i) * 2 + 1) * a.width + col];
-  }
+  const int col = blockIdx.x * 32 + threadIdx.x % 32;
+  float s1, s2;
+  combine_partials(partial, n_partial, a.width, col, s1, s2);
+  if (col >= a.width || threadIdx.x >= 32) return;
   if (a.bn_skip) {  // identity instead of BatchNorm: gamma / beta see no gradient, the bias sees sum(dy)
     if (a.d_gamma) a.d_gamma[col] = 0.f;
     if (a.d_beta) a.d_beta[col] = 0.f;
@@ -392,7 +433,7 @@ unsigned elementwise_grid(int64_t total) {
 }
 
 int stat_ctas(int64_t m) {
-  int64_t c = (m + 63) / 64;  // at least 64 rows per CTA
+  int64_t c = (m + 255) / 256;  // at least 256 rows per CTA
   return static_cast<int>(c < 1 ? 1 : (c > kStatCtas ? kStatCtas : c));
 }
 
@@ -410,7 +451,7 @@ int aread_bn_act_fwd(const aread_bn_act_args* args, aread_stream_t stream_) {
   using namespace aread;
   AREAD_REQUIRE(args != nullptr, "bn_act_fwd: null args");
   const aread_bn_act_args& a = *args;
-  AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width <= kThreads * kMaxColsPerThread, "bn_act_fwd: width %d unsupported",
+  AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width <= 65536, "bn_act_fwd: width %d unsupported",
                 a.width);
   AREAD_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, "bn_act_fwd: dropout %f not in [0, 1)", a.dropout_p);
   if (a.m == 0) return AREAD_OK;
@@ -421,11 +462,14 @@ int aread_bn_act_fwd(const aread_bn_act_args* args, aread_stream_t stream_) {
   float* partial = static_cast<float*>(a.workspace);
   const int n_partial = stat_ctas(a.m);
   if (a.training && !a.bn_skip) {
-    const Geometry g = geometry(a.width);
-    AREAD_LAUNCH(bn_stats_kernel, n_partial, kThreads, sizeof(float) * 2 * g.ty * g.nc * g.tw, stream, a.m, a.width,
-                 g.tw, g.ty, g.nc, a.z, a.ldz, a.z, partial);
+    const Geometry g = geometry(a.width, a.ldz % 4 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0);
+    const size_t smem = sizeof(float) * 2 * kThreads * g.vec;
+    if (g.vec == 4)
+      AREAD_LAUNCH(bn_stats_kernel<4>, n_partial, kThreads, smem, stream, a.m, a.width, g.tw, a.z, a.ldz, partial);
+    else
+      AREAD_LAUNCH(bn_stats_kernel<1>, n_partial, kThreads, smem, stream, a.m, a.width, g.tw, a.z, a.ldz, partial);
   }
-  AREAD_LAUNCH(bn_finalize_kernel, ceil_div(a.width, kThreads), kThreads, 0, stream, a, partial, n_partial);
+  AREAD_LAUNCH(bn_finalize_kernel, ceil_div(a.width, 32), kThreads, 0, stream, a, partial, n_partial);
   if (a.out_f32 || a.out_bf16) {
     const bool drop = a.training && a.dropout_p > 0.f;
     const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;
@@ -447,7 +491,7 @@ int aread_bn_act_bwd(const aread_bn_act_bwd_args* args, aread_stream_t stream_) 
   using namespace aread;
   AREAD_REQUIRE(args != nullptr, "bn_act_bwd: null args");
   const aread_bn_act_bwd_args& a = *args;
-  AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width <= kThreads * kMaxColsPerThread, "bn_act_bwd: width %d unsupported",
+  AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width <= 65536, "bn_act_bwd: width %d unsupported",
                 a.width);
   if (a.m == 0) return AREAD_OK;
   AREAD_REQUIRE(a.z && a.d_out && a.mean && a.rstd && a.scale && a.shift, "bn_act_bwd: null pointer");
@@ -459,10 +503,14 @@ int aread_bn_act_bwd(const aread_bn_act_bwd_args* args, aread_stream_t stream_) 
   const bool drop = a.dropout_p > 0.f;
   const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;
   const float keep_scale = drop ? 1.f / (1.f - a.dropout_p) : 1.f;
-  const Geometry g = geometry(a.width);
-  AREAD_LAUNCH(bn_bwd_stats_kernel, n_partial, kThreads, sizeof(float) * 2 * g.ty * g.nc * g.tw, stream, a, g.tw, g.ty,
-               g.nc, threshold, keep_scale, partial);
-  AREAD_LAUNCH(bn_bwd_finalize_kernel, ceil_div(a.width, kThreads), kThreads, 0, stream, a, partial, n_partial, coef);
+  const Geometry g = geometry(a.width, a.ldz % 4 == 0 && a.ldd % 4 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0 &&
+                                           reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0);
+  const size_t smem = sizeof(float) * 2 * kThreads * g.vec;
+  if (g.vec == 4)
+    AREAD_LAUNCH(bn_bwd_stats_kernel<4>, n_partial, kThreads, smem, stream, a, g.tw, threshold, keep_scale, partial);
+  else
+    AREAD_LAUNCH(bn_bwd_stats_kernel<1>, n_partial, kThreads, smem, stream, a, g.tw, threshold, keep_scale, partial);
+  AREAD_LAUNCH(bn_bwd_finalize_kernel, ceil_div(a.width, 32), kThreads, 0, stream, a, partial, n_partial, coef);
   if (a.dz_f32 || a.dz_bf16) {
     const bool aligned = a.ldz % 4 == 0 && a.ldo % 4 == 0 && a.ldd % 4 == 0 &&
                          reinterpret_cast<uintptr_t>(a.z) % 16 == 0 && reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0 &&

@@ -18,51 +18,56 @@ namespace aread {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kRowsPerWarp = 4;
-constexpr int kJChunk = 32;
+constexpr int kTile = 64;    // rows per tile
+constexpr int kChunk = 64;   // embedding elements per shared-memory chunk
+constexpr int kJ = 32;       // dot products handled per launch
+constexpr int kXs = kChunk + 1;
 
-// P[b, j] = sum_e X[b, e] * W[j, e]; one warp per 4 rows, lanes over e, W staged in shared memory
+// stage X[b0 .. b0+64, e0 .. e0+64) (zero padded) into sX[r][e] with a conflict-free row stride
+__device__ __forceinline__ void load_x_chunk(float* sX, const float* __restrict__ x, int64_t m, int E, int64_t b0,
+                                             int e0) {
+  for (int idx = threadIdx.x; idx < kTile * kChunk; idx += kThreads) {
+    const int r = idx / kChunk, e = idx - r * kChunk;
+    sX[r * kXs + e] = (b0 + r < m && e0 + e < E) ? __ldg(x + (b0 + r) * E + e0 + e) : 0.f;
+  }
+}
+
+// P[b, j] = sum_e X[b, e] * W[j, e], j < nj <= 32.  CTA = 64-row tiles; thread = (row, 8 dot products).
 __global__ void __launch_bounds__(kThreads) rowdots_fwd_kernel(int64_t m, int E, int nj, const float* __restrict__ x,
                                                                const float* __restrict__ w, float* __restrict__ p,
                                                                int ldp) {
-  extern __shared__ float s_w[];  // [jc][E]
-  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
-  const int warps = blockDim.x / 32;
-  for (int j0 = 0; j0 < nj; j0 += kJChunk) {
-    const int jc = min(kJChunk, nj - j0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < jc * E; i += blockDim.x) s_w[i] = w[static_cast<int64_t>(j0) * E + i];
-    __syncthreads();
-    for (int64_t b0 = (static_cast<int64_t>(blockIdx.x) * warps + warp) * kRowsPerWarp; b0 < m;
-         b0 += static_cast<int64_t>(gridDim.x) * warps * kRowsPerWarp) {
-      float acc[kRowsPerWarp][kJChunk];
+  __shared__ float sX[kTile * kXs];
+  __shared__ __align__(16) float sW[kChunk * kJ];  // [e][j]
+  const int r = threadIdx.x / 4, jq = threadIdx.x % 4;
+  const int64_t n_tiles = (m + kTile - 1) / kTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t b0 = tile * kTile;
+    float acc[8];
 #pragma unroll
-      for (int r = 0; r < kRowsPerWarp; ++r)
-#pragma unroll
-        for (int j = 0; j < kJChunk; ++j) acc[r][j] = 0.f;
-      for (int e = lane; e < E; e += 32) {
-        float xv[kRowsPerWarp];
-#pragma unroll
-        for (int r = 0; r < kRowsPerWarp; ++r) xv[r] = b0 + r < m ? __ldg(x + (b0 + r) * E + e) : 0.f;
-#pragma unroll
-        for (int j = 0; j < kJChunk; ++j) {
-          if (j < jc) {
-            const float wv = s_w[j * E + e];
-#pragma unroll
-            for (int r = 0; r < kRowsPerWarp; ++r) acc[r][j] = fmaf(xv[r], wv, acc[r][j]);
-          }
-        }
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int e0 = 0; e0 < E; e0 += kChunk) {
+      __syncthreads();
+      load_x_chunk(sX, x, m, E, b0, e0);
+      for (int idx = threadIdx.x; idx < kChunk * kJ; idx += kThreads) {
+        const int j = idx / kChunk, e = idx - j * kChunk;   // coalesced along e
+        sW[e * kJ + j] = (j < nj && e0 + e < E) ? __ldg(w + static_cast<int64_t>(j) * E + e0 + e) : 0.f;
       }
-#pragma unroll
-      for (int r = 0; r < kRowsPerWarp; ++r) {
-#pragma unroll
-        for (int j = 0; j < kJChunk; ++j) {
-          if (j < jc) {
-            const float v = warp_sum(acc[r][j]);
-            if (lane == 0 && b0 + r < m) p[(b0 + r) * ldp + j0 + j] = v;
-          }
-        }
+      __syncthreads();
+#pragma unroll 8
+      for (int e = 0; e < kChunk; ++e) {
+        const float xv = sX[r * kXs + e];
+        const float4 w0 = *reinterpret_cast<const float4*>(sW + e * kJ + jq * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sW + e * kJ + jq * 8 + 4);
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+        acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+        acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
       }
+    }
+    if (b0 + r < m) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (jq * 8 + j < nj) p[(b0 + r) * ldp + jq * 8 + j] = acc[j];
     }
   }
 }
@@ -139,77 +144,87 @@ __global__ void __launch_bounds__(kThreads) rowpass_prologue_bwd_kernel(const ar
   }
 }
 
-// d_x[b, :] = sum_j d_p[b, j] * W[j, :]  (warp per 4 rows)  and the per-CTA partial of
-// d_w[j, :] = sum_b d_p[b, j] * X[b, :]  (thread per column), over tiles of kTileRows rows.
-constexpr int kTileRows = 32;
-constexpr int kMaxColsPerThread = 6;  // E <= 1536
-
-template <int COLS>
+// d_x[b, e] (+)= sum_j d_p[b, j] * W[j, e]  and the per-CTA partial of  d_w[j, e] = sum_b d_p[b, j] * X[b, e].
+// CTA = 64-row tiles, the embedding row is walked in 64-element chunks staged in shared memory.
+//   d_x phase: thread = (row, 16 consecutive e);   d_w phase: thread = (e, 8 of the 32 dot products),
+//   accumulating over all tiles of the CTA in registers (MAX_CHUNKS x 8).
+template <int MAX_CHUNKS>
 __global__ void __launch_bounds__(kThreads) rowdots_bwd_kernel(int64_t m, int E, int nj, int ldp,
                                                                const float* __restrict__ x,
                                                                const float* __restrict__ w,
                                                                const float* __restrict__ d_p, float* __restrict__ d_x,
-                                                               float* __restrict__ dw_partial) {
-  extern __shared__ float smem[];
-  float* s_w = smem;                 // [nj][E]
-  float* s_dp = smem + nj * E;       // [kTileRows][nj]
-  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, warps = blockDim.x / 32;
-  for (int i = threadIdx.x; i < nj * E; i += blockDim.x) s_w[i] = w[i];
-  float dw[COLS][kJChunk];
+                                                               int accumulate_dx, float* __restrict__ dw_partial) {
+  __shared__ float sX[kTile * kXs];
+  __shared__ __align__(16) float sW[kJ * kChunk];   // [j][e]
+  __shared__ __align__(16) float sDp[kTile * kJ];   // [r][j]
+  const int r = threadIdx.x / 4, eq = threadIdx.x % 4;   // d_x phase
+  const int ec = threadIdx.x % kChunk, jg = threadIdx.x / kChunk;  // d_w phase: 4 groups of 8 j
+  float dw[MAX_CHUNKS][8];
 #pragma unroll
-  for (int c = 0; c < COLS; ++c)
+  for (int c = 0; c < MAX_CHUNKS; ++c)
 #pragma unroll
-    for (int j = 0; j < kJChunk; ++j) dw[c][j] = 0.f;
+    for (int j = 0; j < 8; ++j) dw[c][j] = 0.f;
 
-  const int64_t n_tiles = (m + kTileRows - 1) / kTileRows;
+  const int64_t n_tiles = (m + kTile - 1) / kTile;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t b0 = tile * kTileRows;
-    const int rows = m - b0 < kTileRows ? static_cast<int>(m - b0) : kTileRows;
+    const int64_t b0 = tile * kTile;
     __syncthreads();
-    for (int i = threadIdx.x; i < kTileRows * nj; i += blockDim.x) {
-      const int r = i / nj, j = i - r * nj;
-      s_dp[i] = r < rows ? d_p[(b0 + r) * ldp + j] : 0.f;
+    for (int idx = threadIdx.x; idx < kTile * kJ; idx += kThreads) {
+      const int rr = idx / kJ, j = idx - rr * kJ;
+      sDp[idx] = (b0 + rr < m && j < nj) ? __ldg(d_p + (b0 + rr) * ldp + j) : 0.f;
     }
-    __syncthreads();
-    // ---- d_x: warp `warp` owns rows warp*4 .. warp*4+3 of the tile (8 warps x 4 rows = 32)
-    if (d_x != nullptr) {
-      for (int rr = warp * kRowsPerWarp; rr < kTileRows; rr += warps * kRowsPerWarp) {
-        for (int e = lane; e < E; e += 32) {
-          float acc[kRowsPerWarp];
 #pragma unroll
-          for (int r = 0; r < kRowsPerWarp; ++r) acc[r] = 0.f;
-          for (int j = 0; j < nj; ++j) {
-            const float wv = s_w[j * E + e];
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+      const int e0 = c * kChunk;
+      if (e0 >= E) break;
+      __syncthreads();
+      load_x_chunk(sX, x, m, E, b0, e0);
+      for (int idx = threadIdx.x; idx < kJ * kChunk; idx += kThreads) {
+        const int j = idx / kChunk, e = idx - j * kChunk;
+        sW[idx] = (j < nj && e0 + e < E) ? __ldg(w + static_cast<int64_t>(j) * E + e0 + e) : 0.f;
+      }
+      __syncthreads();
+      if (d_x != nullptr) {
+        float acc[16];
 #pragma unroll
-            for (int r = 0; r < kRowsPerWarp; ++r) acc[r] = fmaf(s_dp[(rr + r) * nj + j], wv, acc[r]);
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        for (int j = 0; j < nj; ++j) {
+          const float dp = sDp[r * kJ + j];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = *reinterpret_cast<const float4*>(sW + j * kChunk + eq * 16 + q * 4);
+            acc[q * 4 + 0] = fmaf(dp, wv.x, acc[q * 4 + 0]);
+            acc[q * 4 + 1] = fmaf(dp, wv.y, acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(dp, wv.z, acc[q * 4 + 2]);
+            acc[q * 4 + 3] = fmaf(dp, wv.w, acc[q * 4 + 3]);
           }
+        }
+        if (b0 + r < m) {
+          float* dst = d_x + (b0 + r) * E + e0 + eq * 16;
 #pragma unroll
-          for (int r = 0; r < kRowsPerWarp; ++r)
-            if (rr + r < rows) d_x[(b0 + rr + r) * E + e] = acc[r];
+          for (int i = 0; i < 16; ++i)
+            if (e0 + eq * 16 + i < E) dst[i] = accumulate_dx ? dst[i] + acc[i] : acc[i];
         }
       }
-    }
-    // ---- d_w partial: thread owns columns threadIdx.x + c * blockDim.x
-    for (int r = 0; r < rows; ++r) {
-#pragma unroll
-      for (int c = 0; c < COLS; ++c) {
-        const int e = threadIdx.x + c * kThreads;
-        if (e < E) {
-          const float xv = __ldg(x + (b0 + r) * E + e);
-#pragma unroll
-          for (int j = 0; j < kJChunk; ++j)
-            if (j < nj) dw[c][j] = fmaf(s_dp[r * nj + j], xv, dw[c][j]);
-        }
+      const int rows = m - b0 < kTile ? static_cast<int>(m - b0) : kTile;
+      for (int rr = 0; rr < rows; ++rr) {
+        const float xv = sX[rr * kXs + ec];
+        const float4 d0 = *reinterpret_cast<const float4*>(sDp + rr * kJ + jg * 8);
+        const float4 d1 = *reinterpret_cast<const float4*>(sDp + rr * kJ + jg * 8 + 4);
+        dw[c][0] = fmaf(d0.x, xv, dw[c][0]); dw[c][1] = fmaf(d0.y, xv, dw[c][1]);
+        dw[c][2] = fmaf(d0.z, xv, dw[c][2]); dw[c][3] = fmaf(d0.w, xv, dw[c][3]);
+        dw[c][4] = fmaf(d1.x, xv, dw[c][4]); dw[c][5] = fmaf(d1.y, xv, dw[c][5]);
+        dw[c][6] = fmaf(d1.z, xv, dw[c][6]); dw[c][7] = fmaf(d1.w, xv, dw[c][7]);
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < COLS; ++c) {
-    const int e = threadIdx.x + c * kThreads;
+  for (int c = 0; c < MAX_CHUNKS; ++c) {
+    const int e = c * kChunk + ec;
     if (e < E) {
 #pragma unroll
-      for (int j = 0; j < kJChunk; ++j)
-        if (j < nj) dw_partial[(static_cast<int64_t>(blockIdx.x) * nj + j) * E + e] = dw[c][j];
+      for (int j = 0; j < 8; ++j)
+        if (jg * 8 + j < nj) dw_partial[(static_cast<int64_t>(blockIdx.x) * nj + jg * 8 + j) * E + e] = dw[c][j];
     }
   }
 }
@@ -227,8 +242,9 @@ __global__ void __launch_bounds__(kThreads) rowdots_bwd_reduce_kernel(int n_part
 }
 
 int bwd_ctas(int64_t m) {
-  const int64_t tiles = (m + kTileRows - 1) / kTileRows;
-  return static_cast<int>(tiles < kNumSMs ? (tiles < 1 ? 1 : tiles) : kNumSMs);
+  const int64_t tiles = (m + kTile - 1) / kTile;
+  const int64_t cap = kNumSMs * 2;
+  return static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
 }
 
 }  // namespace
@@ -249,13 +265,14 @@ int aread_rowpass_fwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   if (a.m == 0) return AREAD_OK;
   AREAD_REQUIRE(a.x && a.w && a.offset && a.p && a.lin && a.alpha, "rowpass_fwd: null pointer");
   AREAD_REQUIRE((a.gate || a.n_gate * a.n_expert == 0) && (a.head || a.n_head == 0), "rowpass_fwd: null output");
-  const size_t smem = static_cast<size_t>(nj < kJChunk ? nj : kJChunk) * a.e * sizeof(float);
-  AREAD_REQUIRE(smem <= 200 * 1024, "rowpass_fwd: embedding row of %d floats is too wide", a.e);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  AREAD_CUDA(cudaFuncSetAttribute(rowdots_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  const int64_t row_groups = (a.m + kRowsPerWarp * (kThreads / 32) - 1) / (kRowsPerWarp * (kThreads / 32));
-  const unsigned grid = static_cast<unsigned>(row_groups < kNumSMs * 2 ? row_groups : kNumSMs * 2);
-  AREAD_LAUNCH(rowdots_fwd_kernel, grid, kThreads, smem, stream, a.m, a.e, nj, a.x, a.w, a.p, a.ldp);
+  {
+    const int64_t tiles = (a.m + kTile - 1) / kTile;
+    const unsigned grid = static_cast<unsigned>(tiles < kNumSMs * 4 ? tiles : kNumSMs * 4);
+    for (int j0 = 0; j0 < nj; j0 += kJ)  // 32 dot products per launch
+      AREAD_LAUNCH(rowdots_fwd_kernel, grid, kThreads, 0, stream, a.m, a.e, nj - j0 < kJ ? nj - j0 : kJ, a.x,
+                   a.w + static_cast<int64_t>(j0) * a.e, a.p + j0, a.ldp);
+  }
   const unsigned egrid = static_cast<unsigned>((a.m + kThreads - 1) / kThreads < kNumSMs * 8
                                                    ? (a.m + kThreads - 1) / kThreads
                                                    : kNumSMs * 8);
@@ -269,8 +286,7 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   const aread_rowpass_args& a = *args;
   const int nj = 1 + a.n_gate * a.n_expert + a.n_cross + a.n_head;
   AREAD_REQUIRE(a.m >= 0 && a.e > 0 && nj <= a.ldp, "rowpass_bwd: bad shape");
-  AREAD_REQUIRE(nj <= kJChunk, "rowpass_bwd: %d dot products exceed the supported %d", nj, kJChunk);
-  AREAD_REQUIRE(a.e <= kThreads * kMaxColsPerThread, "rowpass_bwd: embedding row of %d floats is too wide", a.e);
+  AREAD_REQUIRE(a.e <= 16 * kChunk, "rowpass_bwd: embedding row of %d floats is too wide (max %d)", a.e, 16 * kChunk);
   AREAD_REQUIRE(a.d_w && a.d_p && a.d_c && a.workspace, "rowpass_bwd: null pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (a.m == 0) {
@@ -284,27 +300,26 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
                                                    ? (a.m + kThreads - 1) / kThreads
                                                    : kNumSMs * 8);
   AREAD_LAUNCH(rowpass_prologue_bwd_kernel, egrid, kThreads, 0, stream, a);
-  const size_t smem = (static_cast<size_t>(nj) * a.e + static_cast<size_t>(kTileRows) * nj) * sizeof(float);
-  AREAD_REQUIRE(smem <= 200 * 1024, "rowpass_bwd: embedding row of %d floats is too wide", a.e);
   float* partial = static_cast<float*>(a.workspace);
-#define AREAD_ROWDOTS_BWD(C)                                                                                          \
-  do {                                                                                                                \
-    AREAD_CUDA(cudaFuncSetAttribute(rowdots_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    AREAD_LAUNCH(rowdots_bwd_kernel<C>, ctas, kThreads, smem, stream, a.m, a.e, nj, a.ldp, a.x, a.w, a.d_p, a.d_x,     \
-                 partial);                                                                                            \
-  } while (0)
-  switch ((a.e + kThreads - 1) / kThreads) {
-    case 1: AREAD_ROWDOTS_BWD(1); break;
-    case 2: AREAD_ROWDOTS_BWD(2); break;
-    case 3: AREAD_ROWDOTS_BWD(3); break;
-    case 4: AREAD_ROWDOTS_BWD(4); break;
-    case 5: AREAD_ROWDOTS_BWD(5); break;
-    default: AREAD_ROWDOTS_BWD(6); break;
-  }
+  const int n_chunks = (a.e + kChunk - 1) / kChunk;
+  for (int j0 = 0; j0 < nj; j0 += kJ) {
+    const int njb = nj - j0 < kJ ? nj - j0 : kJ;
+    const float* w = a.w + static_cast<int64_t>(j0) * a.e;
+    float* part = partial + static_cast<int64_t>(ctas) * j0 * a.e;
+    const int acc_dx = j0 > 0 ? 1 : 0;
+#define AREAD_ROWDOTS_BWD(C) \
+  AREAD_LAUNCH(rowdots_bwd_kernel<C>, ctas, kThreads, 0, stream, a.m, a.e, njb, a.ldp, a.x, w, a.d_p + j0, a.d_x, \
+               acc_dx, part)
+    if (n_chunks <= 2) AREAD_ROWDOTS_BWD(2);
+    else if (n_chunks <= 5) AREAD_ROWDOTS_BWD(5);
+    else if (n_chunks <= 8) AREAD_ROWDOTS_BWD(8);
+    else if (n_chunks <= 12) AREAD_ROWDOTS_BWD(12);
+    else AREAD_ROWDOTS_BWD(16);
 #undef AREAD_ROWDOTS_BWD
-  const int64_t elems = static_cast<int64_t>(nj) * a.e;
-  AREAD_LAUNCH(rowdots_bwd_reduce_kernel, static_cast<unsigned>((elems + kThreads - 1) / kThreads), kThreads, 0, stream,
-               ctas, elems, partial, a.d_w);
+    const int64_t elems = static_cast<int64_t>(njb) * a.e;
+    AREAD_LAUNCH(rowdots_bwd_reduce_kernel, static_cast<unsigned>((elems + kThreads - 1) / kThreads), kThreads, 0,
+                 stream, ctas, elems, part, a.d_w + static_cast<int64_t>(j0) * a.e);
+  }
   return AREAD_OK;
 }
 

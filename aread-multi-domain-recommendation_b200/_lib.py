@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_s
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -97,14 +97,23 @@ class L2RegArgs(Structure):
 
 class TowerLinearArgs(Structure):
     _fields_ = [("m", c_int64), ("groups", c_int32), ("in_width", c_int32), ("out_width", c_int32),
-                ("weight_is_out_by_in", c_int32), ("in_", c_void_p), ("ld_in", c_int64), ("weight", c_void_p),
+                ("weight_is_out_by_in", c_int32), ("in_", c_void_p), ("ld_in", c_int64),
+                ("in_group_stride", c_int64), ("weight", c_void_p),
                 ("bias", c_void_p), ("out", c_void_p), ("ld_out", c_int64)]
 
 
 class TowerWgradArgs(Structure):
     _fields_ = [("m", c_int64), ("groups", c_int32), ("n", c_int32), ("k", c_int32), ("dz", c_void_p),
-                ("ld_dz", c_int64), ("in_", c_void_p), ("ld_in", c_int64), ("d_w", c_void_p),
+                ("ld_dz", c_int64), ("in_", c_void_p), ("ld_in", c_int64), ("in_group_stride", c_int64),
+                ("d_w", c_void_p),
                 ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
+
+
+class GateMixArgs(Structure):
+    _fields_ = [("m", c_int64), ("n_tower", c_int32), ("n_prev", c_int32), ("n_prev_active", c_int32),
+                ("width", c_int32), ("logits", c_void_p), ("edges", c_void_p), ("prev_slot", c_void_p),
+                ("slot_tower", c_void_p), ("u_prev", c_void_p), ("out", c_void_p), ("sm", c_void_p),
+                ("d_out", c_void_p), ("d_logits", c_void_p), ("d_u_prev", c_void_p), ("r_scratch", c_void_p)]
 
 
 _SIGNATURES = {
@@ -128,6 +137,7 @@ _SIGNATURES = {
     "aread_tower_linear": (c_int32, [POINTER(TowerLinearArgs), c_void_p]),
     "aread_tower_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "aread_tower_wgrad": (c_int32, [POINTER(TowerWgradArgs), c_void_p]),
+    "aread_gate_mix": (c_int32, [POINTER(GateMixArgs), c_void_p]),
     "aread_l2_reg_chunk": (c_int64, []),
     "aread_l2_reg_fwd": (c_int32, [POINTER(L2RegArgs), c_void_p]),
     "aread_l2_reg_bwd": (c_int32, [POINTER(L2RegArgs), c_void_p, c_void_p]),

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import dense_ops, hemp
+from . import dense_ops, fused, hemp
 from .expert_ops import ExpertLayer
 from .layer import BaseModel, CrossNetwork, MultiLayerPerceptron, _weights_without_bn
 from .packing import PackSet
@@ -118,6 +118,9 @@ class AREAD(BaseModel):
         object.__setattr__(self, "_packs", packs)
         object.__setattr__(self, "_expert_layers", layers)
         object.__setattr__(self, "_tower_layers", tower_layers)
+        object.__setattr__(self, "_fused", fused.ModelPacks(self, packs, layers, tower_layers))
+        object.__setattr__(self, "_fused_params", fused.param_list(self))
+        object.__setattr__(self, "_slot_cache", {})
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -131,7 +134,7 @@ class AREAD(BaseModel):
         clone = cls.__new__(cls)
         memo[id(self)] = clone
         for k, v in self.__dict__.items():
-            if k not in ("_packs", "_expert_layers", "_tower_layers"):
+            if k not in ("_packs", "_expert_layers", "_tower_layers", "_fused", "_fused_params", "_slot_cache"):
                 setattr(clone, k, copy.deepcopy(v, memo))
         clone._build_packs()
         return clone

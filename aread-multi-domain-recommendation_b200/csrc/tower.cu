@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kThreads) tower_linear_kernel(const aread_towe
   }
   for (int idx = threadIdx.x; idx < tile_rows * I; idx += kThreads) {
     const int r = idx / I, i = idx - r * I;
-    sIn[r * (I + 1) + i] = b0 + r < a.m ? __ldg(a.in + (b0 + r) * a.ld_in + static_cast<int64_t>(g) * I + i) : 0.f;
+    sIn[r * (I + 1) + i] = b0 + r < a.m ? __ldg(a.in + (b0 + r) * a.ld_in + static_cast<int64_t>(g) * a.in_group_stride + i) : 0.f;
   }
   __syncthreads();
 
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) tower_wgrad_kernel(const aread_tower
     }
     for (int idx = threadIdx.x; idx < kWgradTile * Kp; idx += kThreads) {
       const int r = idx / Kp, k = idx - r * Kp;
-      sIn[idx] = (r < rows && k < K) ? __ldg(a.in + (b0 + r) * a.ld_in + static_cast<int64_t>(g) * K + k) : 0.f;
+      sIn[idx] = (r < rows && k < K) ? __ldg(a.in + (b0 + r) * a.ld_in + static_cast<int64_t>(g) * a.in_group_stride + k) : 0.f;
     }
     __syncthreads();
     if (live) {
@@ -158,6 +158,103 @@ __global__ void __launch_bounds__(kThreads) tower_wgrad_reduce_kernel(int n_chun
     float acc = 0.f;
     for (int c = 0; c < n_chunks; ++c) acc += partial[static_cast<int64_t>(c) * elems + i];
     d_w[i] = acc;
+  }
+}
+
+
+// ------------------------------------------------------------------------------- gate mixing
+// HEI gate of one level (model/aread.py:282-288): s = softmax(logits); under a HEMP mask
+// sm = s * edge, r = sm / (sum sm + 1e-8), without a mask r = s; the tower's input is the r-weighted
+// sum of the previous level's outputs.  Row-local: one thread per (sample, tower).
+constexpr int kMaxPrev = 32;
+
+__device__ __forceinline__ void gate_weights(const aread_gate_mix_args& a, const float* __restrict__ lg, int t,
+                                             float* s, float* r, float& denom) {
+  float mx = -INFINITY;
+  for (int j = 0; j < a.n_prev; ++j) mx = fmaxf(mx, lg[j]);
+  float sum = 0.f;
+  for (int j = 0; j < a.n_prev; ++j) { s[j] = expf(lg[j] - mx); sum += s[j]; }
+  const float inv = 1.f / sum;
+  denom = 1.f;
+  if (a.edges != nullptr) {
+    float tot = 0.f;
+    for (int j = 0; j < a.n_prev; ++j) { s[j] *= inv; r[j] = s[j] * __ldg(a.edges + t * a.n_prev + j); tot += r[j]; }
+    denom = tot + 1e-8f;
+    for (int j = 0; j < a.n_prev; ++j) r[j] = r[j] / denom;
+  } else {
+    for (int j = 0; j < a.n_prev; ++j) { s[j] *= inv; r[j] = s[j]; }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) gate_mix_fwd_kernel(const aread_gate_mix_args a) {
+  const int64_t total = a.m * a.n_tower;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = p / a.n_tower;
+    const int t = static_cast<int>(p - b * a.n_tower);
+    float s[kMaxPrev], r[kMaxPrev], denom;
+    gate_weights(a, a.logits + p * a.n_prev, t, s, r, denom);
+    if (a.sm != nullptr)
+      for (int j = 0; j < a.n_prev; ++j)
+        a.sm[p * a.n_prev + j] = a.edges ? s[j] * __ldg(a.edges + t * a.n_prev + j) : s[j];
+    float* out = a.out + p * a.width;
+    for (int c = 0; c < a.width; ++c) {
+      float acc = 0.f;
+      for (int j = 0; j < a.n_prev; ++j) {
+        const int slot = __ldg(a.prev_slot + j);
+        if (slot >= 0) acc = fmaf(r[j], __ldg(a.u_prev + (b * a.n_prev_active + slot) * a.width + c), acc);
+      }
+      out[c] = acc;
+    }
+  }
+}
+
+// d_logits[b, t, :] and the mixing weights r[b, t, :] (scratch for the second pass)
+__global__ void __launch_bounds__(kThreads) gate_mix_bwd_logits_kernel(const aread_gate_mix_args a) {
+  const int64_t total = a.m * a.n_tower;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = p / a.n_tower;
+    const int t = static_cast<int>(p - b * a.n_tower);
+    float s[kMaxPrev], r[kMaxPrev], dr[kMaxPrev], denom;
+    gate_weights(a, a.logits + p * a.n_prev, t, s, r, denom);
+    const float* d_out = a.d_out + p * a.width;
+    float dot_r = 0.f;
+    for (int j = 0; j < a.n_prev; ++j) {
+      const int slot = __ldg(a.prev_slot + j);
+      float acc = 0.f;
+      if (slot >= 0) {
+        const float* u = a.u_prev + (b * a.n_prev_active + slot) * a.width;
+        for (int c = 0; c < a.width; ++c) acc = fmaf(__ldg(d_out + c), __ldg(u + c), acc);
+      }
+      dr[j] = acc;
+      dot_r = fmaf(acc, r[j], dot_r);
+      a.r_scratch[p * a.n_prev + j] = r[j];
+    }
+    float dot_s = 0.f;
+    for (int j = 0; j < a.n_prev; ++j) {  // dr -> ds (through the renormalisation and the mask)
+      if (a.edges != nullptr) dr[j] = (dr[j] - dot_r) / denom * __ldg(a.edges + t * a.n_prev + j);
+      dot_s = fmaf(s[j], dr[j], dot_s);
+    }
+    for (int j = 0; j < a.n_prev; ++j) a.d_logits[p * a.n_prev + j] = s[j] * (dr[j] - dot_s);
+  }
+}
+
+// d_u_prev[b, slot, :] = sum_t r[b, t, j(slot)] * d_out[b, t, :]   (towers in ascending order)
+__global__ void __launch_bounds__(kThreads) gate_mix_bwd_prev_kernel(const aread_gate_mix_args a) {
+  const int64_t total = a.m * a.n_prev_active * a.width;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(p % a.width);
+    const int64_t q = p / a.width;
+    const int slot = static_cast<int>(q % a.n_prev_active);
+    const int64_t b = q / a.n_prev_active;
+    const int j = __ldg(a.slot_tower + slot);
+    float acc = 0.f;
+    for (int t = 0; t < a.n_tower; ++t)
+      acc = fmaf(__ldg(a.r_scratch + (b * a.n_tower + t) * a.n_prev + j), __ldg(a.d_out + (b * a.n_tower + t) * a.width + c),
+                 acc);
+    a.d_u_prev[p] = acc;
   }
 }
 
@@ -245,3 +342,30 @@ int aread_tower_wgrad(const aread_tower_wgrad_args* args, aread_stream_t stream_
 }
 
 }  // extern "C"
+
+extern "C" int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "gate_mix: null args");
+  const aread_gate_mix_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.n_tower > 0 && a.n_prev > 0 && a.n_prev <= kMaxPrev && a.n_prev_active >= 0 && a.width > 0,
+                "gate_mix: bad shape (n_prev %d, max %d)", a.n_prev, kMaxPrev);
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.logits && a.prev_slot && (a.u_prev || a.n_prev_active == 0), "gate_mix: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  auto grid_for = [](int64_t total) {
+    int64_t g = (total + kThreads - 1) / kThreads;
+    const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+    return static_cast<unsigned>(g < 1 ? 1 : (g > cap ? cap : g));
+  };
+  if (a.d_out == nullptr) {
+    AREAD_REQUIRE(a.out != nullptr, "gate_mix: null out");
+    AREAD_LAUNCH(gate_mix_fwd_kernel, grid_for(a.m * a.n_tower), kThreads, 0, stream, a);
+  } else {
+    AREAD_REQUIRE(a.d_logits && a.r_scratch && (a.d_u_prev || a.n_prev_active == 0) && a.slot_tower,
+                  "gate_mix: null gradient pointer");
+    AREAD_LAUNCH(gate_mix_bwd_logits_kernel, grid_for(a.m * a.n_tower), kThreads, 0, stream, a);
+    if (a.n_prev_active > 0 && a.d_u_prev != nullptr)
+      AREAD_LAUNCH(gate_mix_bwd_prev_kernel, grid_for(a.m * a.n_prev_active * a.width), kThreads, 0, stream, a);
+  }
+  return AREAD_OK;
+}

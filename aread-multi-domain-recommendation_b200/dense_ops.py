@@ -69,30 +69,12 @@ def _require_cuda(model, x):
 
 
 def aread_forward(model, x, info: Optional[MaskInfo], want_gate_means=False, want_gates=False) -> ForwardOut:
-    """Embedding lookup -> trunk -> HEI levels -> per-tower probabilities."""
+    """Embedding lookup -> trunk -> HEI levels -> per-tower probabilities, as one fused autograd node
+    (fused.py)."""
     _require_cuda(model, x)
-    precise = model.expert_precision == "bf16x3"
-    embed_x, x_bf16 = model.embedding.lookup(x, want_bf16=True, want_lo=precise)
-    domain_embed = embed_x[:, model.domain_idx, :]
-    X = embed_x.flatten(start_dim=1)
-    # towers that do not run: their MMoE gate / output head is never evaluated (parameters keep grad None)
-    active0 = list(range(model.n_tower[0])) if info is None else [int(t) for t in np.nonzero(info.active[0])[0]]
-    active_last = list(range(model.n_tower[-1])) if info is None else [int(t) for t in info.active_last]
-    lin, gate, head_cross = rowpass_ops.rowpass(model, X, active0, active_last)
-    training = model.training
-    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and model.dropout_p > 0) else 0
-    mixed = expert_ops.expert_stack(X, x_bf16, gate, model._expert_layers, training, model.dropout_p, seed, precise)
-    if info is None:
-        group_embed = torch.zeros_like(domain_embed)                                 # aread.py:157
-    else:
-        group_embed = model.group_embedding(info.group_index(x.device))
-        if group_embed.shape[0] > 1:
-            group_embed = group_embed.mean(dim=0, keepdim=True)
-        group_embed = group_embed.expand(x.shape[0], -1)
-    q = torch.cat([domain_embed, group_embed], dim=1)
-    out = hei_levels(model, mixed, q, head_cross, lin, info, seed, want_gate_means, want_gates)
-    out.gate_inputs = q
-    return out
+    from . import fused
+    probs, cfg = fused.forward(model, x, info, want_gate_means, want_gates)
+    return ForwardOut(probs=probs, gate_inputs=cfg["gate_inputs"], gate_means=cfg["gate_means"], gates=cfg["gates"])
 
 
 def hei_levels(model, level0_in, q, head_cross, lin, info: Optional[MaskInfo], seed, want_gate_means=False,

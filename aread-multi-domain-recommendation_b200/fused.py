@@ -1,0 +1,418 @@
+"""The whole AREAD forward (lookup -> row pass -> experts -> HEI levels -> heads) as ONE autograd node.
+
+PyTorch sees a single Function whose inputs are the id batch and every parameter on the path and
+whose output is the stack of per-tower probabilities; inside, forward and backward are straight
+sequences of C-ABI kernel launches (csrc/*.cu) on packed parameter storage.  Nothing here is
+traced or compiled; the few torch calls left operate on parameter-sized vectors (assembling the
+row-pass weight matrix, the cross-network constants) or allocate buffers.
+
+Reference: model/aread.py:129-322 (forward modes + hier_tower_mask_forward).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import dense_kernels as dk
+from . import embedding_ops
+from . import rowpass_ops
+from . import tower_ops
+from .expert_ops import _hi, _lo
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def gate_mix_fwd(logits, edges, prev_slot, u_prev, n_prev_active, width, want_sm):
+    B, na, n_prev = logits.shape
+    out = torch.empty((B, na, width), dtype=torch.float32, device=logits.device)
+    sm = torch.empty((B, na, n_prev), dtype=torch.float32, device=logits.device) if want_sm else None
+    a = _lib.GateMixArgs(B, na, n_prev, n_prev_active, width, logits.data_ptr(),
+                         edges.data_ptr() if edges is not None else None, prev_slot.data_ptr(), None,
+                         u_prev.data_ptr(), out.data_ptr(), sm.data_ptr() if want_sm else None, None, None, None, None)
+    _lib.check(_lib.load().aread_gate_mix(ctypes.byref(a), _stream(logits.device)))
+    return out, sm
+
+
+def gate_mix_bwd(logits, edges, prev_slot, slot_tower, u_prev, d_out):
+    B, na, n_prev = logits.shape
+    nap, width = u_prev.shape[1], u_prev.shape[2]
+    dev = logits.device
+    d_logits = torch.empty((B, na, n_prev), dtype=torch.float32, device=dev)
+    d_u = torch.empty((B, nap, width), dtype=torch.float32, device=dev)
+    scratch = torch.empty((B, na, n_prev), dtype=torch.float32, device=dev)
+    a = _lib.GateMixArgs(B, na, n_prev, nap, width, logits.data_ptr(), edges.data_ptr() if edges is not None else None,
+                         prev_slot.data_ptr(), slot_tower.data_ptr(), u_prev.data_ptr(), None, None, d_out.data_ptr(),
+                         d_logits.data_ptr(), d_u.data_ptr(), scratch.data_ptr())
+    _lib.check(_lib.load().aread_gate_mix(ctypes.byref(a), _stream(dev)))
+    return d_logits, d_u
+
+
+class ModelPacks:
+    """Packed views of every parameter family the fused path reads (packing.py)."""
+
+    def __init__(self, model, packs, expert_layers, tower_layers):
+        self.experts = expert_layers
+        self.towers = tower_layers
+        self.mmoe_w = packs.add(lambda: [g[0].weight for g in model.mmoe_gates])          # [n0, NE, E]
+        self.mmoe_b = packs.add(lambda: [g[0].bias for g in model.mmoe_gates])            # [n0, NE]
+        self.cn_w = packs.add(lambda: [lin.weight for lin in model.cn.w])                 # [nc, 1, E]
+        self.cn_b = packs.add(lambda: list(model.cn.b))                                   # [nc, E]
+        self.tl_w = packs.add(lambda: [lin.weight for lin in model.towers_linear])        # [n_last, 1, E + w]
+        self.gate_w = [None] + [packs.add(lambda l=l: [g[0].weight for g in model.tower_gates[l - 1]])
+                                for l in range(1, model.n_level)]                         # [n_l, n_prev, 2D]
+        self.gate_b = [None] + [packs.add(lambda l=l: [g[0].bias for g in model.tower_gates[l - 1]])
+                                for l in range(1, model.n_level)]
+
+
+def param_list(model):
+    """Every parameter the fused node differentiates, in the order its backward returns gradients."""
+    ps = [model.embedding.embedding_dict.weight, model.linear.fc.weight, model.linear.fc.bias,
+          model.group_embedding.weight]
+    ps += [lin.weight for lin in model.cn.w] + list(model.cn.b)
+    ps += [g[0].weight for g in model.mmoe_gates] + [g[0].bias for g in model.mmoe_gates]
+    for L in model._expert_layers:
+        ps += L.params
+    for level in model._tower_layers:
+        for L in level:
+            ps += L.params
+    for l in range(1, model.n_level):
+        ps += [g[0].weight for g in model.tower_gates[l - 1]] + [g[0].bias for g in model.tower_gates[l - 1]]
+    ps += [lin.weight for lin in model.towers_linear]
+    return ps
+
+
+def _sel(flat, index):
+    return flat if index is None else flat.index_select(0, index)
+
+
+class AreadNode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg, *params):
+        model, info = cfg["model"], cfg["info"]
+        P = model._fused
+        dev = x.device
+        training, p_drop, precise = model.training, model.dropout_p, cfg["precise"]
+        seed = cfg["seed"]
+        n_level, n_tower = model.n_level, model.n_tower
+        D, E = model.embed_dim, model.embed_output_dim
+        B = x.shape[0]
+        bn_skip = B == 1
+        sv = {}                                                     # tensors kept for the backward
+
+        # ---- lookup
+        plan = model.embedding.plan(dev)
+        table = model.embedding.embedding_dict.weight
+        embed, xb = embedding_ops.gather(plan, table, x, want_bf16=True, want_lo=precise)
+        X = embed.view(B, E)
+
+        # ---- which towers run
+        active = [list(range(n)) for n in n_tower] if info is None else info.active_idx
+        index = [None if (info is None or len(active[l]) == n_tower[l]) else info.index(l, dev)
+                 for l in range(n_level)]
+        a0, a_last = active[0], active[-1]
+        n_expert = len(model.mmoe_experts)
+        n_cross = model.cn.num_layers
+
+        # ---- row pass: [linear | gates of active level-0 towers | cross | heads of active last-level towers]
+        w_out = _sel(P.tl_w.flat, index[-1])[:, 0, :]                                  # [na_last, E + w]
+        w_cat = torch.cat([model.linear.fc.weight, _sel(P.mmoe_w.flat, index[0]).reshape(-1, E),
+                           P.cn_w.flat.view(n_cross, E), w_out[:, :E]], dim=0)
+        beta = torch.cumsum(P.cn_b.flat, dim=0)                                          # beta_{k+1} = b_0 + .. + b_k
+        kappa = torch.zeros(n_cross, dtype=torch.float32, device=dev)
+        if n_cross > 1:
+            kappa[1:] = (P.cn_w.flat.view(n_cross, E)[1:] * beta[:-1]).sum(dim=1)
+        beta_n = beta[-1] if n_cross > 0 else torch.zeros(E, dtype=torch.float32, device=dev)
+        offset = torch.cat([model.linear.fc.bias, _sel(P.mmoe_b.flat, index[0]).reshape(-1), kappa,
+                            w_out[:, :E] @ beta_n], dim=0)
+        layout = (len(a0), n_expert, n_cross, len(a_last))
+        nj = w_cat.shape[0]
+        ldp = (nj + 3) // 4 * 4
+        p_dots = torch.empty((B, ldp), dtype=torch.float32, device=dev)
+        lin = torch.empty((B,), dtype=torch.float32, device=dev)
+        gate = torch.empty((B, len(a0), n_expert), dtype=torch.float32, device=dev)
+        alpha = torch.empty((B, n_cross + 1), dtype=torch.float32, device=dev)
+        head_cross = torch.empty((B, len(a_last)), dtype=torch.float32, device=dev)
+        ra = rowpass_ops._args(B, E, layout, ldp, x=X, w=w_cat, offset=offset, p=p_dots, lin=lin, gate=gate,
+                               alpha=alpha, head=head_cross)
+        _lib.check(_lib.load().aread_rowpass_fwd(ctypes.byref(ra), _stream(dev)))
+        sv.update(X=X, w_cat=w_cat, p_dots=p_dots, gate=gate, alpha=alpha, beta=beta, w_out=w_out, layout=layout, ldp=ldp)
+
+        # ---- experts (tensor cores) + MMoE mixture
+        G = P.experts[0].groups
+        a_op = xb
+        ex = []
+        for i, L in enumerate(P.experts):
+            w = dk.split_bf16(L.weight.rows()) if precise else L.weight.rows().to(torch.bfloat16)
+            z = dk.grouped_linear(_hi(a_op), _hi(w), L.bias.rows(), L.n, L.k, G, 0 if i == 0 else L.k,
+                                  a_lo=_lo(a_op), w_lo=_lo(w))
+            last = i == len(P.experts) - 1
+            res = dk.bn_act_fwd(z, L.gamma.rows(), L.beta.rows(), L.running_mean.rows(), L.running_var.rows(),
+                                training, bn_skip, p_drop, seed, L.salt, None if last else torch.bfloat16,
+                                want_lo=precise and not last)
+            out, stats = (res[0], res[-1]) if not (precise and not last) else ((res[0], res[1]), res[2])
+            if training and not bn_skip:
+                torch._foreach_add_(L.tracked, 1)
+            ex.append((a_op, z, stats, w))
+            a_op = out
+        h = dk.mmoe_mix_fwd(ex[-1][1], ex[-1][2], gate, G, len(a0), p_drop if training else 0.0, seed,
+                            P.experts[-1].salt)                                          # [B, na0, H]
+        sv["experts"] = ex
+
+        # ---- gate inputs q = [domain embedding | mean group embedding of the active level-0 towers]
+        if info is None:
+            grp = torch.zeros(D, dtype=torch.float32, device=dev)
+        else:
+            grp = model.group_embedding.weight.index_select(0, info.group_index(dev)).mean(dim=0)
+        q = torch.cat([embed[:, model.domain_idx, :], grp.expand(B, D)], dim=1)          # [B, 2D]
+        sv["q"] = q
+
+        # ---- HEI levels on compact activations
+        gate_means, gates = {}, {}
+        levels = []
+        for l in range(n_level):
+            act, idx = active[l], index[l]
+            rec = {}
+            if l > 0:
+                n_prev = n_tower[l - 1]
+                wg, bg = _sel(P.gate_w[l].flat, idx), _sel(P.gate_b[l].flat, idx)
+                logits = tower_ops.tower_linear(q, wg, bg.reshape(-1), n_prev, groups=len(act))   # [B, na, n_prev]
+                edges = None if info is None else _sel(info.edges(l, dev).t().contiguous(), idx)
+                prev_slot, slot_tower = cfg["slots"][l]
+                want_sm = cfg["want_gate_means"] or cfg["want_gates"]
+                u_prev = h
+                h, sm = gate_mix_fwd(logits, edges, prev_slot, u_prev, len(active[l - 1]), u_prev.shape[2], want_sm)
+                if cfg["want_gates"]:
+                    gates[l] = sm.transpose(1, 2)                                        # [B, n_prev, n_l]
+                if cfg["want_gate_means"] and info is not None:
+                    means = sm.mean(dim=0).t()                                           # [n_prev, na]
+                    if idx is not None:     # towers that do not run report zeros (aread.py:278-280)
+                        means = torch.zeros(n_prev, n_tower[l], dtype=torch.float32,
+                                            device=dev).index_copy_(1, idx, means)
+                    gate_means[l] = means
+                rec.update(wg=wg, logits=logits, edges=edges, u_prev=u_prev)
+            lay = []
+            for L in P.towers[l]:
+                full = idx is None
+                w, bias = _sel(L.weight.flat, idx), _sel(L.bias.flat, idx)
+                gamma, beta_bn = _sel(L.gamma.flat, idx), _sel(L.beta.flat, idx)
+                rm, rv = _sel(L.running_mean.flat, idx), _sel(L.running_var.flat, idx)
+                z = tower_ops.tower_linear(h, w, bias, L.n)
+                na = len(act)
+                out, stats = dk.bn_act_fwd(z.view(B, na * L.n), gamma.reshape(-1), beta_bn.reshape(-1), rm.view(-1),
+                                           rv.view(-1), training, bn_skip, p_drop, seed, L.salt, torch.float32)
+                if training and not bn_skip:
+                    if not full:
+                        L.running_mean.flat.index_copy_(0, idx, rm)
+                        L.running_var.flat.index_copy_(0, idx, rv)
+                    tracked = L.tracked
+                    torch._foreach_add_([tracked[t] for t in act], 1)
+                lay.append((h, z, stats, w))
+                h = out.view(B, na, L.n)
+            rec["layers"] = lay
+            levels.append(rec)
+        sv["levels"] = levels
+
+        # ---- heads: z_t = w_out_t[:E] . cn_out + w_out_t[E:] . u_t + lin ; p = sigmoid(z)
+        w_tail = w_out[:, E:].contiguous()                                               # [na_last, w]
+        tail = tower_ops.tower_linear(h, w_tail.unsqueeze(1), None, 1)                   # [B, na_last, 1]
+        probs = torch.sigmoid(head_cross + tail.view(B, -1) + lin.unsqueeze(1)).t().contiguous()    # [na_last, B]
+        sv.update(h_last=h, w_tail=w_tail, probs=probs)
+
+        cfg["gate_means"], cfg["gates"], cfg["gate_inputs"] = gate_means, gates, q
+        ctx.cfg, ctx.sv = cfg, sv
+        ctx.active, ctx.index, ctx.bn_skip = active, index, bn_skip
+        ctx.x_ids = x
+        return probs
+
+    @staticmethod
+    def backward(ctx, d_probs):
+        cfg, sv = ctx.cfg, ctx.sv
+        model, info = cfg["model"], cfg["info"]
+        P = model._fused
+        active, index, bn_skip = ctx.active, ctx.index, ctx.bn_skip
+        training, precise, seed = model.training, cfg["precise"], cfg["seed"]
+        p_drop = model.dropout_p if training else 0.0
+        n_level, n_tower = model.n_level, model.n_tower
+        D, E = model.embed_dim, model.embed_output_dim
+        X = sv["X"]
+        B = X.shape[0]
+        dev = X.device
+        n_cross = model.cn.num_layers
+        n_expert = len(model.mmoe_experts)
+
+        probs = sv["probs"]
+        dz = (d_probs * probs * (1.0 - probs)).t().contiguous()                          # [B, na_last]
+        d_lin = dz.sum(dim=1)
+        na_last = dz.shape[1]
+        d_w_tail = tower_ops.tower_wgrad(dz.view(B, na_last, 1), sv["h_last"]).view(na_last, -1)
+        d_h = tower_ops.tower_linear(dz.view(B, na_last, 1), sv["w_tail"].unsqueeze(1), None, sv["w_tail"].shape[1],
+                                     weight_is_out_by_in=False)
+
+        tower_grads = [[None] * len(P.towers[l]) for l in range(n_level)]
+        gate_grads = [None] * n_level
+        d_q = None
+        for l in range(n_level - 1, -1, -1):
+            rec = sv["levels"][l]
+            na = len(active[l])
+            for j in range(len(P.towers[l]) - 1, -1, -1):
+                L = P.towers[l][j]
+                h_in, z, stats, w = rec["layers"][j]
+                dzl, d_gamma, d_beta, d_bias = dk.bn_act_bwd(z.view(B, na * L.n), d_h.contiguous().view(B, na * L.n),
+                                                             stats, bn_skip, p_drop, seed, L.salt, torch.float32)
+                dzl = dzl.view(B, na, L.n)
+                d_w = tower_ops.tower_wgrad(dzl, h_in)
+                tower_grads[l][j] = (d_w, d_bias.view(na, L.n), d_gamma.view(na, L.n), d_beta.view(na, L.n))
+                d_h = tower_ops.tower_linear(dzl, w, None, L.k, weight_is_out_by_in=False)
+            if l > 0:
+                prev_slot, slot_tower = cfg["slots"][l]
+                d_logits, d_u = gate_mix_bwd(rec["logits"], rec["edges"], prev_slot, slot_tower, rec["u_prev"],
+                                             d_h.contiguous())
+                n_prev = n_tower[l - 1]
+                d_wg = tower_ops.tower_wgrad(d_logits, sv["q"])                          # [na, n_prev, 2D]
+                d_bg = d_logits.sum(dim=0)                                               # [na, n_prev]
+                gate_grads[l] = (d_wg, d_bg)
+                dq_l = tower_ops.tower_linear(d_logits.view(B, 1, na * n_prev), rec["wg"].reshape(1, na * n_prev, 2 * D),
+                                              None, 2 * D, weight_is_out_by_in=False).view(B, 2 * D)
+                d_q = dq_l if d_q is None else d_q + dq_l
+                d_h = d_u
+
+        # ---- experts
+        ex = sv["experts"]
+        G = P.experts[0].groups
+        na0 = len(active[0])
+        d_act, d_gate = dk.mmoe_mix_bwd(ex[-1][1], ex[-1][2], sv["gate"], d_h.contiguous(), G, na0, p_drop, seed,
+                                        P.experts[-1].salt)
+        expert_grads = [None] * len(P.experts)
+        d_x = None
+
+        def tr(w, fn):
+            return tuple(fn(t) for t in w) if isinstance(w, tuple) else fn(w)
+
+        for i in range(len(P.experts) - 1, -1, -1):
+            L = P.experts[i]
+            a_in, z, stats, w = ex[i]
+            dze, d_gamma, d_beta, d_bias = dk.bn_act_bwd(z, d_act, stats, bn_skip, p_drop, seed, L.salt, want_lo=precise)
+            d_w = dk.grouped_wgrad(_hi(dze), _hi(a_in), L.n, L.k, G, 0 if i == 0 else L.k, dz_lo=_lo(dze), a_lo=_lo(a_in))
+            expert_grads[i] = (d_w.view(G, L.n, L.k), d_bias.view(G, L.n), d_gamma.view(G, L.n), d_beta.view(G, L.n))
+            if i > 0:
+                wt = tr(w, lambda t: t.view(G, L.n, L.k).transpose(1, 2).reshape(G * L.k, L.n).contiguous())
+                d_act = dk.grouped_linear(_hi(dze), _hi(wt), None, L.k, L.n, G, L.n, a_lo=_lo(dze), w_lo=_lo(wt))
+            else:
+                wt = tr(w, lambda t: t.t().contiguous())
+                d_x = dk.grouped_linear(_hi(dze), _hi(wt), None, L.k, G * L.n, 1, 0, a_lo=_lo(dze), w_lo=_lo(wt))
+
+        # ---- row pass
+        layout, ldp = sv["layout"], sv["ldp"]
+        nj = sv["w_cat"].shape[0]
+        d_p = torch.empty((B, ldp), dtype=torch.float32, device=dev)
+        d_c = torch.empty((B, ldp), dtype=torch.float32, device=dev)
+        d_x_row = torch.empty((B, E), dtype=torch.float32, device=dev)
+        d_wcat = torch.empty((nj, E), dtype=torch.float32, device=dev)
+        need = int(_lib.load().aread_rowpass_workspace_bytes(B, E, nj))
+        ws = rowpass_ops._WS.get(dev)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            rowpass_ops._WS[dev] = ws
+        ra = rowpass_ops._args(B, E, layout, ldp, x=X, w=sv["w_cat"], p=sv["p_dots"], gate=sv["gate"], alpha=sv["alpha"],
+                               d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p, d_c=d_c, d_x=d_x_row, d_w=d_wcat,
+                               workspace=ws)
+        ra.workspace_bytes = ws.numel()
+        _lib.check(_lib.load().aread_rowpass_bwd(ctypes.byref(ra), _stream(dev)))
+        d_off = d_c[:, :nj].sum(dim=0)
+
+        # ---- gradient w.r.t. the embedding output -> table
+        d_x = d_x.add_(d_x_row)
+        if d_q is not None:
+            d_x.view(B, -1, D)[:, model.domain_idx, :] += d_q[:, :D]
+        plan = model.embedding.plan(dev)
+        d_table = embedding_ops.scatter(plan, ctx.x_ids, d_x)
+
+        # ---- unpack d_wcat / d_off into parameter gradients
+        ng = na0 * n_expert
+        c_cross, c_head = 1 + ng, 1 + ng + n_cross
+        d_lin_w, d_lin_b = d_wcat[0:1], d_off[0:1]
+        d_mmoe_w, d_mmoe_b = d_wcat[1:c_cross].view(na0, n_expert, E), d_off[1:c_cross].view(na0, n_expert)
+        d_cn_w = d_wcat[c_cross:c_head].clone()                                          # [nc, E]
+        d_head_w = d_wcat[c_head:]                                                       # [na_last, E]
+        d_kappa, d_rho = d_off[c_cross:c_head], d_off[c_head:]
+        beta, w_out = sv["beta"], sv["w_out"]
+        cn_w = P.cn_w.flat.view(n_cross, E)
+        # kappa_k = w_k . beta_{k-1}(cum) ; rho_t = w_out_t[:E] . beta_n
+        d_beta = torch.zeros(n_cross, E, dtype=torch.float32, device=dev)               # d/d beta_cum[k]
+        if n_cross > 1:
+            d_cn_w[1:] += d_kappa[1:, None] * beta[:-1]
+            d_beta[:-1] += d_kappa[1:, None] * cn_w[1:]
+        if n_cross > 0:
+            d_beta[-1] += d_rho @ w_out[:, :E]
+            d_head_w = d_head_w + d_rho[:, None] * beta[-1]
+        d_cn_b = torch.flip(torch.cumsum(torch.flip(d_beta, dims=[0]), dim=0), dims=[0])  # beta_cum[k] = sum_{i<=k} b_i
+        d_tl = torch.cat([d_head_w, d_w_tail], dim=1)                                    # [na_last, E + w]
+
+        # ---- group embedding
+        d_grp_w = None
+        if info is not None and d_q is not None:
+            d_grp_w = torch.zeros_like(model.group_embedding.weight)
+            gi = info.group_index(dev)
+            d_grp_w.index_add_(0, gi, (d_q[:, D:].sum(dim=0) / gi.numel()).expand(gi.numel(), D))
+        elif info is not None:
+            d_grp_w = torch.zeros_like(model.group_embedding.weight)
+
+        # ---- assemble in param_list order
+        def scatter_rows(n_total, act, rows):
+            out = [None] * n_total
+            for i, t in enumerate(act):
+                out[t] = rows[i]
+            return out
+
+        grads = [d_table, d_lin_w, d_lin_b, d_grp_w]
+        grads += [d_cn_w[k:k + 1] for k in range(n_cross)] + [d_cn_b[k] for k in range(n_cross)]
+        grads += scatter_rows(n_tower[0], active[0], d_mmoe_w) + scatter_rows(n_tower[0], active[0], d_mmoe_b)
+        for g4 in expert_grads:
+            for tens in g4:
+                grads += list(tens.unbind(0))
+        for l in range(n_level):
+            for j in range(len(P.towers[l])):
+                for tens in tower_grads[l][j]:
+                    grads += scatter_rows(n_tower[l], active[l], tens)
+        for l in range(1, n_level):
+            grads += scatter_rows(n_tower[l], active[l], gate_grads[l][0]) + \
+                scatter_rows(n_tower[l], active[l], gate_grads[l][1])
+        grads += scatter_rows(n_tower[-1], active[-1], d_tl.unsqueeze(1))
+        return (None, None, *grads)
+
+
+def slot_maps(active_prev, n_prev, device, cache):
+    """(prev_slot [n_prev] int32: compact index of previous-level tower j or -1, slot_tower [n_active])."""
+    key = (tuple(active_prev), n_prev, device)
+    got = cache.get(key)
+    if got is None:
+        slot = np.full(n_prev, -1, dtype=np.int32)
+        slot[np.asarray(active_prev, dtype=np.int64)] = np.arange(len(active_prev), dtype=np.int32)
+        got = (torch.from_numpy(slot).to(device), torch.tensor(active_prev, dtype=torch.int32, device=device))
+        cache[key] = got
+    return got
+
+
+def forward(model, x, info, want_gate_means=False, want_gates=False):
+    """Runs the fused node; returns (probs [n_active_last, B], cfg) where cfg carries the side outputs."""
+    table = model.embedding.embedding_dict.weight
+    x = embedding_ops.prepare_ids(x, table)
+    dev = x.device
+    training = model.training
+    n_level, n_tower = model.n_level, model.n_tower
+    active = [list(range(n)) for n in n_tower] if info is None else info.active_idx
+    slots = [None] + [slot_maps(active[l - 1], n_tower[l - 1], dev, model._slot_cache) for l in range(1, n_level)]
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and model.dropout_p > 0) else 0
+    cfg = {"model": model, "info": info, "precise": model.expert_precision == "bf16x3", "seed": seed, "slots": slots,
+           "want_gate_means": want_gate_means, "want_gates": want_gates}
+    probs = AreadNode.apply(x, cfg, *model._fused_params)
+    model.embedding.plan(dev).post_lookup(embedding_ops_bounds_mode())
+    return probs, cfg
+
+
+def embedding_ops_bounds_mode():
+    from . import layer
+    return layer.BOUNDS_MODE

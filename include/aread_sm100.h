@@ -367,8 +367,9 @@ typedef struct aread_tower_linear_args {
   int32_t in_width;             /* <= 256                                                   */
   int32_t out_width;            /* <= 128                                                   */
   int32_t weight_is_out_by_in;  /* 1: weight[g] is [out_width, in_width]; 0: [in_width, out_width] */
-  const float* in;              /* fp32 [m, ld_in], group g at columns g * in_width         */
+  const float* in;              /* fp32 [m, ld_in], group g at columns g * in_group_stride  */
   int64_t ld_in;
+  int64_t in_group_stride;      /* in_width for side-by-side groups, 0 = all groups read the same input */
   const float* weight;          /* fp32 [groups, ...] contiguous                            */
   const float* bias;            /* optional fp32 [groups * out_width]                       */
   float* out;                   /* fp32 [m, ld_out], group g at columns g * out_width       */
@@ -387,6 +388,7 @@ typedef struct aread_tower_wgrad_args {
   int64_t ld_dz;
   const float* in;              /* fp32 [m, ld_in]                                          */
   int64_t ld_in;
+  int64_t in_group_stride;      /* k for side-by-side groups, 0 = shared input              */
   float* d_w;                   /* fp32 [groups, n, k] contiguous                           */
   void* workspace;              /* aread_tower_wgrad_workspace_bytes(m, groups, n, k)       */
   size_t workspace_bytes;
@@ -394,6 +396,36 @@ typedef struct aread_tower_wgrad_args {
 
 AREAD_API size_t aread_tower_wgrad_workspace_bytes(int64_t m, int32_t groups, int32_t n, int32_t k);
 AREAD_API int aread_tower_wgrad(const aread_tower_wgrad_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * HEI gate mixing of one level, row-local (model/aread.py:282-288, and :169-171 without a mask):
+ *   s = softmax(logits[b, t, :]);  with a mask: sm = s * edges[t, :], r = sm / (sum sm + 1e-8); else r = s
+ *   out[b, t, :] = sum_j r[j] * u_prev[b, slot(j), :]
+ * `logits` are the gate Linear outputs for the towers that run (compact, ascending), `prev_slot[j]`
+ * is the compact index of previous-level tower j in u_prev (-1: that tower does not run, its output
+ * is zero) and `slot_tower` the inverse map.  Forward when d_out == NULL, else backward.
+ * `sm` (optional) receives s * edges: its batch mean is the gate value HEMP thresholds (aread.py:290-295).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_gate_mix_args {
+  int64_t m;
+  int32_t n_tower;          /* towers of this level that run                    */
+  int32_t n_prev;           /* all towers of the previous level (<= 32)         */
+  int32_t n_prev_active;    /* previous-level towers that run                   */
+  int32_t width;            /* output width of the previous level's towers      */
+  const float* logits;      /* [m, n_tower, n_prev]                             */
+  const float* edges;       /* [n_tower, n_prev] of 0/1, or NULL (no mask)      */
+  const int32_t* prev_slot; /* device [n_prev]                                  */
+  const int32_t* slot_tower;/* device [n_prev_active] (backward)                */
+  const float* u_prev;      /* [m, n_prev_active, width]                        */
+  float* out;               /* forward out [m, n_tower, width]                  */
+  float* sm;                /* forward optional out [m, n_tower, n_prev]        */
+  const float* d_out;       /* backward in [m, n_tower, width]                  */
+  float* d_logits;          /* backward out [m, n_tower, n_prev]                */
+  float* d_u_prev;          /* backward out [m, n_prev_active, width]           */
+  float* r_scratch;         /* backward scratch [m, n_tower, n_prev]            */
+} aread_gate_mix_args;
+
+AREAD_API int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t stream);
 
 #ifdef __cplusplus
 }

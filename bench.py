@@ -284,8 +284,9 @@ def run_ours(args, wl, rank, world, local_rank):
         "metric": "aread_train_samples_per_sec", "value": total_samples / (ms_dev * 1e-3), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "bf16" if model.expert_precision == "bf16" else "bf16x3", "data": "synthetic",
         "config": {"workload": f"{wl.name}_singledomain_B{B}", "batch_per_gpu": B, "n_tower": list(N_TOWER),
+                   "expert_precision": model.expert_precision + " operands, fp32 accumulate; everything else fp32",
                    "embed_dim": wl.embed_dim, "table_rows": wl.n_rows, "n_cols": wl.n_cols,
                    "mask_active_percent": args.active, "dropout": args.dropout, "optimizer": "torch.optim.Adam",
                    "parallelism": f"dp{world}",

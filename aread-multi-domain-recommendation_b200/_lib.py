@@ -116,6 +116,13 @@ class GateMixArgs(Structure):
                 ("d_out", c_void_p), ("d_logits", c_void_p), ("d_u_prev", c_void_p), ("r_scratch", c_void_p)]
 
 
+class AdamArgs(Structure):
+    _fields_ = [("n_tensors", c_int32), ("n_chunks", c_int64), ("params", c_void_p), ("grads", c_void_p),
+                ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("sizes", c_void_p), ("chunk_start", c_void_p),
+                ("step_size", c_void_p), ("bc2_sqrt", c_void_p), ("beta1", c_float), ("beta2", c_float),
+                ("eps", c_float), ("weight_decay", c_float)]
+
+
 _SIGNATURES = {
     "aread_last_error": (c_char_p, []),
     "aread_abi_version": (c_int32, []),
@@ -138,6 +145,8 @@ _SIGNATURES = {
     "aread_tower_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "aread_tower_wgrad": (c_int32, [POINTER(TowerWgradArgs), c_void_p]),
     "aread_gate_mix": (c_int32, [POINTER(GateMixArgs), c_void_p]),
+    "aread_adam_chunk": (c_int64, []),
+    "aread_adam_step": (c_int32, [POINTER(AdamArgs), c_void_p]),
     "aread_l2_reg_chunk": (c_int64, []),
     "aread_l2_reg_fwd": (c_int32, [POINTER(L2RegArgs), c_void_p]),
     "aread_l2_reg_bwd": (c_int32, [POINTER(L2RegArgs), c_void_p, c_void_p]),

@@ -1,0 +1,72 @@
+// Multi-tensor Adam step in one launch (coupled weight decay, the trainer's settings run.py:830-831).
+// Replaces torch.optim.Adam.step over the ~460 parameter tensors of AREAD: one pass that reads
+// p, g, m, v and writes p, m, v (7 x 4 B per element) instead of ~20 foreach passes.  Per-tensor step
+// counts arrive as precomputed bias corrections, so tensors whose gradient is None this step are
+// simply not in the list (their moments and step count stay untouched, like the reference).
+//
+// Arithmetic per element, in torch's order (torch/optim/adam.py _single_tensor_adam):
+//   g' = g + wd * p ;  m += (g' - m) * (1 - b1) ;  v = v * b2 + (1 - b2) * g' * g'
+//   p -= step_size * m / (sqrt(v) / bc2_sqrt + eps),  step_size = lr / (1 - b1^t), bc2_sqrt = sqrt(1 - b2^t)
+#include "common.cuh"
+
+namespace aread {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 4096;
+
+__device__ __forceinline__ int find_tensor(const int64_t* __restrict__ chunk_start, int n, int64_t chunk) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (chunk_start[mid] <= chunk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kThreads) adam_kernel(const aread_adam_args a) {
+  for (int64_t chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x) {
+    const int t = find_tensor(a.chunk_start, a.n_tensors, chunk);
+    float* __restrict__ p = a.params[t];
+    const float* __restrict__ g = a.grads[t];
+    float* __restrict__ m = a.exp_avg[t];
+    float* __restrict__ v = a.exp_avg_sq[t];
+    const float step_size = a.step_size[t], bc2_sqrt = a.bc2_sqrt[t];
+    const int64_t begin = (chunk - a.chunk_start[t]) * kChunk;
+    const int64_t end = min(a.sizes[t], begin + kChunk);
+    for (int64_t i = begin + threadIdx.x; i < end; i += kThreads) {
+      const float pi = p[i];
+      const float gi = __ldg(g + i) + a.weight_decay * pi;
+      float mi = m[i];
+      mi = mi + (gi - mi) * (1.f - a.beta1);
+      const float vi = v[i] * a.beta2 + (1.f - a.beta2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
+      p[i] = pi - step_size * (mi / denom);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace aread
+
+extern "C" {
+
+int64_t aread_adam_chunk(void) { return aread::kChunk; }
+
+int aread_adam_step(const aread_adam_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "adam_step: null args");
+  const aread_adam_args& a = *args;
+  if (a.n_tensors <= 0 || a.n_chunks <= 0) return AREAD_OK;
+  AREAD_REQUIRE(a.params && a.grads && a.exp_avg && a.exp_avg_sq && a.sizes && a.chunk_start && a.step_size &&
+                    a.bc2_sqrt,
+                "adam_step: null pointer");
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+  AREAD_LAUNCH(adam_kernel, static_cast<unsigned>(a.n_chunks < cap ? a.n_chunks : cap), kThreads, 0,
+               static_cast<cudaStream_t>(stream_), a);
+  return AREAD_OK;
+}
+
+}  // extern "C"

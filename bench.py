@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--active", type=float, default=0.7, help="HEMP init_active_percent of the per-domain masks")
     ap.add_argument("--dropout", type=float, default=0.2)
     ap.add_argument("--seed", type=int, default=2000)
+    ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
+                    help="torch.optim.Adam as run.py:830 builds it (default), or the library's FusedAdam")
     return ap.parse_args()
 
 
@@ -192,7 +194,9 @@ def run_ours(args, wl, rank, world, local_rank):
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
     model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=LR, betas=(0.9, 0.99), eps=1e-8, weight_decay=WD)
+    fused_adam = importlib.import_module("aread-multi-domain-recommendation_b200.optim").FusedAdam
+    adam_cls = fused_adam if args.optimizer == "fused" else torch.optim.Adam
+    opt = adam_cls(model.parameters(), lr=LR, betas=(0.9, 0.99), eps=1e-8, weight_decay=WD)
     crit = torch.nn.BCELoss()
     dense_params = [p for p in model.parameters()]
 
@@ -288,7 +292,8 @@ def run_ours(args, wl, rank, world, local_rank):
         "config": {"workload": f"{wl.name}_singledomain_B{B}", "batch_per_gpu": B, "n_tower": list(N_TOWER),
                    "expert_precision": model.expert_precision + " operands, fp32 accumulate; everything else fp32",
                    "embed_dim": wl.embed_dim, "table_rows": wl.n_rows, "n_cols": wl.n_cols,
-                   "mask_active_percent": args.active, "dropout": args.dropout, "optimizer": "torch.optim.Adam",
+                   "mask_active_percent": args.active, "dropout": args.dropout,
+                   "optimizer": "torch.optim.Adam" if args.optimizer == "torch" else "aread_b200 FusedAdam",
                    "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2: table %d MB + per-step activations" % (wl.n_rows * wl.embed_dim * 4 >> 20)},
         "e2e": {"value": total_samples / (ms_e2e * 1e-3), "unit": "samples/s",

@@ -427,6 +427,30 @@ typedef struct aread_gate_mix_args {
 
 AREAD_API int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Adam step over a list of fp32 tensors in one launch (coupled weight decay).  Replaces
+ * torch.optim.Adam.step as the trainer configures it (run.py:830-831: betas (0.9, 0.99), eps 1e-8,
+ * weight_decay 1e-8) -- SURVEY.md 8(f) rank 1.  Tensors without a gradient this step are left out of
+ * the list by the caller (moments and step counts untouched).  Chunking as in aread_l2_reg_args with
+ * aread_adam_chunk() elements per chunk.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_adam_args {
+  int32_t n_tensors;
+  int64_t n_chunks;
+  float* const* params;          /* device arrays [n_tensors] of device pointers        */
+  const float* const* grads;
+  float* const* exp_avg;
+  float* const* exp_avg_sq;
+  const int64_t* sizes;          /* device [n_tensors]                                  */
+  const int64_t* chunk_start;    /* device [n_tensors]                                  */
+  const float* step_size;        /* device [n_tensors]: lr / (1 - beta1^t)              */
+  const float* bc2_sqrt;         /* device [n_tensors]: sqrt(1 - beta2^t)               */
+  float beta1, beta2, eps, weight_decay;
+} aread_adam_args;
+
+AREAD_API int64_t aread_adam_chunk(void);
+AREAD_API int aread_adam_step(const aread_adam_args* args, aread_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,7 +59,7 @@ def test_every_declared_symbol_is_exported(lib):
                                          ("aread_bn_act_args", "BnActArgs"), ("aread_bn_act_bwd_args", "BnActBwdArgs"),
                                          ("aread_mmoe_mix_args", "MmoeMixArgs"), ("aread_rowpass_args", "RowpassArgs"),
                                          ("aread_l2_reg_args", "L2RegArgs"), ("aread_tower_linear_args", "TowerLinearArgs"),
-                                         ("aread_tower_wgrad_args", "TowerWgradArgs"), ("aread_gate_mix_args", "GateMixArgs")])
+                                         ("aread_tower_wgrad_args", "TowerWgradArgs"), ("aread_gate_mix_args", "GateMixArgs"), ("aread_adam_args", "AdamArgs")])
 def test_struct_fields_match_header(cname, ctype):
     fields = [f.rstrip("_") for f, _ in getattr(_lib, ctype)._fields_]      # `in` is a Python keyword
     assert fields == struct_fields(cname)

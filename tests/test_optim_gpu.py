@@ -1,0 +1,40 @@
+"""FusedAdam (C ABI: aread_adam_step) against torch.optim.Adam with the trainer's settings
+(run.py:830-831).  Same arithmetic order, so the tolerance is fp32 contraction noise."""
+import importlib
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+optim = importlib.import_module("aread-multi-domain-recommendation_b200.optim")
+DEV = "cuda:0"
+
+
+def test_fused_adam_matches_torch_adam():
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    shapes = [(50000, 32), (1, 288), (256, 288), (256,), (7,), (4097,), (64, 64), (3, 32)]
+    ref = [torch.randn(*s, device=DEV, generator=gen).requires_grad_(True) for s in shapes]
+    mine = [p.detach().clone().requires_grad_(True) for p in ref]
+    kw = dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+    o_ref, o_mine = torch.optim.Adam(ref, **kw), optim.FusedAdam(mine, **kw)
+    for step in range(6):
+        for i, (a, b) in enumerate(zip(ref, mine)):
+            if (step + i) % 4 == 3:                   # parameters without gradient are skipped entirely
+                a.grad = b.grad = None
+                continue
+            g = torch.randn(a.shape, device=DEV, generator=gen) * (10.0 ** ((i % 5) - 3))
+            a.grad, b.grad = g.clone(), g.clone()
+        o_ref.step()
+        o_mine.step()
+        for i, (a, b) in enumerate(zip(ref, mine)):
+            torch.testing.assert_close(b, a, rtol=1e-6, atol=1e-7, msg=f"param {i} step {step}")
+    for a, b in zip(ref, mine):
+        sa, sb = o_ref.state[a], o_mine.state[b]
+        assert float(sa["step"]) == float(sb["step"])
+        torch.testing.assert_close(sb["exp_avg"], sa["exp_avg"], rtol=5e-6, atol=1e-9)
+        torch.testing.assert_close(sb["exp_avg_sq"], sa["exp_avg_sq"], rtol=5e-6, atol=1e-12)
+    # state_dict round trip into a torch Adam keeps training identically
+    sd = o_mine.state_dict()
+    o_back = torch.optim.Adam(mine, **kw)
+    o_back.load_state_dict(sd)
+    assert len(o_back.state) == len(o_mine.state)

@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_s
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -32,13 +32,15 @@ class EmbedPlan(Structure):
 
 class GatherArgs(Structure):
     _fields_ = [("plan", EmbedPlan), ("batch", c_int64), ("x", c_void_p), ("table", c_void_p),
-                ("out", c_void_p), ("out_bf16", c_void_p), ("out_bf16_lo", c_void_p), ("status", c_void_p)]
+                ("out", c_void_p), ("out_bf16", c_void_p), ("out_bf16_lo", c_void_p), ("status", c_void_p),
+                ("shard_shift", c_int32), ("shards", c_void_p)]
 
 
 class ScatterArgs(Structure):
     _fields_ = [("plan", EmbedPlan), ("batch", c_int64), ("x", c_void_p), ("d_out", c_void_p),
                 ("d_table", c_void_p), ("zero_fill", c_int32), ("workspace", c_void_p),
-                ("workspace_bytes", c_size_t), ("sorted_rows", c_void_p), ("sorted_pos", c_void_p)]
+                ("workspace_bytes", c_size_t), ("sorted_rows", c_void_p), ("sorted_pos", c_void_p),
+                ("shard_shift", c_int32), ("shard_rows", c_int64)]
 
 
 class GroupedLinearArgs(Structure):
@@ -145,6 +147,9 @@ _SIGNATURES = {
     "aread_tower_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "aread_tower_wgrad": (c_int32, [POINTER(TowerWgradArgs), c_void_p]),
     "aread_gate_mix": (c_int32, [POINTER(GateMixArgs), c_void_p]),
+    "aread_ipc_export": (c_int32, [c_void_p, c_char_p, POINTER(c_int64)]),
+    "aread_ipc_open": (c_int32, [c_char_p, c_int64, c_int32, POINTER(c_void_p)]),
+    "aread_ipc_close": (c_int32, [c_void_p, c_int64]),
     "aread_adam_chunk": (c_int64, []),
     "aread_adam_step": (c_int32, [POINTER(AdamArgs), c_void_p]),
     "aread_l2_reg_chunk": (c_int64, []),

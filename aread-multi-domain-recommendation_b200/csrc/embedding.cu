@@ -77,13 +77,20 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const aread_gather_arg
   const int64_t n_rows = p.n_rows;
   const float* __restrict__ table = a.table + lane * 4;
   int* __restrict__ status = a.status;
+  const int shard_shift = a.shard_shift;
+  const int shard_mask = (1 << shard_shift) - 1;
 
   auto fetch = [&](const int* __restrict__ xr, int c, float4& v) {
     const int row = row_of(__ldg(xr + c), pv.col_offset[c]);
     if (row < 0 || row >= n_rows) {
       if (lane == 0 && atomicExch(status, 1) == 0) status[1] = row;
     } else if (lane_on) {
-      v = ldg4(table + static_cast<int64_t>(row) * D);
+      if (shard_shift == 0) {
+        v = ldg4(table + static_cast<int64_t>(row) * D);
+      } else {  // the owner's shard, local or peer-mapped over NVLink
+        const float* shard = a.shards[row & shard_mask];
+        v = *reinterpret_cast<const float4*>(shard + static_cast<int64_t>(row >> shard_shift) * D + lane * 4);
+      }
     }
   };
 
@@ -176,11 +183,17 @@ __global__ void __launch_bounds__(kThreads) scatter_unpack_kernel(const int* __r
 // keys / positions are loaded once (kTile / LPR per lane) and handed round by shuffles; gradient
 // rows are fetched eight at a time so the reads overlap, then consumed strictly in order.
 // ---------------------------------------------------------------------------------------------
+// row of the (possibly owner-major) gradient buffer that receives table row `key`
+__device__ __forceinline__ int64_t dest_row(unsigned key, int shard_shift, int64_t shard_rows) {
+  return shard_shift == 0 ? static_cast<int64_t>(key)
+                          : static_cast<int64_t>(key & ((1u << shard_shift) - 1u)) * shard_rows + (key >> shard_shift);
+}
+
 template <int LPR>
 __global__ void __launch_bounds__(kThreads) scatter_tile_kernel(
     const aread_embed_plan p, const unsigned* __restrict__ keys, const int* __restrict__ pos, int64_t n,
     int64_t n_tiles, int col_shift, const float* __restrict__ d_out, float* __restrict__ d_table,
-    float* __restrict__ carry_in, float* __restrict__ carry_out) {
+    float* __restrict__ carry_in, float* __restrict__ carry_out, int shard_shift, int64_t shard_rows) {
   extern __shared__ int smem[];
   int* s_field = smem;                                        // column -> output field
   float* s_div = reinterpret_cast<float*>(smem + p.n_cols);   // column -> fl32(1 / pooling divisor)
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(kThreads) scatter_tile_kernel(
     } else if (trailing) {
       if (lane_on) *reinterpret_cast<float4*>(carry_out + t * D + lane * 4) = acc;
     } else if (lane_on) {
-      *reinterpret_cast<float4*>(d_table + static_cast<int64_t>(key) * D + lane * 4) = acc;
+      *reinterpret_cast<float4*>(d_table + dest_row(key, shard_shift, shard_rows) * D + lane * 4) = acc;
     }
   };
 
@@ -283,7 +296,7 @@ template <int LPR>
 __global__ void __launch_bounds__(kThreads) scatter_level_kernel(
     int D, unsigned n_rows, const unsigned* __restrict__ keys, int64_t n, int64_t child_size, int64_t n_children,
     int64_t n_blocks, const float* __restrict__ in_c, const float* __restrict__ out_c, float* __restrict__ in_p,
-    float* __restrict__ out_p, float* __restrict__ d_table) {
+    float* __restrict__ out_p, float* __restrict__ d_table, int shard_shift, int64_t shard_rows) {
   constexpr int PER = 32 / LPR;  // children held per lane
   constexpr int BATCH = 4;       // children whose partials are fetched together
   const int lane = threadIdx.x % LPR;
@@ -318,7 +331,8 @@ __global__ void __launch_bounds__(kThreads) scatter_level_kernel(
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   auto flush = [&](bool trailing) {
     if (cur >= n_rows) return;
-    float* dst = leading ? in_p + J * D : (trailing ? out_p + J * D : d_table + static_cast<int64_t>(cur) * D);
+    float* dst = leading ? in_p + J * D
+                         : (trailing ? out_p + J * D : d_table + dest_row(cur, shard_shift, shard_rows) * D);
     if (lane_on) *reinterpret_cast<float4*>(dst + lane * 4) = acc;
   };
   auto element = [&](unsigned key, const float4& v, bool first_of_block) {
@@ -448,7 +462,7 @@ int launch_scatter(const aread_scatter_args& a, const ScatterWorkspace& w, int64
   const size_t smem = sizeof(int) * 2 * static_cast<size_t>(a.plan.n_cols);
   AREAD_LAUNCH((scatter_tile_kernel<LPR>), static_cast<unsigned>((n_tiles + groups_per_cta - 1) / groups_per_cta),
                kThreads, smem, stream, a.plan, w.keys_out, w.pos_out, n, n_tiles, col_shift, a.d_out, a.d_table,
-               w.in_a, w.out_a);
+               w.in_a, w.out_a, a.shard_shift, a.shard_rows);
   const float *in_c = w.in_a, *out_c = w.out_a;
   float *in_p = w.in_b, *out_p = w.out_b;
   int64_t child_size = kTile, n_children = n_tiles;
@@ -456,7 +470,7 @@ int launch_scatter(const aread_scatter_args& a, const ScatterWorkspace& w, int64
     const int64_t n_blocks = (n_children + 31) / 32;
     AREAD_LAUNCH((scatter_level_kernel<LPR>), static_cast<unsigned>((n_blocks + groups_per_cta - 1) / groups_per_cta),
                  kThreads, 0, stream, D, static_cast<unsigned>(a.plan.n_rows), w.keys_out, n, child_size, n_children,
-                 n_blocks, in_c, out_c, in_p, out_p, a.d_table);
+                 n_blocks, in_c, out_c, in_p, out_p, a.d_table, a.shard_shift, a.shard_rows);
     const float* t_in = in_c;
     const float* t_out = out_c;
     in_c = in_p;
@@ -481,7 +495,9 @@ int aread_gather_fwd(const aread_gather_args* args, aread_stream_t stream_) {
   if (int rc = check_plan(a.plan)) return rc;
   AREAD_REQUIRE(a.batch >= 0, "gather: negative batch");
   if (a.batch == 0) return AREAD_OK;
-  AREAD_REQUIRE(a.x && a.table && a.out && a.status, "gather: null pointer");
+  AREAD_REQUIRE(a.x && a.out && a.status, "gather: null pointer");
+  AREAD_REQUIRE(a.shard_shift >= 0 && a.shard_shift <= 6, "gather: shard_shift %d out of range", a.shard_shift);
+  AREAD_REQUIRE(a.shard_shift == 0 ? a.table != nullptr : a.shards != nullptr, "gather: null table");
   AREAD_REQUIRE((reinterpret_cast<uintptr_t>(a.table) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0,
                 "gather: table/out must be 16-byte aligned");
   AREAD_REQUIRE(a.out_bf16 == nullptr || reinterpret_cast<uintptr_t>(a.out_bf16) % 8 == 0,
@@ -514,8 +530,11 @@ int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream_) {
   AREAD_REQUIRE(a.d_table != nullptr, "scatter: null d_table");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int D = a.plan.embed_dim;
-  if (a.zero_fill)
-    AREAD_CUDA(cudaMemsetAsync(a.d_table, 0, static_cast<size_t>(a.plan.n_rows) * D * sizeof(float), stream));
+  AREAD_REQUIRE(a.shard_shift >= 0 && a.shard_shift <= 6 && (a.shard_shift == 0 || a.shard_rows > 0),
+                "scatter: bad shard layout");
+  const size_t grad_rows = a.shard_shift == 0 ? static_cast<size_t>(a.plan.n_rows)
+                                              : static_cast<size_t>(a.shard_rows) << a.shard_shift;
+  if (a.zero_fill) AREAD_CUDA(cudaMemsetAsync(a.d_table, 0, grad_rows * D * sizeof(float), stream));
   const int64_t n = a.batch * a.plan.n_cols;
   if (n == 0) return AREAD_OK;
   int col_shift = 0;

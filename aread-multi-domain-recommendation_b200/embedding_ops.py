@@ -58,6 +58,7 @@ class LookupPlan:
         self._status_host = torch.zeros(2, dtype=torch.int32).pin_memory()
         self._status_event = None
         self._workspace = None
+        self.shards = None               # sharding.TableShards when the table is row-sharded over GPUs
 
     def c_plan(self):
         return _lib.EmbedPlan(self.n_cols, self.n_fields, self.max_src, self.embed_dim, self.n_rows,
@@ -107,9 +108,13 @@ def gather(plan, table, x, want_bf16=False, want_lo=False):
     shape16 = (B, plan.n_fields * plan.embed_dim)
     out_bf16 = torch.empty(shape16, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     out_lo = torch.empty(shape16, dtype=torch.bfloat16, device=x.device) if (want_bf16 and want_lo) else None
+    sh = plan.shards
+    if sh is not None:
+        sh.fence()
     args = _lib.GatherArgs(plan.c_plan(), B, x.data_ptr(), table.data_ptr(), out.data_ptr(),
                            out_bf16.data_ptr() if want_bf16 else None,
-                           out_lo.data_ptr() if out_lo is not None else None, plan.status.data_ptr())
+                           out_lo.data_ptr() if out_lo is not None else None, plan.status.data_ptr(),
+                           sh.shift if sh is not None else 0, sh.ptrs.data_ptr() if sh is not None else None)
     _lib.check(_lib.load().aread_gather_fwd(ctypes.byref(args), _stream_ptr(x.device)))
     return out, ((out_bf16, out_lo) if want_lo else out_bf16)
 
@@ -119,15 +124,21 @@ def scatter(plan, x, d_out, d_table=None, zero_fill=True, want_sorted=False):
     (and, for the bookkeeping tests, the sorted rows / positions)."""
     B = x.shape[0]
     n = B * plan.n_cols
-    if d_table is None:
+    sh = plan.shards
+    if sh is not None:                   # owner-major full-size buffer, then reduce-scatter to the shard owner
+        d_table = sh.grad_buffer(x.device)
+    elif d_table is None:
         d_table = torch.empty((plan.n_rows, plan.embed_dim), dtype=torch.float32, device=x.device)
     ws = plan.workspace(n)
     rows = torch.empty(n, dtype=torch.int32, device=x.device) if want_sorted else None
     pos = torch.empty(n, dtype=torch.int32, device=x.device) if want_sorted else None
     args = _lib.ScatterArgs(plan.c_plan(), B, x.data_ptr(), d_out.data_ptr(), d_table.data_ptr(),
                             1 if zero_fill else 0, ws.data_ptr(), ws.numel(),
-                            rows.data_ptr() if want_sorted else None, pos.data_ptr() if want_sorted else None)
+                            rows.data_ptr() if want_sorted else None, pos.data_ptr() if want_sorted else None,
+                            sh.shift if sh is not None else 0, sh.rows if sh is not None else 0)
     _lib.check(_lib.load().aread_scatter_bwd(ctypes.byref(args), _stream_ptr(x.device)))
+    if sh is not None:
+        d_table = sh.reduce_grad(d_table)
     if want_sorted:
         return d_table, rows, pos
     return d_table

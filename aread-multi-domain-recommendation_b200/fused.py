@@ -399,6 +399,8 @@ def slot_maps(active_prev, n_prev, device, cache):
 def forward(model, x, info, want_gate_means=False, want_gates=False):
     """Runs the fused node; returns (probs [n_active_last, B], cfg) where cfg carries the side outputs."""
     table = model.embedding.embedding_dict.weight
+    if model._fused_params[0] is not table:        # the table parameter was replaced (shard_table, load)
+        model._fused_params[0] = table
     x = embedding_ops.prepare_ids(x, table)
     dev = x.device
     training = model.training

@@ -42,7 +42,8 @@ class FeaturesEmbedding(nn.Module):
         self.embed_dim = embed_dim
 
         dims = np.asarray(one_hot_field_dims, dtype=np.int64)
-        self.embedding_dict = nn.Embedding(int(dims.sum()), embed_dim)      # N(0, 1) init, as the reference
+        self._n_rows = int(dims.sum())
+        self.embedding_dict = nn.Embedding(self._n_rows, embed_dim)         # N(0, 1) init, as the reference
         starts = np.concatenate(([0], np.cumsum(dims)[:-1])).astype(np.int64)
         if self.multi_hot_field_num > 0:
             starts = np.concatenate((starts, np.full(n_mh_cols, starts[multi_hot_dict["itemid_idx"]])))
@@ -57,9 +58,24 @@ class FeaturesEmbedding(nn.Module):
             if flag.size != len(self.offsets):      # flag shorter than x: treat the missing columns as one-hot
                 flag = np.concatenate((flag, np.zeros(len(self.offsets) - flag.size, dtype=bool)))
             plan = embedding_ops.LookupPlan(self.offsets, flag, self.seq_maxlen, self.multi_hot_method,
-                                            self.embed_dim, self.embedding_dict.num_embeddings, device)
+                                            self.embed_dim, self._n_rows, device)
             self._plans[key] = plan
         return plan
+
+    def shard_table(self, group=None):
+        """Row-shard the table over the ranks of `group` (call after .to(device) and before building the
+        optimizer): `embedding_dict.weight` becomes this rank's [ceil(R / world), D] shard, lookups read
+        the other shards over NVLink and the gradient arrives reduce-scattered (sharding.py)."""
+        import torch.distributed as dist
+        from . import sharding
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        full = self.embedding_dict.weight.data
+        n_rows = full.shape[0]
+        self.embedding_dict.weight = nn.Parameter(sharding.split_table(full, world, rank))
+        shards = sharding.TableShards(self.embedding_dict.weight, n_rows, group)
+        plan = self.plan(full.device)
+        plan.shards = shards
+        return shards
 
     def lookup(self, x, want_bf16=False, want_lo=False):
         """(fp32 [batch, output_dim0, embed_dim], bf16 [batch, output_dim0 * embed_dim] or None); with

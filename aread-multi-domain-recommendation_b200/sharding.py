@@ -1,0 +1,109 @@
+"""Row-sharded embedding table over the GPUs of one NVSwitch box (one process per GPU).
+
+Global row r lives on rank r mod N at local row r // N (N a power of two: balances the skewed big
+fields).  Every rank maps all peers' shards into its own address space (CUDA IPC through torch's
+tensor-sharing plumbing) and the gather kernel reads remote rows straight over NVLink -- the lookup
+is the all-to-all of rows, no index exchange, no staging.  The gradient is scattered locally into an
+owner-major [N, rows_per_shard, D] buffer and reduce-scattered (NCCL) so that each rank receives the
+batch-averaged gradient of its own shard; dense parameters are all-reduced in one flat bucket.
+"""
+import ctypes
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_rows(n_rows, world):
+    return (n_rows + world - 1) // world
+
+
+def split_table(full, world, rank):
+    """Rows rank, rank + world, ... of `full` ([R, D]) padded with zero rows to shard_rows(R, world)."""
+    n = shard_rows(full.shape[0], world)
+    out = torch.zeros((n, full.shape[1]), dtype=full.dtype, device=full.device)
+    mine = full[rank::world]
+    out[:mine.shape[0]] = mine
+    return out
+
+
+def merge_shards(shards, n_rows):
+    """Inverse of split_table for a list of all ranks' shards (checkpointing / tests)."""
+    world = len(shards)
+    full = torch.empty((n_rows, shards[0].shape[1]), dtype=shards[0].dtype, device=shards[0].device)
+    for r, s in enumerate(shards):
+        full[r::world] = s[:full[r::world].shape[0]]
+    return full
+
+
+class TableShards:
+    """Peer-mapped views of every rank's shard + the collectives of the sharded lookup."""
+
+    def __init__(self, shard_param, n_rows, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world & (self.world - 1):
+            raise ValueError("row sharding needs a power-of-two number of GPUs")
+        self.shift = int(math.log2(self.world))
+        self.n_rows = n_rows
+        self.rows = shard_param.shape[0]
+        self.dim = shard_param.shape[1]
+        dev = shard_param.device
+        lib = _lib.load()
+        handle = ctypes.create_string_buffer(64)
+        offset = ctypes.c_int64(0)
+        _lib.check(lib.aread_ipc_export(ctypes.c_void_p(shard_param.data_ptr()), handle, ctypes.byref(offset)))
+        metas = [None] * self.world
+        dist.all_gather_object(metas, (dev.index, handle.raw, int(offset.value)), group=group)
+        self._shard = shard_param                          # the exported allocation must stay alive
+        self._opened = []
+        ptrs = []
+        for r, (peer_index, raw, off) in enumerate(metas):
+            if r == self.rank:
+                ptrs.append(shard_param.data_ptr())
+                continue
+            if not torch.cuda.can_device_access_peer(dev.index, peer_index):
+                raise RuntimeError(f"GPU {dev.index} cannot access GPU {peer_index} (no NVLink/P2P path)")
+            out = ctypes.c_void_p(0)
+            _lib.check(lib.aread_ipc_open(raw, off, dev.index, ctypes.byref(out)))
+            self._opened.append((out.value, off))
+            ptrs.append(out.value)
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self._token = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._grad = None
+        dist.barrier(group=group)
+
+    def close(self):
+        lib = _lib.load()
+        for ptr, off in self._opened:
+            lib.aread_ipc_close(ctypes.c_void_p(ptr), off)
+        self._opened = []
+
+    def fence(self):
+        """Stream-ordered barrier: peers may read this rank's shard only after its optimizer step, and
+        it may read theirs only after theirs."""
+        dist.all_reduce(self._token, group=self.group)
+
+    def grad_buffer(self, device):
+        if self._grad is None:
+            self._grad = torch.empty((self.world * self.rows, self.dim), dtype=torch.float32, device=device)
+        return self._grad
+
+    def reduce_grad(self, d_full):
+        """owner-major [world * rows, D] local gradient -> batch-averaged gradient of this rank's shard."""
+        out = torch.empty((self.rows, self.dim), dtype=torch.float32, device=d_full.device)
+        dist.reduce_scatter_tensor(out, d_full, op=dist.ReduceOp.AVG, group=self.group)
+        return out
+
+
+def allreduce_dense_grads(params, group=None):
+    """One flat-bucket NCCL all-reduce (average) of the gradients of the replicated parameters."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])

@@ -84,6 +84,12 @@ typedef struct aread_gather_args {
   int32_t* status;     /* [2] device ints: status[0] != 0 after an out-of-range id, status[1] = the
                           offending row index.  Zero it before the first call.  Rows that are out
                           of range produce zeros.                                                 */
+  /* Row-sharded table over 2^shard_shift GPUs of one NVSwitch box (0 = not sharded, `table` is used).
+     Global row r lives on GPU r mod 2^shard_shift at local row r >> shard_shift; shards[g] is the
+     device pointer of GPU g's shard [shard_rows, D], peer-mapped into this process, so the gather
+     reads remote rows straight over NVLink: the lookup IS the all-to-all of rows.                 */
+  int32_t shard_shift;
+  const float* const* shards; /* device array [2^shard_shift] of device pointers                  */
 } aread_gather_args;
 
 AREAD_API int aread_gather_fwd(const aread_gather_args* args, aread_stream_t stream);
@@ -116,6 +122,11 @@ typedef struct aread_scatter_args {
   size_t workspace_bytes;
   int32_t* sorted_rows; /* optional out [B * n_cols]: table rows in sorted order, or NULL       */
   int32_t* sorted_pos;  /* optional out [B * n_cols]: flattened (b, c) position of each, or NULL */
+  /* Owner-major output for a row-sharded table: with shard_shift > 0, d_table is
+     [2^shard_shift, shard_rows, D] and global row r is written at (r mod 2^shard_shift, r >> shard_shift),
+     ready for a reduce-scatter that hands every GPU the summed gradient of its own shard.       */
+  int32_t shard_shift;
+  int64_t shard_rows;
 } aread_scatter_args;
 
 AREAD_API size_t aread_scatter_workspace_bytes(int64_t n_lookups, int32_t embed_dim);
@@ -450,6 +461,17 @@ typedef struct aread_adam_args {
 
 AREAD_API int64_t aread_adam_chunk(void);
 AREAD_API int aread_adam_step(const aread_adam_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CUDA IPC plumbing of the row-sharded table (one process per GPU).  aread_ipc_export gives the
+ * 64-byte handle of the allocation that contains `ptr` and ptr's offset inside it; a peer process
+ * passes both to aread_ipc_open (with ITS compute device) and receives a pointer its kernels can
+ * dereference over NVLink -- that pointer goes into aread_gather_args.shards.
+ * ---------------------------------------------------------------------------------------------- */
+#define AREAD_IPC_HANDLE_BYTES 64
+AREAD_API int aread_ipc_export(const void* ptr, unsigned char* handle_out, int64_t* offset_out);
+AREAD_API int aread_ipc_open(const unsigned char* handle, int64_t offset, int32_t device, void** ptr_out);
+AREAD_API int aread_ipc_close(void* ptr, int64_t offset);
 
 #ifdef __cplusplus
 }

@@ -67,8 +67,8 @@ def test_struct_fields_match_header(cname, ctype):
 
 def test_struct_sizes_are_native(lib):
     assert ctypes.sizeof(_lib.EmbedPlan) == 56
-    assert ctypes.sizeof(_lib.GatherArgs) == 56 + 8 * 7
-    assert ctypes.sizeof(_lib.ScatterArgs) == 56 + 8 * 9
+    assert ctypes.sizeof(_lib.GatherArgs) == 56 + 8 * 9
+    assert ctypes.sizeof(_lib.ScatterArgs) == 56 + 8 * 11
 
 
 def test_argument_validation_without_gpu(lib):

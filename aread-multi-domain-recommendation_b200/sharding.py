@@ -29,6 +29,13 @@ def split_table(full, world, rank):
     return out
 
 
+def owner_major_index(n_rows, world):
+    """Position of every global row in the owner-major [world * shard_rows, D] gradient buffer the
+    scatter kernel writes (embedding.cu dest_row): owner * shard_rows + local row."""
+    r = torch.arange(n_rows, dtype=torch.int64)
+    return (r % world) * shard_rows(n_rows, world) + r // world
+
+
 def merge_shards(shards, n_rows):
     """Inverse of split_table for a list of all ranks' shards (checkpointing / tests)."""
     world = len(shards)
@@ -105,5 +112,9 @@ def allreduce_dense_grads(params, group=None):
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:                                  # gloo (the CPU tests of this host logic) has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat /= dist.get_world_size(group)
     torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])

@@ -190,15 +190,21 @@ def run_ours(args, wl, rank, world, local_rank):
     model.reset_for_mask_update()
     for d in range(wl.n_domain):
         model.domain_mask[d] = model.generate_mask("rand", d, init_active_percent=args.active)
+    shards = None
     if world > 1:
+        # replicas of the dense part, ONE copy of the table: row r lives on rank r % world and is read by its
+        # peers over NVLink inside the lookup kernel (sharding.py)
+        sharding = importlib.import_module("aread-multi-domain-recommendation_b200.sharding")
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
+        shards = model.embedding.shard_table()
     model.train()
     fused_adam = importlib.import_module("aread-multi-domain-recommendation_b200.optim").FusedAdam
     adam_cls = fused_adam if args.optimizer == "fused" else torch.optim.Adam
     opt = adam_cls(model.parameters(), lr=LR, betas=(0.9, 0.99), eps=1e-8, weight_decay=WD)
     crit = torch.nn.BCELoss()
-    dense_params = [p for p in model.parameters()]
+    table_param = model.embedding.embedding_dict.weight
+    dense_params = [p for p in model.parameters() if p is not table_param]
 
     B = args.batch
     n_batches = args.warmup + args.steps
@@ -214,10 +220,8 @@ def run_ours(args, wl, rank, world, local_rank):
         loss = loss + model.get_regularization_loss(device=dev)
         model.zero_grad()
         loss.backward()
-        if world > 1:
-            for p in dense_params:
-                if p.grad is not None:
-                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+        if world > 1:                              # the table gradient arrives reduce-scattered from the backward
+            sharding.allreduce_dense_grads(dense_params)
         opt.step()
         return loss
 
@@ -294,7 +298,8 @@ def run_ours(args, wl, rank, world, local_rank):
                    "embed_dim": wl.embed_dim, "table_rows": wl.n_rows, "n_cols": wl.n_cols,
                    "mask_active_percent": args.active, "dropout": args.dropout,
                    "optimizer": "torch.optim.Adam" if args.optimizer == "torch" else "aread_b200 FusedAdam",
-                   "parallelism": f"dp{world}",
+                   "parallelism": f"dp{world}" + ("" if world == 1 else f" + table row-sharded over {world} GPUs (P2P lookup, "
+                                                   "reduce-scatter of the table gradient, flat all-reduce of the rest)"),
                    "l2": "inputs larger than L2: table %d MB + per-step activations" % (wl.n_rows * wl.embed_dim * 4 >> 20)},
         "e2e": {"value": total_samples / (ms_e2e * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": int(host_x[0].numel() * 4 + host_y[0].numel() * 2), "d2h_bytes_per_step": 4},

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import dense_ops, fused, hemp
+from . import _mem, dense_ops, fused, hemp
 from .expert_ops import ExpertLayer
 from .layer import BaseModel, CrossNetwork, MultiLayerPerceptron, _weights_without_bn
 from .packing import PackSet
@@ -121,6 +121,14 @@ class AREAD(BaseModel):
         object.__setattr__(self, "_fused", fused.ModelPacks(self, packs, layers, tower_layers))
         object.__setattr__(self, "_fused_params", fused.param_list(self))
         object.__setattr__(self, "_slot_cache", {})
+        object.__setattr__(self, "_arenas", {})
+
+    def arena(self, device):
+        """The activation arena of the fused step on `device` (_mem.py)."""
+        a = self._arenas.get(device)
+        if a is None:
+            a = self._arenas[device] = _mem.Arena(device)
+        return a
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -134,7 +142,7 @@ class AREAD(BaseModel):
         clone = cls.__new__(cls)
         memo[id(self)] = clone
         for k, v in self.__dict__.items():
-            if k not in ("_packs", "_expert_layers", "_tower_layers", "_fused", "_fused_params", "_slot_cache"):
+            if k not in ("_packs", "_expert_layers", "_tower_layers", "_fused", "_fused_params", "_slot_cache", "_arenas"):
                 setattr(clone, k, copy.deepcopy(v, memo))
         clone._build_packs()
         return clone

@@ -4,6 +4,7 @@ import ctypes
 import torch
 
 from . import _lib
+from . import _mem
 
 
 def _stream(device):
@@ -28,8 +29,8 @@ def grouped_linear(a, w, bias, n, k, groups, a_group_cols=0, group_mask=None, ou
     full = (1 << groups) - 1
     mask = full if group_mask is None else int(group_mask) & full
     if out is None:
-        alloc = torch.empty if mask == full else torch.zeros
-        out = alloc((m, groups * n), dtype=out_dtype, device=a.device)
+        alloc = _mem.empty if mask == full else _mem.zeros
+        out = alloc((m, groups * n), out_dtype, a.device)
     assert out.stride(1) == 1 and out.dtype in (torch.float32, torch.bfloat16)
     args = _lib.GroupedLinearArgs(
         m, n, k, groups, a_group_cols, mask, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
@@ -95,9 +96,9 @@ def bn_act_fwd(z, gamma, beta, running_mean, running_var, training, bn_skip, p, 
     """(out, saved) or (out, out_lo, saved) with want_lo: out = dropout(relu(bn(z))) as `out_dtype`
     (None: statistics only); saved = [4, width] fp32 rows (mean, rstd, scale, shift)."""
     m, width = z.shape
-    saved = torch.empty((4, width), dtype=torch.float32, device=z.device)
-    out = torch.empty((m, width), dtype=out_dtype, device=z.device) if out_dtype is not None else None
-    out_lo = torch.empty((m, width), dtype=torch.bfloat16, device=z.device) if want_lo else None
+    saved = _mem.empty((4, width), torch.float32, z.device)
+    out = _mem.empty((m, width), out_dtype, z.device) if out_dtype is not None else None
+    out_lo = _mem.empty((m, width), torch.bfloat16, z.device) if want_lo else None
     ws = _bn_workspace(z.device, width)
     args = _lib.BnActArgs(m, width, 1 if training else 0, 1 if bn_skip else 0, BN_MOMENTUM, BN_EPS,
                           float(p) if training else 0.0, seed, salt, z.data_ptr(), z.stride(0), _ptr(gamma),
@@ -113,9 +114,9 @@ def bn_act_fwd(z, gamma, beta, running_mean, running_var, training, bn_skip, p, 
 def bn_act_bwd(z, d_out, saved, bn_skip, p, seed, salt, dz_dtype=torch.bfloat16, want_lo=False):
     """(dz, d_gamma, d_beta, d_bias) for out = dropout(relu(bn(z))); with want_lo dz is (hi, lo)."""
     m, width = z.shape
-    grads = torch.empty((3, width), dtype=torch.float32, device=z.device)
-    dz = torch.empty((m, width), dtype=dz_dtype, device=z.device)
-    dz_lo = torch.empty((m, width), dtype=torch.bfloat16, device=z.device) if want_lo else None
+    grads = torch.empty((3, width), dtype=torch.float32, device=z.device)     # parameter gradients: never arena
+    dz = _mem.empty((m, width), dz_dtype, z.device)
+    dz_lo = _mem.empty((m, width), torch.bfloat16, z.device) if want_lo else None
     ws = _bn_workspace(z.device, width)
     args = _lib.BnActBwdArgs(m, width, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), z.stride(0),
                              d_out.data_ptr(), d_out.stride(0), saved[0].data_ptr(), saved[1].data_ptr(),
@@ -130,7 +131,7 @@ def bn_act_bwd(z, d_out, saved, bn_skip, p, seed, salt, dz_dtype=torch.bfloat16,
 def mmoe_mix_fwd(z, saved, gate, n_expert, n_gate, p, seed, salt):
     m = z.shape[0]
     width = z.shape[1] // n_expert
-    out = torch.empty((m, n_gate, width), dtype=torch.float32, device=z.device)
+    out = _mem.empty((m, n_gate, width), torch.float32, z.device)
     args = _lib.MmoeMixArgs(m, width, n_expert, n_gate, float(p), seed, salt, z.data_ptr(), z.stride(0),
                             saved[2].data_ptr(), saved[3].data_ptr(), gate.data_ptr(), out.data_ptr(), None, None,
                             None)
@@ -141,8 +142,8 @@ def mmoe_mix_fwd(z, saved, gate, n_expert, n_gate, p, seed, salt):
 def mmoe_mix_bwd(z, saved, gate, d_out, n_expert, n_gate, p, seed, salt):
     m = z.shape[0]
     width = z.shape[1] // n_expert
-    d_h = torch.empty((m, n_expert * width), dtype=torch.float32, device=z.device)
-    d_gate = torch.empty((m, n_gate, n_expert), dtype=torch.float32, device=z.device)
+    d_h = _mem.empty((m, n_expert * width), torch.float32, z.device)
+    d_gate = _mem.empty((m, n_gate, n_expert), torch.float32, z.device)
     args = _lib.MmoeMixArgs(m, width, n_expert, n_gate, float(p), seed, salt, z.data_ptr(), z.stride(0),
                             saved[2].data_ptr(), saved[3].data_ptr(), gate.data_ptr(), None, d_out.data_ptr(),
                             d_h.data_ptr(), d_gate.data_ptr())

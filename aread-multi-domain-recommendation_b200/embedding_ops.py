@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import _mem
 
 
 def _require_cuda(t, what):
@@ -104,10 +105,10 @@ def gather(plan, table, x, want_bf16=False, want_lo=False):
     """[B, n_cols] int32 ids -> [B, n_fields, D] fp32 (and optionally the bf16 copy; with want_lo the
     bf16 result is the (hi, lo) split pair)."""
     B = x.shape[0]
-    out = torch.empty((B, plan.n_fields, plan.embed_dim), dtype=torch.float32, device=x.device)
+    out = _mem.empty((B, plan.n_fields, plan.embed_dim), torch.float32, x.device)
     shape16 = (B, plan.n_fields * plan.embed_dim)
-    out_bf16 = torch.empty(shape16, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    out_lo = torch.empty(shape16, dtype=torch.bfloat16, device=x.device) if (want_bf16 and want_lo) else None
+    out_bf16 = _mem.empty(shape16, torch.bfloat16, x.device) if want_bf16 else None
+    out_lo = _mem.empty(shape16, torch.bfloat16, x.device) if (want_bf16 and want_lo) else None
     sh = plan.shards
     if sh is not None:
         sh.fence()

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import _mem
 from . import dense_kernels as dk
 from . import embedding_ops
 from . import rowpass_ops
@@ -25,10 +26,13 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def gate_mix_fwd(logits, edges, prev_slot, u_prev, n_prev_active, width, want_sm):
+def gate_mix_fwd(logits, edges, prev_slot, u_prev, n_prev_active, width, want_sm, sm_escapes=False):
     B, na, n_prev = logits.shape
-    out = torch.empty((B, na, width), dtype=torch.float32, device=logits.device)
-    sm = torch.empty((B, na, n_prev), dtype=torch.float32, device=logits.device) if want_sm else None
+    out = _mem.empty((B, na, width), torch.float32, logits.device)
+    sm = None
+    if want_sm:       # gates handed back to the caller must not live in the arena
+        sm = (torch.empty((B, na, n_prev), dtype=torch.float32, device=logits.device) if sm_escapes
+              else _mem.empty((B, na, n_prev), torch.float32, logits.device))
     a = _lib.GateMixArgs(B, na, n_prev, n_prev_active, width, logits.data_ptr(),
                          edges.data_ptr() if edges is not None else None, prev_slot.data_ptr(), None,
                          u_prev.data_ptr(), out.data_ptr(), sm.data_ptr() if want_sm else None, None, None, None, None)
@@ -40,9 +44,9 @@ def gate_mix_bwd(logits, edges, prev_slot, slot_tower, u_prev, d_out):
     B, na, n_prev = logits.shape
     nap, width = u_prev.shape[1], u_prev.shape[2]
     dev = logits.device
-    d_logits = torch.empty((B, na, n_prev), dtype=torch.float32, device=dev)
-    d_u = torch.empty((B, nap, width), dtype=torch.float32, device=dev)
-    scratch = torch.empty((B, na, n_prev), dtype=torch.float32, device=dev)
+    d_logits = _mem.empty((B, na, n_prev), torch.float32, dev)
+    d_u = _mem.empty((B, nap, width), torch.float32, dev)
+    scratch = _mem.empty((B, na, n_prev), torch.float32, dev)
     a = _lib.GateMixArgs(B, na, n_prev, nap, width, logits.data_ptr(), edges.data_ptr() if edges is not None else None,
                          prev_slot.data_ptr(), slot_tower.data_ptr(), u_prev.data_ptr(), None, None, d_out.data_ptr(),
                          d_logits.data_ptr(), d_u.data_ptr(), scratch.data_ptr())
@@ -91,6 +95,26 @@ def _sel(flat, index):
 class AreadNode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, cfg, *params):
+        arena = cfg["model"].arena(x.device)
+        ctx.lease = lease = arena.acquire()              # None: another forward of this model awaits its backward
+        with _mem.use(arena if lease is not None else None):
+            return AreadNode._forward(ctx, x, cfg)
+
+    @staticmethod
+    def backward(ctx, d_probs):
+        lease = ctx.lease
+        if lease is not None and not lease.active:
+            raise RuntimeError("the fused AREAD node recycles its activations after the backward; a second backward "
+                               "through the same graph (retain_graph=True) needs AREAD_WORKSPACE=0")
+        try:
+            with _mem.use(lease.arena if lease is not None else None):
+                return AreadNode._backward(ctx, d_probs)
+        finally:
+            if lease is not None:
+                lease.release()
+
+    @staticmethod
+    def _forward(ctx, x, cfg):
         model, info = cfg["model"], cfg["info"]
         P = model._fused
         dev = x.device
@@ -130,11 +154,11 @@ class AreadNode(torch.autograd.Function):
         layout = (len(a0), n_expert, n_cross, len(a_last))
         nj = w_cat.shape[0]
         ldp = (nj + 3) // 4 * 4
-        p_dots = torch.empty((B, ldp), dtype=torch.float32, device=dev)
-        lin = torch.empty((B,), dtype=torch.float32, device=dev)
-        gate = torch.empty((B, len(a0), n_expert), dtype=torch.float32, device=dev)
-        alpha = torch.empty((B, n_cross + 1), dtype=torch.float32, device=dev)
-        head_cross = torch.empty((B, len(a_last)), dtype=torch.float32, device=dev)
+        p_dots = _mem.empty((B, ldp), torch.float32, dev)
+        lin = _mem.empty((B,), torch.float32, dev)
+        gate = _mem.empty((B, len(a0), n_expert), torch.float32, dev)
+        alpha = _mem.empty((B, n_cross + 1), torch.float32, dev)
+        head_cross = _mem.empty((B, len(a_last)), torch.float32, dev)
         ra = rowpass_ops._args(B, E, layout, ldp, x=X, w=w_cat, offset=offset, p=p_dots, lin=lin, gate=gate,
                                alpha=alpha, head=head_cross)
         _lib.check(_lib.load().aread_rowpass_fwd(ctypes.byref(ra), _stream(dev)))
@@ -183,7 +207,8 @@ class AreadNode(torch.autograd.Function):
                 prev_slot, slot_tower = cfg["slots"][l]
                 want_sm = cfg["want_gate_means"] or cfg["want_gates"]
                 u_prev = h
-                h, sm = gate_mix_fwd(logits, edges, prev_slot, u_prev, len(active[l - 1]), u_prev.shape[2], want_sm)
+                h, sm = gate_mix_fwd(logits, edges, prev_slot, u_prev, len(active[l - 1]), u_prev.shape[2], want_sm,
+                                     sm_escapes=cfg["want_gates"])
                 if cfg["want_gates"]:
                     gates[l] = sm.transpose(1, 2)                                        # [B, n_prev, n_l]
                 if cfg["want_gate_means"] and info is not None:
@@ -228,7 +253,7 @@ class AreadNode(torch.autograd.Function):
         return probs
 
     @staticmethod
-    def backward(ctx, d_probs):
+    def _backward(ctx, d_probs):
         cfg, sv = ctx.cfg, ctx.sv
         model, info = cfg["model"], cfg["info"]
         P = model._fused
@@ -307,10 +332,10 @@ class AreadNode(torch.autograd.Function):
         # ---- row pass
         layout, ldp = sv["layout"], sv["ldp"]
         nj = sv["w_cat"].shape[0]
-        d_p = torch.empty((B, ldp), dtype=torch.float32, device=dev)
-        d_c = torch.empty((B, ldp), dtype=torch.float32, device=dev)
-        d_x_row = torch.empty((B, E), dtype=torch.float32, device=dev)
-        d_wcat = torch.empty((nj, E), dtype=torch.float32, device=dev)
+        d_p = _mem.empty((B, ldp), torch.float32, dev)
+        d_c = _mem.empty((B, ldp), torch.float32, dev)
+        d_x_row = _mem.empty((B, E), torch.float32, dev)
+        d_wcat = torch.empty((nj, E), dtype=torch.float32, device=dev)                   # parameter gradients
         need = int(_lib.load().aread_rowpass_workspace_bytes(B, E, nj))
         ws = rowpass_ops._WS.get(dev)
         if ws is None or ws.numel() < need:

@@ -107,14 +107,24 @@ class TableShards:
 
 
 def allreduce_dense_grads(params, group=None):
-    """One flat-bucket NCCL all-reduce (average) of the gradients of the replicated parameters."""
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+    """One flat-bucket all-reduce (average) of the gradients of the replicated parameters.
+
+    EVERY parameter takes part on every rank: ranks train different domains, so a tower that is masked
+    out on one rank (gradient None) is live on another; a missing gradient counts as zero, like DDP's
+    unused parameters.  Afterwards each p.grad is a view into the reduced bucket."""
+    params = list(params)
+    if not params:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    sizes = [p.numel() for p in params]
+    flat = torch.zeros(sum(sizes), dtype=params[0].dtype, device=params[0].device)
+    views = [c.view_as(p) for c, p in zip(flat.split(sizes), params)]
+    have = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None]
+    if have:
+        torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
     if dist.get_backend(group) == "nccl":
         dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
     else:                                  # gloo (the CPU tests of this host logic) has no AVG
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat /= dist.get_world_size(group)
-    torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])
+    for p, v in zip(params, views):
+        p.grad = v

@@ -9,6 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
+from . import _mem
 from . import dense_kernels as dk
 
 _WS = {}
@@ -27,7 +28,7 @@ def tower_linear(x, weight, bias, out_width, weight_is_out_by_in=True, groups=No
     else:
         B, G, I = x.shape
         ld, gs = G * I, I
-    out = torch.empty((B, G, out_width), dtype=torch.float32, device=x.device)
+    out = _mem.empty((B, G, out_width), torch.float32, x.device)
     args = _lib.TowerLinearArgs(B, G, I, out_width, 1 if weight_is_out_by_in else 0, x.data_ptr(), ld, gs,
                                 weight.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
                                 G * out_width)

@@ -31,7 +31,9 @@ def test_fused_adam_matches_torch_adam():
     for a, b in zip(ref, mine):
         sa, sb = o_ref.state[a], o_mine.state[b]
         assert float(sa["step"]) == float(sb["step"])
-        torch.testing.assert_close(sb["exp_avg"], sa["exp_avg"], rtol=5e-6, atol=1e-9)
+        # torch forms m with lerp, the kernel with two fmas: where beta1*m and (1-beta1)*g cancel, the difference
+        # is an ulp of the operands, not of the result
+        torch.testing.assert_close(sb["exp_avg"], sa["exp_avg"], rtol=5e-6, atol=1e-6 * float(sa["exp_avg"].abs().max()))
         torch.testing.assert_close(sb["exp_avg_sq"], sa["exp_avg_sq"], rtol=5e-6, atol=1e-12)
     # state_dict round trip into a torch Adam keeps training identically
     sd = o_mine.state_dict()

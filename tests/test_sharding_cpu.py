@@ -51,18 +51,19 @@ def _worker(rank, world, port, result_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # (1) flat-bucket all-reduce == per-tensor average, None gradients skipped
+        # (1) flat-bucket all-reduce == per-tensor average; a gradient that is None on one rank counts as zero
         torch.manual_seed(7)
         shapes = [(3, 5), (7,), (1, 1), (2, 3, 4)]
         params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes] + [torch.nn.Parameter(torch.zeros(4))]
         all_grads = [[torch.randn(s) for s in shapes] for _ in range(world)]
-        for p, g in zip(params, all_grads[rank]):
-            p.grad = g.clone()
+        for i, (p, g) in enumerate(zip(params, all_grads[rank])):
+            if not (rank == 1 and i == 2):               # rank 1 did not touch parameter 2 (a masked-out tower)
+                p.grad = g.clone()
         sharding.allreduce_dense_grads(params)
         for i, p in enumerate(params[:-1]):
-            want = sum(all_grads[r][i] for r in range(world)) / world
+            want = sum(all_grads[r][i] for r in range(world) if not (r == 1 and i == 2)) / world
             torch.testing.assert_close(p.grad, want, rtol=1e-6, atol=1e-7)
-        assert params[-1].grad is None
+        assert not params[-1].grad.any()                 # untouched everywhere: zero, present on every rank
 
         # (2) sharded table gradient: every rank scatters ITS batch into the owner-major layout, the
         # buffers are summed and averaged (the GPU path's reduce-scatter), and rank r's slice must be the

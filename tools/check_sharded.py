@@ -54,11 +54,12 @@ want = sharding.split_table(g_full, world, rank)
 got = model.embedding.embedding_dict.weight.grad
 torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-7)
 # dense gradients: flat-bucket all-reduce equals per-tensor averaging
-dense = [p for n, p in model.named_parameters() if p.grad is not None and not n.startswith("embedding.")]
+dense = [p for n, p in model.named_parameters() if not n.startswith("embedding.")]
 expect = []
 for n, p in ref.named_parameters():
-    if p.grad is not None and not n.startswith("embedding."):
-        g = p.grad.clone(); dist.all_reduce(g, op=dist.ReduceOp.AVG); expect.append(g)
+    if not n.startswith("embedding."):
+        g = torch.zeros_like(p) if p.grad is None else p.grad.clone()
+        dist.all_reduce(g, op=dist.ReduceOp.AVG); expect.append(g)
 sharding.allreduce_dense_grads(dense)
 for a, b in zip(dense, expect):
     torch.testing.assert_close(a.grad, b, rtol=1e-5, atol=1e-8)

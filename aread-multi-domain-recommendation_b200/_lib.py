@@ -97,6 +97,11 @@ class L2RegArgs(Structure):
                 ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
 
 
+class BaggingBceArgs(Structure):
+    _fields_ = [("m", c_int64), ("n_tower", c_int32), ("probs", c_void_p), ("labels", c_void_p), ("loss", c_void_p),
+                ("d_probs", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
+
+
 class TowerLinearArgs(Structure):
     _fields_ = [("m", c_int64), ("groups", c_int32), ("in_width", c_int32), ("out_width", c_int32),
                 ("weight_is_out_by_in", c_int32), ("in_", c_void_p), ("ld_in", c_int64),
@@ -153,6 +158,8 @@ _SIGNATURES = {
     "aread_adam_chunk": (c_int64, []),
     "aread_adam_step": (c_int32, [POINTER(AdamArgs), c_void_p]),
     "aread_l2_reg_chunk": (c_int64, []),
+    "aread_bagging_bce_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "aread_bagging_bce": (c_int32, [POINTER(BaggingBceArgs), c_void_p]),
     "aread_l2_reg_fwd": (c_int32, [POINTER(L2RegArgs), c_void_p]),
     "aread_l2_reg_bwd": (c_int32, [POINTER(L2RegArgs), c_void_p, c_void_p]),
 }

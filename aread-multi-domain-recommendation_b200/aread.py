@@ -13,7 +13,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import _mem, dense_ops, fused, hemp
+from . import _mem, dense_ops, fused, hemp, loss_ops
 from .expert_ops import ExpertLayer
 from .layer import BaseModel, CrossNetwork, MultiLayerPerceptron, _weights_without_bn
 from .packing import PackSet
@@ -122,6 +122,12 @@ class AREAD(BaseModel):
         object.__setattr__(self, "_fused_params", fused.param_list(self))
         object.__setattr__(self, "_slot_cache", {})
         object.__setattr__(self, "_arenas", {})
+
+    @staticmethod
+    def bagging_loss(y_stack, targets):
+        """sum_t BCELoss(y_stack[t], targets) / n_act -- the trainer's loss of the 'domain_mask_bagging' output
+        (run.py:643-644, 672-677) as one kernel."""
+        return loss_ops.bagging_bce(y_stack, targets)
 
     def arena(self, device):
         """The activation arena of the fused step on `device` (_mem.py)."""

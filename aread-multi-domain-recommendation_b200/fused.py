@@ -244,7 +244,7 @@ class AreadNode(torch.autograd.Function):
         w_tail = w_out[:, E:].contiguous()                                               # [na_last, w]
         tail = tower_ops.tower_linear(h, w_tail.unsqueeze(1), None, 1)                   # [B, na_last, 1]
         probs = torch.sigmoid(head_cross + tail.view(B, -1) + lin.unsqueeze(1)).t().contiguous()    # [na_last, B]
-        sv.update(h_last=h, w_tail=w_tail, probs=probs)
+        sv.update(h_last=h, w_tail=w_tail, probs=probs.detach())      # detached alias: no ctx <-> output cycle
 
         cfg["gate_means"], cfg["gates"], cfg["gate_inputs"] = gate_means, gates, q
         ctx.cfg, ctx.sv = cfg, sv

@@ -12,12 +12,72 @@ import torch
 from . import _lib
 
 
+class _Plan:
+    """Launch table of one (param group, set of parameters that have a gradient): everything that does not
+    change from step to step, laid out as the rows of the pinned block the kernel reads."""
+
+    def __init__(self, params, idx, states, chunk):
+        self.params = params
+        self.idx = np.asarray(idx, dtype=np.int64)
+        self.ptrs = [p.data_ptr() for p in params]
+        n = len(params)
+        self.static = np.zeros((8, n), dtype=np.int64)
+        h = self.static
+        start = 0
+        for i, (p, st) in enumerate(zip(params, states)):
+            h[0, i] = p.data_ptr()
+            h[2, i], h[3, i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            h[4, i], h[5, i] = p.numel(), start
+            start += (p.numel() + chunk - 1) // chunk
+        self.n_chunks = start
+        self.moments = [(st["exp_avg"], st["exp_avg_sq"]) for st in states]     # keeps the addresses valid
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._chunk = None
+        self._bind_steps()
+
+    def _bind_steps(self):
+        """state[p]["step"] (a host scalar tensor, as in torch.optim.Adam) becomes a view into one array per
+        group, so that a step bumps all counters with one vector add."""
+        self._steps, self._plans = [], {}
+        for group in self.param_groups:
+            arr = np.zeros(len(group["params"]), dtype=np.float32)
+            view = torch.from_numpy(arr)
+            for i, p in enumerate(group["params"]):
+                st = self.state.get(p)
+                if st:
+                    arr[i] = float(st["step"])
+                    st["step"] = view[i]
+            self._steps.append((arr, view))
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._bind_steps()
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        if hasattr(self, "_steps"):
+            self._bind_steps()
+
+    def _plan(self, gi, group, idx):
+        params = [group["params"][i] for i in idx]
+        arr, view = self._steps[gi]
+        states = []
+        for i, p in zip(idx, params):
+            if p.grad.is_sparse or not p.is_cuda or p.dtype != torch.float32:
+                raise RuntimeError("FusedAdam handles dense fp32 CUDA parameters only")
+            st = self.state[p]
+            if not st:
+                st["step"] = view[i]                                            # host scalar, like torch's default
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            states.append(st)
+        return _Plan(params, idx, states, self._chunk)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -28,50 +88,38 @@ class FusedAdam(torch.optim.Optimizer):
         lib = _lib.load()
         if self._chunk is None:
             self._chunk = int(lib.aread_adam_chunk())
-        chunk = self._chunk
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             beta1, beta2 = group["betas"]
             lr, eps, wd = group["lr"], group["eps"], group["weight_decay"]
-            todo = []
-            for p in group["params"]:
-                g = p.grad
-                if g is None:
-                    continue
-                if g.is_sparse or not p.is_cuda or p.dtype != torch.float32:
-                    raise RuntimeError("FusedAdam handles dense fp32 CUDA parameters only")
-                st = self.state[p]
-                if not st:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)       # host scalar, like torch's default
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["step"] += 1
-                if not g.is_contiguous():
-                    g = g.contiguous()
-                todo.append((p, g, st))
-            if not todo:
+            grads = [p.grad for p in group["params"]]
+            idx = tuple(i for i, g in enumerate(grads) if g is not None)        # parameters without gradient: skipped
+            if not idx:
                 continue
-            n = len(todo)
-            device = todo[0][0].device
+            plan = self._plans.get((gi, idx))
+            if plan is None or plan.ptrs != [p.data_ptr() for p in plan.params]:
+                if len(self._plans) > 256:
+                    self._plans.clear()
+                plan = self._plans[(gi, idx)] = self._plan(gi, group, idx)
+            grads = [grads[i] if grads[i].is_contiguous() else grads[i].contiguous() for i in idx]
+            n = len(idx)
+            device = plan.params[0].device
+            steps = self._steps[gi][0]
+            steps[plan.idx] += 1
+            t = steps[plan.idx].astype(np.float64)
             # rows: params, grads, exp_avg, exp_avg_sq, sizes, chunk_start (int64); step_size, bc2_sqrt (fp32).
             # A fresh pinned block per step: torch's host allocator will not recycle it before the copy ran.
             host = torch.empty((8, n), dtype=torch.int64, pin_memory=True)
             dev = torch.empty((8, n), dtype=torch.int64, device=device)
             h = host.numpy()
+            np.copyto(h, plan.static)
+            h[1, :] = [g.data_ptr() for g in grads]
             f = h.view(np.float32).reshape(8, -1)                               # fp32 view of the same rows
-            start = 0
-            for i, (p, g, st) in enumerate(todo):
-                t = float(st["step"])
-                h[0, i], h[1, i] = p.data_ptr(), g.data_ptr()
-                h[2, i], h[3, i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-                h[4, i], h[5, i] = p.numel(), start
-                start += (p.numel() + chunk - 1) // chunk
-                f[6, i] = lr / (1.0 - beta1 ** t)
-                f[7, i] = math.sqrt(1.0 - beta2 ** t)
+            f[6, :n] = lr / (1.0 - beta1 ** t)
+            f[7, :n] = np.sqrt(1.0 - beta2 ** t)
             dev.copy_(host, non_blocking=True)
             base, row = dev.data_ptr(), dev.stride(0) * 8
-            args = _lib.AdamArgs(n, start, base, base + row, base + 2 * row, base + 3 * row, base + 4 * row,
+            args = _lib.AdamArgs(n, plan.n_chunks, base, base + row, base + 2 * row, base + 3 * row, base + 4 * row,
                                  base + 5 * row, base + 6 * row, base + 7 * row, beta1, beta2, eps, wd)
             _lib.check(lib.aread_adam_step(ctypes.byref(args),
                                            ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
-            self._keep = [g for _, g, _ in todo]       # contiguous copies stay alive until the kernel has run
         return loss

@@ -28,6 +28,15 @@ class _Plan:
         self.chunk_start = torch.tensor(starts, dtype=torch.int64, device=device)
         self.workspace = torch.empty(max(n, 1), dtype=torch.float32, device=device)
         self.numel = sizes
+        # gradient buffer of the backward, one slice per tensor.  It is reused every step: the plan keeps the
+        # views referenced, so autograd never adopts one as a .grad in place (it copies / adds out of place).
+        self.flat_grad = torch.empty(sum(sizes), dtype=torch.float32, device=device)
+        self.grads, off = [], 0
+        for t, s in zip(tensors, sizes):
+            self.grads.append(self.flat_grad[off:off + s].view(t.shape))
+            off += s
+        self.grad_ptrs = torch.tensor([g.data_ptr() for g in self.grads], dtype=torch.int64, device=device)
+        self.seq = 0
 
 
 _PLANS = {}
@@ -40,7 +49,7 @@ class L2Reg(torch.autograd.Function):
         key = tuple(t.data_ptr() for t in tensors)
         plan = _PLANS.get(key)
         if plan is None:
-            if len(_PLANS) > 64:
+            if len(_PLANS) > 8:
                 _PLANS.clear()
             plan = _Plan(tensors, l2s, dev)
             _PLANS[key] = plan
@@ -50,20 +59,24 @@ class L2Reg(torch.autograd.Function):
                               plan.workspace.data_ptr(), plan.workspace.numel() * 4)
         _lib.check(_lib.load().aread_l2_reg_fwd(ctypes.byref(args), _stream(dev)))
         ctx.plan = plan
-        ctx.shapes = [t.shape for t in tensors]
+        plan.seq += 1
+        ctx.seq = plan.seq
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         plan = ctx.plan
         dev = g_out.device
-        flat = torch.empty(sum(plan.numel), dtype=torch.float32, device=dev)
-        grads, off = [], 0
-        for n, shape in zip(plan.numel, ctx.shapes):
-            grads.append(flat[off:off + n].view(shape))
-            off += n
-        gptrs = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64, device=dev)
         g_out = g_out.contiguous()
+        if ctx.seq == plan.seq:          # the latest evaluation owns the plan's buffer
+            grads, gptrs = plan.grads, plan.grad_ptrs
+        else:                            # an older graph that is still alive: private buffer
+            flat = torch.empty_like(plan.flat_grad)
+            grads, off = [], 0
+            for g in plan.grads:
+                grads.append(flat[off:off + g.numel()].view(g.shape))
+                off += g.numel()
+            gptrs = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64, device=dev)
         args = _lib.L2RegArgs(len(grads), plan.n_chunks, plan.ptrs.data_ptr(), gptrs.data_ptr(),
                               plan.sizes.data_ptr(), plan.l2.data_ptr(), plan.chunk_start.data_ptr(), None, None, 0)
         _lib.check(_lib.load().aread_l2_reg_bwd(ctypes.byref(args), ctypes.c_void_p(g_out.data_ptr()), _stream(dev)))

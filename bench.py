@@ -46,8 +46,11 @@ def parse_args():
     ap.add_argument("--active", type=float, default=0.7, help="HEMP init_active_percent of the per-domain masks")
     ap.add_argument("--dropout", type=float, default=0.2)
     ap.add_argument("--seed", type=int, default=2000)
-    ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
-                    help="torch.optim.Adam as run.py:830 builds it (default), or the library's FusedAdam")
+    ap.add_argument("--optimizer", default="fused", choices=["torch", "fused"],
+                    help="the library's FusedAdam (one launch; same arithmetic as torch.optim.Adam, tests/test_optim_gpu.py) or "
+                         "torch.optim.Adam as run.py:830 builds it")
+    ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
+                    help="bagging BCE through AREAD.bagging_loss (one kernel) or as the trainer's sum of BCELoss calls")
     return ap.parse_args()
 
 
@@ -215,8 +218,11 @@ def run_ours(args, wl, rank, world, local_rank):
 
     def step(x, y, d):
         preds = model(x, mode="domain_mask_bagging", domain_i=d)
-        tgt = y.squeeze().float()
-        loss = sum(crit(p, tgt) for p in preds.unbind(dim=0)) / preds.shape[0]
+        if args.loss == "fused":                   # run.py:672-677 as one kernel (loss_ops.py)
+            loss = model.bagging_loss(preds, y)
+        else:
+            tgt = y.squeeze().float()
+            loss = sum(crit(p, tgt) for p in preds.unbind(dim=0)) / preds.shape[0]
         loss = loss + model.get_regularization_loss(device=dev)
         model.zero_grad()
         loss.backward()
@@ -298,6 +304,7 @@ def run_ours(args, wl, rank, world, local_rank):
                    "embed_dim": wl.embed_dim, "table_rows": wl.n_rows, "n_cols": wl.n_cols,
                    "mask_active_percent": args.active, "dropout": args.dropout,
                    "optimizer": "torch.optim.Adam" if args.optimizer == "torch" else "aread_b200 FusedAdam",
+                   "loss": "AREAD.bagging_loss" if args.loss == "fused" else "sum of torch BCELoss",
                    "parallelism": f"dp{world}" + ("" if world == 1 else f" + table row-sharded over {world} GPUs (P2P lookup, "
                                                    "reduce-scatter of the table gradient, flat all-reduce of the rest)"),
                    "l2": "inputs larger than L2: table %d MB + per-step activations" % (wl.n_rows * wl.embed_dim * 4 >> 20)},

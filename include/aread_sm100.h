@@ -463,6 +463,25 @@ AREAD_API int64_t aread_adam_chunk(void);
 AREAD_API int aread_adam_step(const aread_adam_args* args, aread_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Bagging loss of the HEI heads: loss[0] = (1 / n_tower) * sum_t mean_b BCE(probs[t, b], labels[b])
+ * and d loss / d probs in the same pass.  Replaces the trainer's per-tower BCELoss sum (run.py:643-644,
+ * 672-677, criterion run.py:833); element arithmetic as torch.nn.BCELoss (logs clamped at -100).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_bagging_bce_args {
+  int64_t m;             /* samples                                         */
+  int32_t n_tower;       /* active last-level towers (rows of probs)        */
+  const float* probs;    /* [n_tower, m], in [0, 1]                         */
+  const float* labels;   /* [m] fp32                                        */
+  float* loss;           /* device scalar                                   */
+  float* d_probs;        /* [n_tower, m] or NULL                            */
+  void* workspace;       /* aread_bagging_bce_workspace_bytes(m, n_tower)   */
+  size_t workspace_bytes;
+} aread_bagging_bce_args;
+
+AREAD_API size_t aread_bagging_bce_workspace_bytes(int64_t m, int32_t n_tower);
+AREAD_API int aread_bagging_bce(const aread_bagging_bce_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * CUDA IPC plumbing of the row-sharded table (one process per GPU).  aread_ipc_export gives the
  * 64-byte handle of the allocation that contains `ptr` and ptr's offset inside it; a peer process
  * passes both to aread_ipc_open (with ITS compute device) and receives a pointer its kernels can

@@ -48,3 +48,41 @@ def test_l2_regulariser_kernel():
         torch.testing.assert_close(w.grad, 3.0 * 2 * l2 * w.detach(), rtol=1e-6, atol=0)
     again = ro.regularization_loss(reg, torch.device(DEV))
     assert torch.equal(out, again)                                       # bit-reproducible
+    # the backward's buffer is reused from step to step: .grad must never alias it, and two live graphs of the
+    # same tensor list must not share it
+    first = [w.grad.clone() for w in ws]
+    a, b = ro.regularization_loss(reg, torch.device(DEV)), ro.regularization_loss(reg, torch.device(DEV))
+    for w in ws:
+        w.grad = None
+    (0.5 * a + 2.0 * b).backward()
+    for w, l2, g3 in zip(ws, l2s, first):
+        torch.testing.assert_close(w.grad, 2.5 * 2 * l2 * w.detach(), rtol=1e-6, atol=0)
+        torch.testing.assert_close(g3, 3.0 * 2 * l2 * w.detach(), rtol=1e-6, atol=0)
+    kept = [w.grad for w in ws]
+    snap = [g.clone() for g in kept]
+    ro.regularization_loss(reg, torch.device(DEV)).backward()            # accumulates into .grad, does not replace it
+    for w, g, s0, l2 in zip(ws, kept, snap, l2s):
+        assert w.grad is g
+        torch.testing.assert_close(g, s0 + 2 * l2 * w.detach(), rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("T,m", [(1, 1), (3, 37), (9, 4096), (12, 70001)])
+def test_bagging_bce_matches_bceloss(T, m):
+    lo = importlib.import_module("aread-multi-domain-recommendation_b200.loss_ops")
+    gen = torch.Generator(device=DEV).manual_seed(T * 1000 + m)
+    probs = torch.sigmoid(4 * torch.randn(T, m, device=DEV, generator=gen))
+    probs[0, 0] = 0.0                                  # log clamped at -100, like BCELoss
+    if m > 1:
+        probs[-1, 1] = 1.0
+    y = (torch.rand(m, 1, device=DEV, generator=gen) < 0.3).to(torch.int16)
+    p_ref = probs.clone().requires_grad_(True)
+    crit = torch.nn.BCELoss()
+    ref = sum(crit(p, y.squeeze(1).float()) for p in p_ref.unbind(0)) / T
+    (ref * 1.5).backward()
+    p_mine = probs.clone().requires_grad_(True)
+    mine = lo.bagging_bce(p_mine, y)
+    (mine * 1.5).backward()
+    assert mine.shape == ref.shape
+    torch.testing.assert_close(mine, ref, rtol=2e-6, atol=1e-7)
+    torch.testing.assert_close(p_mine.grad, p_ref.grad, rtol=1e-6, atol=0)
+    assert torch.equal(lo.bagging_bce(probs, y), mine.detach())          # bit-reproducible

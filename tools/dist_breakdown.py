@@ -25,7 +25,8 @@ if world > 1:
         dist.broadcast(p.data, src=0)
     model.embedding.shard_table()
 model.train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+Adam = importlib.import_module("aread-multi-domain-recommendation_b200.optim").FusedAdam if os.environ.get("OPT", "fused") == "fused" else torch.optim.Adam
+opt = Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
 crit = torch.nn.BCELoss()
 table = model.embedding.embedding_dict.weight
 dense = [p for p in model.parameters() if p is not table]
@@ -42,7 +43,7 @@ def step(i, record):
     x, y, d = batches[i % len(batches)]
     t = time.perf_counter(); preds = model(x, mode="domain_mask_bagging", domain_i=d)
     if record: tick("forward", t)
-    t = time.perf_counter(); tgt = y.squeeze().float(); loss = sum(crit(p, tgt) for p in preds.unbind(dim=0)) / preds.shape[0]
+    t = time.perf_counter(); loss = model.bagging_loss(preds, y)
     if record: tick("bce", t)
     t = time.perf_counter(); loss = loss + model.get_regularization_loss(device=dev)
     if record: tick("reg", t)

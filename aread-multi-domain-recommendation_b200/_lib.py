@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_s
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -97,6 +97,27 @@ class L2RegArgs(Structure):
                 ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
 
 
+class HeiLayerFwdArgs(Structure):
+    _fields_ = [("m", c_int64), ("groups", c_int32), ("k", c_int32), ("n", c_int32), ("training", c_int32),
+                ("bn_skip", c_int32), ("momentum", c_float), ("eps", c_float), ("src", c_void_p), ("ld_src", c_int64),
+                ("src_scale", c_void_p), ("src_shift", c_void_p), ("src_p", c_float), ("src_salt", c_uint32),
+                ("seed", c_uint64), ("weight", c_void_p), ("bias", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+                ("running_mean", c_void_p), ("running_var", c_void_p), ("z", c_void_p), ("mean", c_void_p),
+                ("rstd", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("workspace", c_void_p),
+                ("workspace_bytes", c_size_t)]
+
+
+class HeiLayerBwdArgs(Structure):
+    _fields_ = [("m", c_int64), ("groups", c_int32), ("k", c_int32), ("n", c_int32), ("bn_skip", c_int32),
+                ("p", c_float), ("salt", c_uint32), ("seed", c_uint64), ("z", c_void_p), ("d_out", c_void_p),
+                ("mean", c_void_p), ("rstd", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("coef", c_void_p),
+                ("src", c_void_p), ("ld_src", c_int64), ("src_scale", c_void_p), ("src_shift", c_void_p),
+                ("src_mean", c_void_p), ("src_rstd", c_void_p), ("src_p", c_float), ("src_salt", c_uint32),
+                ("weight", c_void_p), ("d_in", c_void_p), ("d_w", c_void_p), ("src_coef", c_void_p),
+                ("src_d_gamma", c_void_p), ("src_d_beta", c_void_p), ("src_d_bias", c_void_p), ("workspace", c_void_p),
+                ("workspace_bytes", c_size_t)]
+
+
 class BaggingBceArgs(Structure):
     _fields_ = [("m", c_int64), ("n_tower", c_int32), ("probs", c_void_p), ("labels", c_void_p), ("loss", c_void_p),
                 ("d_probs", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
@@ -158,6 +179,12 @@ _SIGNATURES = {
     "aread_adam_chunk": (c_int64, []),
     "aread_adam_step": (c_int32, [POINTER(AdamArgs), c_void_p]),
     "aread_l2_reg_chunk": (c_int64, []),
+    "aread_bn_act_apply": (c_int32, [POINTER(BnActArgs), c_void_p]),
+    "aread_bn_bwd_coef": (c_int32, [POINTER(BnActBwdArgs), c_void_p, c_void_p]),
+    "aread_hei_layer_supported": (c_int32, [c_int32, c_int32, c_int32]),
+    "aread_hei_layer_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
+    "aread_hei_layer_fwd": (c_int32, [POINTER(HeiLayerFwdArgs), c_void_p]),
+    "aread_hei_layer_bwd": (c_int32, [POINTER(HeiLayerBwdArgs), c_void_p]),
     "aread_bagging_bce_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "aread_bagging_bce": (c_int32, [POINTER(BaggingBceArgs), c_void_p]),
     "aread_l2_reg_fwd": (c_int32, [POINTER(L2RegArgs), c_void_p]),

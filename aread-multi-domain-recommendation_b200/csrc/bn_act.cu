@@ -9,29 +9,12 @@
 // Column reductions are deterministic: every CTA reduces a fixed row range into a partial, and the
 // partials are summed in CTA order.
 #include "common.cuh"
+#include "bn_common.cuh"
 
 namespace aread {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kStatCtas = kNumSMs * 4;
-
-// counter-based dropout stream: keep(element) is a pure function of (seed, salt, element index)
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x;
-}
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t salt, uint64_t idx, uint32_t threshold) {
-  const uint32_t h = mix32(static_cast<uint32_t>(idx) ^ mix32(static_cast<uint32_t>(idx >> 32) ^ salt ^
-                                                               static_cast<uint32_t>(seed)) ^
-                           static_cast<uint32_t>(seed >> 32));
-  return h >= threshold;
-}
-inline uint32_t dropout_threshold(float p) {
-  if (p <= 0.f) return 0u;
-  const double t = static_cast<double>(p) * 4294967296.0;
-  return t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
-}
+constexpr int kThreads = kBnThreads;
 
 struct Geometry {  // how 256 threads cover [rows, width] in the column-sum kernels
   int tw, vec;
@@ -101,28 +84,6 @@ __device__ __forceinline__ void column_partials(int64_t m, int width, int tw, fl
   }
 }
 
-// Sum of the CTA partials of one column pair, by 8 threads in interleaved order then in thread order.
-// Block = 32 columns x 8; returns the totals to the threads with threadIdx.x < 32.
-__device__ __forceinline__ void combine_partials(const float* __restrict__ partial, int n_partial, int width, int col,
-                                                 float& s, float& q) {
-  __shared__ float s_c[2][8][32];
-  const int cx = threadIdx.x % 32, py = threadIdx.x / 32;
-  float a = 0.f, b = 0.f;
-  if (col < width) {
-    for (int i = py; i < n_partial; i += 8) {
-      a += partial[(static_cast<int64_t>(i) * 2 + 0) * width + col];
-      b += partial[(static_cast<int64_t>(i) * 2 + 1) * width + col];
-    }
-  }
-  s_c[0][py][cx] = a;
-  s_c[1][py][cx] = b;
-  __syncthreads();
-  s = q = 0.f;
-  if (py == 0) {
-    for (int y = 0; y < 8; ++y) { s += s_c[0][y][cx]; q += s_c[1][y][cx]; }
-  }
-}
-
 // ---------------------------------------------------------------------------------- forward
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) bn_stats_kernel(int64_t m, int width, int tw, const float* __restrict__ z,
@@ -140,47 +101,6 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(int64_t m, int width
 #pragma unroll
     for (int v = 0; v < VEC; ++v) b[v] = a[v] * a[v];
   });
-}
-
-__global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const aread_bn_act_args a, const float* partial,
-                                                               int n_partial) {
-  const int col = blockIdx.x * 32 + threadIdx.x % 32;
-  float s = 0.f, q = 0.f;
-  if (a.training && !a.bn_skip) combine_partials(partial, n_partial, a.width, col, s, q);
-  if (col >= a.width || threadIdx.x >= 32) return;
-  float scale, shift;
-  if (a.bn_skip) {
-    scale = 1.f;
-    shift = 0.f;
-    a.mean[col] = 0.f;
-    a.rstd[col] = 1.f;
-  } else if (a.training) {
-    const float inv_m = 1.f / static_cast<float>(a.m);
-    const float d = s * inv_m;                       // mean - pivot
-    const float mean = a.z[col] + d;                 // the pivot is the column's first row
-    const float var = fmaxf(q * inv_m - d * d, 0.f);
-    const float rstd = 1.f / sqrtf(var + a.eps);
-    a.mean[col] = mean;
-    a.rstd[col] = rstd;
-    scale = a.gamma[col] * rstd;
-    shift = a.beta[col] - mean * scale;
-    const float unbiased = a.m > 1 ? var * (static_cast<float>(a.m) / static_cast<float>(a.m - 1)) : var;
-    a.running_mean[col] = (1.f - a.momentum) * a.running_mean[col] + a.momentum * mean;
-    a.running_var[col] = (1.f - a.momentum) * a.running_var[col] + a.momentum * unbiased;
-  } else {
-    const float rstd = 1.f / sqrtf(a.running_var[col] + a.eps);
-    a.mean[col] = a.running_mean[col];
-    a.rstd[col] = rstd;
-    scale = a.gamma[col] * rstd;
-    shift = a.beta[col] - a.running_mean[col] * scale;
-  }
-  a.scale[col] = scale;
-  a.shift[col] = shift;
-}
-
-__device__ __forceinline__ float act_value(float z, float scale, float shift, bool keep, float keep_scale) {
-  const float y = fmaf(z, scale, shift);
-  return (y > 0.f && keep) ? y * keep_scale : 0.f;
 }
 
 // rows by (blockIdx.x, ty), columns by tx, VEC consecutive columns per thread: no index divisions
@@ -262,28 +182,6 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const aread_bn_a
       s2[v] = dy * (z[v] - __ldg(a.mean + c)) * __ldg(a.rstd + c);
     }
   });
-}
-
-__global__ void __launch_bounds__(kThreads) bn_bwd_finalize_kernel(const aread_bn_act_bwd_args a, const float* partial,
-                                                                   int n_partial, float* coef) {
-  const int col = blockIdx.x * 32 + threadIdx.x % 32;
-  float s1, s2;
-  combine_partials(partial, n_partial, a.width, col, s1, s2);
-  if (col >= a.width || threadIdx.x >= 32) return;
-  if (a.bn_skip) {  // identity instead of BatchNorm: gamma / beta see no gradient, the bias sees sum(dy)
-    if (a.d_gamma) a.d_gamma[col] = 0.f;
-    if (a.d_beta) a.d_beta[col] = 0.f;
-    if (a.d_bias) a.d_bias[col] = s1;
-    coef[col] = 0.f;
-    coef[a.width + col] = 0.f;
-  } else {
-    if (a.d_gamma) a.d_gamma[col] = s2;
-    if (a.d_beta) a.d_beta[col] = s1;
-    if (a.d_bias) a.d_bias[col] = 0.f;  // BatchNorm removes the column mean: the exact gradient is zero
-    const float inv_m = 1.f / static_cast<float>(a.m);
-    coef[col] = s1 * inv_m;
-    coef[a.width + col] = s2 * inv_m;
-  }
 }
 
 template <int VEC>
@@ -523,6 +421,56 @@ int aread_bn_act_bwd(const aread_bn_act_bwd_args* args, aread_stream_t stream_) 
     else
       AREAD_LAUNCH(bn_bwd_apply_kernel<1>, rg.grid, kThreads, 0, stream, a, rg.tw, threshold, keep_scale, coef);
   }
+  return AREAD_OK;
+}
+
+// Activation pass alone, with the statistics (scale / shift) already finalised by the caller.
+int aread_bn_act_apply(const aread_bn_act_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "bn_act_apply: null args");
+  const aread_bn_act_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.width > 0, "bn_act_apply: bad shape");
+  AREAD_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, "bn_act_apply: dropout %f not in [0, 1)", a.dropout_p);
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.z && a.scale && a.shift && (a.out_f32 || a.out_bf16), "bn_act_apply: null pointer");
+  const bool drop = a.training && a.dropout_p > 0.f;
+  const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;
+  const float keep_scale = drop ? 1.f / (1.f - a.dropout_p) : 1.f;
+  const bool aligned = a.ldz % 4 == 0 && a.ldo % 4 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0 &&
+                       reinterpret_cast<uintptr_t>(a.out_f32) % 16 == 0 &&
+                       reinterpret_cast<uintptr_t>(a.out_bf16) % 8 == 0 &&
+                       reinterpret_cast<uintptr_t>(a.out_bf16_lo) % 8 == 0;
+  const RowGrid rg = row_grid(a.m, a.width, aligned);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rg.vec == 4)
+    AREAD_LAUNCH(bn_act_kernel<4>, rg.grid, kThreads, 0, stream, a, rg.tw, threshold, keep_scale);
+  else
+    AREAD_LAUNCH(bn_act_kernel<1>, rg.grid, kThreads, 0, stream, a, rg.tw, threshold, keep_scale);
+  return AREAD_OK;
+}
+
+// Reduction half of the backward alone: d_gamma / d_beta / d_bias and coef = [sum(dy) / m | sum(dy * xhat) / m].
+int aread_bn_bwd_coef(const aread_bn_act_bwd_args* args, float* coef, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr && coef != nullptr, "bn_bwd_coef: null args");
+  const aread_bn_act_bwd_args& a = *args;
+  AREAD_REQUIRE(a.m > 0 && a.width > 0 && a.width <= 65536, "bn_bwd_coef: bad shape");
+  AREAD_REQUIRE(a.z && a.d_out && a.mean && a.rstd && a.scale && a.shift, "bn_bwd_coef: null pointer");
+  AREAD_REQUIRE(a.workspace_bytes >= aread_bn_workspace_bytes(a.width), "bn_bwd_coef: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* partial = static_cast<float*>(a.workspace);
+  const int n_partial = stat_ctas(a.m);
+  const bool drop = a.dropout_p > 0.f;
+  const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;
+  const float keep_scale = drop ? 1.f / (1.f - a.dropout_p) : 1.f;
+  const Geometry g = geometry(a.width, a.ldz % 4 == 0 && a.ldd % 4 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0 &&
+                                           reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0);
+  const size_t smem = sizeof(float) * 2 * kThreads * g.vec;
+  if (g.vec == 4)
+    AREAD_LAUNCH(bn_bwd_stats_kernel<4>, n_partial, kThreads, smem, stream, a, g.tw, threshold, keep_scale, partial);
+  else
+    AREAD_LAUNCH(bn_bwd_stats_kernel<1>, n_partial, kThreads, smem, stream, a, g.tw, threshold, keep_scale, partial);
+  AREAD_LAUNCH(bn_bwd_finalize_kernel, ceil_div(a.width, 32), kThreads, 0, stream, a, partial, n_partial, coef);
   return AREAD_OK;
 }
 

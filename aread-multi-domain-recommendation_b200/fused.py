@@ -9,6 +9,7 @@ row-pass weight matrix, the cross-network constants) or allocate buffers.
 Reference: model/aread.py:129-322 (forward modes + hier_tower_mask_forward).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -17,9 +18,14 @@ from . import _lib
 from . import _mem
 from . import dense_kernels as dk
 from . import embedding_ops
+from . import hei_ops
 from . import rowpass_ops
 from . import tower_ops
 from .expert_ops import _hi, _lo
+
+
+# fused tower-layer kernels (csrc/hei.cu); AREAD_HEI_FUSED=0 selects the per-op kernels of tower.cu / bn_act.cu
+USE_HEI_LAYER = os.environ.get("AREAD_HEI_FUSED", "1") != "0"
 
 
 def _stream(device):
@@ -219,23 +225,37 @@ class AreadNode(torch.autograd.Function):
                     gate_means[l] = means
                 rec.update(wg=wg, logits=logits, edges=edges, u_prev=u_prev)
             lay = []
-            for L in P.towers[l]:
+            na = len(act)
+            hei = USE_HEI_LAYER and all(hei_ops.supported(na, L.k, L.n) for L in P.towers[l])
+            rec["hei"] = hei
+            z = stats = None
+            for j, L in enumerate(P.towers[l]):
                 full = idx is None
                 w, bias = _sel(L.weight.flat, idx), _sel(L.bias.flat, idx)
                 gamma, beta_bn = _sel(L.gamma.flat, idx), _sel(L.beta.flat, idx)
                 rm, rv = _sel(L.running_mean.flat, idx), _sel(L.running_var.flat, idx)
-                z = tower_ops.tower_linear(h, w, bias, L.n)
-                na = len(act)
-                out, stats = dk.bn_act_fwd(z.view(B, na * L.n), gamma.reshape(-1), beta_bn.reshape(-1), rm.view(-1),
-                                           rv.view(-1), training, bn_skip, p_drop, seed, L.salt, torch.float32)
+                if hei:     # the layer reads its input straight from the previous pre-activation
+                    src = h.view(B, na * L.k) if j == 0 else z
+                    src_saved = None if j == 0 else stats
+                    src_salt = 0 if j == 0 else P.towers[l][j - 1].salt
+                    z, stats = hei_ops.layer_fwd(src, src_saved, src_salt, w, bias, gamma.reshape(-1), beta_bn.reshape(-1),
+                                                 rm.view(-1), rv.view(-1), na, L.k, L.n, training, bn_skip, p_drop, seed)
+                    lay.append((src, src_saved, z, stats, w))
+                else:
+                    z = tower_ops.tower_linear(h, w, bias, L.n)
+                    out, stats = dk.bn_act_fwd(z.view(B, na * L.n), gamma.reshape(-1), beta_bn.reshape(-1), rm.view(-1),
+                                               rv.view(-1), training, bn_skip, p_drop, seed, L.salt, torch.float32)
+                    lay.append((h, z, stats, w))
+                    h = out.view(B, na, L.n)
                 if training and not bn_skip:
                     if not full:
                         L.running_mean.flat.index_copy_(0, idx, rm)
                         L.running_var.flat.index_copy_(0, idx, rv)
                     tracked = L.tracked
                     torch._foreach_add_([tracked[t] for t in act], 1)
-                lay.append((h, z, stats, w))
-                h = out.view(B, na, L.n)
+            if hei:
+                L = P.towers[l][-1]
+                h = hei_ops.bn_apply(z, stats, training, p_drop, seed, L.salt).view(B, na, L.n)
             rec["layers"] = lay
             levels.append(rec)
         sv["levels"] = levels
@@ -282,7 +302,22 @@ class AreadNode(torch.autograd.Function):
         for l in range(n_level - 1, -1, -1):
             rec = sv["levels"][l]
             na = len(active[l])
-            for j in range(len(P.towers[l]) - 1, -1, -1):
+            if rec["hei"]:
+                layers = P.towers[l]
+                L = layers[-1]
+                d_out = d_h.contiguous().view(B, na * L.n)
+                coef, g3 = hei_ops.bn_bwd_coef(rec["layers"][-1][2], d_out, rec["layers"][-1][3], bn_skip, p_drop, seed,
+                                               L.salt)
+                for j in range(len(layers) - 1, -1, -1):
+                    L = layers[j]
+                    src, src_saved, z, stats, w = rec["layers"][j]
+                    d_out, d_w, src_coef, src_g3 = hei_ops.layer_bwd(z, d_out, stats, coef, p_drop, L.salt, seed, bn_skip,
+                                                                     src, src_saved, layers[j - 1].salt if j > 0 else 0,
+                                                                     w, na, L.k, L.n)
+                    tower_grads[l][j] = (d_w, g3[2].view(na, L.n), g3[0].view(na, L.n), g3[1].view(na, L.n))
+                    coef, g3 = src_coef, src_g3
+                d_h = d_out.view(B, na, layers[0].k)
+            for j in range(len(P.towers[l]) - 1, -1, -1) if not rec["hei"] else ():
                 L = P.towers[l][j]
                 h_in, z, stats, w = rec["layers"][j]
                 dzl, d_gamma, d_beta, d_bias = dk.bn_act_bwd(z.view(B, na * L.n), d_h.contiguous().view(B, na * L.n),

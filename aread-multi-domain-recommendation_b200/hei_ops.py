@@ -1,0 +1,96 @@
+"""Torch-tensor wrappers over the fused HEI tower-layer entry points (csrc/hei.cu); no arithmetic here.
+
+`saved` is the [4, width] fp32 block (mean, rstd, scale, shift) the BatchNorm kernels share; `src_saved`
+is the same block of the layer below when the layer input is that layer's pre-activation."""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import _mem
+from .dense_kernels import BN_EPS, BN_MOMENTUM, _bn_workspace, _ptr
+
+_WS = {}
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def supported(groups, k, n):
+    return bool(_lib.load().aread_hei_layer_supported(groups, k, n))
+
+
+def _workspace(device, m, groups, k, n):
+    need = int(_lib.load().aread_hei_layer_workspace_bytes(m, groups, k, n))
+    ws = _WS.get(device)
+    if ws is None or ws.numel() < need:
+        ws = _WS[device] = torch.empty(need, dtype=torch.uint8, device=device)
+    return ws
+
+
+def layer_fwd(src, src_saved, src_salt, weight, bias, gamma, beta, running_mean, running_var, groups, k, n, training,
+              bn_skip, p, seed):
+    """src [m, groups * k] -> (z [m, groups * n], saved [4, groups * n])."""
+    m = src.shape[0]
+    dev = src.device
+    z = _mem.empty((m, groups * n), torch.float32, dev)
+    saved = _mem.empty((4, groups * n), torch.float32, dev)
+    ws = _workspace(dev, m, groups, k, n)
+    has = src_saved is not None
+    args = _lib.HeiLayerFwdArgs(
+        m, groups, k, n, 1 if training else 0, 1 if bn_skip else 0, BN_MOMENTUM, BN_EPS, src.data_ptr(), src.stride(0),
+        src_saved[2].data_ptr() if has else None, src_saved[3].data_ptr() if has else None,
+        float(p) if training else 0.0, src_salt, seed, weight.data_ptr(), _ptr(bias), _ptr(gamma), _ptr(beta),
+        _ptr(running_mean), _ptr(running_var), z.data_ptr(), saved[0].data_ptr(), saved[1].data_ptr(),
+        saved[2].data_ptr(), saved[3].data_ptr(), ws.data_ptr(), ws.numel())
+    _lib.check(_lib.load().aread_hei_layer_fwd(ctypes.byref(args), _stream(dev)))
+    return z, saved
+
+
+def bn_apply(z, saved, training, p, seed, salt):
+    """dropout(relu(z * scale + shift)) as fp32 [m, width]."""
+    m, width = z.shape
+    out = _mem.empty((m, width), torch.float32, z.device)
+    args = _lib.BnActArgs(m, width, 1 if training else 0, 0, BN_MOMENTUM, BN_EPS, float(p) if training else 0.0, seed,
+                          salt, z.data_ptr(), z.stride(0), None, None, None, None, saved[0].data_ptr(),
+                          saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(), out.data_ptr(), None, width,
+                          None, 0, None)
+    _lib.check(_lib.load().aread_bn_act_apply(ctypes.byref(args), _stream(z.device)))
+    return out
+
+
+def bn_bwd_coef(z, d_out, saved, bn_skip, p, seed, salt):
+    """(coef [2, width], grads [3, width] = d_gamma, d_beta, d_bias) of out = dropout(relu(bn(z)))."""
+    m, width = z.shape
+    coef = _mem.empty((2, width), torch.float32, z.device)
+    grads = torch.empty((3, width), dtype=torch.float32, device=z.device)        # parameter gradients: never arena
+    ws = _bn_workspace(z.device, width)
+    args = _lib.BnActBwdArgs(m, width, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), z.stride(0),
+                             d_out.data_ptr(), d_out.stride(0), saved[0].data_ptr(), saved[1].data_ptr(),
+                             saved[2].data_ptr(), saved[3].data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(),
+                             grads[2].data_ptr(), None, None, width, ws.data_ptr(), ws.numel(), None)
+    _lib.check(_lib.load().aread_bn_bwd_coef(ctypes.byref(args), ctypes.c_void_p(coef.data_ptr()), _stream(z.device)))
+    return coef, grads
+
+
+def layer_bwd(z, d_out, saved, coef, p, salt, seed, bn_skip, src, src_saved, src_salt, weight, groups, k, n):
+    """-> (d_in [m, groups * k], d_w [groups, n, k], src_coef or None, src_grads [3, groups * k] or None)."""
+    m = z.shape[0]
+    dev = z.device
+    d_in = _mem.empty((m, groups * k), torch.float32, dev)
+    d_w = torch.empty((groups, n, k), dtype=torch.float32, device=dev)           # parameter gradient: never arena
+    has = src_saved is not None
+    src_coef = _mem.empty((2, groups * k), torch.float32, dev) if has else None
+    src_grads = torch.empty((3, groups * k), dtype=torch.float32, device=dev) if has else None
+    ws = _workspace(dev, m, groups, k, n)
+    args = _lib.HeiLayerBwdArgs(
+        m, groups, k, n, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), d_out.data_ptr(), saved[0].data_ptr(),
+        saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(), coef.data_ptr(), src.data_ptr(), src.stride(0),
+        src_saved[2].data_ptr() if has else None, src_saved[3].data_ptr() if has else None,
+        src_saved[0].data_ptr() if has else None, src_saved[1].data_ptr() if has else None, float(p), src_salt,
+        weight.data_ptr(), d_in.data_ptr(), d_w.data_ptr(), _ptr(src_coef),
+        src_grads[0].data_ptr() if has else None, src_grads[1].data_ptr() if has else None,
+        src_grads[2].data_ptr() if has else None, ws.data_ptr(), ws.numel())
+    _lib.check(_lib.load().aread_hei_layer_bwd(ctypes.byref(args), _stream(dev)))
+    return d_in, d_w, src_coef, src_grads

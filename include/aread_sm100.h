@@ -262,6 +262,92 @@ AREAD_API int aread_bn_act_fwd(const aread_bn_act_args* args, aread_stream_t str
 AREAD_API int aread_bn_act_bwd(const aread_bn_act_bwd_args* args, aread_stream_t stream);
 AREAD_API int aread_dropout_mask(uint64_t seed, uint32_t salt, int64_t n, float p, uint8_t* out, aread_stream_t stream);
 
+/* Activation pass of aread_bn_act_fwd alone: out = dropout(relu(z * scale + shift)) with scale / shift given. */
+AREAD_API int aread_bn_act_apply(const aread_bn_act_args* args, aread_stream_t stream);
+/* Reduction half of aread_bn_act_bwd alone: d_gamma / d_beta / d_bias and
+ * coef[0:width] = sum(dy) / m, coef[width:2*width] = sum(dy * xhat) / m. */
+AREAD_API int aread_bn_bwd_coef(const aread_bn_act_bwd_args* args, float* coef, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One HEI tower layer for all towers that run under the mask, fused with its surroundings
+ * (model/layer.py:221-229 inside model/aread.py:297-321).  `src` is [m, groups * k]: either a plain
+ * activation (src_scale == NULL) or the PREVIOUS layer's pre-activation z, in which case
+ * dropout(relu(src * src_scale + src_shift)) is formed on the fly with the dropout stream
+ * (seed, src_salt) -- the activation between two layers never exists in memory.
+ *
+ * forward:  z = act(src) W^T + bias, plus this layer's BatchNorm statistics (mean, rstd, scale, shift,
+ *           running update) in the same pass over z.
+ * backward: given d_out (gradient w.r.t. this layer's activation) and coef (aread_bn_bwd_coef of
+ *           (z, d_out), or the src_coef a previous call produced): d_w = dz^T act(src),
+ *           d_in = dz W (gradient w.r.t. act(src)), and when src is a pre-activation the coefficients
+ *           and parameter gradients of ITS BatchNorm backward (src_coef, src_d_gamma / _beta / _bias).
+ * k, n <= 64 (aread_hei_layer_supported); wider layers go through aread_tower_linear & co.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_hei_layer_fwd_args {
+  int64_t m;
+  int32_t groups, k, n;
+  int32_t training, bn_skip;
+  float momentum, eps;
+  const float* src;          /* [m, ld_src], group g at columns g*k .. g*k + k                */
+  int64_t ld_src;
+  const float* src_scale;    /* [groups * k] or NULL                                          */
+  const float* src_shift;
+  float src_p;               /* dropout of the src activation (applied when training)         */
+  uint32_t src_salt;
+  uint64_t seed;
+  const float* weight;       /* [groups, n, k]                                                */
+  const float* bias;         /* [groups, n] or NULL                                           */
+  const float* gamma;        /* [groups * n]                                                  */
+  const float* beta;
+  float* running_mean;       /* [groups * n], updated in place when training                  */
+  float* running_var;
+  float* z;                  /* out [m, groups * n]                                           */
+  float* mean;               /* out [groups * n] each                                         */
+  float* rstd;
+  float* scale;
+  float* shift;
+  void* workspace;           /* aread_hei_layer_workspace_bytes(m, groups, k, n)              */
+  size_t workspace_bytes;
+} aread_hei_layer_fwd_args;
+
+typedef struct aread_hei_layer_bwd_args {
+  int64_t m;
+  int32_t groups, k, n;
+  int32_t bn_skip;
+  float p;                   /* dropout of THIS layer's activation in the forward (0 in eval)  */
+  uint32_t salt;
+  uint64_t seed;
+  const float* z;            /* [m, groups * n]                                               */
+  const float* d_out;        /* [m, groups * n]                                               */
+  const float* mean;         /* this layer's saved statistics, [groups * n] each              */
+  const float* rstd;
+  const float* scale;
+  const float* shift;
+  const float* coef;         /* [2, groups * n]                                               */
+  const float* src;          /* as in the forward                                             */
+  int64_t ld_src;
+  const float* src_scale;
+  const float* src_shift;
+  const float* src_mean;
+  const float* src_rstd;
+  float src_p;
+  uint32_t src_salt;
+  const float* weight;       /* [groups, n, k]                                                */
+  float* d_in;               /* out [m, groups * k] or NULL                                   */
+  float* d_w;                /* out [groups, n, k]                                            */
+  float* src_coef;           /* out [2, groups * k]      (src_scale != NULL)                  */
+  float* src_d_gamma;        /* out [groups * k] each, optional                               */
+  float* src_d_beta;
+  float* src_d_bias;
+  void* workspace;
+  size_t workspace_bytes;
+} aread_hei_layer_bwd_args;
+
+AREAD_API int aread_hei_layer_supported(int32_t groups, int32_t k, int32_t n);
+AREAD_API size_t aread_hei_layer_workspace_bytes(int64_t m, int32_t groups, int32_t k, int32_t n);
+AREAD_API int aread_hei_layer_fwd(const aread_hei_layer_fwd_args* args, aread_stream_t stream);
+AREAD_API int aread_hei_layer_bwd(const aread_hei_layer_bwd_args* args, aread_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * MMoE mixture fused with the last expert layer's BatchNorm/ReLU/Dropout.
  * Replaces model/aread.py:150-153: h_e = expert_e(x) (here: dropout(relu(z_e * scale + shift))),

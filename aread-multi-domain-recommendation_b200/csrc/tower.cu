@@ -165,96 +165,148 @@ __global__ void __launch_bounds__(kThreads) tower_wgrad_reduce_kernel(int n_chun
 // ------------------------------------------------------------------------------- gate mixing
 // HEI gate of one level (model/aread.py:282-288): s = softmax(logits); under a HEMP mask
 // sm = s * edge, r = sm / (sum sm + 1e-8), without a mask r = s; the tower's input is the r-weighted
-// sum of the previous level's outputs.  Row-local: one thread per (sample, tower).
+// sum of the previous level's outputs.  Row-local.  A CTA stages kGateRows samples in shared memory with
+// straight coalesced copies (every operand is a contiguous block of rows), one thread per (sample, tower)
+// turns logits into weights in place, and the outputs are produced element by element, coalesced.
 constexpr int kMaxPrev = 32;
+constexpr int kGateRows = 32;
 
-__device__ __forceinline__ void gate_weights(const aread_gate_mix_args& a, const float* __restrict__ lg, int t,
-                                             float* s, float* r, float& denom) {
+// in-place: lg[0..n_prev) holds logits on entry; on exit s[] = softmax (times nothing) and r[] the mixing weights
+__device__ __forceinline__ void gate_weights(int n_prev, const float* __restrict__ edges_t, const float* lg, float* s,
+                                             float* r, float& denom) {
   float mx = -INFINITY;
-  for (int j = 0; j < a.n_prev; ++j) mx = fmaxf(mx, lg[j]);
+  for (int j = 0; j < n_prev; ++j) mx = fmaxf(mx, lg[j]);
   float sum = 0.f;
-  for (int j = 0; j < a.n_prev; ++j) { s[j] = expf(lg[j] - mx); sum += s[j]; }
+  for (int j = 0; j < n_prev; ++j) { const float e = expf(lg[j] - mx); s[j] = e; sum += e; }
   const float inv = 1.f / sum;
   denom = 1.f;
-  if (a.edges != nullptr) {
+  if (edges_t != nullptr) {
     float tot = 0.f;
-    for (int j = 0; j < a.n_prev; ++j) { s[j] *= inv; r[j] = s[j] * __ldg(a.edges + t * a.n_prev + j); tot += r[j]; }
+    for (int j = 0; j < n_prev; ++j) { const float v = s[j] * inv; s[j] = v; const float w = v * edges_t[j]; r[j] = w; tot += w; }
     denom = tot + 1e-8f;
-    for (int j = 0; j < a.n_prev; ++j) r[j] = r[j] / denom;
+    for (int j = 0; j < n_prev; ++j) r[j] = r[j] / denom;
   } else {
-    for (int j = 0; j < a.n_prev; ++j) { s[j] *= inv; r[j] = s[j]; }
+    for (int j = 0; j < n_prev; ++j) { const float v = s[j] * inv; s[j] = v; r[j] = v; }
+  }
+}
+
+// Stage `n_valid` consecutive floats (whole rows of `w` elements) into shared memory with row stride wp >= w.
+// Odd strides keep the per-(sample, tower) threads of the weight phase off each other's banks.
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int64_t n_valid, int n_total, int w,
+                                           int wp) {
+  for (int i = threadIdx.x; i < n_total; i += kThreads) {
+    const int r = i / w, c = i - r * w;
+    dst[r * wp + c] = i < n_valid ? __ldg(src + i) : 0.f;
   }
 }
 
 __global__ void __launch_bounds__(kThreads) gate_mix_fwd_kernel(const aread_gate_mix_args a) {
-  const int64_t total = a.m * a.n_tower;
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t b = p / a.n_tower;
-    const int t = static_cast<int>(p - b * a.n_tower);
-    float s[kMaxPrev], r[kMaxPrev], denom;
-    gate_weights(a, a.logits + p * a.n_prev, t, s, r, denom);
+  extern __shared__ float smem[];
+  const int NT = a.n_tower, NP = a.n_prev, NA = a.n_prev_active, W = a.width;
+  const int NPp = NP | 1, Wp = W | 1;
+  const int LP = NT * NP, UP = NA * W, OP = NT * W;
+  float* sS = smem;                            // [rows * NT][NPp]  logits -> softmax s
+  float* sR = sS + kGateRows * NT * NPp;       // [rows * NT][NPp]  mixing weights r
+  float* sU = sR + kGateRows * NT * NPp;       // [rows * NA][Wp]
+  float* sE = sU + kGateRows * NA * Wp;        // [LP] edges (1 when unmasked)
+  int* sSlot = reinterpret_cast<int*>(sE + LP);  // [NP]
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kGateRows;
+  const int rows = a.m - b0 < kGateRows ? static_cast<int>(a.m - b0) : kGateRows;
+  stage_rows(sS, a.logits + b0 * LP, static_cast<int64_t>(rows) * LP, kGateRows * LP, NP, NPp);
+  if (UP > 0) stage_rows(sU, a.u_prev + b0 * UP, static_cast<int64_t>(rows) * UP, kGateRows * UP, W, Wp);
+  for (int i = threadIdx.x; i < LP; i += kThreads) sE[i] = a.edges ? __ldg(a.edges + i) : 1.f;
+  for (int i = threadIdx.x; i < NP; i += kThreads) sSlot[i] = __ldg(a.prev_slot + i);
+  __syncthreads();
+  for (int it = threadIdx.x; it < rows * NT; it += kThreads) {
+    const int t = it % NT;
+    float denom;
+    gate_weights(NP, a.edges ? sE + t * NP : nullptr, sS + it * NPp, sS + it * NPp, sR + it * NPp, denom);
     if (a.sm != nullptr)
-      for (int j = 0; j < a.n_prev; ++j)
-        a.sm[p * a.n_prev + j] = a.edges ? s[j] * __ldg(a.edges + t * a.n_prev + j) : s[j];
-    float* out = a.out + p * a.width;
-    for (int c = 0; c < a.width; ++c) {
-      float acc = 0.f;
-      for (int j = 0; j < a.n_prev; ++j) {
-        const int slot = __ldg(a.prev_slot + j);
-        if (slot >= 0) acc = fmaf(r[j], __ldg(a.u_prev + (b * a.n_prev_active + slot) * a.width + c), acc);
-      }
-      out[c] = acc;
+      for (int j = 0; j < NP; ++j) a.sm[(b0 * NT + it) * NP + j] = sS[it * NPp + j] * sE[t * NP + j];
+  }
+  __syncthreads();
+  float* out = a.out + b0 * OP;
+  for (int i = threadIdx.x; i < rows * OP; i += kThreads) {
+    const int r = i / OP, rem = i - r * OP;
+    const int t = rem / W, c = rem - t * W;
+    const float* w = sR + (r * NT + t) * NPp;
+    const float* u = sU + r * NA * Wp + c;
+    float acc = 0.f;
+    for (int j = 0; j < NP; ++j) {
+      const int slot = sSlot[j];
+      if (slot >= 0) acc = fmaf(w[j], u[slot * Wp], acc);
     }
+    out[i] = acc;
   }
 }
 
-// d_logits[b, t, :] and the mixing weights r[b, t, :] (scratch for the second pass)
-__global__ void __launch_bounds__(kThreads) gate_mix_bwd_logits_kernel(const aread_gate_mix_args a) {
-  const int64_t total = a.m * a.n_tower;
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t b = p / a.n_tower;
-    const int t = static_cast<int>(p - b * a.n_tower);
-    float s[kMaxPrev], r[kMaxPrev], dr[kMaxPrev], denom;
-    gate_weights(a, a.logits + p * a.n_prev, t, s, r, denom);
-    const float* d_out = a.d_out + p * a.width;
+// d_logits[b, t, :] and d_u_prev[b, slot, :] = sum_t r[b, t, j(slot)] * d_out[b, t, :]   (towers in ascending order)
+__global__ void __launch_bounds__(kThreads) gate_mix_bwd_kernel(const aread_gate_mix_args a) {
+  extern __shared__ float smem[];
+  const int NT = a.n_tower, NP = a.n_prev, NA = a.n_prev_active, W = a.width;
+  const int NPp = NP | 1, Wp = W | 1;
+  const int LP = NT * NP, UP = NA * W, OP = NT * W;
+  float* sS = smem;                            // [rows * NT][NPp]  logits -> s -> d_logits
+  float* sR = sS + kGateRows * NT * NPp;       // r
+  float* sD = sR + kGateRows * NT * NPp;       // dr
+  float* sU = sD + kGateRows * NT * NPp;       // [rows * NA][Wp]
+  float* sG = sU + kGateRows * NA * Wp;        // [rows * NT][Wp]  d_out
+  float* sE = sG + kGateRows * NT * Wp;        // [LP]
+  int* sSlot = reinterpret_cast<int*>(sE + LP);  // [NP] then [NA]
+  int* sTower = sSlot + NP;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kGateRows;
+  const int rows = a.m - b0 < kGateRows ? static_cast<int>(a.m - b0) : kGateRows;
+  stage_rows(sS, a.logits + b0 * LP, static_cast<int64_t>(rows) * LP, kGateRows * LP, NP, NPp);
+  if (UP > 0) stage_rows(sU, a.u_prev + b0 * UP, static_cast<int64_t>(rows) * UP, kGateRows * UP, W, Wp);
+  stage_rows(sG, a.d_out + b0 * OP, static_cast<int64_t>(rows) * OP, kGateRows * OP, W, Wp);
+  for (int i = threadIdx.x; i < LP; i += kThreads) sE[i] = a.edges ? __ldg(a.edges + i) : 1.f;
+  for (int i = threadIdx.x; i < NP; i += kThreads) sSlot[i] = __ldg(a.prev_slot + i);
+  for (int i = threadIdx.x; i < NA; i += kThreads) sTower[i] = __ldg(a.slot_tower + i);
+  __syncthreads();
+  for (int it = threadIdx.x; it < rows * NT; it += kThreads) {
+    const int r = it / NT, t = it - r * NT;
+    float* s = sS + it * NPp;
+    float* w = sR + it * NPp;
+    float* dr = sD + it * NPp;
+    float denom;
+    gate_weights(NP, a.edges ? sE + t * NP : nullptr, s, s, w, denom);
+    const float* g = sG + it * Wp;
     float dot_r = 0.f;
-    for (int j = 0; j < a.n_prev; ++j) {
-      const int slot = __ldg(a.prev_slot + j);
+    for (int j = 0; j < NP; ++j) {
+      const int slot = sSlot[j];
       float acc = 0.f;
       if (slot >= 0) {
-        const float* u = a.u_prev + (b * a.n_prev_active + slot) * a.width;
-        for (int c = 0; c < a.width; ++c) acc = fmaf(__ldg(d_out + c), __ldg(u + c), acc);
+        const float* u = sU + (r * NA + slot) * Wp;
+        for (int c = 0; c < W; ++c) acc = fmaf(g[c], u[c], acc);
       }
       dr[j] = acc;
-      dot_r = fmaf(acc, r[j], dot_r);
-      a.r_scratch[p * a.n_prev + j] = r[j];
+      dot_r = fmaf(acc, w[j], dot_r);
     }
     float dot_s = 0.f;
-    for (int j = 0; j < a.n_prev; ++j) {  // dr -> ds (through the renormalisation and the mask)
-      if (a.edges != nullptr) dr[j] = (dr[j] - dot_r) / denom * __ldg(a.edges + t * a.n_prev + j);
+    for (int j = 0; j < NP; ++j) {  // dr -> ds (through the renormalisation and the mask)
+      if (a.edges != nullptr) dr[j] = (dr[j] - dot_r) / denom * sE[t * NP + j];
       dot_s = fmaf(s[j], dr[j], dot_s);
     }
-    for (int j = 0; j < a.n_prev; ++j) a.d_logits[p * a.n_prev + j] = s[j] * (dr[j] - dot_s);
+    for (int j = 0; j < NP; ++j) s[j] = s[j] * (dr[j] - dot_s);
   }
-}
-
-// d_u_prev[b, slot, :] = sum_t r[b, t, j(slot)] * d_out[b, t, :]   (towers in ascending order)
-__global__ void __launch_bounds__(kThreads) gate_mix_bwd_prev_kernel(const aread_gate_mix_args a) {
-  const int64_t total = a.m * a.n_prev_active * a.width;
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(p % a.width);
-    const int64_t q = p / a.width;
-    const int slot = static_cast<int>(q % a.n_prev_active);
-    const int64_t b = q / a.n_prev_active;
-    const int j = __ldg(a.slot_tower + slot);
-    float acc = 0.f;
-    for (int t = 0; t < a.n_tower; ++t)
-      acc = fmaf(__ldg(a.r_scratch + (b * a.n_tower + t) * a.n_prev + j), __ldg(a.d_out + (b * a.n_tower + t) * a.width + c),
-                 acc);
-    a.d_u_prev[p] = acc;
+  __syncthreads();
+  float* d_logits = a.d_logits + b0 * LP;
+  for (int i = threadIdx.x; i < rows * LP; i += kThreads) {
+    const int q = i / NP;
+    d_logits[i] = sS[q * NPp + (i - q * NP)];
+  }
+  if (UP > 0 && a.d_u_prev != nullptr) {
+    float* d_u = a.d_u_prev + b0 * UP;
+    for (int i = threadIdx.x; i < rows * UP; i += kThreads) {
+      const int r = i / UP, rem = i - r * UP;
+      const int slot = rem / W, c = rem - slot * W;
+      const int j = sTower[slot];
+      const float* w = sR + r * NT * NPp + j;
+      const float* g = sG + r * NT * Wp + c;
+      float acc = 0.f;
+      for (int t = 0; t < NT; ++t) acc = fmaf(w[t * NPp], g[t * Wp], acc);
+      d_u[i] = acc;
+    }
   }
 }
 
@@ -352,20 +404,26 @@ extern "C" int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t st
   if (a.m == 0) return AREAD_OK;
   AREAD_REQUIRE(a.logits && a.prev_slot && (a.u_prev || a.n_prev_active == 0), "gate_mix: null pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  auto grid_for = [](int64_t total) {
-    int64_t g = (total + kThreads - 1) / kThreads;
-    const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
-    return static_cast<unsigned>(g < 1 ? 1 : (g > cap ? cap : g));
-  };
+  const size_t lp = static_cast<size_t>(a.n_tower) * a.n_prev;
+  const size_t ltp = static_cast<size_t>(a.n_tower) * (a.n_prev | 1), utp = static_cast<size_t>(a.n_prev_active) * (a.width | 1),
+               otp = static_cast<size_t>(a.n_tower) * (a.width | 1);   // padded shared-memory rows
+  const unsigned grid = static_cast<unsigned>((a.m + kGateRows - 1) / kGateRows);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AREAD_CUDA(cudaFuncSetAttribute(gate_mix_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AREAD_CUDA(cudaFuncSetAttribute(gate_mix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
   if (a.d_out == nullptr) {
     AREAD_REQUIRE(a.out != nullptr, "gate_mix: null out");
-    AREAD_LAUNCH(gate_mix_fwd_kernel, grid_for(a.m * a.n_tower), kThreads, 0, stream, a);
+    const size_t smem = sizeof(float) * (kGateRows * (2 * ltp + utp) + lp + a.n_prev);
+    AREAD_REQUIRE(smem <= 200 * 1024, "gate_mix: level too wide for shared memory (%zu bytes)", smem);
+    AREAD_LAUNCH(gate_mix_fwd_kernel, grid, kThreads, smem, stream, a);
   } else {
-    AREAD_REQUIRE(a.d_logits && a.r_scratch && (a.d_u_prev || a.n_prev_active == 0) && a.slot_tower,
-                  "gate_mix: null gradient pointer");
-    AREAD_LAUNCH(gate_mix_bwd_logits_kernel, grid_for(a.m * a.n_tower), kThreads, 0, stream, a);
-    if (a.n_prev_active > 0 && a.d_u_prev != nullptr)
-      AREAD_LAUNCH(gate_mix_bwd_prev_kernel, grid_for(a.m * a.n_prev_active * a.width), kThreads, 0, stream, a);
+    AREAD_REQUIRE(a.d_logits && (a.d_u_prev || a.n_prev_active == 0) && a.slot_tower, "gate_mix: null gradient pointer");
+    const size_t smem = sizeof(float) * (kGateRows * (3 * ltp + utp + otp) + lp + a.n_prev + a.n_prev_active);
+    AREAD_REQUIRE(smem <= 200 * 1024, "gate_mix: level too wide for shared memory (%zu bytes)", smem);
+    AREAD_LAUNCH(gate_mix_bwd_kernel, grid, kThreads, smem, stream, a);
   }
   return AREAD_OK;
 }

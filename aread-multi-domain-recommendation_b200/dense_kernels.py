@@ -91,6 +91,12 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def _rows(t, n):
+    """Device addresses of the first n rows of a contiguous 2-D fp32 tensor (no view objects)."""
+    base, step = t.data_ptr(), t.stride(0) * 4
+    return [base + i * step for i in range(n)]
+
+
 def bn_act_fwd(z, gamma, beta, running_mean, running_var, training, bn_skip, p, seed, salt, out_dtype,
                want_lo=False):
     """(out, saved) or (out, out_lo, saved) with want_lo: out = dropout(relu(bn(z))) as `out_dtype`
@@ -102,8 +108,7 @@ def bn_act_fwd(z, gamma, beta, running_mean, running_var, training, bn_skip, p, 
     ws = _bn_workspace(z.device, width)
     args = _lib.BnActArgs(m, width, 1 if training else 0, 1 if bn_skip else 0, BN_MOMENTUM, BN_EPS,
                           float(p) if training else 0.0, seed, salt, z.data_ptr(), z.stride(0), _ptr(gamma),
-                          _ptr(beta), _ptr(running_mean), _ptr(running_var), saved[0].data_ptr(),
-                          saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(),
+                          _ptr(beta), _ptr(running_mean), _ptr(running_var), *_rows(saved, 4),
                           _ptr(out) if out_dtype == torch.float32 else None,
                           _ptr(out) if out_dtype == torch.bfloat16 else None, width, ws.data_ptr(), ws.numel(),
                           _ptr(out_lo))
@@ -119,9 +124,8 @@ def bn_act_bwd(z, d_out, saved, bn_skip, p, seed, salt, dz_dtype=torch.bfloat16,
     dz_lo = _mem.empty((m, width), torch.bfloat16, z.device) if want_lo else None
     ws = _bn_workspace(z.device, width)
     args = _lib.BnActBwdArgs(m, width, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), z.stride(0),
-                             d_out.data_ptr(), d_out.stride(0), saved[0].data_ptr(), saved[1].data_ptr(),
-                             saved[2].data_ptr(), saved[3].data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(),
-                             grads[2].data_ptr(), _ptr(dz) if dz_dtype == torch.float32 else None,
+                             d_out.data_ptr(), d_out.stride(0), *_rows(saved, 4), *_rows(grads, 3),
+                             _ptr(dz) if dz_dtype == torch.float32 else None,
                              _ptr(dz) if dz_dtype == torch.bfloat16 else None, width, ws.data_ptr(), ws.numel(),
                              _ptr(dz_lo))
     _lib.check(_lib.load().aread_bn_act_bwd(ctypes.byref(args), _stream(z.device)))
@@ -132,9 +136,9 @@ def mmoe_mix_fwd(z, saved, gate, n_expert, n_gate, p, seed, salt):
     m = z.shape[0]
     width = z.shape[1] // n_expert
     out = _mem.empty((m, n_gate, width), torch.float32, z.device)
+    rows = _rows(saved, 4)
     args = _lib.MmoeMixArgs(m, width, n_expert, n_gate, float(p), seed, salt, z.data_ptr(), z.stride(0),
-                            saved[2].data_ptr(), saved[3].data_ptr(), gate.data_ptr(), out.data_ptr(), None, None,
-                            None)
+                            rows[2], rows[3], gate.data_ptr(), out.data_ptr(), None, None, None)
     _lib.check(_lib.load().aread_mmoe_mix(ctypes.byref(args), _stream(z.device)))
     return out
 
@@ -144,9 +148,10 @@ def mmoe_mix_bwd(z, saved, gate, d_out, n_expert, n_gate, p, seed, salt):
     width = z.shape[1] // n_expert
     d_h = _mem.empty((m, n_expert * width), torch.float32, z.device)
     d_gate = _mem.empty((m, n_gate, n_expert), torch.float32, z.device)
+    rows = _rows(saved, 4)
     args = _lib.MmoeMixArgs(m, width, n_expert, n_gate, float(p), seed, salt, z.data_ptr(), z.stride(0),
-                            saved[2].data_ptr(), saved[3].data_ptr(), gate.data_ptr(), None, d_out.data_ptr(),
-                            d_h.data_ptr(), d_gate.data_ptr())
+                            rows[2], rows[3], gate.data_ptr(), None, d_out.data_ptr(), d_h.data_ptr(),
+                            d_gate.data_ptr())
     _lib.check(_lib.load().aread_mmoe_mix(ctypes.byref(args), _stream(z.device)))
     return d_h, d_gate
 

@@ -52,10 +52,9 @@ def gate_mix_bwd(logits, edges, prev_slot, slot_tower, u_prev, d_out):
     dev = logits.device
     d_logits = _mem.empty((B, na, n_prev), torch.float32, dev)
     d_u = _mem.empty((B, nap, width), torch.float32, dev)
-    scratch = _mem.empty((B, na, n_prev), torch.float32, dev)
     a = _lib.GateMixArgs(B, na, n_prev, nap, width, logits.data_ptr(), edges.data_ptr() if edges is not None else None,
                          prev_slot.data_ptr(), slot_tower.data_ptr(), u_prev.data_ptr(), None, None, d_out.data_ptr(),
-                         d_logits.data_ptr(), d_u.data_ptr(), scratch.data_ptr())
+                         d_logits.data_ptr(), d_u.data_ptr(), None)
     _lib.check(_lib.load().aread_gate_mix(ctypes.byref(a), _stream(dev)))
     return d_logits, d_u
 
@@ -423,8 +422,8 @@ class AreadNode(torch.autograd.Function):
         # ---- assemble in param_list order
         def scatter_rows(n_total, act, rows):
             out = [None] * n_total
-            for i, t in enumerate(act):
-                out[t] = rows[i]
+            for t, row in zip(act, rows.unbind(0)):
+                out[t] = row
             return out
 
         grads = [d_table, d_lin_w, d_lin_b, d_grp_w]

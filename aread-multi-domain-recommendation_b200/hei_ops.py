@@ -8,7 +8,7 @@ import torch
 
 from . import _lib
 from . import _mem
-from .dense_kernels import BN_EPS, BN_MOMENTUM, _bn_workspace, _ptr
+from .dense_kernels import BN_EPS, BN_MOMENTUM, _bn_workspace, _ptr, _rows
 
 _WS = {}
 
@@ -37,13 +37,11 @@ def layer_fwd(src, src_saved, src_salt, weight, bias, gamma, beta, running_mean,
     z = _mem.empty((m, groups * n), torch.float32, dev)
     saved = _mem.empty((4, groups * n), torch.float32, dev)
     ws = _workspace(dev, m, groups, k, n)
-    has = src_saved is not None
+    sp = _rows(src_saved, 4) if src_saved is not None else (None,) * 4
     args = _lib.HeiLayerFwdArgs(
         m, groups, k, n, 1 if training else 0, 1 if bn_skip else 0, BN_MOMENTUM, BN_EPS, src.data_ptr(), src.stride(0),
-        src_saved[2].data_ptr() if has else None, src_saved[3].data_ptr() if has else None,
-        float(p) if training else 0.0, src_salt, seed, weight.data_ptr(), _ptr(bias), _ptr(gamma), _ptr(beta),
-        _ptr(running_mean), _ptr(running_var), z.data_ptr(), saved[0].data_ptr(), saved[1].data_ptr(),
-        saved[2].data_ptr(), saved[3].data_ptr(), ws.data_ptr(), ws.numel())
+        sp[2], sp[3], float(p) if training else 0.0, src_salt, seed, weight.data_ptr(), _ptr(bias), _ptr(gamma),
+        _ptr(beta), _ptr(running_mean), _ptr(running_var), z.data_ptr(), *_rows(saved, 4), ws.data_ptr(), ws.numel())
     _lib.check(_lib.load().aread_hei_layer_fwd(ctypes.byref(args), _stream(dev)))
     return z, saved
 
@@ -53,9 +51,8 @@ def bn_apply(z, saved, training, p, seed, salt):
     m, width = z.shape
     out = _mem.empty((m, width), torch.float32, z.device)
     args = _lib.BnActArgs(m, width, 1 if training else 0, 0, BN_MOMENTUM, BN_EPS, float(p) if training else 0.0, seed,
-                          salt, z.data_ptr(), z.stride(0), None, None, None, None, saved[0].data_ptr(),
-                          saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(), out.data_ptr(), None, width,
-                          None, 0, None)
+                          salt, z.data_ptr(), z.stride(0), None, None, None, None, *_rows(saved, 4), out.data_ptr(),
+                          None, width, None, 0, None)
     _lib.check(_lib.load().aread_bn_act_apply(ctypes.byref(args), _stream(z.device)))
     return out
 
@@ -67,9 +64,8 @@ def bn_bwd_coef(z, d_out, saved, bn_skip, p, seed, salt):
     grads = torch.empty((3, width), dtype=torch.float32, device=z.device)        # parameter gradients: never arena
     ws = _bn_workspace(z.device, width)
     args = _lib.BnActBwdArgs(m, width, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), z.stride(0),
-                             d_out.data_ptr(), d_out.stride(0), saved[0].data_ptr(), saved[1].data_ptr(),
-                             saved[2].data_ptr(), saved[3].data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(),
-                             grads[2].data_ptr(), None, None, width, ws.data_ptr(), ws.numel(), None)
+                             d_out.data_ptr(), d_out.stride(0), *_rows(saved, 4), *_rows(grads, 3), None, None, width,
+                             ws.data_ptr(), ws.numel(), None)
     _lib.check(_lib.load().aread_bn_bwd_coef(ctypes.byref(args), ctypes.c_void_p(coef.data_ptr()), _stream(z.device)))
     return coef, grads
 
@@ -84,13 +80,11 @@ def layer_bwd(z, d_out, saved, coef, p, salt, seed, bn_skip, src, src_saved, src
     src_coef = _mem.empty((2, groups * k), torch.float32, dev) if has else None
     src_grads = torch.empty((3, groups * k), dtype=torch.float32, device=dev) if has else None
     ws = _workspace(dev, m, groups, k, n)
+    sp = _rows(src_saved, 4) if has else (None,) * 4
+    gp = _rows(src_grads, 3) if has else (None,) * 3
     args = _lib.HeiLayerBwdArgs(
-        m, groups, k, n, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), d_out.data_ptr(), saved[0].data_ptr(),
-        saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(), coef.data_ptr(), src.data_ptr(), src.stride(0),
-        src_saved[2].data_ptr() if has else None, src_saved[3].data_ptr() if has else None,
-        src_saved[0].data_ptr() if has else None, src_saved[1].data_ptr() if has else None, float(p), src_salt,
-        weight.data_ptr(), d_in.data_ptr(), d_w.data_ptr(), _ptr(src_coef),
-        src_grads[0].data_ptr() if has else None, src_grads[1].data_ptr() if has else None,
-        src_grads[2].data_ptr() if has else None, ws.data_ptr(), ws.numel())
+        m, groups, k, n, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), d_out.data_ptr(), *_rows(saved, 4),
+        coef.data_ptr(), src.data_ptr(), src.stride(0), sp[2], sp[3], sp[0], sp[1], float(p), src_salt,
+        weight.data_ptr(), d_in.data_ptr(), d_w.data_ptr(), _ptr(src_coef), *gp, ws.data_ptr(), ws.numel())
     _lib.check(_lib.load().aread_hei_layer_bwd(ctypes.byref(args), _stream(dev)))
     return d_in, d_w, src_coef, src_grads

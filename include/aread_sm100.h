@@ -519,7 +519,7 @@ typedef struct aread_gate_mix_args {
   const float* d_out;       /* backward in [m, n_tower, width]                  */
   float* d_logits;          /* backward out [m, n_tower, n_prev]                */
   float* d_u_prev;          /* backward out [m, n_prev_active, width]           */
-  float* r_scratch;         /* backward scratch [m, n_tower, n_prev]            */
+  float* r_scratch;         /* unused (kept for layout stability); may be NULL  */
 } aread_gate_mix_args;
 
 AREAD_API int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t stream);

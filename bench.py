@@ -40,8 +40,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="amazon", choices=["amazon", "aliccp", "cloudtheme"])
     ap.add_argument("--batch", type=int, default=65536, help="samples per step per GPU")
-    ap.add_argument("--cpu-batch", type=int, default=2048, help="rows per step of the bounded CPU sample")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-batch", type=int, default=4096, help="rows per step of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=30, help="timed steps of the cpu_baseline leg (about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--active", type=float, default=0.7, help="HEMP init_active_percent of the per-domain masks")
     ap.add_argument("--dropout", type=float, default=0.2)
@@ -169,6 +169,11 @@ def run_reference(args, wl, rank):
             "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one gather_kernel launch at the default workload (amazon, B=65536),
+# from the committed ncu --set full capture
+GATHER_DRAM_BYTES = 21_772_800 + 56_982_272
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -313,7 +318,12 @@ def run_ours(args, wl, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "gather_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": GATHER_DRAM_BYTES if (world == 1 and args.workload == "amazon" and B == 65536) else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                       "(profiles/r1_gather_kernel_full.txt); below the algorithmic bytes because the "
+                                       "hot rows of the Zipf ids and part of the output stay in the 126 MB L2",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": gather_bytes, "launch_ms": gather_ms},
     }
     if not args.no_cpu_baseline and world == 1:

@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_s
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -148,7 +148,7 @@ class AdamArgs(Structure):
     _fields_ = [("n_tensors", c_int32), ("n_chunks", c_int64), ("params", c_void_p), ("grads", c_void_p),
                 ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("sizes", c_void_p), ("chunk_start", c_void_p),
                 ("step_size", c_void_p), ("bc2_sqrt", c_void_p), ("beta1", c_float), ("beta2", c_float),
-                ("eps", c_float), ("weight_decay", c_float)]
+                ("eps", c_float), ("weight_decay", c_float), ("l2_twice", c_void_p)]
 
 
 _SIGNATURES = {

@@ -32,11 +32,14 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const aread_adam_args a)
     float* __restrict__ m = a.exp_avg[t];
     float* __restrict__ v = a.exp_avg_sq[t];
     const float step_size = a.step_size[t], bc2_sqrt = a.bc2_sqrt[t];
+    const float c = a.l2_twice ? a.l2_twice[t] : 0.f;
     const int64_t begin = (chunk - a.chunk_start[t]) * kChunk;
     const int64_t end = min(a.sizes[t], begin + kChunk);
     for (int64_t i = begin + threadIdx.x; i < end; i += kThreads) {
       const float pi = p[i];
-      const float gi = __ldg(g + i) + a.weight_decay * pi;
+      float gi = g ? __ldg(g + i) : 0.f;
+      if (c != 0.f) gi = __fadd_rn(gi, __fmul_rn(c, pi));   // rounded like the separate regulariser gradient + add
+      gi = gi + a.weight_decay * pi;
       float mi = m[i];
       mi = mi + (gi - mi) * (1.f - a.beta1);
       const float vi = v[i] * a.beta2 + (1.f - a.beta2) * gi * gi;

@@ -16,19 +16,25 @@ class _Plan:
     """Launch table of one (param group, set of parameters that have a gradient): everything that does not
     change from step to step, laid out as the rows of the pinned block the kernel reads."""
 
-    def __init__(self, params, idx, states, chunk):
+    def __init__(self, params, idx, states, chunk, l2):
         self.params = params
         self.idx = np.asarray(idx, dtype=np.int64)
         self.ptrs = [p.data_ptr() for p in params]
         n = len(params)
-        self.static = np.zeros((8, n), dtype=np.int64)
+        self.static = np.zeros((9, n), dtype=np.int64)
         h = self.static
+        f = h.view(np.float32).reshape(9, -1)
+        self.has_l2 = False
         start = 0
         for i, (p, st) in enumerate(zip(params, states)):
             h[0, i] = p.data_ptr()
             h[2, i], h[3, i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
             h[4, i], h[5, i] = p.numel(), start
             start += (p.numel() + chunk - 1) // chunk
+            c = l2.get(p, 0.0)
+            if c > 0:
+                f[8, i] = np.float32(2.0) * np.float32(c)
+                self.has_l2 = True
         self.n_chunks = start
         self.moments = [(st["exp_avg"], st["exp_avg_sq"]) for st in states]     # keeps the addresses valid
 
@@ -39,7 +45,19 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError("invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._chunk = None
+        self._l2 = {}
         self._bind_steps()
+
+    def fold_l2(self, terms):
+        """terms: {parameter: l2}.  The step then uses grad + 2 * l2 * p for these parameters (a missing
+        gradient counts as zero: a regularised parameter is updated every step, exactly as when the
+        regulariser is part of the loss)."""
+        known = {p for group in self.param_groups for p in group["params"]}
+        missing = [p for p in terms if p not in known]
+        if missing:
+            raise ValueError(f"{len(missing)} regularised parameter(s) are not managed by this optimizer")
+        self._l2 = dict(terms)
+        self._plans = {}
 
     def _bind_steps(self):
         """state[p]["step"] (a host scalar tensor, as in torch.optim.Adam) becomes a view into one array per
@@ -69,7 +87,7 @@ class FusedAdam(torch.optim.Optimizer):
         arr, view = self._steps[gi]
         states = []
         for i, p in zip(idx, params):
-            if p.grad.is_sparse or not p.is_cuda or p.dtype != torch.float32:
+            if (p.grad is not None and p.grad.is_sparse) or not p.is_cuda or p.dtype != torch.float32:
                 raise RuntimeError("FusedAdam handles dense fp32 CUDA parameters only")
             st = self.state[p]
             if not st:
@@ -77,7 +95,7 @@ class FusedAdam(torch.optim.Optimizer):
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
             states.append(st)
-        return _Plan(params, idx, states, self._chunk)
+        return _Plan(params, idx, states, self._chunk, self._l2)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -92,7 +110,11 @@ class FusedAdam(torch.optim.Optimizer):
             beta1, beta2 = group["betas"]
             lr, eps, wd = group["lr"], group["eps"], group["weight_decay"]
             grads = [p.grad for p in group["params"]]
-            idx = tuple(i for i, g in enumerate(grads) if g is not None)        # parameters without gradient: skipped
+            if self._l2:    # a folded regulariser gives its parameters a gradient every step
+                l2 = self._l2
+                idx = tuple(i for i, (g, p) in enumerate(zip(grads, group["params"])) if g is not None or p in l2)
+            else:
+                idx = tuple(i for i, g in enumerate(grads) if g is not None)    # parameters without gradient: skipped
             if not idx:
                 continue
             plan = self._plans.get((gi, idx))
@@ -100,26 +122,27 @@ class FusedAdam(torch.optim.Optimizer):
                 if len(self._plans) > 256:
                     self._plans.clear()
                 plan = self._plans[(gi, idx)] = self._plan(gi, group, idx)
-            grads = [grads[i] if grads[i].is_contiguous() else grads[i].contiguous() for i in idx]
+            grads = [g if (g is None or g.is_contiguous()) else g.contiguous() for g in (grads[i] for i in idx)]
             n = len(idx)
             device = plan.params[0].device
             steps = self._steps[gi][0]
             steps[plan.idx] += 1
             t = steps[plan.idx].astype(np.float64)
-            # rows: params, grads, exp_avg, exp_avg_sq, sizes, chunk_start (int64); step_size, bc2_sqrt (fp32).
+            # rows: params, grads, exp_avg, exp_avg_sq, sizes, chunk_start (int64); step_size, bc2_sqrt, 2 * l2 (fp32).
             # A fresh pinned block per step: torch's host allocator will not recycle it before the copy ran.
-            host = torch.empty((8, n), dtype=torch.int64, pin_memory=True)
-            dev = torch.empty((8, n), dtype=torch.int64, device=device)
+            host = torch.empty((9, n), dtype=torch.int64, pin_memory=True)
+            dev = torch.empty((9, n), dtype=torch.int64, device=device)
             h = host.numpy()
             np.copyto(h, plan.static)
-            h[1, :] = [g.data_ptr() for g in grads]
-            f = h.view(np.float32).reshape(8, -1)                               # fp32 view of the same rows
+            h[1, :] = [0 if g is None else g.data_ptr() for g in grads]
+            f = h.view(np.float32).reshape(9, -1)                               # fp32 view of the same rows
             f[6, :n] = lr / (1.0 - beta1 ** t)
             f[7, :n] = np.sqrt(1.0 - beta2 ** t)
             dev.copy_(host, non_blocking=True)
             base, row = dev.data_ptr(), dev.stride(0) * 8
             args = _lib.AdamArgs(n, plan.n_chunks, base, base + row, base + 2 * row, base + 3 * row, base + 4 * row,
-                                 base + 5 * row, base + 6 * row, base + 7 * row, beta1, beta2, eps, wd)
+                                 base + 5 * row, base + 6 * row, base + 7 * row, beta1, beta2, eps, wd,
+                                 base + 8 * row if plan.has_l2 else None)
             _lib.check(lib.aread_adam_step(ctypes.byref(args),
                                            ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
         return loss

@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--optimizer", default="fused", choices=["torch", "fused"],
                     help="the library's FusedAdam (one launch; same arithmetic as torch.optim.Adam, tests/test_optim_gpu.py) or "
                          "torch.optim.Adam as run.py:830 builds it")
+    ap.add_argument("--reg", default="fold", choices=["fold", "loss"],
+                    help="gradient of the L2 regulariser: folded into FusedAdam (value still part of the loss) or "
+                         "through autograd as in run.py:644")
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="bagging BCE through AREAD.bagging_loss (one kernel) or as the trainer's sum of BCELoss calls")
     return ap.parse_args()
@@ -205,11 +208,15 @@ def run_ours(args, wl, rank, world, local_rank):
         sharding = importlib.import_module("aread-multi-domain-recommendation_b200.sharding")
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
-        shards = model.embedding.shard_table()
+        shards = model.shard_table()
     model.train()
     fused_adam = importlib.import_module("aread-multi-domain-recommendation_b200.optim").FusedAdam
     adam_cls = fused_adam if args.optimizer == "fused" else torch.optim.Adam
     opt = adam_cls(model.parameters(), lr=LR, betas=(0.9, 0.99), eps=1e-8, weight_decay=WD)
+    if args.reg == "fold":                         # L2 gradient applied inside the optimizer step
+        if args.optimizer != "fused":
+            raise SystemExit("--reg fold needs --optimizer fused")
+        model.fold_regularization_into(opt)
     crit = torch.nn.BCELoss()
     table_param = model.embedding.embedding_dict.weight
     dense_params = [p for p in model.parameters() if p is not table_param]
@@ -310,6 +317,8 @@ def run_ours(args, wl, rank, world, local_rank):
                    "mask_active_percent": args.active, "dropout": args.dropout,
                    "optimizer": "torch.optim.Adam" if args.optimizer == "torch" else "aread_b200 FusedAdam",
                    "loss": "AREAD.bagging_loss" if args.loss == "fused" else "sum of torch BCELoss",
+                   "l2_regulariser": "value in the loss, gradient folded into FusedAdam" if args.reg == "fold"
+                   else "autograd node",
                    "parallelism": f"dp{world}" + ("" if world == 1 else f" + table row-sharded over {world} GPUs (P2P lookup, "
                                                    "reduce-scatter of the table gradient, flat all-reduce of the rest)"),
                    "l2": "inputs larger than L2: table %d MB + per-step activations" % (wl.n_rows * wl.embed_dim * 4 >> 20)},

@@ -543,6 +543,9 @@ typedef struct aread_adam_args {
   const float* step_size;        /* device [n_tensors]: lr / (1 - beta1^t)              */
   const float* bc2_sqrt;         /* device [n_tensors]: sqrt(1 - beta2^t)               */
   float beta1, beta2, eps, weight_decay;
+  const float* l2_twice;         /* device [n_tensors] or NULL: 2 * l2 of an L2 regulariser folded into  */
+                                 /* the step (g += l2_twice * p before the weight decay); grads[t] may   */
+                                 /* be NULL for such tensors (a gradient of zero)                        */
 } aread_adam_args;
 
 AREAD_API int64_t aread_adam_chunk(void);

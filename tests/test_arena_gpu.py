@@ -109,3 +109,29 @@ def test_second_backward_is_refused():
     loss.backward(retain_graph=True)
     with pytest.raises(RuntimeError, match="second backward"):
         loss.backward()
+
+
+def test_folded_regulariser_trains_like_the_loss_term():
+    """BaseModel.fold_regularization_into: value still in the loss, gradient applied by FusedAdam."""
+    optim = importlib.import_module("aread-multi-domain-recommendation_b200.optim")
+    fx, model_a, masks, batches = _setup()
+    _, model_b, _, _ = _setup()
+    kw = dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+    opt_a, opt_b = optim.FusedAdam(model_a.parameters(), **kw), optim.FusedAdam(model_b.parameters(), **kw)
+    model_b.fold_regularization_into(opt_b)
+    for i in range(6):
+        losses = []
+        for model, opt in ((model_a, opt_a), (model_b, opt_b)):
+            x, y = batches[i % 4][0].to(DEV), batches[i % 4][1].to(DEV)
+            preds = model(x, mode="domain_mask_bagging", domain_i=fx["domain"],
+                          current_mask=[m.to(DEV) for m in masks[i % 4]])
+            loss = model.bagging_loss(preds, y) + model.get_regularization_loss(device=torch.device(DEV))
+            model.zero_grad()
+            loss.backward()
+            opt.step()
+            losses.append(loss.detach())
+        torch.testing.assert_close(losses[1], losses[0], rtol=1e-5, atol=1e-6)
+    sa, sb = model_a.state_dict(), model_b.state_dict()
+    for k in sa:
+        if sa[k].dtype.is_floating_point:
+            torch.testing.assert_close(sb[k], sa[k], rtol=2e-5, atol=2e-6, msg=k)

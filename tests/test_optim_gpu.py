@@ -40,3 +40,29 @@ def test_fused_adam_matches_torch_adam():
     o_back = torch.optim.Adam(mine, **kw)
     o_back.load_state_dict(sd)
     assert len(o_back.state) == len(o_mine.state)
+
+
+def test_folded_l2_matches_regulariser_in_the_loss():
+    """FusedAdam.fold_l2: same weights as adding l2 * sum(w^2) to the loss, including parameters whose only
+    gradient is the regulariser's (grad None otherwise)."""
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    shapes = [(20000, 32), (256, 288), (256,), (64, 64), (5,)]
+    l2 = [1e-5, 1e-5, 0.0, 2e-5, 0.0]
+    a = [torch.randn(*s, device=DEV, generator=gen).requires_grad_(True) for s in shapes]
+    b = [p.detach().clone().requires_grad_(True) for p in a]
+    kw = dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+    o_a, o_b = torch.optim.Adam(a, **kw), optim.FusedAdam(b, **kw)
+    o_b.fold_l2({p: c for p, c in zip(b, l2) if c > 0})
+    for step in range(5):
+        data = [None if (step + i) % 3 == 2 else torch.randn(s, device=DEV, generator=gen) * 1e-3
+                for i, s in enumerate(shapes)]
+        for p, q, g, c in zip(a, b, data, l2):
+            reg = 2 * c * p.detach() if c > 0 else None
+            p.grad = g.clone() + reg if (g is not None and reg is not None) else (g.clone() if g is not None else reg)
+            q.grad = None if g is None else g.clone()
+        o_a.step()
+        o_b.step()
+        for i, (p, q) in enumerate(zip(a, b)):
+            torch.testing.assert_close(q, p, rtol=1e-6, atol=1e-7, msg=f"param {i} step {step}")
+    with pytest.raises(ValueError):
+        o_b.fold_l2({torch.nn.Parameter(torch.zeros(3, device=DEV)): 1e-5})

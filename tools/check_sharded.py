@@ -31,7 +31,7 @@ def build():
     return m.train()
 
 ref, model = build(), build()
-shards = model.embedding.shard_table()
+shards = model.shard_table()
 B = 4096
 x, y, d = wl.batch(B, seed=100 + rank)
 x, y = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
@@ -40,9 +40,11 @@ def step(m):
     preds = m(x, mode="domain_mask_bagging", domain_i=d)
     tgt = y.squeeze().float()
     loss = sum(torch.nn.functional.binary_cross_entropy(p, tgt) for p in preds.unbind(0)) / preds.shape[0]
+    loss = loss + REG * m.get_regularization_loss(device=dev)
     m.zero_grad(); loss.backward()
     return preds.detach()
 
+REG = 0.0
 with torch.no_grad():
     e_ref, e_sh = ref.embedding(x), model.embedding(x)
 assert torch.equal(e_ref, e_sh), "sharded lookup differs from the single-table lookup"
@@ -53,6 +55,16 @@ dist.all_reduce(g_full, op=dist.ReduceOp.AVG)
 want = sharding.split_table(g_full, world, rank)
 got = model.embedding.embedding_dict.weight.grad
 torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-7)
+# with the regulariser in the loss: every rank adds the same 2 * l2 * w, so the average keeps it; on the sharded
+# model the term follows the shard parameter (BaseModel.shard_table)
+REG = 1.0
+step(ref); step(model)
+g_full = ref.embedding.embedding_dict.weight.grad.clone()
+dist.all_reduce(g_full, op=dist.ReduceOp.AVG)
+torch.testing.assert_close(model.embedding.embedding_dict.weight.grad, sharding.split_table(g_full, world, rank),
+                           rtol=1e-5, atol=1e-7)
+REG = 0.0
+step(ref); step(model)
 # dense gradients: flat-bucket all-reduce equals per-tensor averaging
 dense = [p for n, p in model.named_parameters() if not n.startswith("embedding.")]
 expect = []

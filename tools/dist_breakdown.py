@@ -23,10 +23,12 @@ for d in range(wl.n_domain):
 if world > 1:
     for p in model.parameters():
         dist.broadcast(p.data, src=0)
-    model.embedding.shard_table()
+    model.shard_table()
 model.train()
 Adam = importlib.import_module("aread-multi-domain-recommendation_b200.optim").FusedAdam if os.environ.get("OPT", "fused") == "fused" else torch.optim.Adam
 opt = Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+if os.environ.get("REG", "fold") == "fold" and os.environ.get("OPT", "fused") == "fused":
+    model.fold_regularization_into(opt)
 crit = torch.nn.BCELoss()
 table = model.embedding.embedding_dict.weight
 dense = [p for p in model.parameters() if p is not table]

@@ -36,6 +36,7 @@ struct GemmParams {
   const float* bias;
   int n_m_tiles, n_n_tiles, n_k_blocks;
   int n_seg;  // 1: bf16 operands; 3: split operands, A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
+  int tma_store;  // fp32 output in whole 32-column chunks: the epilogue stages them in smem and stores with TMA
   int64_t total_tiles;
   unsigned char group_ids[kMaxGroups];
 };
@@ -45,7 +46,9 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarrierOffset = kStages * kStageBytes;
+  static constexpr int kStoreOffset = kStages * kStageBytes;           // epilogue staging: 4 warps x 2 x [32][32] fp32
+  static constexpr int kStoreBytes = 4 * 2 * 32 * 128;
+  static constexpr int kBarrierOffset = kStoreOffset + kStoreBytes;
   static constexpr int kTotal = kBarrierOffset + 256 + 1024;  // barriers + slack for 1024-byte alignment
 };
 
@@ -66,7 +69,7 @@ template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo,
-                      const GemmParams p) {
+                      const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -153,6 +156,7 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   } else {  // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
     const int quad = warp % 4;
     int acc = 0;
+    int store_buf = 0;
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile(p, tile);
@@ -171,6 +175,25 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col_in_group + j < p.n) v[j] += __ldg(p.bias + col + j);
+        }
+        if (p.tma_store) {
+          // stage the warp's [32 rows][32 fp32] chunk in 128B-swizzled shared memory (what the tensor map expects)
+          // and let the TMA unit write whole 128-byte rows; rows past m are clipped by the map
+          uint8_t* stage_buf = smem + L::kStoreOffset + (quad * 2 + store_buf) * (32 * 128);
+          if (lane == 0) ptx::tma_store_wait_read<1>();       // the store that used this buffer two chunks ago
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&map_c, stage_buf, static_cast<int32_t>(col), c.m_t * BM + quad * 32);
+            ptx::tma_store_commit();
+          }
+          store_buf ^= 1;
+          continue;
         }
         if (row < p.m) {
           const bool full = col_in_group + 32 <= p.n;
@@ -210,6 +233,7 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && lane == 0) ptx::tma_store_wait_read<0>();   // shared memory must outlive the last stores
   }
 
   ptx::tc_fence_before_sync();
@@ -446,9 +470,24 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
   return AREAD_OK;
 }
 
+// fp32 row-major [rows, cols] output, box = [32 rows, 32 cols] (one 128-byte swizzle row per matrix row)
+int make_store_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t elem[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, elem,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled (store) failed with CUresult %d", (int)r);
+  return AREAD_OK;
+}
+
 template <int BN>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma_lo, const CUtensorMap& mb_lo,
-                const GemmParams& p, cudaStream_t stream) {
+                const CUtensorMap& mc, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool configured = false;
   if (!configured) {
@@ -457,7 +496,7 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     configured = true;
   }
   const unsigned grid = static_cast<unsigned>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
-  AREAD_LAUNCH((grouped_linear_kernel<BN>), grid, kGemmThreads, L::kTotal, stream, ma, mb, ma_lo, mb_lo, p);
+  AREAD_LAUNCH((grouped_linear_kernel<BN>), grid, kGemmThreads, L::kTotal, stream, ma, mb, ma_lo, mb_lo, mc, p);
   return AREAD_OK;
 }
 
@@ -551,8 +590,14 @@ extern "C" int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, 
     if (int rc = make_map(&ma_lo, a.a_lo, a.m, a_cols, a.lda, BM)) return rc;
     if (int rc = make_map(&mb_lo, a.b_lo, static_cast<int64_t>(a.groups) * a.n, a.k, a.ldb, bn)) return rc;
   }
+  CUtensorMap mc = ma;
+  p.tma_store = (a.c_f32 != nullptr && a.n % 32 == 0 && a.ldc % 4 == 0 && reinterpret_cast<uintptr_t>(a.c_f32) % 16 == 0)
+                    ? 1 : 0;
+  if (p.tma_store)
+    if (int rc = make_store_map(&mc, a.c_f32, a.m, static_cast<int64_t>(a.groups) * a.n, a.ldc)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  return bn == 128 ? launch_gemm<128>(ma, mb, ma_lo, mb_lo, p, stream) : launch_gemm<64>(ma, mb, ma_lo, mb_lo, p, stream);
+  return bn == 128 ? launch_gemm<128>(ma, mb, ma_lo, mb_lo, mc, p, stream)
+                   : launch_gemm<64>(ma, mb, ma_lo, mb_lo, mc, p, stream);
 }
 
 extern "C" size_t aread_grouped_wgrad_workspace_bytes(const aread_grouped_wgrad_args* args) {

@@ -495,8 +495,16 @@ Tiling tiling(int64_t m, int quads, int groups, int sm_multiple) {
   return t;
 }
 
-// CTAs per SM that are resident at once (registers / shared memory): the grid is one full wave of them
-constexpr int kFwdSmMultiple = 4, kBwdSmMultiple = 2;
+// Upper bounds on the CTAs per SM that can be resident at once (registers); the launch asks the runtime for the
+// real figure at its shared-memory size and makes the grid ONE full wave of them.
+constexpr int kFwdSmMultiple = 2, kBwdSmMultiple = 2;
+
+template <typename Kernel>
+int resident_ctas(Kernel kernel, size_t smem, int fallback) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = fallback;
+  return n;
+}
 
 size_t fwd_smem(const Tiling& t, int K, int N) {
   const int Np = (N + 3) & ~3, Kp = (K + 3) & ~3;
@@ -548,7 +556,7 @@ int aread_hei_layer_fwd(const aread_hei_layer_fwd_args* args, aread_stream_t str
                 "hei_layer_fwd: workspace too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int Np = (a.n + 3) & ~3;
-  const Tiling t = tiling(a.m, Np / 4, a.groups, kFwdSmMultiple);
+  Tiling t = tiling(a.m, Np / 4, a.groups, kFwdSmMultiple);
   const size_t smem = fwd_smem(t, a.k, a.n);
   static bool attr_set = false;
   if (!attr_set) {
@@ -556,6 +564,10 @@ int aread_hei_layer_fwd(const aread_hei_layer_fwd_args* args, aread_stream_t str
     attr_set = true;
   }
   AREAD_REQUIRE(smem <= 160 * 1024, "hei_layer_fwd: tile needs %zu bytes of shared memory", smem);
+  {  // fewer, longer CTAs when fewer than kFwdSmMultiple fit per SM (never more: the workspace is sized for that)
+    const int occ = resident_ctas(hei_layer_fwd_kernel, smem, 1);
+    if (occ < kFwdSmMultiple) t = tiling(a.m, Np / 4, a.groups, occ);
+  }
   const Drop d = make_drop(a.training ? a.src_p : 0.f);
   const int do_stats = (a.training && !a.bn_skip) ? 1 : 0;
   float* partial = static_cast<float*>(a.workspace);
@@ -598,7 +610,7 @@ int aread_hei_layer_bwd(const aread_hei_layer_bwd_args* args, aread_stream_t str
                 "hei_layer_bwd: workspace too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int Np = (a.n + 3) & ~3, Kp = (a.k + 3) & ~3;
-  const Tiling t = tiling(a.m, Kp / 4, a.groups, kBwdSmMultiple);
+  Tiling t = tiling(a.m, Kp / 4, a.groups, kBwdSmMultiple);
   const int mt_n = (Np / 4) * (Kp / 4);
   const int rs_n = kThreads / mt_n;
   const size_t smem = bwd_smem(t, a.k, a.n, src_bn);
@@ -608,6 +620,10 @@ int aread_hei_layer_bwd(const aread_hei_layer_bwd_args* args, aread_stream_t str
     attr_set = true;
   }
   AREAD_REQUIRE(smem <= 200 * 1024, "hei_layer_bwd: tile needs %zu bytes of shared memory", smem);
+  {
+    const int occ = resident_ctas(hei_layer_bwd_kernel, smem, 1);
+    if (occ < kBwdSmMultiple) t = tiling(a.m, Kp / 4, a.groups, occ);
+  }
   const Drop d = make_drop(a.p), ds = make_drop(a.src_p);
   float* partial_w = static_cast<float*>(a.workspace);
   float* partial_s = partial_w + static_cast<size_t>(t.n_cta) * a.groups * a.n * a.k;

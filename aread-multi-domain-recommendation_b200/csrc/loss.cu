@@ -54,10 +54,68 @@ __global__ void __launch_bounds__(256) bce_final_kernel(int64_t n, const float* 
   if (threadIdx.x == 0) out[0] = s[0] * scale;
 }
 
+// ---------------------------------------------------------------------------------------- output heads
+// p[t, b] = sigmoid(head_cross[b, t] + <h[b, t, :], w_tail[t, :]> + lin[b])      (model/aread.py:307-310; the part
+// of towers_linear that multiplies cn_out arrives pre-reduced in head_cross, see rowpass.cu)
+// One thread per sample; the transposed [T, m] output is written coalesced (threads run along b).
+__global__ void __launch_bounds__(kThreads) head_fwd_kernel(const aread_head_args a) {
+  const int T = a.n_tower, W = a.width;
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < a.m;
+       b += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const float lin = __ldg(a.lin + b);
+    const float* h = a.h + b * T * W;
+    for (int t = 0; t < T; ++t) {
+      float acc = 0.f;
+      for (int c = 0; c < W; ++c) acc = fmaf(__ldg(h + t * W + c), __ldg(a.w_tail + t * W + c), acc);
+      const float z = __ldg(a.head_cross + b * T + t) + acc + lin;
+      a.probs[static_cast<int64_t>(t) * a.m + b] = 1.f / (1.f + expf(-z));
+    }
+  }
+}
+
+// dz[b, t] = d_p[t, b] * p (1 - p);  d_lin[b] = sum_t dz;  d_h[b, t, :] = dz * w_tail[t, :]
+__global__ void __launch_bounds__(kThreads) head_bwd_kernel(const aread_head_args a) {
+  const int T = a.n_tower, W = a.width;
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < a.m;
+       b += static_cast<int64_t>(gridDim.x) * kThreads) {
+    float dl = 0.f;
+    float* dh = a.d_h + b * T * W;
+    for (int t = 0; t < T; ++t) {
+      const float p = __ldg(a.probs + static_cast<int64_t>(t) * a.m + b);
+      const float dz = __ldg(a.d_probs + static_cast<int64_t>(t) * a.m + b) * p * (1.f - p);
+      a.dz[b * T + t] = dz;
+      dl += dz;
+      for (int c = 0; c < W; ++c) dh[t * W + c] = dz * __ldg(a.w_tail + t * W + c);
+    }
+    a.d_lin[b] = dl;
+  }
+}
+
 }  // namespace
 }  // namespace aread
 
 extern "C" {
+
+int aread_head(const aread_head_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "head: null args");
+  const aread_head_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.n_tower > 0 && a.width > 0, "head: bad shape");
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.h && a.w_tail && a.probs, "head: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int64_t g = (a.m + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+  const unsigned grid = static_cast<unsigned>(g > cap ? cap : g);
+  if (a.d_probs == nullptr) {
+    AREAD_REQUIRE(a.head_cross && a.lin, "head: null forward input");
+    AREAD_LAUNCH(head_fwd_kernel, grid, kThreads, 0, stream, a);
+  } else {
+    AREAD_REQUIRE(a.dz && a.d_lin && a.d_h, "head: null gradient output");
+    AREAD_LAUNCH(head_bwd_kernel, grid, kThreads, 0, stream, a);
+  }
+  return AREAD_OK;
+}
 
 size_t aread_bagging_bce_workspace_bytes(int64_t m, int32_t n_tower) {
   const int64_t chunks = (m + aread::kChunk - 1) / aread::kChunk;

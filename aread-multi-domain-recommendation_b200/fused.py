@@ -207,7 +207,12 @@ class AreadNode(torch.autograd.Function):
             if l > 0:
                 n_prev = n_tower[l - 1]
                 wg, bg = _sel(P.gate_w[l].flat, idx), _sel(P.gate_b[l].flat, idx)
-                logits = tower_ops.tower_linear(q, wg, bg.reshape(-1), n_prev, groups=len(act))   # [B, na, n_prev]
+                # all gates of the level share the input q: ONE [B, 2D] x [2D, na * n_prev] product
+                if len(act) * n_prev <= 128:
+                    logits = tower_ops.tower_linear(q, wg.view(1, len(act) * n_prev, -1), bg.reshape(-1),
+                                                    len(act) * n_prev, groups=1).view(B, len(act), n_prev)
+                else:
+                    logits = tower_ops.tower_linear(q, wg, bg.reshape(-1), n_prev, groups=len(act))
                 edges = None if info is None else _sel(info.edges(l, dev).t().contiguous(), idx)
                 prev_slot, slot_tower = cfg["slots"][l]
                 want_sm = cfg["want_gate_means"] or cfg["want_gates"]
@@ -261,8 +266,10 @@ class AreadNode(torch.autograd.Function):
 
         # ---- heads: z_t = w_out_t[:E] . cn_out + w_out_t[E:] . u_t + lin ; p = sigmoid(z)
         w_tail = w_out[:, E:].contiguous()                                               # [na_last, w]
-        tail = tower_ops.tower_linear(h, w_tail.unsqueeze(1), None, 1)                   # [B, na_last, 1]
-        probs = torch.sigmoid(head_cross + tail.view(B, -1) + lin.unsqueeze(1)).t().contiguous()    # [na_last, B]
+        probs = torch.empty((len(a_last), B), dtype=torch.float32, device=dev)           # leaves the node: not arena
+        ha = _lib.HeadArgs(B, len(a_last), w_tail.shape[1], head_cross.data_ptr(), lin.data_ptr(), h.data_ptr(),
+                           w_tail.data_ptr(), probs.data_ptr(), None, None, None, None)
+        _lib.check(_lib.load().aread_head(ctypes.byref(ha), _stream(dev)))
         sv.update(h_last=h, w_tail=w_tail, probs=probs.detach())      # detached alias: no ctx <-> output cycle
 
         cfg["gate_means"], cfg["gates"], cfg["gate_inputs"] = gate_means, gates, q
@@ -288,12 +295,15 @@ class AreadNode(torch.autograd.Function):
         n_expert = len(model.mmoe_experts)
 
         probs = sv["probs"]
-        dz = (d_probs * probs * (1.0 - probs)).t().contiguous()                          # [B, na_last]
-        d_lin = dz.sum(dim=1)
-        na_last = dz.shape[1]
+        na_last, w_last = probs.shape[0], sv["w_tail"].shape[1]
+        dz = _mem.empty((B, na_last), torch.float32, dev)
+        d_lin = _mem.empty((B,), torch.float32, dev)
+        d_h = _mem.empty((B, na_last, w_last), torch.float32, dev)
+        ha = _lib.HeadArgs(B, na_last, w_last, None, None, sv["h_last"].data_ptr(), sv["w_tail"].data_ptr(),
+                           probs.data_ptr(), d_probs.contiguous().data_ptr(), dz.data_ptr(), d_lin.data_ptr(),
+                           d_h.data_ptr())
+        _lib.check(_lib.load().aread_head(ctypes.byref(ha), _stream(dev)))
         d_w_tail = tower_ops.tower_wgrad(dz.view(B, na_last, 1), sv["h_last"]).view(na_last, -1)
-        d_h = tower_ops.tower_linear(dz.view(B, na_last, 1), sv["w_tail"].unsqueeze(1), None, sv["w_tail"].shape[1],
-                                     weight_is_out_by_in=False)
 
         tower_grads = [[None] * len(P.towers[l]) for l in range(n_level)]
         gate_grads = [None] * n_level
@@ -330,7 +340,10 @@ class AreadNode(torch.autograd.Function):
                 d_logits, d_u = gate_mix_bwd(rec["logits"], rec["edges"], prev_slot, slot_tower, rec["u_prev"],
                                              d_h.contiguous())
                 n_prev = n_tower[l - 1]
-                d_wg = tower_ops.tower_wgrad(d_logits, sv["q"])                          # [na, n_prev, 2D]
+                if ((na * n_prev + 3) // 4) * ((2 * D + 3) // 4) <= 256:                 # one group: q is read once
+                    d_wg = tower_ops.tower_wgrad(d_logits.view(B, 1, na * n_prev), sv["q"]).view(na, n_prev, 2 * D)
+                else:
+                    d_wg = tower_ops.tower_wgrad(d_logits, sv["q"])                      # [na, n_prev, 2D]
                 d_bg = d_logits.sum(dim=0)                                               # [na, n_prev]
                 gate_grads[l] = (d_wg, d_bg)
                 dq_l = tower_ops.tower_linear(d_logits.view(B, 1, na * n_prev), rec["wg"].reshape(1, na * n_prev, 2 * D),

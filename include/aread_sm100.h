@@ -571,6 +571,29 @@ AREAD_API size_t aread_bagging_bce_workspace_bytes(int64_t m, int32_t n_tower);
 AREAD_API int aread_bagging_bce(const aread_bagging_bce_args* args, aread_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Output heads of the active last-level towers (model/aread.py:307-310):
+ *   probs[t, b] = sigmoid(head_cross[b, t] + <h[b, t, :], w_tail[t, :]> + lin[b])
+ * head_cross is the cross-network part of towers_linear (aread_rowpass_fwd), w_tail the columns of
+ * towers_linear that multiply the tower output.  Forward when d_probs == NULL; else
+ *   dz[b, t] = d_probs[t, b] * p (1 - p), d_lin[b] = sum_t dz, d_h[b, t, :] = dz * w_tail[t, :].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_head_args {
+  int64_t m;
+  int32_t n_tower, width;
+  const float* head_cross;   /* [m, n_tower]            (forward)              */
+  const float* lin;          /* [m]                     (forward)              */
+  const float* h;            /* [m, n_tower, width]                            */
+  const float* w_tail;       /* [n_tower, width]                               */
+  float* probs;              /* [n_tower, m]: out (forward) / in (backward)    */
+  const float* d_probs;      /* [n_tower, m]            (backward)             */
+  float* dz;                 /* out [m, n_tower]                               */
+  float* d_lin;              /* out [m]                                        */
+  float* d_h;                /* out [m, n_tower, width]                        */
+} aread_head_args;
+
+AREAD_API int aread_head(const aread_head_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * CUDA IPC plumbing of the row-sharded table (one process per GPU).  aread_ipc_export gives the
  * 64-byte handle of the allocation that contains `ptr` and ptr's offset inside it; a peer process
  * passes both to aread_ipc_open (with ITS compute device) and receives a pointer its kernels can

@@ -46,7 +46,7 @@ __device__ __forceinline__ float src_value(float raw, const float* __restrict__ 
 // CTA = (chunk of row tiles, group).  Thread = 4 rows x 4 output columns of the tile; the reduction dimension is
 // walked four at a time with 128-bit shared-memory reads (rows are padded by 4 floats: conflict-free per
 // quarter warp).
-__global__ void __launch_bounds__(kThreads) hei_layer_fwd_kernel(const aread_hei_layer_fwd_args a, int tx_n, int ty_n,
+__global__ void __launch_bounds__(kThreads, 3) hei_layer_fwd_kernel(const aread_hei_layer_fwd_args a, int tx_n, int ty_n,
                                                                  int tiles_per_cta, uint32_t thr, float keep_scale,
                                                                  int do_stats, float* __restrict__ partial) {
   extern __shared__ __align__(16) float smem[];
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) hei_layer_fwd_kernel(const aread_hei
 // fixed quad of columns, 128-bit global loads), then every thread adds its share of dz^T x (a 4 x 4 block of
 // [N, K] over an interleaved row subset) and computes 4 rows x 4 columns of d_in = dz W together with the
 // BatchNorm-backward sums of the layer below.
-__global__ void __launch_bounds__(kThreads, 2) hei_layer_bwd_kernel(const aread_hei_layer_bwd_args a, int tx_n, int ty_n,
+__global__ void __launch_bounds__(kThreads, 3) hei_layer_bwd_kernel(const aread_hei_layer_bwd_args a, int tx_n, int ty_n,
                                                                     int mt_n, int rs_n, int tiles_per_cta, uint32_t thr,
                                                                     float keep_scale, uint32_t src_thr,
                                                                     float src_keep_scale, float* __restrict__ partial_w,
@@ -497,7 +497,7 @@ Tiling tiling(int64_t m, int quads, int groups, int sm_multiple) {
 
 // Upper bounds on the CTAs per SM that can be resident at once (registers); the launch asks the runtime for the
 // real figure at its shared-memory size and makes the grid ONE full wave of them.
-constexpr int kFwdSmMultiple = 2, kBwdSmMultiple = 2;
+constexpr int kFwdSmMultiple = 3, kBwdSmMultiple = 3;
 
 template <typename Kernel>
 int resident_ctas(Kernel kernel, size_t smem, int fallback) {

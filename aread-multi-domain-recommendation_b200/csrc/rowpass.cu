@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) rowpass_prologue_bwd_kernel(const ar
 //   d_x phase: thread = (row, 16 consecutive e);   d_w phase: thread = (e, 8 of the 32 dot products),
 //   accumulating over all tiles of the CTA in registers (MAX_CHUNKS x 8).
 template <int MAX_CHUNKS>
-__global__ void __launch_bounds__(kThreads) rowdots_bwd_kernel(int64_t m, int E, int nj, int ldp,
+__global__ void __launch_bounds__(kThreads, MAX_CHUNKS <= 5 ? 2 : 1) rowdots_bwd_kernel(int64_t m, int E, int nj, int ldp,
                                                                const float* __restrict__ x,
                                                                const float* __restrict__ w,
                                                                const float* __restrict__ d_p, float* __restrict__ d_x,

@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_s
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -121,7 +121,8 @@ class HeiLayerBwdArgs(Structure):
 class HeadArgs(Structure):
     _fields_ = [("m", c_int64), ("n_tower", c_int32), ("width", c_int32), ("head_cross", c_void_p), ("lin", c_void_p),
                 ("h", c_void_p), ("w_tail", c_void_p), ("probs", c_void_p), ("d_probs", c_void_p), ("dz", c_void_p),
-                ("d_lin", c_void_p), ("d_h", c_void_p)]
+                ("d_lin", c_void_p), ("d_h", c_void_p), ("d_w_tail", c_void_p), ("workspace", c_void_p),
+                ("workspace_bytes", c_size_t)]
 
 
 class BaggingBceArgs(Structure):
@@ -192,6 +193,7 @@ _SIGNATURES = {
     "aread_hei_layer_fwd": (c_int32, [POINTER(HeiLayerFwdArgs), c_void_p]),
     "aread_hei_layer_bwd": (c_int32, [POINTER(HeiLayerBwdArgs), c_void_p]),
     "aread_head": (c_int32, [POINTER(HeadArgs), c_void_p]),
+    "aread_head_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "aread_bagging_bce_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "aread_bagging_bce": (c_int32, [POINTER(BaggingBceArgs), c_void_p]),
     "aread_l2_reg_fwd": (c_int32, [POINTER(L2RegArgs), c_void_p]),

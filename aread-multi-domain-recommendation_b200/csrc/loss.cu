@@ -73,28 +73,73 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const aread_head_arg
   }
 }
 
-// dz[b, t] = d_p[t, b] * p (1 - p);  d_lin[b] = sum_t dz;  d_h[b, t, :] = dz * w_tail[t, :]
-__global__ void __launch_bounds__(kThreads) head_bwd_kernel(const aread_head_args a) {
-  const int T = a.n_tower, W = a.width;
-  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < a.m;
-       b += static_cast<int64_t>(gridDim.x) * kThreads) {
+// dz[b, t] = d_p[t, b] * p (1 - p);  d_lin[b] = sum_t dz;  d_h[b, t, :] = dz * w_tail[t, :];
+// d_w_tail[t, :] = sum_b dz[b, t] * h[b, t, :]  -- warp sums into per-warp shared accumulators, warps added in
+// order, one partial per CTA, CTAs added in order by head_wgrad_reduce_kernel (bit-reproducible).
+constexpr int kHeadCtas = kNumSMs * 2;
+
+__global__ void __launch_bounds__(kThreads) head_bwd_kernel(const aread_head_args a, float* __restrict__ partial) {
+  extern __shared__ float s_acc[];  // [warps][T * W]
+  const int T = a.n_tower, W = a.width, TW = T * W;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int i = threadIdx.x; i < (kThreads / 32) * TW; i += kThreads) s_acc[i] = 0.f;
+  __syncthreads();
+  float* acc = s_acc + warp * TW;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * kThreads; base < a.m; base += stride) {
+    const int64_t b = base + threadIdx.x;
+    const bool valid = b < a.m;
     float dl = 0.f;
-    float* dh = a.d_h + b * T * W;
     for (int t = 0; t < T; ++t) {
-      const float p = __ldg(a.probs + static_cast<int64_t>(t) * a.m + b);
-      const float dz = __ldg(a.d_probs + static_cast<int64_t>(t) * a.m + b) * p * (1.f - p);
-      a.dz[b * T + t] = dz;
-      dl += dz;
-      for (int c = 0; c < W; ++c) dh[t * W + c] = dz * __ldg(a.w_tail + t * W + c);
+      float dz = 0.f;
+      if (valid) {
+        const float p = __ldg(a.probs + static_cast<int64_t>(t) * a.m + b);
+        dz = __ldg(a.d_probs + static_cast<int64_t>(t) * a.m + b) * p * (1.f - p);
+        a.dz[b * T + t] = dz;
+        dl += dz;
+      }
+      for (int c = 0; c < W; ++c) {
+        float g = 0.f;
+        if (valid) {
+          a.d_h[(b * T + t) * W + c] = dz * __ldg(a.w_tail + t * W + c);
+          g = dz * __ldg(a.h + (b * T + t) * W + c);
+        }
+        if (a.d_w_tail != nullptr) {
+          g = warp_sum(g);
+          if (lane == 0) acc[t * W + c] += g;
+        }
+      }
     }
-    a.d_lin[b] = dl;
+    if (valid) a.d_lin[b] = dl;
   }
+  if (a.d_w_tail == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW; i += kThreads) {
+    float v = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) v += s_acc[w * TW + i];
+    partial[static_cast<int64_t>(blockIdx.x) * TW + i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) head_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial,
+                                                                     int n, float* __restrict__ out) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  float v = 0.f;
+  for (int p = 0; p < n_partial; ++p) v += partial[static_cast<int64_t>(p) * n + i];
+  out[i] = v;
 }
 
 }  // namespace
 }  // namespace aread
 
 extern "C" {
+
+size_t aread_head_workspace_bytes(int32_t n_tower, int32_t width) {
+  return aread::align_up(sizeof(float) * static_cast<size_t>(aread::kHeadCtas) * (n_tower > 0 ? n_tower : 1) *
+                             (width > 0 ? width : 1),
+                         256);
+}
 
 int aread_head(const aread_head_args* args, aread_stream_t stream_) {
   using namespace aread;
@@ -112,7 +157,17 @@ int aread_head(const aread_head_args* args, aread_stream_t stream_) {
     AREAD_LAUNCH(head_fwd_kernel, grid, kThreads, 0, stream, a);
   } else {
     AREAD_REQUIRE(a.dz && a.d_lin && a.d_h, "head: null gradient output");
-    AREAD_LAUNCH(head_bwd_kernel, grid, kThreads, 0, stream, a);
+    const int tw = a.n_tower * a.width;
+    const unsigned bgrid = grid < static_cast<unsigned>(kHeadCtas) ? grid : static_cast<unsigned>(kHeadCtas);
+    const size_t smem = sizeof(float) * (kThreads / 32) * tw;
+    AREAD_REQUIRE(smem <= 48 * 1024, "head: %d x %d head weights do not fit the reduction buffer", a.n_tower, a.width);
+    AREAD_REQUIRE(a.d_w_tail == nullptr || (a.workspace && a.workspace_bytes >= aread_head_workspace_bytes(a.n_tower, a.width)),
+                  "head: workspace too small");
+    float* partial = static_cast<float*>(a.workspace);
+    AREAD_LAUNCH(head_bwd_kernel, bgrid, kThreads, smem, stream, a, partial);
+    if (a.d_w_tail != nullptr)
+      AREAD_LAUNCH(head_wgrad_reduce_kernel, ceil_div(tw, kThreads), kThreads, 0, stream, partial, static_cast<int>(bgrid),
+                   tw, a.d_w_tail);
   }
   return AREAD_OK;
 }

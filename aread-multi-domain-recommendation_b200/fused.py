@@ -28,6 +28,9 @@ from .expert_ops import _hi, _lo
 USE_HEI_LAYER = os.environ.get("AREAD_HEI_FUSED", "1") != "0"
 
 
+_HEAD_WS = {}
+
+
 def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -268,7 +271,7 @@ class AreadNode(torch.autograd.Function):
         w_tail = w_out[:, E:].contiguous()                                               # [na_last, w]
         probs = torch.empty((len(a_last), B), dtype=torch.float32, device=dev)           # leaves the node: not arena
         ha = _lib.HeadArgs(B, len(a_last), w_tail.shape[1], head_cross.data_ptr(), lin.data_ptr(), h.data_ptr(),
-                           w_tail.data_ptr(), probs.data_ptr(), None, None, None, None)
+                           w_tail.data_ptr(), probs.data_ptr(), None, None, None, None, None, None, 0)
         _lib.check(_lib.load().aread_head(ctypes.byref(ha), _stream(dev)))
         sv.update(h_last=h, w_tail=w_tail, probs=probs.detach())      # detached alias: no ctx <-> output cycle
 
@@ -299,11 +302,15 @@ class AreadNode(torch.autograd.Function):
         dz = _mem.empty((B, na_last), torch.float32, dev)
         d_lin = _mem.empty((B,), torch.float32, dev)
         d_h = _mem.empty((B, na_last, w_last), torch.float32, dev)
+        d_w_tail = torch.empty((na_last, w_last), dtype=torch.float32, device=dev)       # parameter gradient
+        need = int(_lib.load().aread_head_workspace_bytes(na_last, w_last))
+        ws = _HEAD_WS.get(dev)
+        if ws is None or ws.numel() < need:
+            ws = _HEAD_WS[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
         ha = _lib.HeadArgs(B, na_last, w_last, None, None, sv["h_last"].data_ptr(), sv["w_tail"].data_ptr(),
                            probs.data_ptr(), d_probs.contiguous().data_ptr(), dz.data_ptr(), d_lin.data_ptr(),
-                           d_h.data_ptr())
+                           d_h.data_ptr(), d_w_tail.data_ptr(), ws.data_ptr(), ws.numel())
         _lib.check(_lib.load().aread_head(ctypes.byref(ha), _stream(dev)))
-        d_w_tail = tower_ops.tower_wgrad(dz.view(B, na_last, 1), sv["h_last"]).view(na_last, -1)
 
         tower_grads = [[None] * len(P.towers[l]) for l in range(n_level)]
         gate_grads = [None] * n_level

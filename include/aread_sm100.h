@@ -575,7 +575,8 @@ AREAD_API int aread_bagging_bce(const aread_bagging_bce_args* args, aread_stream
  *   probs[t, b] = sigmoid(head_cross[b, t] + <h[b, t, :], w_tail[t, :]> + lin[b])
  * head_cross is the cross-network part of towers_linear (aread_rowpass_fwd), w_tail the columns of
  * towers_linear that multiply the tower output.  Forward when d_probs == NULL; else
- *   dz[b, t] = d_probs[t, b] * p (1 - p), d_lin[b] = sum_t dz, d_h[b, t, :] = dz * w_tail[t, :].
+ *   dz[b, t] = d_probs[t, b] * p (1 - p), d_lin[b] = sum_t dz, d_h[b, t, :] = dz * w_tail[t, :],
+ *   d_w_tail[t, :] = sum_b dz[b, t] * h[b, t, :] (fixed reduction order).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct aread_head_args {
   int64_t m;
@@ -589,8 +590,12 @@ typedef struct aread_head_args {
   float* dz;                 /* out [m, n_tower]                               */
   float* d_lin;              /* out [m]                                        */
   float* d_h;                /* out [m, n_tower, width]                        */
+  float* d_w_tail;           /* optional out [n_tower, width]: sum_b dz[b, t] * h[b, t, :] */
+  void* workspace;           /* aread_head_workspace_bytes(n_tower, width) when d_w_tail is set */
+  size_t workspace_bytes;
 } aread_head_args;
 
+AREAD_API size_t aread_head_workspace_bytes(int32_t n_tower, int32_t width);
 AREAD_API int aread_head(const aread_head_args* args, aread_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

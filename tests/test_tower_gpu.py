@@ -86,3 +86,38 @@ def test_bagging_bce_matches_bceloss(T, m):
     torch.testing.assert_close(mine, ref, rtol=2e-6, atol=1e-7)
     torch.testing.assert_close(p_mine.grad, p_ref.grad, rtol=1e-6, atol=0)
     assert torch.equal(lo.bagging_bce(probs, y), mine.detach())          # bit-reproducible
+
+
+@pytest.mark.parametrize("m,T,W", [(1, 1, 8), (37, 3, 8), (5000, 9, 8), (70001, 12, 4)])
+def test_head_kernels_match_autograd(m, T, W):
+    import ctypes
+    _lib = importlib.import_module("aread-multi-domain-recommendation_b200._lib")
+    gen = torch.Generator(device=DEV).manual_seed(m + T)
+    head_cross = torch.randn(m, T, device=DEV, generator=gen)
+    lin = torch.randn(m, device=DEV, generator=gen)
+    h = torch.randn(m, T, W, device=DEV, generator=gen).requires_grad_(True)
+    w = torch.randn(T, W, device=DEV, generator=gen).requires_grad_(True)
+    hc = head_cross.clone().requires_grad_(True)
+    ln = lin.clone().requires_grad_(True)
+    ref = torch.sigmoid(hc + (h * w).sum(dim=2) + ln.unsqueeze(1)).t().contiguous()
+    d_probs = torch.randn(T, m, device=DEV, generator=gen)
+    ref.backward(d_probs)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    probs = torch.empty(T, m, device=DEV)
+    a = _lib.HeadArgs(m, T, W, head_cross.data_ptr(), lin.data_ptr(), h.data_ptr(), w.data_ptr(), probs.data_ptr(),
+                      None, None, None, None, None, None, 0)
+    _lib.check(_lib.load().aread_head(ctypes.byref(a), stream))
+    torch.testing.assert_close(probs, ref.detach(), rtol=1e-5, atol=1e-6)
+    dz, d_lin, d_h, d_w = (torch.empty(m, T, device=DEV), torch.empty(m, device=DEV), torch.empty(m, T, W, device=DEV),
+                           torch.empty(T, W, device=DEV))
+    ws = torch.empty(int(_lib.load().aread_head_workspace_bytes(T, W)), dtype=torch.uint8, device=DEV)
+    a = _lib.HeadArgs(m, T, W, None, None, h.data_ptr(), w.data_ptr(), probs.data_ptr(), d_probs.data_ptr(),
+                      dz.data_ptr(), d_lin.data_ptr(), d_h.data_ptr(), d_w.data_ptr(), ws.data_ptr(), ws.numel())
+    _lib.check(_lib.load().aread_head(ctypes.byref(a), stream))
+    torch.testing.assert_close(dz, hc.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(d_lin, ln.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(d_h, h.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(d_w, w.grad, rtol=1e-4, atol=1e-4 * max(1.0, m ** 0.5))
+    first = d_w.clone()
+    _lib.check(_lib.load().aread_head(ctypes.byref(a), stream))
+    assert torch.equal(d_w, first)                                       # fixed reduction order

@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="amazon", choices=["amazon", "aliccp", "cloudtheme"])
+    ap.add_argument("--workload", default="amazon", choices=["amazon", "aliccp", "cloudtheme", "stress"])
     ap.add_argument("--batch", type=int, default=65536, help="samples per step per GPU")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="rows per step of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=30, help="timed steps of the cpu_baseline leg (about 15 s)")

@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_s
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -63,7 +63,8 @@ class BnActArgs(Structure):
                 ("salt", c_uint32), ("z", c_void_p), ("ldz", c_int64), ("gamma", c_void_p), ("beta", c_void_p),
                 ("running_mean", c_void_p), ("running_var", c_void_p), ("mean", c_void_p), ("rstd", c_void_p),
                 ("scale", c_void_p), ("shift", c_void_p), ("out_f32", c_void_p), ("out_bf16", c_void_p),
-                ("ldo", c_int64), ("workspace", c_void_p), ("workspace_bytes", c_size_t), ("out_bf16_lo", c_void_p)]
+                ("ldo", c_int64), ("workspace", c_void_p), ("workspace_bytes", c_size_t), ("out_bf16_lo", c_void_p),
+                ("seed_ptr", c_void_p)]
 
 
 class BnActBwdArgs(Structure):
@@ -72,14 +73,14 @@ class BnActBwdArgs(Structure):
                 ("ldd", c_int64), ("mean", c_void_p), ("rstd", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
                 ("d_gamma", c_void_p), ("d_beta", c_void_p), ("d_bias", c_void_p), ("dz_f32", c_void_p),
                 ("dz_bf16", c_void_p), ("ldo", c_int64), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
-                ("dz_bf16_lo", c_void_p)]
+                ("dz_bf16_lo", c_void_p), ("seed_ptr", c_void_p)]
 
 
 class MmoeMixArgs(Structure):
     _fields_ = [("m", c_int64), ("width", c_int32), ("n_expert", c_int32), ("n_gate", c_int32),
                 ("dropout_p", c_float), ("seed", c_uint64), ("salt", c_uint32), ("z", c_void_p), ("ldz", c_int64),
                 ("scale", c_void_p), ("shift", c_void_p), ("gate", c_void_p), ("out", c_void_p),
-                ("d_out", c_void_p), ("d_h", c_void_p), ("d_gate", c_void_p)]
+                ("d_out", c_void_p), ("d_h", c_void_p), ("d_gate", c_void_p), ("seed_ptr", c_void_p)]
 
 
 class RowpassArgs(Structure):
@@ -104,7 +105,7 @@ class HeiLayerFwdArgs(Structure):
                 ("seed", c_uint64), ("weight", c_void_p), ("bias", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
                 ("running_mean", c_void_p), ("running_var", c_void_p), ("z", c_void_p), ("mean", c_void_p),
                 ("rstd", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("workspace", c_void_p),
-                ("workspace_bytes", c_size_t)]
+                ("workspace_bytes", c_size_t), ("seed_ptr", c_void_p)]
 
 
 class HeiLayerBwdArgs(Structure):
@@ -115,7 +116,7 @@ class HeiLayerBwdArgs(Structure):
                 ("src_mean", c_void_p), ("src_rstd", c_void_p), ("src_p", c_float), ("src_salt", c_uint32),
                 ("weight", c_void_p), ("d_in", c_void_p), ("d_w", c_void_p), ("src_coef", c_void_p),
                 ("src_d_gamma", c_void_p), ("src_d_beta", c_void_p), ("src_d_bias", c_void_p), ("workspace", c_void_p),
-                ("workspace_bytes", c_size_t)]
+                ("workspace_bytes", c_size_t), ("seed_ptr", c_void_p)]
 
 
 class HeadArgs(Structure):
@@ -162,6 +163,7 @@ _SIGNATURES = {
     "aread_last_error": (c_char_p, []),
     "aread_abi_version": (c_int32, []),
     "aread_launch_count": (c_uint64, []),
+    "aread_launch_count_add": (None, [c_uint64]),
     "aread_gather_fwd": (c_int32, [POINTER(GatherArgs), c_void_p]),
     "aread_scatter_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "aread_scatter_bwd": (c_int32, [POINTER(ScatterArgs), c_void_p]),

@@ -122,12 +122,37 @@ class AREAD(BaseModel):
         object.__setattr__(self, "_fused_params", fused.param_list(self))
         object.__setattr__(self, "_slot_cache", {})
         object.__setattr__(self, "_arenas", {})
+        object.__setattr__(self, "_graphs", fused.GraphCache())
 
     @staticmethod
     def bagging_loss(y_stack, targets):
         """sum_t BCELoss(y_stack[t], targets) / n_act -- the trainer's loss of the 'domain_mask_bagging' output
         (run.py:643-644, 672-677) as one kernel."""
         return loss_ops.bagging_bce(y_stack, targets)
+
+    def record_graphs(self, x, domains=None, mode="domain_mask_bagging", backward=True):
+        """Record the CUDA-graph launch sequences (fused.py) for batches shaped like `x` under the masks of
+        `domains` ahead of time -- e.g. once after `update_all_mask`.  Without this call they are recorded lazily
+        after a few eager steps per mask.  Parameters, buffers, gradients and the CPU random stream are left as
+        they were."""
+        domains = range(self.n_domain) if domains is None else domains
+        buffers = {n: b.detach().clone() for n, b in self.named_buffers()}
+        had_grad = any(p.grad is not None for p in self.parameters())
+        rng = torch.get_rng_state()
+        # largest masks first: the activation arena then reaches its final size before most sequences are recorded
+        order = sorted(domains, key=lambda d: -sum(len(a) for a in self.mask_info(self.domain_mask[d]).active_idx))
+        for d in order:
+            for _ in range(fused.GRAPH_AFTER + 1):
+                if backward and not had_grad and self.training:
+                    self(x, mode=mode, domain_i=d).sum().backward()
+                    self.zero_grad()
+                else:
+                    with torch.no_grad():
+                        self(x, mode=mode, domain_i=d)
+        with torch.no_grad():
+            for n, b in self.named_buffers():
+                b.copy_(buffers[n])
+        torch.set_rng_state(rng)
 
     def arena(self, device):
         """The activation arena of the fused step on `device` (_mem.py)."""
@@ -141,6 +166,7 @@ class AREAD(BaseModel):
         if getattr(self, "_packs", None) is not None:
             for pack in self._packs.packs:          # .to() / .cuda() replaced every .data: pack again
                 pack.repack()
+            self._graphs.clear()                    # recorded launch sequences point at the old storage
         return out
 
     def __deepcopy__(self, memo):
@@ -148,7 +174,7 @@ class AREAD(BaseModel):
         clone = cls.__new__(cls)
         memo[id(self)] = clone
         for k, v in self.__dict__.items():
-            if k not in ("_packs", "_expert_layers", "_tower_layers", "_fused", "_fused_params", "_slot_cache", "_arenas"):
+            if k not in ("_packs", "_expert_layers", "_tower_layers", "_fused", "_fused_params", "_slot_cache", "_arenas", "_graphs"):
                 setattr(clone, k, copy.deepcopy(v, memo))
         clone._build_packs()
         return clone

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(int64_t m, int width
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) bn_act_kernel(const aread_bn_act_args a, int tw, uint32_t threshold,
                                                           float keep_scale) {
+  const uint64_t seed = seed_of(a);
   const int tx = threadIdx.x % tw, ty = threadIdx.x / tw, ty_n = kThreads / tw;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * ty_n + ty; r < a.m; r += static_cast<int64_t>(gridDim.x) * ty_n) {
     for (int col = tx * VEC; col < a.width; col += tw * VEC) {
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const aread_bn_act_arg
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const bool keep = threshold == 0u ||
-                          dropout_keep(a.seed, a.salt, static_cast<uint64_t>(r) * a.width + col + j, threshold);
+                          dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + col + j, threshold);
         v[j] = act_value(z[j], __ldg(a.scale + col + j), __ldg(a.shift + col + j), keep, keep_scale);
       }
       if (VEC == 4) {
@@ -160,6 +161,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const aread_bn_act_bwd_args a, int tw,
                                                                 uint32_t threshold, float keep_scale,
                                                                 float* __restrict__ partial) {
+  const uint64_t seed = seed_of(a);
   column_partials<VEC>(a.m, a.width, tw, partial, [&](int64_t r, int col, float (&s1)[VEC], float (&s2)[VEC]) {
     float z[VEC], d[VEC];
     if (VEC == 4) {
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const aread_bn_a
       const int c = col + v;
       const float y = fmaf(z[v], __ldg(a.scale + c), __ldg(a.shift + c));
       const bool keep = threshold == 0u ||
-                        dropout_keep(a.seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
+                        dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
       const float dy = (y > 0.f && keep) ? d[v] * keep_scale : 0.f;
       s1[v] = dy;
       s2[v] = dy * (z[v] - __ldg(a.mean + c)) * __ldg(a.rstd + c);
@@ -188,6 +190,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const aread_bn_act_bwd_args a, int tw,
                                                                 uint32_t threshold, float keep_scale,
                                                                 const float* __restrict__ coef) {
+  const uint64_t seed = seed_of(a);
   const int tx = threadIdx.x % tw, ty = threadIdx.x / tw, ty_n = kThreads / tw;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * ty_n + ty; r < a.m; r += static_cast<int64_t>(gridDim.x) * ty_n) {
     for (int col = tx * VEC; col < a.width; col += tw * VEC) {
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const aread_bn_a
         const float scale = __ldg(a.scale + c);
         const float y = fmaf(z[j], scale, __ldg(a.shift + c));
         const bool keep = threshold == 0u ||
-                          dropout_keep(a.seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
+                          dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
         const float dy = (y > 0.f && keep) ? d[j] * keep_scale : 0.f;
         const float xhat = (z[j] - __ldg(a.mean + c)) * __ldg(a.rstd + c);
         dz[j] = a.bn_skip ? dy : scale * (dy - coef[c] - xhat * coef[a.width + c]);
@@ -247,6 +250,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const aread_bn_a
 // h[b, e, :] = dropout(relu(bn(z[b, e, :]))) ;  out[b, g, :] = sum_e gate[b, g, e] * h[b, e, :]
 __global__ void __launch_bounds__(kThreads) mmoe_mix_fwd_kernel(const aread_mmoe_mix_args a, uint32_t threshold,
                                                                 float keep_scale) {
+  const uint64_t seed = seed_of(a);
   const int H = a.width, NE = a.n_expert, G = a.n_gate;
   const int64_t total = a.m * H;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(kThreads) mmoe_mix_fwd_kernel(const aread_mmoe
     for (int e = 0; e < NE; ++e) {
       const int col = e * H + c;
       const bool keep = threshold == 0u ||
-                        dropout_keep(a.seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
+                        dropout_keep(seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
       h[e] = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep, keep_scale);
     }
     for (int g = 0; g < G; ++g) {
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(kThreads) mmoe_mix_fwd_kernel(const aread_mmoe
 // one warp per sample
 __global__ void __launch_bounds__(kThreads) mmoe_mix_bwd_kernel(const aread_mmoe_mix_args a, uint32_t threshold,
                                                                 float keep_scale) {
+  const uint64_t seed = seed_of(a);
   const int H = a.width, NE = a.n_expert, G = a.n_gate;
   const int lane = threadIdx.x % 32;
   const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x / 32);
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(kThreads) mmoe_mix_bwd_kernel(const aread_mmoe
       for (int e = 0; e < NE; ++e) {
         const int col = e * H + c;
         const bool keep = threshold == 0u ||
-                          dropout_keep(a.seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
+                          dropout_keep(seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
         h[e] = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep, keep_scale);
         float acc = 0.f;
         for (int g = 0; g < G; ++g) acc = fmaf(__ldg(a.gate + b * (G * NE) + g * NE + e), dout[g], acc);

@@ -22,6 +22,12 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t salt, uint6
                            static_cast<uint32_t>(seed >> 32));
   return h >= threshold;
 }
+// the dropout seed of a launch: read from device memory when the caller gave a slot (CUDA-graph replay: the
+// launch parameters are frozen, the seed is not), else the by-value field
+template <typename Args>
+__device__ __forceinline__ uint64_t seed_of(const Args& a) {
+  return a.seed_ptr != nullptr ? __ldg(a.seed_ptr) : a.seed;
+}
 inline uint32_t dropout_threshold(float p) {
   if (p <= 0.f) return 0u;
   const double t = static_cast<double>(p) * 4294967296.0;

@@ -49,6 +49,7 @@ __device__ __forceinline__ float src_value(float raw, const float* __restrict__ 
 __global__ void __launch_bounds__(kThreads, 3) hei_layer_fwd_kernel(const aread_hei_layer_fwd_args a, int tx_n, int ty_n,
                                                                  int tiles_per_cta, uint32_t thr, float keep_scale,
                                                                  int do_stats, float* __restrict__ partial) {
+  const uint64_t seed = seed_of(a);
   extern __shared__ __align__(16) float smem[];
   const int K = a.k, N = a.n, G = a.groups;
   const int Np = (N + 3) & ~3, Kp = (K + 3) & ~3;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, 3) hei_layer_fwd_kernel(const aread_
   if (do_stats) {  // z of row 0, same arithmetic as below: the pivot of the variance sums (bn_finalize reads z[0])
     for (int i = threadIdx.x; i < Kp; i += kThreads) {
       const int col = g * K + i;
-      sIn[i] = i < K ? src_value(__ldg(a.src + col), sscale, sshift, col, a.seed, a.src_salt, static_cast<uint64_t>(col),
+      sIn[i] = i < K ? src_value(__ldg(a.src + col), sscale, sshift, col, seed, a.src_salt, static_cast<uint64_t>(col),
                                  thr, keep_scale)
                      : 0.f;
     }
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 3) hei_layer_fwd_kernel(const aread_
             const uint64_t flat = static_cast<uint64_t>(row) * src_width + lcol;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const bool keep = thr == 0u || dropout_keep(a.seed, a.src_salt, flat + c, thr);
+              const bool keep = thr == 0u || dropout_keep(seed, a.src_salt, flat + c, thr);
               v[c] = (lk * 4 + c < K) ? act_value(v[c], lsc[c], lsh[c], keep, keep_scale) : 0.f;
             }
           }
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(kThreads, 3) hei_layer_bwd_kernel(const aread_
                                                                     float keep_scale, uint32_t src_thr,
                                                                     float src_keep_scale, float* __restrict__ partial_w,
                                                                     float* __restrict__ partial_s) {
+  const uint64_t seed = seed_of(a);
   extern __shared__ __align__(16) float smem[];
   const int K = a.k, N = a.n, G = a.groups;
   const int Np = (N + 3) & ~3, Kp = (K + 3) & ~3;
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 3) hei_layer_bwd_kernel(const aread_
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float y = fmaf(z[c], pa[c], psh[c]);
-            const bool keep = thr == 0u || dropout_keep(a.seed, a.salt, flat + c, thr);
+            const bool keep = thr == 0u || dropout_keep(seed, a.salt, flat + c, thr);
             const float dy = (y > 0.f && keep) ? d[c] * keep_scale : 0.f;
             dz[c] = a.bn_skip ? dy : fmaf(pa[c], dy, -pb[c]) - (z[c] - pmu[c]) * pc[c];
             if (an * 4 + c >= N) dz[c] = 0.f;
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 3) hei_layer_bwd_kernel(const aread_
             const uint64_t flat = static_cast<uint64_t>(row) * src_width + bcol;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const bool keep = src_thr == 0u || dropout_keep(a.seed, a.src_salt, flat + c, src_thr);
+              const bool keep = src_thr == 0u || dropout_keep(seed, a.src_salt, flat + c, src_thr);
               x[c] = (bk * 4 + c < K) ? act_value(zp[c], qs[c], qh[c], keep, src_keep_scale) : 0.f;
             }
           } else {

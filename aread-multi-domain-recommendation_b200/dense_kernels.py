@@ -73,6 +73,10 @@ def grouped_wgrad(dz, a, n, k, groups, a_group_cols=0, group_mask=None, out=None
     return out
 
 
+# device address of the dropout seed while the fused node records / replays a CUDA graph (fused.py); None: the
+# seed travels by value in the launch arguments
+SEED_PTR = None
+
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 _BN_WS = {}
@@ -111,7 +115,7 @@ def bn_act_fwd(z, gamma, beta, running_mean, running_var, training, bn_skip, p, 
                           _ptr(beta), _ptr(running_mean), _ptr(running_var), *_rows(saved, 4),
                           _ptr(out) if out_dtype == torch.float32 else None,
                           _ptr(out) if out_dtype == torch.bfloat16 else None, width, ws.data_ptr(), ws.numel(),
-                          _ptr(out_lo))
+                          _ptr(out_lo), SEED_PTR)
     _lib.check(_lib.load().aread_bn_act_fwd(ctypes.byref(args), _stream(z.device)))
     return (out, out_lo, saved) if want_lo else (out, saved)
 
@@ -127,7 +131,7 @@ def bn_act_bwd(z, d_out, saved, bn_skip, p, seed, salt, dz_dtype=torch.bfloat16,
                              d_out.data_ptr(), d_out.stride(0), *_rows(saved, 4), *_rows(grads, 3),
                              _ptr(dz) if dz_dtype == torch.float32 else None,
                              _ptr(dz) if dz_dtype == torch.bfloat16 else None, width, ws.data_ptr(), ws.numel(),
-                             _ptr(dz_lo))
+                             _ptr(dz_lo), SEED_PTR)
     _lib.check(_lib.load().aread_bn_act_bwd(ctypes.byref(args), _stream(z.device)))
     return ((dz, dz_lo) if want_lo else dz), grads[0], grads[1], grads[2]
 
@@ -138,7 +142,7 @@ def mmoe_mix_fwd(z, saved, gate, n_expert, n_gate, p, seed, salt):
     out = _mem.empty((m, n_gate, width), torch.float32, z.device)
     rows = _rows(saved, 4)
     args = _lib.MmoeMixArgs(m, width, n_expert, n_gate, float(p), seed, salt, z.data_ptr(), z.stride(0),
-                            rows[2], rows[3], gate.data_ptr(), out.data_ptr(), None, None, None)
+                            rows[2], rows[3], gate.data_ptr(), out.data_ptr(), None, None, None, SEED_PTR)
     _lib.check(_lib.load().aread_mmoe_mix(ctypes.byref(args), _stream(z.device)))
     return out
 
@@ -151,7 +155,7 @@ def mmoe_mix_bwd(z, saved, gate, d_out, n_expert, n_gate, p, seed, salt):
     rows = _rows(saved, 4)
     args = _lib.MmoeMixArgs(m, width, n_expert, n_gate, float(p), seed, salt, z.data_ptr(), z.stride(0),
                             rows[2], rows[3], gate.data_ptr(), None, d_out.data_ptr(), d_h.data_ptr(),
-                            d_gate.data_ptr())
+                            d_gate.data_ptr(), SEED_PTR)
     _lib.check(_lib.load().aread_mmoe_mix(ctypes.byref(args), _stream(z.device)))
     return d_h, d_gate
 

@@ -16,8 +16,11 @@ from . import embedding_ops, expert_ops, rowpass_ops, tower_ops
 class MaskInfo:
     """Host view of one HEMP mask: which towers run, which edges are open.  Built once per distinct
     mask; the forward consults it instead of synchronising on device booleans."""
+    _serials = 0
 
     def __init__(self, arrays, n_tower):
+        MaskInfo._serials += 1
+        self.serial = MaskInfo._serials                              # never reused (keys the CUDA-graph cache)
         self.arrays = [np.asarray(a, dtype=bool) for a in arrays]
         self.n_tower = tuple(n_tower)
         n_level = len(self.n_tower)

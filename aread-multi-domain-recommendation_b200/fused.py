@@ -30,6 +30,95 @@ USE_HEI_LAYER = os.environ.get("AREAD_HEI_FUSED", "1") != "0"
 
 _HEAD_WS = {}
 
+# CUDA-graph replay of the fused node (AREAD_GRAPHS=0 disables).  After GRAPH_AFTER eager calls of one configuration
+# (mask, batch shape, train / eval, precision) its forward -- and on the first backward its backward -- launch
+# sequence is recorded once and replayed from then on: the activation arena makes every address repeat, the dropout
+# seed lives in device memory (dense_kernels.SEED_PTR), the ids are copied into a fixed buffer.
+USE_GRAPHS = os.environ.get("AREAD_GRAPHS", "1") != "0"
+GRAPH_AFTER = 2
+MAX_GRAPHS = 64
+
+
+class _Stub:
+    """Stands in for the autograd context while a launch sequence is recorded."""
+
+
+class GraphEntry:
+    def __init__(self):
+        self.calls = 0
+        self.fwd = self.bwd = None
+        self.x = self.probs = self.ctx = self.d_probs = self.grads = None
+        self.fwd_end = 0
+        self.sig = None
+        self.n_fwd = self.n_bwd = 0      # library launches inside the recorded sequences (for aread_launch_count)
+
+
+class GraphCache:
+    def __init__(self):
+        self.entries = {}
+        # Two private memory pools: the gradients a recorded backward leaves behind are adopted as .grad and must
+        # survive the NEXT forward replay (gradient accumulation), so they may not share blocks with a forward's
+        # temporaries.
+        self.pool = self.pool_bwd = None
+        self.seed = {}                  # device -> int64 [1] seed slot
+
+    def clear(self):
+        self.entries.clear()
+
+    def get(self, key):
+        e = self.entries.get(key)
+        if e is None:
+            if len(self.entries) >= MAX_GRAPHS:
+                self.entries.pop(next(iter(self.entries)))
+            e = self.entries[key] = GraphEntry()
+        return e
+
+    def seed_slot(self, device):
+        t = self.seed.get(device)
+        if t is None:
+            t = self.seed[device] = torch.zeros(1, dtype=torch.int64, device=device)
+        return t
+
+
+def _signature(model, arena):
+    """Everything a recorded sequence has baked in besides its key: the arena buffer and the parameter storage."""
+    return (id(arena.buf), model.embedding.embedding_dict.weight.data_ptr()) + \
+        tuple(pk.flat.data_ptr() for pk in model._packs.packs)
+
+
+class _recording:
+    """Stream capture into `graph` without torch.cuda.graph's device synchronisation, garbage collection and
+    cache flush (tens of milliseconds each): a side stream that waits for the current one, capture, and back."""
+
+    def __init__(self, graph, pool, device):
+        self.graph, self.pool, self.device = graph, pool, device
+
+    def __enter__(self):
+        self.side = torch.cuda.Stream(self.device)
+        self.side.wait_stream(torch.cuda.current_stream(self.device))
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        self.graph.capture_begin(pool=self.pool)
+
+    def __exit__(self, exc_type, exc, tb):
+        try:
+            self.graph.capture_end()
+        finally:
+            self.ctx.__exit__(exc_type, exc, tb)
+        if exc_type is None:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+
+
+class _seed_ptr:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __enter__(self):
+        self.prev, dk.SEED_PTR = dk.SEED_PTR, self.ptr
+
+    def __exit__(self, *exc):
+        dk.SEED_PTR = self.prev
+
 
 def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
@@ -103,10 +192,43 @@ def _sel(flat, index):
 class AreadNode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, cfg, *params):
-        arena = cfg["model"].arena(x.device)
+        model = cfg["model"]
+        arena = model.arena(x.device)
         ctx.lease = lease = arena.acquire()              # None: another forward of this model awaits its backward
-        with _mem.use(arena if lease is not None else None):
+        entry = cfg.get("graph") if lease is not None else None
+        ctx.entry = None
+        if entry is not None:
+            sig = _signature(model, arena)
+            if entry.fwd is not None and entry.sig != sig:                   # storage moved: record again
+                entry.fwd = entry.bwd = None
+            if entry.fwd is None and entry.calls > GRAPH_AFTER and arena.need <= arena.cap:
+                AreadNode._record_forward(entry, model, arena, x, cfg, sig)
+            if entry.fwd is not None:
+                entry.x.copy_(x)
+                entry.fwd.replay()
+                _lib.load().aread_launch_count_add(entry.n_fwd)
+                ctx.entry = entry
+                cfg["gate_means"], cfg["gates"], cfg["gate_inputs"] = {}, {}, entry.ctx.cfg["gate_inputs"]
+                return entry.probs.clone()
+        with _mem.use(arena if lease is not None else None), _seed_ptr(cfg.get("seed_ptr")):
             return AreadNode._forward(ctx, x, cfg)
+
+    @staticmethod
+    def _record_forward(entry, model, arena, x, cfg, sig):
+        graphs = model._graphs
+        if graphs.pool is None:
+            graphs.pool, graphs.pool_bwd = torch.cuda.graph_pool_handle(), torch.cuda.graph_pool_handle()
+        entry.x = x.clone()
+        stub, g = _Stub(), torch.cuda.CUDAGraph()
+        arena.off = 0
+        n0 = _lib.launch_count()
+        with _recording(g, graphs.pool, x.device):
+            with _mem.use(arena), _seed_ptr(cfg.get("seed_ptr")):
+                probs = AreadNode._forward(stub, entry.x, dict(cfg))
+        entry.n_fwd = _lib.launch_count() - n0
+        _lib.load().aread_launch_count_add(-entry.n_fwd & 0xFFFFFFFFFFFFFFFF)   # recorded, not run: replay counts them
+        entry.fwd, entry.ctx, entry.probs, entry.fwd_end, entry.sig = g, stub, probs, arena.off, sig
+        entry.bwd = entry.grads = None
 
     @staticmethod
     def backward(ctx, d_probs):
@@ -115,8 +237,30 @@ class AreadNode(torch.autograd.Function):
             raise RuntimeError("the fused AREAD node recycles its activations after the backward; a second backward "
                                "through the same graph (retain_graph=True) needs AREAD_WORKSPACE=0")
         try:
-            with _mem.use(lease.arena if lease is not None else None):
-                return AreadNode._backward(ctx, d_probs)
+            entry = ctx.entry
+            if entry is None:
+                with _mem.use(lease.arena if lease is not None else None), _seed_ptr(ctx.cfg.get("seed_ptr")):
+                    return AreadNode._backward(ctx, d_probs)
+            arena, inner = lease.arena, entry.ctx
+            arena.off = entry.fwd_end                    # the backward's temporaries follow the forward's
+            # the recorded backward writes its gradients into fixed buffers which autograd then adopts as .grad:
+            # only sound when no earlier gradient is being accumulated into
+            if all(p.grad is None for p in inner.cfg["model"]._fused_params):
+                if entry.bwd is None:
+                    entry.d_probs = d_probs.contiguous().clone()
+                    g = torch.cuda.CUDAGraph()
+                    n0 = _lib.launch_count()
+                    with _recording(g, inner.cfg["model"]._graphs.pool_bwd, d_probs.device):
+                        with _mem.use(arena), _seed_ptr(inner.cfg.get("seed_ptr")):
+                            out = AreadNode._backward(inner, entry.d_probs)
+                    entry.bwd, entry.grads, entry.n_bwd = g, out[2:], _lib.launch_count() - n0
+                    _lib.load().aread_launch_count_add(-entry.n_bwd & 0xFFFFFFFFFFFFFFFF)
+                entry.d_probs.copy_(d_probs)
+                entry.bwd.replay()
+                _lib.load().aread_launch_count_add(entry.n_bwd)
+                return (None, None, *[None if t is None else t.detach() for t in entry.grads])
+            with _mem.use(arena), _seed_ptr(inner.cfg.get("seed_ptr")):
+                return AreadNode._backward(inner, d_probs)
         finally:
             if lease is not None:
                 lease.release()
@@ -489,6 +633,20 @@ def forward(model, x, info, want_gate_means=False, want_gates=False):
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and model.dropout_p > 0) else 0
     cfg = {"model": model, "info": info, "precise": model.expert_precision == "bf16x3", "seed": seed, "slots": slots,
            "want_gate_means": want_gate_means, "want_gates": want_gates}
+    if USE_GRAPHS and _mem.ENABLED and not want_gate_means and not want_gates and \
+            model.embedding.plan(dev).shards is None:
+        key = (0 if info is None else info.serial, tuple(x.shape), training, model.expert_precision,
+               model.dropout_p if training else 0.0, torch.is_grad_enabled(), dev)
+        entry = model._graphs.get(key)
+        entry.calls += 1
+        cfg["graph"] = entry
+        if entry.fwd is not None or entry.calls > GRAPH_AFTER:
+            # the seed travels through device memory so that a recorded sequence sees a new one at every replay
+            slot = model._graphs.seed_slot(dev)
+            host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+            host[0] = seed
+            slot.copy_(host, non_blocking=True)
+            cfg["seed"], cfg["seed_ptr"] = 0, slot.data_ptr()
     probs = AreadNode.apply(x, cfg, *model._fused_params)
     model.embedding.plan(dev).post_lookup(embedding_ops_bounds_mode())
     return probs, cfg

@@ -8,6 +8,7 @@ import torch
 
 from . import _lib
 from . import _mem
+from . import dense_kernels as dk
 from .dense_kernels import BN_EPS, BN_MOMENTUM, _bn_workspace, _ptr, _rows
 
 _WS = {}
@@ -41,7 +42,8 @@ def layer_fwd(src, src_saved, src_salt, weight, bias, gamma, beta, running_mean,
     args = _lib.HeiLayerFwdArgs(
         m, groups, k, n, 1 if training else 0, 1 if bn_skip else 0, BN_MOMENTUM, BN_EPS, src.data_ptr(), src.stride(0),
         sp[2], sp[3], float(p) if training else 0.0, src_salt, seed, weight.data_ptr(), _ptr(bias), _ptr(gamma),
-        _ptr(beta), _ptr(running_mean), _ptr(running_var), z.data_ptr(), *_rows(saved, 4), ws.data_ptr(), ws.numel())
+        _ptr(beta), _ptr(running_mean), _ptr(running_var), z.data_ptr(), *_rows(saved, 4), ws.data_ptr(), ws.numel(),
+        dk.SEED_PTR)
     _lib.check(_lib.load().aread_hei_layer_fwd(ctypes.byref(args), _stream(dev)))
     return z, saved
 
@@ -52,7 +54,7 @@ def bn_apply(z, saved, training, p, seed, salt):
     out = _mem.empty((m, width), torch.float32, z.device)
     args = _lib.BnActArgs(m, width, 1 if training else 0, 0, BN_MOMENTUM, BN_EPS, float(p) if training else 0.0, seed,
                           salt, z.data_ptr(), z.stride(0), None, None, None, None, *_rows(saved, 4), out.data_ptr(),
-                          None, width, None, 0, None)
+                          None, width, None, 0, None, dk.SEED_PTR)
     _lib.check(_lib.load().aread_bn_act_apply(ctypes.byref(args), _stream(z.device)))
     return out
 
@@ -65,7 +67,7 @@ def bn_bwd_coef(z, d_out, saved, bn_skip, p, seed, salt):
     ws = _bn_workspace(z.device, width)
     args = _lib.BnActBwdArgs(m, width, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), z.stride(0),
                              d_out.data_ptr(), d_out.stride(0), *_rows(saved, 4), *_rows(grads, 3), None, None, width,
-                             ws.data_ptr(), ws.numel(), None)
+                             ws.data_ptr(), ws.numel(), None, dk.SEED_PTR)
     _lib.check(_lib.load().aread_bn_bwd_coef(ctypes.byref(args), ctypes.c_void_p(coef.data_ptr()), _stream(z.device)))
     return coef, grads
 
@@ -85,6 +87,7 @@ def layer_bwd(z, d_out, saved, coef, p, salt, seed, bn_skip, src, src_saved, src
     args = _lib.HeiLayerBwdArgs(
         m, groups, k, n, 1 if bn_skip else 0, float(p), salt, seed, z.data_ptr(), d_out.data_ptr(), *_rows(saved, 4),
         coef.data_ptr(), src.data_ptr(), src.stride(0), sp[2], sp[3], sp[0], sp[1], float(p), src_salt,
-        weight.data_ptr(), d_in.data_ptr(), d_w.data_ptr(), _ptr(src_coef), *gp, ws.data_ptr(), ws.numel())
+        weight.data_ptr(), d_in.data_ptr(), d_w.data_ptr(), _ptr(src_coef), *gp, ws.data_ptr(), ws.numel(),
+        dk.SEED_PTR)
     _lib.check(_lib.load().aread_hei_layer_bwd(ctypes.byref(args), _stream(dev)))
     return d_in, d_w, src_coef, src_grads

@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--optimizer", default="fused", choices=["torch", "fused"],
                     help="the library's FusedAdam (one launch; same arithmetic as torch.optim.Adam, tests/test_optim_gpu.py) or "
                          "torch.optim.Adam as run.py:830 builds it")
+    ap.add_argument("--graphs", default="prerecord", choices=["prerecord", "lazy"],
+                    help="CUDA-graph sequences of the fused node: recorded per domain mask during setup "
+                         "(AREAD.record_graphs) or lazily after a few eager steps per mask; AREAD_GRAPHS=0 disables them")
     ap.add_argument("--reg", default="fold", choices=["fold", "loss"],
                     help="gradient of the L2 regulariser: folded into FusedAdam (value still part of the loss) or "
                          "through autograd as in run.py:644")
@@ -264,6 +267,10 @@ def run_ours(args, wl, rank, world, local_rank):
     # ---- device-resident pass
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
+    if args.graphs == "prerecord" and world == 1:
+        # setup, like building the model: the per-mask CUDA-graph launch sequences are recorded once per domain
+        # (what a trainer does after every HEMP regroup); parameters, buffers and RNG are left untouched
+        model.record_graphs(dev_x[0], domains=sorted(set(domains)))
     for i in range(args.warmup):
         step(dev_x[i], dev_y[i], domains[i])
     sampler = ClockSampler(local_rank)
@@ -368,6 +375,9 @@ def run_ours(args, wl, rank, world, local_rank):
                    "loss": "AREAD.bagging_loss" if args.loss == "fused" else "sum of torch BCELoss",
                    "l2_regulariser": "value in the loss, gradient folded into FusedAdam" if args.reg == "fold"
                    else "autograd node",
+                   "cuda_graphs": ("off (AREAD_GRAPHS=0)" if os.environ.get("AREAD_GRAPHS", "1") == "0" else
+                                   "off (row-sharded table: NCCL inside the node)" if world > 1 else
+                                   "per-mask forward/backward sequences, " + args.graphs),
                    "parallelism": f"dp{world}" + ("" if world == 1 else f" + table row-sharded over {world} GPUs (P2P lookup, "
                                                    "reduce-scatter of the table gradient, flat all-reduce of the rest)"),
                    "l2": "inputs larger than L2: table %d MB + per-step activations" % (wl.n_rows * wl.embed_dim * 4 >> 20)},

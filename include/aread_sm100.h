@@ -48,6 +48,9 @@ AREAD_API const char* aread_last_error(void);
 AREAD_API int aread_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process so far. */
 AREAD_API uint64_t aread_launch_count(void);
+/* A host that replays library launches recorded in a CUDA graph reports them here (the counter itself only
+ * sees launches made through the entry points). */
+AREAD_API void aread_launch_count_add(uint64_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-field embedding lookup.
@@ -229,6 +232,8 @@ typedef struct aread_bn_act_args {
   void* workspace;        /* aread_bn_workspace_bytes(width)                                       */
   size_t workspace_bytes;
   uint16_t* out_bf16_lo;  /* optional out [m, ldo]: bf16(value - bf16(value)), the split residual  */
+  const uint64_t* seed_ptr; /* optional device scalar: when set, the dropout seed is read from it at run time   */
+                            /* (CUDA-graph replay) and `seed` is ignored                                        */
 } aread_bn_act_args;
 
 typedef struct aread_bn_act_bwd_args {
@@ -255,6 +260,8 @@ typedef struct aread_bn_act_bwd_args {
   void* workspace;
   size_t workspace_bytes;
   uint16_t* dz_bf16_lo;   /* optional out [m, ldo]: the split residual of dz                       */
+  const uint64_t* seed_ptr; /* optional device scalar: when set, the dropout seed is read from it at run time   */
+                            /* (CUDA-graph replay) and `seed` is ignored                                        */
 } aread_bn_act_bwd_args;
 
 AREAD_API size_t aread_bn_workspace_bytes(int32_t width);
@@ -308,6 +315,8 @@ typedef struct aread_hei_layer_fwd_args {
   float* shift;
   void* workspace;           /* aread_hei_layer_workspace_bytes(m, groups, k, n)              */
   size_t workspace_bytes;
+  const uint64_t* seed_ptr; /* optional device scalar: when set, the dropout seed is read from it at run time   */
+                            /* (CUDA-graph replay) and `seed` is ignored                                        */
 } aread_hei_layer_fwd_args;
 
 typedef struct aread_hei_layer_bwd_args {
@@ -341,6 +350,8 @@ typedef struct aread_hei_layer_bwd_args {
   float* src_d_bias;
   void* workspace;
   size_t workspace_bytes;
+  const uint64_t* seed_ptr; /* optional device scalar: when set, the dropout seed is read from it at run time   */
+                            /* (CUDA-graph replay) and `seed` is ignored                                        */
 } aread_hei_layer_bwd_args;
 
 AREAD_API int aread_hei_layer_supported(int32_t groups, int32_t k, int32_t n);
@@ -371,6 +382,7 @@ typedef struct aread_mmoe_mix_args {
   const float* d_out;     /* backward in [m, n_gate, width]                                        */
   float* d_h;             /* backward out [m, n_expert * width]                                    */
   float* d_gate;          /* backward out [m, n_gate, n_expert]                                    */
+  const uint64_t* seed_ptr; /* optional device scalar replacing `seed` at run time (CUDA-graph replay)   */
 } aread_mmoe_mix_args;
 
 AREAD_API int aread_mmoe_mix(const aread_mmoe_mix_args* args, aread_stream_t stream);

@@ -58,7 +58,7 @@ def step(i, record):
         if record: tick("allreduce", t)
     t = time.perf_counter(); opt.step()
     if record: tick("opt.step", t)
-for i in range(5): step(i, False)
+for i in range(int(os.environ.get('WARM', 5))): step(i, False)
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 N = 16

@@ -101,7 +101,7 @@ class LookupPlan:
             self._status_event.record(torch.cuda.current_stream(self.device))
 
 
-def gather(plan, table, x, want_bf16=False, want_lo=False):
+def gather(plan, table, x, want_bf16=False, want_lo=False, fence=True):
     """[B, n_cols] int32 ids -> [B, n_fields, D] fp32 (and optionally the bf16 copy; with want_lo the
     bf16 result is the (hi, lo) split pair)."""
     B = x.shape[0]
@@ -110,7 +110,7 @@ def gather(plan, table, x, want_bf16=False, want_lo=False):
     out_bf16 = _mem.empty(shape16, torch.bfloat16, x.device) if want_bf16 else None
     out_lo = _mem.empty(shape16, torch.bfloat16, x.device) if (want_bf16 and want_lo) else None
     sh = plan.shards
-    if sh is not None:
+    if sh is not None and fence:         # fence=False: the caller has already ordered this lookup after the peers' updates
         sh.fence()
     args = _lib.GatherArgs(plan.c_plan(), B, x.data_ptr(), table.data_ptr(), out.data_ptr(),
                            out_bf16.data_ptr() if want_bf16 else None,
@@ -120,7 +120,7 @@ def gather(plan, table, x, want_bf16=False, want_lo=False):
     return out, ((out_bf16, out_lo) if want_lo else out_bf16)
 
 
-def scatter(plan, x, d_out, d_table=None, zero_fill=True, want_sorted=False):
+def scatter(plan, x, d_out, d_table=None, zero_fill=True, want_sorted=False, reduce=True):
     """Deterministic gradient of `gather` w.r.t. the table.  Returns the dense [n_rows, D] gradient
     (and, for the bookkeeping tests, the sorted rows / positions)."""
     B = x.shape[0]
@@ -138,7 +138,7 @@ def scatter(plan, x, d_out, d_table=None, zero_fill=True, want_sorted=False):
                             rows.data_ptr() if want_sorted else None, pos.data_ptr() if want_sorted else None,
                             sh.shift if sh is not None else 0, sh.rows if sh is not None else 0)
     _lib.check(_lib.load().aread_scatter_bwd(ctypes.byref(args), _stream_ptr(x.device)))
-    if sh is not None:
+    if sh is not None and reduce:        # reduce=False: the caller runs the reduce-scatter itself (fused.py)
         d_table = sh.reduce_grad(d_table)
     if want_sorted:
         return d_table, rows, pos

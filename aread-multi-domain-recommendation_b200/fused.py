@@ -197,6 +197,9 @@ class AreadNode(torch.autograd.Function):
         ctx.lease = lease = arena.acquire()              # None: another forward of this model awaits its backward
         entry = cfg.get("graph") if lease is not None else None
         ctx.entry = None
+        ctx.shards = shards = model.embedding.plan(x.device).shards
+        if shards is not None:       # the two collectives of the sharded table stay outside the recorded sequences
+            shards.fence()
         if entry is not None:
             sig = _signature(model, arena)
             if entry.fwd is not None and entry.sig != sig:                   # storage moved: record again
@@ -232,6 +235,13 @@ class AreadNode(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_probs):
+        grads = AreadNode._backward_local(ctx, d_probs)
+        if ctx.shards is not None:   # owner-major [N * rows, D] buffer -> this rank's averaged shard gradient
+            grads = grads[:2] + (ctx.shards.reduce_grad(grads[2]),) + grads[3:]
+        return grads
+
+    @staticmethod
+    def _backward_local(ctx, d_probs):
         lease = ctx.lease
         if lease is not None and not lease.active:
             raise RuntimeError("the fused AREAD node recycles its activations after the backward; a second backward "
@@ -281,7 +291,7 @@ class AreadNode(torch.autograd.Function):
         # ---- lookup
         plan = model.embedding.plan(dev)
         table = model.embedding.embedding_dict.weight
-        embed, xb = embedding_ops.gather(plan, table, x, want_bf16=True, want_lo=precise)
+        embed, xb = embedding_ops.gather(plan, table, x, want_bf16=True, want_lo=precise, fence=False)
         X = embed.view(B, E)
 
         # ---- which towers run
@@ -551,7 +561,7 @@ class AreadNode(torch.autograd.Function):
         if d_q is not None:
             d_x.view(B, -1, D)[:, model.domain_idx, :] += d_q[:, :D]
         plan = model.embedding.plan(dev)
-        d_table = embedding_ops.scatter(plan, ctx.x_ids, d_x)
+        d_table = embedding_ops.scatter(plan, ctx.x_ids, d_x, reduce=False)     # sharded: owner-major, reduced by the caller
 
         # ---- unpack d_wcat / d_off into parameter gradients
         ng = na0 * n_expert
@@ -633,8 +643,7 @@ def forward(model, x, info, want_gate_means=False, want_gates=False):
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and model.dropout_p > 0) else 0
     cfg = {"model": model, "info": info, "precise": model.expert_precision == "bf16x3", "seed": seed, "slots": slots,
            "want_gate_means": want_gate_means, "want_gates": want_gates}
-    if USE_GRAPHS and _mem.ENABLED and not want_gate_means and not want_gates and \
-            model.embedding.plan(dev).shards is None:
+    if USE_GRAPHS and _mem.ENABLED and not want_gate_means and not want_gates:
         key = (0 if info is None else info.serial, tuple(x.shape), training, model.expert_precision,
                model.dropout_p if training else 0.0, torch.is_grad_enabled(), dev)
         entry = model._graphs.get(key)

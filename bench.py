@@ -267,10 +267,12 @@ def run_ours(args, wl, rank, world, local_rank):
     # ---- device-resident pass
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
-    if args.graphs == "prerecord" and world == 1:
+    if args.graphs == "prerecord":
         # setup, like building the model: the per-mask CUDA-graph launch sequences are recorded once per domain
         # (what a trainer does after every HEMP regroup); parameters, buffers and RNG are left untouched
-        model.record_graphs(dev_x[0], domains=sorted(set(domains)))
+        # (sharded table: every rank records ALL domains so that the lookup fences / gradient reduce-scatters, which
+        # stay outside the recorded sequences, are issued the same number of times everywhere)
+        model.record_graphs(dev_x[0], domains=sorted(set(domains)) if world == 1 else range(wl.n_domain))
     for i in range(args.warmup):
         step(dev_x[i], dev_y[i], domains[i])
     sampler = ClockSampler(local_rank)
@@ -376,7 +378,6 @@ def run_ours(args, wl, rank, world, local_rank):
                    "l2_regulariser": "value in the loss, gradient folded into FusedAdam" if args.reg == "fold"
                    else "autograd node",
                    "cuda_graphs": ("off (AREAD_GRAPHS=0)" if os.environ.get("AREAD_GRAPHS", "1") == "0" else
-                                   "off (row-sharded table: NCCL inside the node)" if world > 1 else
                                    "per-mask forward/backward sequences, " + args.graphs),
                    "parallelism": f"dp{world}" + ("" if world == 1 else f" + table row-sharded over {world} GPUs (P2P lookup, "
                                                    "reduce-scatter of the table gradient, flat all-reduce of the rest)"),

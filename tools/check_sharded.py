@@ -65,6 +65,16 @@ torch.testing.assert_close(model.embedding.embedding_dict.weight.grad, sharding.
                            rtol=1e-5, atol=1e-7)
 REG = 0.0
 step(ref); step(model)
+# the same step a few more times: from the third call on both models replay their recorded CUDA-graph sequences
+# (the sharded one with its fence and reduce-scatter issued around them)
+for _ in range(4):
+    p_ref, p_sh = step(ref), step(model)
+    torch.testing.assert_close(p_sh, p_ref, rtol=1e-5, atol=1e-6)
+    g_full = ref.embedding.embedding_dict.weight.grad.clone()
+    dist.all_reduce(g_full, op=dist.ReduceOp.AVG)
+    torch.testing.assert_close(model.embedding.embedding_dict.weight.grad, sharding.split_table(g_full, world, rank),
+                               rtol=1e-5, atol=1e-7)
+assert any(e.bwd is not None for e in model._graphs.entries.values()), "sharded model never replayed a graph"
 # dense gradients: flat-bucket all-reduce equals per-tensor averaging
 dense = [p for n, p in model.named_parameters() if not n.startswith("embedding.")]
 expect = []

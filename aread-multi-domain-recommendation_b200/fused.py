@@ -61,9 +61,11 @@ class GraphCache:
         # temporaries.
         self.pool = self.pool_bwd = None
         self.seed = {}                  # device -> int64 [1] seed slot
+        self.tgrad = {}
 
     def clear(self):
         self.entries.clear()
+        self.tgrad.clear()
 
     def get(self, key):
         e = self.entries.get(key)
@@ -72,6 +74,16 @@ class GraphCache:
                 self.entries.pop(next(iter(self.entries)))
             e = self.entries[key] = GraphEntry()
         return e
+
+    def table_grad(self, like):
+        """ONE gradient buffer for the embedding table, shared by every recorded backward: a table-sized buffer per
+        mask would not fit for large tables, and a recorded gradient only has to live until the optimizer step."""
+        key = (like.device, tuple(like.shape))
+        t = self.tgrad.get(key)
+        if t is None:
+            self.tgrad.clear()
+            t = self.tgrad[key] = torch.empty_like(like)
+        return t
 
     def seed_slot(self, device):
         t = self.seed.get(device)
@@ -260,9 +272,15 @@ class AreadNode(torch.autograd.Function):
                     entry.d_probs = d_probs.contiguous().clone()
                     g = torch.cuda.CUDAGraph()
                     n0 = _lib.launch_count()
-                    with _recording(g, inner.cfg["model"]._graphs.pool_bwd, d_probs.device):
-                        with _mem.use(arena), _seed_ptr(inner.cfg.get("seed_ptr")):
-                            out = AreadNode._backward(inner, entry.d_probs)
+                    model = inner.cfg["model"]
+                    if ctx.shards is None:       # (sharded: the owner-major buffer is already one per model)
+                        inner.cfg["table_grad"] = model._graphs.table_grad(model.embedding.embedding_dict.weight)
+                    try:
+                        with _recording(g, model._graphs.pool_bwd, d_probs.device):
+                            with _mem.use(arena), _seed_ptr(inner.cfg.get("seed_ptr")):
+                                out = AreadNode._backward(inner, entry.d_probs)
+                    finally:
+                        inner.cfg.pop("table_grad", None)    # eager launches keep allocating their own
                     entry.bwd, entry.grads, entry.n_bwd = g, out[2:], _lib.launch_count() - n0
                     _lib.load().aread_launch_count_add(-entry.n_bwd & 0xFFFFFFFFFFFFFFFF)
                 entry.d_probs.copy_(d_probs)
@@ -561,7 +579,8 @@ class AreadNode(torch.autograd.Function):
         if d_q is not None:
             d_x.view(B, -1, D)[:, model.domain_idx, :] += d_q[:, :D]
         plan = model.embedding.plan(dev)
-        d_table = embedding_ops.scatter(plan, ctx.x_ids, d_x, reduce=False)     # sharded: owner-major, reduced by the caller
+        d_table = embedding_ops.scatter(plan, ctx.x_ids, d_x, d_table=cfg.get("table_grad"),
+                                        reduce=False)            # sharded: owner-major, reduced by the caller
 
         # ---- unpack d_wcat / d_off into parameter gradients
         ng = na0 * n_expert

@@ -35,18 +35,41 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const aread_adam_args a)
     const float c = a.l2_twice ? a.l2_twice[t] : 0.f;
     const int64_t begin = (chunk - a.chunk_start[t]) * kChunk;
     const int64_t end = min(a.sizes[t], begin + kChunk);
-    for (int64_t i = begin + threadIdx.x; i < end; i += kThreads) {
-      const float pi = p[i];
-      float gi = g ? __ldg(g + i) : 0.f;
+    const float wd = a.weight_decay, b1 = a.beta1, b2 = a.beta2, eps = a.eps;
+    auto update = [&](float& pi, float gi, float& mi, float& vi) {
       if (c != 0.f) gi = __fadd_rn(gi, __fmul_rn(c, pi));   // rounded like the separate regulariser gradient + add
-      gi = gi + a.weight_decay * pi;
-      float mi = m[i];
-      mi = mi + (gi - mi) * (1.f - a.beta1);
-      const float vi = v[i] * a.beta2 + (1.f - a.beta2) * gi * gi;
+      gi = gi + wd * pi;
+      mi = mi + (gi - mi) * (1.f - b1);
+      vi = vi * b2 + (1.f - b2) * gi * gi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      pi = pi - step_size * (mi / denom);
+    };
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
+                       reinterpret_cast<uintptr_t>(g)) & 15) == 0;          // (chunks start at multiples of 4096 elements)
+    int64_t i0 = begin;
+    if (vec) {
+      const int64_t n4 = (end - begin) / 4;
+      for (int64_t q = threadIdx.x; q < n4; q += kThreads) {
+        const int64_t i = begin + q * 4;
+        float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i),
+               v4 = *reinterpret_cast<float4*>(v + i);
+        const float4 g4 = g ? __ldg(reinterpret_cast<const float4*>(g + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        update(p4.x, g4.x, m4.x, v4.x);
+        update(p4.y, g4.y, m4.y, v4.y);
+        update(p4.z, g4.z, m4.z, v4.z);
+        update(p4.w, g4.w, m4.w, v4.w);
+        *reinterpret_cast<float4*>(p + i) = p4;
+        *reinterpret_cast<float4*>(m + i) = m4;
+        *reinterpret_cast<float4*>(v + i) = v4;
+      }
+      i0 = begin + n4 * 4;
+    }
+    for (int64_t i = i0 + threadIdx.x; i < end; i += kThreads) {
+      float pi = p[i], mi = m[i], vi = v[i];
+      update(pi, g ? __ldg(g + i) : 0.f, mi, vi);
+      p[i] = pi;
       m[i] = mi;
       v[i] = vi;
-      const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
-      p[i] = pi - step_size * (mi / denom);
     }
   }
 }

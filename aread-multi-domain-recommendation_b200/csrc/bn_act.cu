@@ -248,25 +248,34 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const aread_bn_a
 
 // ---------------------------------------------------------------------------------- MMoE mixture
 // h[b, e, :] = dropout(relu(bn(z[b, e, :]))) ;  out[b, g, :] = sum_e gate[b, g, e] * h[b, e, :]
+// NE / NG are compile-time bounds of the loops (NE_ == 0: generic, bounded by 16 / 8) so that the per-thread
+// arrays live in registers.
+template <int NE_, int NG_>
 __global__ void __launch_bounds__(kThreads) mmoe_mix_fwd_kernel(const aread_mmoe_mix_args a, uint32_t threshold,
                                                                 float keep_scale) {
   const uint64_t seed = seed_of(a);
-  const int H = a.width, NE = a.n_expert, G = a.n_gate;
+  constexpr int MAXE = NE_ > 0 ? NE_ : 16;
+  const int H = a.width, NE = NE_ > 0 ? NE_ : a.n_expert, G = NG_ > 0 ? NG_ : a.n_gate;
   const int64_t total = a.m * H;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t b = i / H;
     const int c = static_cast<int>(i - b * H);
-    float h[16];
-    for (int e = 0; e < NE; ++e) {
-      const int col = e * H + c;
-      const bool keep = threshold == 0u ||
-                        dropout_keep(seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
-      h[e] = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep, keep_scale);
+    float h[MAXE];
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+      if (e < NE) {
+        const int col = e * H + c;
+        const bool keep = threshold == 0u ||
+                          dropout_keep(seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
+        h[e] = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep, keep_scale);
+      }
     }
     for (int g = 0; g < G; ++g) {
       float acc = 0.f;
-      for (int e = 0; e < NE; ++e) acc = fmaf(__ldg(a.gate + b * (G * NE) + g * NE + e), h[e], acc);
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e)
+        if (e < NE) acc = fmaf(__ldg(a.gate + b * (G * NE) + g * NE + e), h[e], acc);
       a.out[b * (G * H) + g * H + c] = acc;
     }
   }
@@ -274,34 +283,53 @@ __global__ void __launch_bounds__(kThreads) mmoe_mix_fwd_kernel(const aread_mmoe
 
 // d_h[b, e, :] = sum_g gate[b, g, e] * d_out[b, g, :] ;  d_gate[b, g, e] = <d_out[b, g, :], h[b, e, :]>
 // one warp per sample
+template <int NE_, int NG_>
 __global__ void __launch_bounds__(kThreads) mmoe_mix_bwd_kernel(const aread_mmoe_mix_args a, uint32_t threshold,
                                                                 float keep_scale) {
   const uint64_t seed = seed_of(a);
-  const int H = a.width, NE = a.n_expert, G = a.n_gate;
+  constexpr int MAXE = NE_ > 0 ? NE_ : 16, MAXG = NG_ > 0 ? NG_ : 8;
+  const int H = a.width, NE = NE_ > 0 ? NE_ : a.n_expert, G = NG_ > 0 ? NG_ : a.n_gate;
   const int lane = threadIdx.x % 32;
   const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x / 32);
   for (int64_t b = static_cast<int64_t>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32; b < a.m; b += warps) {
-    float dg[64];  // [G][NE] partial dot products of this lane
-    for (int j = 0; j < G * NE; ++j) dg[j] = 0.f;
-    for (int c = lane; c < H; c += 32) {
-      float h[16], dout[8];
-      for (int g = 0; g < G; ++g) dout[g] = __ldg(a.d_out + b * (G * H) + g * H + c);
-      for (int e = 0; e < NE; ++e) {
-        const int col = e * H + c;
-        const bool keep = threshold == 0u ||
-                          dropout_keep(seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
-        h[e] = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep, keep_scale);
-        float acc = 0.f;
-        for (int g = 0; g < G; ++g) acc = fmaf(__ldg(a.gate + b * (G * NE) + g * NE + e), dout[g], acc);
-        a.d_h[b * (NE * H) + col] = acc;
+    float dg[MAXG][MAXE], gt[MAXG][MAXE];
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g)
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) {
+        dg[g][e] = 0.f;
+        gt[g][e] = (g < G && e < NE) ? __ldg(a.gate + b * (G * NE) + g * NE + e) : 0.f;
       }
-      for (int g = 0; g < G; ++g)
-        for (int e = 0; e < NE; ++e) dg[g * NE + e] = fmaf(dout[g], h[e], dg[g * NE + e]);
+    for (int c = lane; c < H; c += 32) {
+      float dout[MAXG];
+#pragma unroll
+      for (int g = 0; g < MAXG; ++g) dout[g] = g < G ? __ldg(a.d_out + b * (G * H) + g * H + c) : 0.f;
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) {
+        if (e < NE) {
+          const int col = e * H + c;
+          const bool keep = threshold == 0u ||
+                            dropout_keep(seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
+          const float h = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep,
+                                    keep_scale);
+          float acc = 0.f;
+#pragma unroll
+          for (int g = 0; g < MAXG; ++g) {
+            acc = fmaf(gt[g][e], dout[g], acc);
+            dg[g][e] = fmaf(dout[g], h, dg[g][e]);
+          }
+          a.d_h[b * (NE * H) + col] = acc;
+        }
+      }
     }
-    for (int j = 0; j < G * NE; ++j) {
-      const float v = warp_sum(dg[j]);
-      if (lane == 0) a.d_gate[b * (G * NE) + j] = v;
-    }
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g)
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e)
+        if (g < G && e < NE) {
+          const float v = warp_sum(dg[g][e]);
+          if (lane == 0) a.d_gate[b * (G * NE) + g * NE + e] = v;
+        }
   }
 }
 
@@ -491,13 +519,22 @@ int aread_mmoe_mix(const aread_mmoe_mix_args* args, aread_stream_t stream_) {
   const bool drop = a.dropout_p > 0.f;
   const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;
   const float keep_scale = drop ? 1.f / (1.f - a.dropout_p) : 1.f;
+  // the shipped configuration (4 experts, up to 3 level-0 towers) gets fully unrolled kernels
+#define AREAD_MMOE(KERNEL, GRID)                                                                                    \
+  do {                                                                                                              \
+    if (a.n_expert == 4 && a.n_gate == 3) AREAD_LAUNCH((KERNEL<4, 3>), GRID, kThreads, 0, stream, a, threshold, keep_scale); \
+    else if (a.n_expert == 4 && a.n_gate == 2) AREAD_LAUNCH((KERNEL<4, 2>), GRID, kThreads, 0, stream, a, threshold, keep_scale); \
+    else if (a.n_expert == 4 && a.n_gate == 1) AREAD_LAUNCH((KERNEL<4, 1>), GRID, kThreads, 0, stream, a, threshold, keep_scale); \
+    else AREAD_LAUNCH((KERNEL<0, 0>), GRID, kThreads, 0, stream, a, threshold, keep_scale);                          \
+  } while (0)
   if (a.d_out == nullptr) {
     AREAD_REQUIRE(a.out != nullptr, "mmoe_mix: null out");
-    AREAD_LAUNCH(mmoe_mix_fwd_kernel, elementwise_grid(a.m * a.width), kThreads, 0, stream, a, threshold, keep_scale);
+    AREAD_MMOE(mmoe_mix_fwd_kernel, elementwise_grid(a.m * a.width));
   } else {
     AREAD_REQUIRE(a.d_h && a.d_gate, "mmoe_mix: null gradient output");
-    AREAD_LAUNCH(mmoe_mix_bwd_kernel, elementwise_grid(a.m * 32), kThreads, 0, stream, a, threshold, keep_scale);
+    AREAD_MMOE(mmoe_mix_bwd_kernel, elementwise_grid(a.m * 32));
   }
+#undef AREAD_MMOE
   return AREAD_OK;
 }
 

@@ -310,6 +310,10 @@ def run_ours(args, wl, rank, world, local_rank):
     # ---- the rest of BASELINE's metric, reported beside the headline: eval samples/s (mode 'domain_with_mask',
     # eval(), no_grad -- run.py:712-727) and the scatter (lookup gradient) kernels against HBM
     model.eval()
+    if args.graphs == "prerecord":
+        with torch.no_grad():
+            model.record_graphs(dev_x[0], domains=sorted(set(domains)) if world == 1 else range(wl.n_domain),
+                                mode="domain_with_mask", backward=False)
 
     def eval_step(i):
         with torch.no_grad():

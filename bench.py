@@ -284,13 +284,35 @@ def run_ours(args, wl, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the module API from pinned host memory (H2D of ids+labels, D2H of the loss)
-    def e2e_step(i):
+    # The loss of every step is copied to pinned host memory and READ one step late (after the next step has been
+    # enqueued), the way a trainer logs it, so the device->host read does not drain the pipeline; the last step's
+    # loss is read inside the timed region as well.
+    loss_host = torch.zeros(n_batches, dtype=torch.float32).pin_memory()
+    loss_done = [torch.cuda.Event() for _ in range(n_batches)]
+    losses = []
+
+    def read_loss(i):
+        loss_done[i].synchronize()
+        losses.append(float(loss_host[i]))
+
+    def e2e_step(i, first):
         x = host_x[i].to(dev, non_blocking=True)
         y = host_y[i].to(dev, non_blocking=True)
-        return float(step(x, y, domains[i]).item())
+        loss_host[i:i + 1].copy_(step(x, y, domains[i]).detach().reshape(1), non_blocking=True)
+        loss_done[i].record()
+        if i > first:
+            read_loss(i - 1)
+
+    def e2e_run(first, count):
+        def run_one(i):
+            e2e_step(i, first)
+            if i == first + count - 1:
+                read_loss(i)
+        return run_one
     for i in range(min(2, args.warmup)):
-        e2e_step(i)
-    ms_e2e = timed(e2e_step, args.warmup, args.steps)
+        e2e_run(i, 1)(i)
+    ms_e2e = timed(e2e_run(args.warmup, args.steps), args.warmup, args.steps)
+    assert len(losses) == min(2, args.warmup) + args.steps and all(np.isfinite(losses))
 
     # ---- gather kernel alone, on its launch stream, over the same batches (roofline numerator)
     plan = model.embedding.plan(dev)

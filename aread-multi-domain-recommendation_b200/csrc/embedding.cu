@@ -4,7 +4,6 @@
 // (aten::embedding_dense_backward).  Both kernels are HBM-bound byte movers: one table row is
 // D fp32 = 128 B at the default D = 32, moved by D/4 lanes as one float4 each, so a warp moves
 // four rows per instruction and every global access is a full 128-byte line.
-#include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
 
@@ -380,6 +379,150 @@ int lanes_per_row(int D) {
   return lpr;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (row, position) pairs by row: 1 or 3 passes (always odd, so the result lands in the
+// "out" buffers) over digits of up to 11 bits.  The unit of work is one WARP (a 32-thread CTA) that owns a
+// contiguous chunk of the input and walks it 32 elements at a time, so the order inside a chunk is the input
+// order by construction and no block-wide synchronisation is needed:
+//   radix_hist_kernel     per-unit digit counts                          -> counts[digit][unit]
+//   radix_scan_units / _digits  exclusive prefix over (digit-major, unit-minor) -> where each unit's run of a digit starts
+//   radix_scatter_kernel  per element: match_any over the warp gives its rank among equal digits of the round
+// Equal rows therefore keep their input order (sample-major), which fixes the accumulation order of the scatter.
+constexpr int kSortMaxDigitBits = 11;
+constexpr int kSortMaxCounts = 2 * 1024 * 1024;  // digit values x units (8 MB of counters)
+constexpr int kSortMaxUnits = kNumSMs * 16;
+
+struct SortPlan {
+  int passes, digit_bits, radix, units;
+  int64_t per_unit;
+};
+
+SortPlan sort_plan(int64_t n, int bits) {
+  SortPlan p;
+  p.passes = bits <= kSortMaxDigitBits ? 1 : 3;
+  p.digit_bits = p.passes == 1 ? bits : (bits + 2) / 3;
+  p.radix = 1 << p.digit_bits;
+  int64_t units = (n + 255) / 256;                       // at least 8 rounds per unit
+  if (units > kSortMaxUnits) units = kSortMaxUnits;
+  if (units > kSortMaxCounts / p.radix) units = kSortMaxCounts / p.radix;
+  if (units < 1) units = 1;
+  p.units = static_cast<int>(units);
+  p.per_unit = ((n + units - 1) / units + 31) / 32 * 32;
+  return p;
+}
+
+__global__ void __launch_bounds__(32) radix_hist_kernel(const unsigned* __restrict__ keys, int64_t n, int64_t per_unit,
+                                                        int shift, int radix, int* __restrict__ counts) {
+  extern __shared__ int s_hist[];
+  for (int i = threadIdx.x; i < radix; i += 32) s_hist[i] = 0;
+  __syncwarp();
+  const int64_t begin = static_cast<int64_t>(blockIdx.x) * per_unit;
+  const int64_t end = begin + per_unit < n ? begin + per_unit : n;
+  for (int64_t i = begin + threadIdx.x; i < end; i += 32) atomicAdd(&s_hist[(__ldg(keys + i) >> shift) & (radix - 1)], 1);
+  __syncwarp();
+  for (int i = threadIdx.x; i < radix; i += 32) counts[static_cast<int64_t>(i) * gridDim.x + blockIdx.x] = s_hist[i];
+}
+
+// counts[digit][unit] -> exclusive prefix over the units of that digit (one warp per digit, coalesced), digit totals
+__global__ void __launch_bounds__(256) radix_scan_units_kernel(int* __restrict__ counts, int radix, int units,
+                                                                int* __restrict__ totals) {
+  const int digit = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (digit >= radix) return;
+  int* row = counts + static_cast<int64_t>(digit) * units;
+  int carry = 0;
+  for (int u0 = 0; u0 < units; u0 += 32) {
+    const int u = u0 + lane;
+    const int c = u < units ? row[u] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (u < units) row[u] = carry + incl - c;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) totals[digit] = carry;
+}
+
+// totals[digit] -> exclusive prefix over the digits (radix <= 2048: one CTA, two values per thread)
+__global__ void __launch_bounds__(1024) radix_scan_digits_kernel(int* __restrict__ totals, int radix) {
+  __shared__ int s_part[1024];
+  const int i0 = threadIdx.x * 2;
+  const int a = i0 < radix ? totals[i0] : 0, b = i0 + 1 < radix ? totals[i0 + 1] : 0;
+  s_part[threadIdx.x] = a + b;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const int excl = s_part[threadIdx.x] - (a + b);
+  if (i0 < radix) totals[i0] = excl;
+  if (i0 + 1 < radix) totals[i0 + 1] = excl + a;
+}
+
+__global__ void __launch_bounds__(32) radix_scatter_kernel(const unsigned* __restrict__ keys_in,
+                                                           const int* __restrict__ vals_in, int64_t n, int64_t per_unit,
+                                                           int shift, int radix, const int* __restrict__ offsets,
+                                                           const int* __restrict__ digit_base,
+                                                           unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
+  extern __shared__ int s_base[];
+  for (int i = threadIdx.x; i < radix; i += 32)
+    s_base[i] = digit_base[i] + offsets[static_cast<int64_t>(i) * gridDim.x + blockIdx.x];
+  __syncwarp();
+  const int lane = threadIdx.x;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int64_t begin = static_cast<int64_t>(blockIdx.x) * per_unit;
+  const int64_t end = begin + per_unit < n ? begin + per_unit : n;
+  for (int64_t i0 = begin; i0 < end; i0 += 32) {
+    const int64_t i = i0 + lane;
+    const bool valid = i < end;
+    unsigned key = 0;
+    int val = 0;
+    if (valid) {
+      key = __ldg(keys_in + i);
+      val = __ldg(vals_in + i);
+    }
+    const int digit = valid ? static_cast<int>((key >> shift) & (radix - 1)) : radix;   // padding lanes: own class
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const int leader = __ffs(peers) - 1;
+    int start = 0;
+    if (valid && lane == leader) {
+      start = s_base[digit];
+      s_base[digit] = start + __popc(peers);
+    }
+    start = __shfl_sync(0xffffffffu, start, leader);
+    if (valid) {
+      const int dst = start + __popc(peers & lt_mask);
+      keys_out[dst] = key;
+      vals_out[dst] = val;
+    }
+    __syncwarp();
+  }
+}
+
+int radix_sort_pairs(unsigned* keys_in, unsigned* keys_out, int* vals_in, int* vals_out, int64_t n, int bits, int* counts,
+                     cudaStream_t stream) {
+  const SortPlan p = sort_plan(n, bits);
+  const size_t smem = sizeof(int) * p.radix;
+  int* totals = counts + static_cast<int64_t>(p.radix) * p.units;     // [radix], after the counts matrix
+  unsigned *ki = keys_in, *ko = keys_out;
+  int *vi = vals_in, *vo = vals_out;
+  for (int pass = 0; pass < p.passes; ++pass) {
+    const int shift = pass * p.digit_bits;
+    AREAD_LAUNCH(radix_hist_kernel, p.units, 32, smem, stream, ki, n, p.per_unit, shift, p.radix, counts);
+    AREAD_LAUNCH(radix_scan_units_kernel, ceil_div(p.radix, 8), 256, 0, stream, counts, p.radix, p.units, totals);
+    AREAD_LAUNCH(radix_scan_digits_kernel, 1, 1024, 0, stream, totals, p.radix);
+    AREAD_LAUNCH(radix_scatter_kernel, p.units, 32, smem, stream, ki, vi, n, p.per_unit, shift, p.radix, counts, totals, ko,
+                 vo);
+    unsigned* tk = ki; ki = ko; ko = tk;
+    int* tv = vi; vi = vo; vo = tv;
+  }
+  return AREAD_OK;   // passes is odd: the sorted pairs are in keys_out / vals_out
+}
+
 int key_bits(int64_t n_rows) {  // bits needed for keys 0 .. n_rows (inclusive: the skip sentinel)
   int bits = 1;
   while ((int64_t{1} << bits) <= n_rows) ++bits;
@@ -395,20 +538,13 @@ struct ScatterWorkspace {
   float* out_a;
   float* in_b;   // open partials of the even levels (sized for tiles / 32)
   float* out_b;
-  void* cub_temp;
-  size_t cub_bytes;
+  int* sort_counts;   // radix_sort_pairs: digit values x units
   size_t total;
 };
 
 int carve_scatter_workspace(void* base, int64_t n, int D, ScatterWorkspace* w) {
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   const int64_t n_l2 = (n_tiles + 31) / 32;
-  size_t cub_bytes = 0;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<unsigned*>(nullptr),
-                                                  static_cast<unsigned*>(nullptr), static_cast<int*>(nullptr),
-                                                  static_cast<int*>(nullptr), n > 0 ? n : 1, 0, 32,
-                                                  static_cast<cudaStream_t>(nullptr));
-  if (e != cudaSuccess) return fail(AREAD_ERR_CUDA, "cub size query failed: %s", cudaGetErrorString(e));
   char* p = static_cast<char*>(base);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -425,8 +561,7 @@ int carve_scatter_workspace(void* base, int64_t n, int D, ScatterWorkspace* w) {
   w->out_a = reinterpret_cast<float*>(take(static_cast<size_t>(n_tiles + 1) * D * 4));
   w->in_b = reinterpret_cast<float*>(take(static_cast<size_t>(n_l2 + 1) * D * 4));
   w->out_b = reinterpret_cast<float*>(take(static_cast<size_t>(n_l2 + 1) * D * 4));
-  w->cub_temp = take(cub_bytes);
-  w->cub_bytes = cub_bytes;
+  w->sort_counts = reinterpret_cast<int*>(take((static_cast<size_t>(kSortMaxCounts) + (1 << kSortMaxDigitBits)) * 4));
   w->total = off;
   return AREAD_OK;
 }
@@ -556,12 +691,11 @@ int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream_) {
     AREAD_LAUNCH(scatter_keys_kernel, static_cast<unsigned>(grid), kThreads, 0, stream, a.plan, a.x, n, col_shift,
                  w.keys_in, w.pos_in);
   }
-  // Stable LSD radix sort by table row (CUB, the CUDA toolkit's header library); the payload is the
-  // flattened (sample, column) position, so equal rows keep the reference's accumulation order.
-  size_t cub_bytes = w.cub_bytes;
-  AREAD_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, cub_bytes, w.keys_in, w.keys_out, w.pos_in, w.pos_out, n, 0,
-                                             key_bits(a.plan.n_rows), stream));
-  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  // Stable LSD radix sort by table row; the payload is the flattened (sample, column) position, so equal rows keep
+  // the reference's accumulation order.
+  if (int rc = radix_sort_pairs(w.keys_in, w.keys_out, w.pos_in, w.pos_out, n, key_bits(a.plan.n_rows), w.sort_counts,
+                                stream))
+    return rc;
   int rc;
   switch (lanes_per_row(D)) {
     case 1: rc = launch_scatter<1>(a, w, n, col_shift, stream); break;

@@ -4,13 +4,10 @@ Reference: model/aread.py:131-153 (trunk), :263-322 (HEI under a HEMP mask), :15
 walk), model/layer.py:96-112 (regulariser).
 """
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import numpy as np
 import torch
-import torch.nn.functional as F
-
-from . import embedding_ops, expert_ops, rowpass_ops, tower_ops
 
 
 class MaskInfo:
@@ -78,53 +75,6 @@ def aread_forward(model, x, info: Optional[MaskInfo], want_gate_means=False, wan
     from . import fused
     probs, cfg = fused.forward(model, x, info, want_gate_means, want_gates)
     return ForwardOut(probs=probs, gate_inputs=cfg["gate_inputs"], gate_means=cfg["gate_means"], gates=cfg["gates"])
-
-
-def hei_levels(model, level0_in, q, head_cross, lin, info: Optional[MaskInfo], seed, want_gate_means=False,
-               want_gates=False) -> ForwardOut:
-    """The HEI levels on compact activations ([B, n_active, width]: only towers that run).
-
-    level0_in [B, n_active0, h]: MMoE mixtures of the active level-0 towers; head_cross [B, n_active_last]:
-    the cross-network part of the active heads; lin [B]."""
-    n_level, n_tower = model.n_level, model.n_tower
-    dev = q.device
-    training, p = model.training, model.dropout_p
-    out = ForwardOut(probs=None)
-    h = level0_in
-    prev_active = None
-    for l in range(n_level):
-        active = list(range(n_tower[l])) if info is None else info.active_idx[l]
-        index = None if (info is None or len(active) == n_tower[l]) else info.index(l, dev)
-        if l > 0:
-            # gates over ALL towers of the previous level (aread.py:282-285), evaluated only for towers that run
-            w_g = torch.stack([model.tower_gates[l - 1][t][0].weight for t in active], dim=0)   # [na, n_prev, 2D]
-            b_g = torch.stack([model.tower_gates[l - 1][t][0].bias for t in active], dim=0)     # [na, n_prev]
-            s = torch.softmax(torch.einsum('bd,tjd->btj', q, w_g) + b_g, dim=2)                 # [B, na, n_prev]
-            if want_gates:
-                out.gates[l] = s.detach().transpose(1, 2)                                       # [B, n_prev, n_l]
-            if info is None:
-                r = s
-            else:
-                edges = info.edges(l, dev).t()                                                  # [n_l, n_prev]
-                sm = s * (edges if index is None else edges.index_select(0, index))
-                r = sm / (sm.sum(dim=2, keepdim=True) + 1e-8)
-                if want_gate_means:
-                    means = sm.detach().mean(dim=0).t()                                         # [n_prev, na]
-                    if index is not None:       # towers that do not run report zeros (aread.py:278-280)
-                        means = torch.zeros(n_tower[l - 1], n_tower[l], dtype=torch.float32,
-                                            device=dev).index_copy_(1, index, means)
-                    out.gate_means[l] = means
-            if len(prev_active) != n_tower[l - 1]:
-                r = r.index_select(2, info.index(l - 1, dev))
-            h = torch.einsum('btj,bjw->btw', r, h)                                              # [B, na, w_prev]
-        for layer in model._tower_layers[l]:
-            h = tower_ops.tower_layer(h, layer, active, index, training, p, seed)
-        prev_active = active
-    E = model.embed_output_dim
-    w_tail = torch.stack([model.towers_linear[t].weight[0, E:] for t in prev_active], dim=0)     # [na, w_last]
-    z = head_cross + (h * w_tail).sum(dim=2) + lin.unsqueeze(1)                                  # [B, na]
-    out.probs = torch.sigmoid(z).t()
-    return out
 
 
 def hei_forward(model, tower_inputs, q, cn, lin, info: Optional[MaskInfo], want_gate_means=False,

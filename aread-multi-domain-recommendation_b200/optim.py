@@ -4,7 +4,6 @@ torch.optim.Adam, so it can replace `torch.optim.Adam(model.parameters(), lr=...
 weight_decay=...)` at run.py:830 / 632 without other changes.  Parameters whose `.grad` is None are
 skipped entirely (moments, step count and weights untouched), exactly like torch."""
 import ctypes
-import math
 
 import numpy as np
 import torch

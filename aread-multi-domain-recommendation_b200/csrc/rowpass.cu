@@ -33,26 +33,48 @@ __device__ __forceinline__ void load_x_chunk(float* sX, const float* __restrict_
 }
 
 // P[b, j] = sum_e X[b, e] * W[j, e], j < nj <= 32.  CTA = 64-row tiles; thread = (row, 8 dot products).
-__global__ void __launch_bounds__(kThreads) rowdots_fwd_kernel(int64_t m, int E, int nj, const float* __restrict__ x,
+// The next 64-element chunk of X is fetched into registers while the current one is multiplied (the loads are the
+// long pole: one pass over X), and W is staged with the lanes running along j so that the transposed
+// shared-memory stores do not collide.
+__global__ void __launch_bounds__(kThreads, 3) rowdots_fwd_kernel(int64_t m, int E, int nj, const float* __restrict__ x,
                                                                const float* __restrict__ w, float* __restrict__ p,
                                                                int ldp) {
   __shared__ float sX[kTile * kXs];
   __shared__ __align__(16) float sW[kChunk * kJ];  // [e][j]
   const int r = threadIdx.x / 4, jq = threadIdx.x % 4;
+  const int lr = threadIdx.x / kChunk, le = threadIdx.x % kChunk;      // loader role: rows lr, lr + 4, ...; column le
+  const int wj = threadIdx.x % kJ, we = threadIdx.x / kJ;             // W loader: column wj, rows we, we + 8, ...
   const int64_t n_tiles = (m + kTile - 1) / kTile;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int n_chunks = (E + kChunk - 1) / kChunk;
+  float pre[kTile / 4];
+  auto fetch = [&](int64_t b0, int e0) {
+#pragma unroll
+    for (int k = 0; k < kTile / 4; ++k) {
+      const int64_t row = b0 + lr + 4 * k;
+      pre[k] = (row < m && e0 + le < E) ? __ldg(x + row * E + e0 + le) : 0.f;
+    }
+  };
+  int64_t tile = blockIdx.x;
+  if (tile < n_tiles) fetch(tile * kTile, 0);
+  for (; tile < n_tiles; tile += gridDim.x) {
     const int64_t b0 = tile * kTile;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int e0 = 0; e0 < E; e0 += kChunk) {
+    for (int c = 0; c < n_chunks; ++c) {
+      const int e0 = c * kChunk;
       __syncthreads();
-      load_x_chunk(sX, x, m, E, b0, e0);
-      for (int idx = threadIdx.x; idx < kChunk * kJ; idx += kThreads) {
-        const int j = idx / kChunk, e = idx - j * kChunk;   // coalesced along e
-        sW[e * kJ + j] = (j < nj && e0 + e < E) ? __ldg(w + static_cast<int64_t>(j) * E + e0 + e) : 0.f;
+#pragma unroll
+      for (int k = 0; k < kTile / 4; ++k) sX[(lr + 4 * k) * kXs + le] = pre[k];
+#pragma unroll
+      for (int k = 0; k < kChunk / 8; ++k) {
+        const int e = we + 8 * k;
+        sW[e * kJ + wj] = (wj < nj && e0 + e < E) ? __ldg(w + static_cast<int64_t>(wj) * E + e0 + e) : 0.f;
       }
       __syncthreads();
+      // prefetch the next chunk (of this tile, or the first chunk of the CTA's next tile)
+      if (c + 1 < n_chunks) fetch(b0, e0 + kChunk);
+      else if (tile + gridDim.x < n_tiles) fetch((tile + gridDim.x) * kTile, 0);
 #pragma unroll 8
       for (int e = 0; e < kChunk; ++e) {
         const float xv = sX[r * kXs + e];

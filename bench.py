@@ -281,7 +281,6 @@ def run_ours(args, wl, rank, world, local_rank):
     launches0 = lib.launch_count()
     ms_dev = timed(lambda i: step(dev_x[i], dev_y[i], domains[i]), args.warmup, args.steps)
     launches = lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the module API from pinned host memory (H2D of ids+labels, D2H of the loss)
     # The loss of every step is copied to pinned host memory and READ one step late (after the next step has been
@@ -312,6 +311,7 @@ def run_ours(args, wl, rank, world, local_rank):
     for i in range(min(2, args.warmup)):
         e2e_run(i, 1)(i)
     ms_e2e = timed(e2e_run(args.warmup, args.steps), args.warmup, args.steps)
+    clocks = sampler.stop() if rank == 0 else None         # sampled across both timed regions (all of it under load)
     assert len(losses) == min(2, args.warmup) + args.steps and all(np.isfinite(losses))
 
     # ---- gather kernel alone, on its launch stream, over the same batches (roofline numerator)

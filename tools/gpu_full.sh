@@ -3,7 +3,7 @@
 # usage: tools/gpu_full.sh <tag> <kernel-regex> [<kernel-regex> ...]
 set -u
 TAG=$1; shift
-ARGS="--steps 2 --warmup 3 --no-cpu-baseline"
+ARGS="--steps 2 --warmup 3 --no-cpu-baseline --graphs lazy"
 mkdir -p gpurun_out
 timeout 600 python bench.py $ARGS > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 for K in "$@"; do

@@ -110,7 +110,9 @@ class _recording:
         self.side.wait_stream(torch.cuda.current_stream(self.device))
         self.ctx = torch.cuda.stream(self.side)
         self.ctx.__enter__()
-        self.graph.capture_begin(pool=self.pool)
+        # thread_local: only this thread is held to the capture rules -- NCCL's watchdog and other helper threads keep
+        # polling events while the sequence is recorded
+        self.graph.capture_begin(pool=self.pool, capture_error_mode="thread_local")
 
     def __exit__(self, exc_type, exc, tb):
         try:

@@ -159,6 +159,11 @@ class AdamArgs(Structure):
                 ("eps", c_float), ("weight_decay", c_float), ("l2_twice", c_void_p)]
 
 
+class MultiCopyArgs(Structure):
+    _fields_ = [("n_tensors", c_int32), ("n_chunks", c_int64), ("dst", c_void_p), ("src", c_void_p),
+                ("bytes", c_void_p), ("chunk_start", c_void_p)]
+
+
 _SIGNATURES = {
     "aread_last_error": (c_char_p, []),
     "aread_abi_version": (c_int32, []),
@@ -187,6 +192,8 @@ _SIGNATURES = {
     "aread_ipc_close": (c_int32, [c_void_p, c_int64]),
     "aread_adam_chunk": (c_int64, []),
     "aread_adam_step": (c_int32, [POINTER(AdamArgs), c_void_p]),
+    "aread_multi_copy_chunk": (c_int64, []),
+    "aread_multi_copy": (c_int32, [POINTER(MultiCopyArgs), c_void_p]),
     "aread_l2_reg_chunk": (c_int64, []),
     "aread_bn_act_apply": (c_int32, [POINTER(BnActArgs), c_void_p]),
     "aread_bn_bwd_coef": (c_int32, [POINTER(BnActBwdArgs), c_void_p, c_void_p]),

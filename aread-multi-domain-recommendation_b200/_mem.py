@@ -49,6 +49,7 @@ class Arena:
         self.off = 0
         self.need = 0          # high-water mark of any step so far (bytes)
         self.gen = 0
+        self.buf_gen = 0       # bumped whenever `buf` is reallocated (recorded CUDA graphs key on it)
         self.busy = False
         self.views = {}
 
@@ -61,6 +62,7 @@ class Arena:
             self.views.clear()
             self.cap = int(self.need * _GROW) // _ALIGN * _ALIGN
             self.buf = torch.empty(self.cap, dtype=torch.uint8, device=self.device)
+            self.buf_gen += 1
         elif len(self.views) > 65536:
             self.views.clear()
         self.off = 0
@@ -113,3 +115,21 @@ def zeros(shape, dtype, device):
     if a is None or a.device != device:
         return torch.zeros(shape, dtype=dtype, device=device)
     return a.alloc(tuple(shape), dtype).zero_()
+
+
+_WORKSPACES = {}
+
+
+def workspace(name, device, need):
+    """Scratch bytes for ONE kernel call (partial sums, sort buffers).  Inside the fused node they come from the
+    activation arena like every other intermediate, so a recorded CUDA graph never points at a buffer that a later,
+    larger call reallocates; outside it from a grow-only buffer per (name, device)."""
+    need = max(int(need), 256)
+    a = _current
+    if a is not None and a.device == device:
+        return a.alloc((need,), torch.uint8)
+    key = (name, device)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _WORKSPACES[key] = torch.empty(need, dtype=torch.uint8, device=device)
+    return ws

@@ -123,6 +123,7 @@ class AREAD(BaseModel):
         object.__setattr__(self, "_slot_cache", {})
         object.__setattr__(self, "_arenas", {})
         object.__setattr__(self, "_graphs", fused.GraphCache())
+        object.__setattr__(self, "_rollback", None)
 
     @staticmethod
     def bagging_loss(y_stack, targets):
@@ -139,16 +140,31 @@ class AREAD(BaseModel):
         buffers = {n: b.detach().clone() for n, b in self.named_buffers()}
         had_grad = any(p.grad is not None for p in self.parameters())
         rng = torch.get_rng_state()
-        # largest masks first: the activation arena then reaches its final size before most sequences are recorded
-        order = sorted(domains, key=lambda d: -sum(len(a) for a in self.mask_info(self.domain_mask[d]).active_idx))
-        for d in order:
-            for _ in range(fused.GRAPH_AFTER + 1):
-                if backward and not had_grad and self.training:
-                    self(x, mode=mode, domain_i=d).sum().backward()
-                    self.zero_grad()
-                else:
-                    with torch.no_grad():
-                        self(x, mode=mode, domain_i=d)
+        # one pass per DISTINCT mask, largest first: the activation arena then has its final size before most
+        # sequences are recorded (a pass that finds the arena too small runs eagerly and is repeated once)
+        infos = {}
+        for d in domains:
+            info = self.mask_info(self.domain_mask[d])
+            infos.setdefault(info.serial, (d, info))
+        order = sorted(infos.values(), key=lambda di: -sum(len(a) for a in di[1].active_idx))
+
+        def one_pass(d):
+            if backward and not had_grad and self.training:
+                self(x, mode=mode, domain_i=d).sum().backward()
+                self.zero_grad()
+            else:
+                with torch.no_grad():
+                    self(x, mode=mode, domain_i=d)
+
+        self._graphs.force = True
+        try:
+            for d, info in order:
+                for _ in range(3):
+                    one_pass(d)
+                    if self._graphs.recorded(info.serial):
+                        break
+        finally:
+            self._graphs.force = False
         with torch.no_grad():
             for n, b in self.named_buffers():
                 b.copy_(buffers[n])
@@ -174,7 +190,8 @@ class AREAD(BaseModel):
         clone = cls.__new__(cls)
         memo[id(self)] = clone
         for k, v in self.__dict__.items():
-            if k not in ("_packs", "_expert_layers", "_tower_layers", "_fused", "_fused_params", "_slot_cache", "_arenas", "_graphs"):
+            if k not in ("_packs", "_expert_layers", "_tower_layers", "_fused", "_fused_params", "_slot_cache", "_arenas", "_graphs",
+                         "_rollback"):
                 setattr(clone, k, copy.deepcopy(v, memo))
         clone._build_packs()
         return clone
@@ -199,12 +216,14 @@ class AREAD(BaseModel):
         info = self.mask_info(mask)
         if mode == 'domain_mask_final':
             with torch.no_grad():
-                out = dense_ops.aread_forward(self, x, info, want_gate_means=memory_gate_value)
+                out = dense_ops.aread_forward(self, x, info, want_gate_means=memory_gate_value, want_gate_inputs=True)
             self._store_gate_means(out, info, domain_i, memory_gate_value, False)
             gate = self.final_gate(out.gate_inputs.detach()) * mask[-1].squeeze(1)
             gate = gate / (gate.sum(dim=1, keepdim=True) + 1e-8)
             return torch.sum(out.probs.transpose(0, 1) * gate, dim=1)
-        out = dense_ops.aread_forward(self, x, info, want_gate_means=memory_gate_value or tmp_memory_gate_value)
+        # candidate masks of the HEMP search (current_mask=...) are scored a handful of times: not worth a CUDA graph
+        out = dense_ops.aread_forward(self, x, info, want_gate_means=memory_gate_value or tmp_memory_gate_value,
+                                      may_record=current_mask is None)
         self._store_gate_means(out, info, domain_i, memory_gate_value, tmp_memory_gate_value)
         return out.probs if mode == 'domain_mask_bagging' else out.probs.mean(dim=0)
 
@@ -418,11 +437,46 @@ class AREAD(BaseModel):
                           'embedding', 'linear', 'reg_loss', 'regularization_weight')
 
     def save_model_state(self):                                                      # aread.py:534-543
+        """Snapshot of every state entry under the roll-back prefixes.  The snapshot buffers persist from regroup to
+        regroup (the reference deep-copies the whole table every time) and are refreshed with ONE multi-tensor
+        copy launch; `model_state` stays the {key: tensor} dict the reference exposes."""
         pattern = re.compile('^(' + '|'.join(self._ROLLBACK_PREFIXES) + ')')
-        self.model_state = {k: v.detach().clone() for k, v in self.state_dict().items() if pattern.match(k)}
+        live = {k: v for k, v in self.state_dict().items() if pattern.match(k)}
+        fast = all(v.is_cuda and v.is_contiguous() and v.element_size() * v.numel() % 4 == 0 and v.numel() > 0
+                   for v in live.values())
+        if not fast:                                     # CPU module (host-logic tests): plain clones
+            self.model_state = {k: v.detach().clone() for k, v in live.items()}
+            object.__setattr__(self, "_rollback", None)
+            return
+        snap = self.model_state
+        if (snap is None or snap.keys() != live.keys() or
+                any(snap[k].shape != v.shape or snap[k].dtype != v.dtype or snap[k].device != v.device
+                    for k, v in live.items())):
+            snap = self.model_state = {k: torch.empty_like(v) for k, v in live.items()}
+            object.__setattr__(self, "_rollback", None)
+        rb = getattr(self, "_rollback", None)
+        keys = list(live)
+        ptrs = [live[k].data_ptr() for k in keys]
+        if rb is None or rb["ptrs"] != ptrs or any(rb["snap"][i] is not snap[k] for i, k in enumerate(keys)):
+            from .optim import MultiCopy
+            dsts, srcs = [snap[k] for k in keys], [live[k].detach() for k in keys]
+            owners = []
+            for k in keys:                               # (module, attribute) of every entry: looked up again at
+                path, _, leaf = k.rpartition('.')        # each restore, so a replaced Parameter is noticed
+                owners.append((self.get_submodule(path) if path else self, leaf))
+            rb = {"save": MultiCopy(dsts, srcs), "load": MultiCopy(srcs, dsts), "ptrs": ptrs, "snap": dsts,
+                  "owners": owners}
+            object.__setattr__(self, "_rollback", rb)
+        rb["save"].run()
 
     def load_model_state(self):                                                      # aread.py:545-546
-        self.load_state_dict(self.model_state, strict=False)
+        """`load_state_dict(model_state, strict=False)` of the reference = in-place copies into the live tensors;
+        here as one launch over all of them (falls back to load_state_dict when storage moved since the save)."""
+        rb = getattr(self, "_rollback", None)
+        if rb is not None and all(getattr(m, leaf).data_ptr() == p for (m, leaf), p in zip(rb["owners"], rb["ptrs"])):
+            rb["load"].run()
+        else:
+            self.load_state_dict(self.model_state, strict=False)
 
     def create_single_full_mask(self, fill_value=0):                                 # aread.py:548-568
         return hemp.full_mask(self.n_tower, fill_value)

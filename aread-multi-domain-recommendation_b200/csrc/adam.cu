@@ -74,10 +74,49 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const aread_adam_args a)
   }
 }
 
+constexpr int64_t kCopyChunk = 64 * 1024;   // bytes
+
+// dst[t] = src[t] (or zero) for a list of tensors, 16-byte accesses where the pair is aligned
+__global__ void __launch_bounds__(kThreads) multi_copy_kernel(const aread_multi_copy_args a) {
+  for (int64_t chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x) {
+    const int t = find_tensor(a.chunk_start, a.n_tensors, chunk);
+    char* __restrict__ d = static_cast<char*>(a.dst[t]);
+    const char* __restrict__ s = a.src ? static_cast<const char*>(a.src[t]) : nullptr;
+    const int64_t begin = (chunk - a.chunk_start[t]) * kCopyChunk;
+    const int64_t end = min(a.bytes[t], begin + kCopyChunk);
+    const bool vec = ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(s)) & 15) == 0;
+    int64_t i0 = begin;
+    if (vec) {
+      const int64_t n16 = (end - begin) / 16;
+      for (int64_t q = threadIdx.x; q < n16; q += kThreads) {
+        const int64_t i = begin + q * 16;
+        *reinterpret_cast<uint4*>(d + i) = s ? *reinterpret_cast<const uint4*>(s + i) : make_uint4(0, 0, 0, 0);
+      }
+      i0 = begin + n16 * 16;
+    }
+    for (int64_t i = i0 + threadIdx.x * 4; i < end; i += kThreads * 4)
+      *reinterpret_cast<uint32_t*>(d + i) = s ? *reinterpret_cast<const uint32_t*>(s + i) : 0u;
+  }
+}
+
 }  // namespace
 }  // namespace aread
 
 extern "C" {
+
+int64_t aread_multi_copy_chunk(void) { return aread::kCopyChunk; }
+
+int aread_multi_copy(const aread_multi_copy_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "multi_copy: null args");
+  const aread_multi_copy_args& a = *args;
+  if (a.n_tensors <= 0 || a.n_chunks <= 0) return AREAD_OK;
+  AREAD_REQUIRE(a.dst && a.bytes && a.chunk_start, "multi_copy: null pointer");
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+  AREAD_LAUNCH(multi_copy_kernel, static_cast<unsigned>(a.n_chunks < cap ? a.n_chunks : cap), kThreads, 0,
+               static_cast<cudaStream_t>(stream_), a);
+  return AREAD_OK;
+}
 
 int64_t aread_adam_chunk(void) { return aread::kChunk; }
 

@@ -44,8 +44,6 @@ def grouped_linear(a, w, bias, n, k, groups, a_group_cols=0, group_mask=None, ou
     return out
 
 
-_WGRAD_WS = {}
-
 
 def grouped_wgrad(dz, a, n, k, groups, a_group_cols=0, group_mask=None, out=None, dz_lo=None, a_lo=None):
     """dW[g*n + j, i] = sum_b dz[b, g*n + j] * a[b, g*a_group_cols + i] (fp32 [groups*n, k]).
@@ -64,10 +62,7 @@ def grouped_wgrad(dz, a, n, k, groups, a_group_cols=0, group_mask=None, out=None
                                  dz_lo.data_ptr() if dz_lo is not None else None,
                                  a_lo.data_ptr() if a_lo is not None else None)
     need = int(_lib.load().aread_grouped_wgrad_workspace_bytes(ctypes.byref(args)))
-    ws = _WGRAD_WS.get(dz.device)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.uint8, device=dz.device)
-        _WGRAD_WS[dz.device] = ws
+    ws = _mem.workspace("wgrad", dz.device, need)
     args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
     _lib.check(_lib.load().aread_grouped_wgrad_bf16(ctypes.byref(args), _stream(dz.device)))
     return out
@@ -79,16 +74,11 @@ SEED_PTR = None
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
-_BN_WS = {}
 
 
 def _bn_workspace(device, width):
     need = int(_lib.load().aread_bn_workspace_bytes(width))
-    ws = _BN_WS.get(device)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.uint8, device=device)
-        _BN_WS[device] = ws
-    return ws
+    return _mem.workspace("bn", device, need)
 
 
 def _ptr(t):
@@ -167,3 +157,15 @@ def dropout_mask(seed, salt, shape, p, device):
     out = torch.empty(n, dtype=torch.uint8, device=device)
     _lib.check(_lib.load().aread_dropout_mask(seed, salt, n, float(p), out.data_ptr(), _stream(device)))
     return out.view(*shape).bool()
+
+
+def bench_expert_layer1(a_op, w_op, n, k, groups):
+    """(run, output bytes per launch, description) of the expert layer-1 GEMM exactly as the fused node launches
+    it -- bench.py times `run()` alone for the roofline line."""
+    m = a_op.shape[0]
+    bias = torch.zeros(groups * n, dtype=torch.float32, device=a_op.device)
+    out = torch.empty(m, groups * n, dtype=torch.float32, device=a_op.device)
+
+    def run():
+        grouped_linear(a_op, w_op, bias, n, k, groups, 0, out=out)
+    return run, m * groups * n * 4, "grouped_linear_kernel<128> (tcgen05 / TMEM, TMA in, TMA out, fp32 output)"

@@ -68,12 +68,13 @@ def _require_cuda(model, x):
                            "has no CPU fallback")
 
 
-def aread_forward(model, x, info: Optional[MaskInfo], want_gate_means=False, want_gates=False) -> ForwardOut:
+def aread_forward(model, x, info: Optional[MaskInfo], want_gate_means=False, want_gates=False,
+                  want_gate_inputs=False, may_record=True) -> ForwardOut:
     """Embedding lookup -> trunk -> HEI levels -> per-tower probabilities, as one fused autograd node
     (fused.py)."""
     _require_cuda(model, x)
     from . import fused
-    probs, cfg = fused.forward(model, x, info, want_gate_means, want_gates)
+    probs, cfg = fused.forward(model, x, info, want_gate_means, want_gates, want_gate_inputs, may_record)
     return ForwardOut(probs=probs, gate_inputs=cfg["gate_inputs"], gate_means=cfg["gate_means"], gates=cfg["gates"])
 
 

@@ -58,7 +58,6 @@ class LookupPlan:
         self.status = torch.zeros(2, dtype=torch.int32, device=device)
         self._status_host = torch.zeros(2, dtype=torch.int32).pin_memory()
         self._status_event = None
-        self._workspace = None
         self.shards = None               # sharding.TableShards when the table is row-sharded over GPUs
 
     def c_plan(self):
@@ -70,9 +69,7 @@ class LookupPlan:
         need = int(_lib.load().aread_scatter_workspace_bytes(n_lookups, self.embed_dim))
         if need == 0:
             _lib.check(_lib.AREAD_ERR_CUDA)
-        if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._workspace
+        return _mem.workspace("scatter", self.device, need)
 
     # --- bounds reporting -------------------------------------------------------------------
     # torch raises IndexError for idx >= n_rows; the kernel records it in `status`.  'sync' checks

@@ -28,15 +28,13 @@ from .expert_ops import _hi, _lo
 USE_HEI_LAYER = os.environ.get("AREAD_HEI_FUSED", "1") != "0"
 
 
-_HEAD_WS = {}
-
 # CUDA-graph replay of the fused node (AREAD_GRAPHS=0 disables).  After GRAPH_AFTER eager calls of one configuration
 # (mask, batch shape, train / eval, precision) its forward -- and on the first backward its backward -- launch
 # sequence is recorded once and replayed from then on: the activation arena makes every address repeat, the dropout
 # seed lives in device memory (dense_kernels.SEED_PTR), the ids are copied into a fixed buffer.
 USE_GRAPHS = os.environ.get("AREAD_GRAPHS", "1") != "0"
 GRAPH_AFTER = 2
-MAX_GRAPHS = 64
+MAX_GRAPHS = int(os.environ.get("AREAD_MAX_GRAPHS", "1024"))
 
 
 class _Stub:
@@ -50,6 +48,8 @@ class GraphEntry:
         self.x = self.probs = self.ctx = self.d_probs = self.grads = None
         self.fwd_end = 0
         self.sig = None
+        self.seed = None                 # int64 [1] device slot: the dropout seed this entry's sequences read
+        self.last_use = 0
         self.n_fwd = self.n_bwd = 0      # library launches inside the recorded sequences (for aread_launch_count)
 
 
@@ -60,8 +60,9 @@ class GraphCache:
         # survive the NEXT forward replay (gradient accumulation), so they may not share blocks with a forward's
         # temporaries.
         self.pool = self.pool_bwd = None
-        self.seed = {}                  # device -> int64 [1] seed slot
         self.tgrad = {}
+        self.clock = 0
+        self.force = False              # AREAD.record_graphs: record on the first call instead of after GRAPH_AFTER
 
     def clear(self):
         self.entries.clear()
@@ -70,10 +71,16 @@ class GraphCache:
     def get(self, key):
         e = self.entries.get(key)
         if e is None:
-            if len(self.entries) >= MAX_GRAPHS:
-                self.entries.pop(next(iter(self.entries)))
+            if len(self.entries) >= MAX_GRAPHS:          # least recently used goes first
+                self.entries.pop(min(self.entries, key=lambda k: self.entries[k].last_use))
             e = self.entries[key] = GraphEntry()
+        self.clock += 1
+        e.last_use = self.clock
         return e
+
+    def recorded(self, serial):
+        """True when some entry of the mask with this serial holds a recorded forward."""
+        return any(k[0] == serial and e.fwd is not None for k, e in self.entries.items())
 
     def table_grad(self, like):
         """ONE gradient buffer for the embedding table, shared by every recorded backward: a table-sized buffer per
@@ -85,16 +92,11 @@ class GraphCache:
             t = self.tgrad[key] = torch.empty_like(like)
         return t
 
-    def seed_slot(self, device):
-        t = self.seed.get(device)
-        if t is None:
-            t = self.seed[device] = torch.zeros(1, dtype=torch.int64, device=device)
-        return t
 
 
 def _signature(model, arena):
     """Everything a recorded sequence has baked in besides its key: the arena buffer and the parameter storage."""
-    return (id(arena.buf), model.embedding.embedding_dict.weight.data_ptr()) + \
+    return (arena.buf_gen, model.embedding.embedding_dict.weight.data_ptr()) + \
         tuple(pk.flat.data_ptr() for pk in model._packs.packs)
 
 
@@ -218,14 +220,27 @@ class AreadNode(torch.autograd.Function):
             sig = _signature(model, arena)
             if entry.fwd is not None and entry.sig != sig:                   # storage moved: record again
                 entry.fwd = entry.bwd = None
-            if entry.fwd is None and entry.calls > GRAPH_AFTER and arena.need <= arena.cap:
+            record = entry.fwd is None and cfg["may_record"] and entry.calls > GRAPH_AFTER and arena.need <= arena.cap
+            if (entry.fwd is not None or record) and cfg["seed"] != 0:
+                # the seed travels through device memory so that a recorded sequence sees a new one at every replay.
+                # One slot per entry, written only here: the forward that holds the arena lease is the only one whose
+                # backward can replay this entry, so nothing overwrites the seed between the two.
+                if entry.seed is None:
+                    entry.seed = torch.zeros(1, dtype=torch.int64, device=x.device)
+                host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+                host[0] = cfg["seed"]
+                entry.seed.copy_(host, non_blocking=True)
+                cfg["seed"], cfg["seed_ptr"] = 0, entry.seed.data_ptr()
+            if record:
                 AreadNode._record_forward(entry, model, arena, x, cfg, sig)
             if entry.fwd is not None:
                 entry.x.copy_(x)
                 entry.fwd.replay()
                 _lib.load().aread_launch_count_add(entry.n_fwd)
                 ctx.entry = entry
-                cfg["gate_means"], cfg["gates"], cfg["gate_inputs"] = {}, {}, entry.ctx.cfg["gate_inputs"]
+                # graph-owned buffers never reach the caller: the next replay would overwrite them
+                cfg["gate_means"], cfg["gates"] = {}, {}
+                cfg["gate_inputs"] = entry.ctx.cfg["gate_inputs"].clone() if cfg.get("want_gate_inputs") else None
                 return entry.probs.clone()
         with _mem.use(arena if lease is not None else None), _seed_ptr(cfg.get("seed_ptr")):
             return AreadNode._forward(ctx, x, cfg)
@@ -478,9 +493,7 @@ class AreadNode(torch.autograd.Function):
         d_h = _mem.empty((B, na_last, w_last), torch.float32, dev)
         d_w_tail = torch.empty((na_last, w_last), dtype=torch.float32, device=dev)       # parameter gradient
         need = int(_lib.load().aread_head_workspace_bytes(na_last, w_last))
-        ws = _HEAD_WS.get(dev)
-        if ws is None or ws.numel() < need:
-            ws = _HEAD_WS[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
+        ws = _mem.workspace("head", dev, need)
         ha = _lib.HeadArgs(B, na_last, w_last, None, None, sv["h_last"].data_ptr(), sv["w_tail"].data_ptr(),
                            probs.data_ptr(), d_probs.contiguous().data_ptr(), dz.data_ptr(), d_lin.data_ptr(),
                            d_h.data_ptr(), d_w_tail.data_ptr(), ws.data_ptr(), ws.numel())
@@ -565,10 +578,7 @@ class AreadNode(torch.autograd.Function):
         d_x_row = _mem.empty((B, E), torch.float32, dev)
         d_wcat = torch.empty((nj, E), dtype=torch.float32, device=dev)                   # parameter gradients
         need = int(_lib.load().aread_rowpass_workspace_bytes(B, E, nj))
-        ws = rowpass_ops._WS.get(dev)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.uint8, device=dev)
-            rowpass_ops._WS[dev] = ws
+        ws = _mem.workspace("rowpass", dev, need)
         ra = rowpass_ops._args(B, E, layout, ldp, x=X, w=sv["w_cat"], p=sv["p_dots"], gate=sv["gate"], alpha=sv["alpha"],
                                d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p, d_c=d_c, d_x=d_x_row, d_w=d_wcat,
                                workspace=ws)
@@ -650,8 +660,10 @@ def slot_maps(active_prev, n_prev, device, cache):
     return got
 
 
-def forward(model, x, info, want_gate_means=False, want_gates=False):
-    """Runs the fused node; returns (probs [n_active_last, B], cfg) where cfg carries the side outputs."""
+def forward(model, x, info, want_gate_means=False, want_gates=False, want_gate_inputs=False, may_record=True):
+    """Runs the fused node; returns (probs [n_active_last, B], cfg) where cfg carries the side outputs.
+    `may_record=False` (candidate masks of the HEMP search, which are evaluated a handful of times) keeps the call
+    from recording a CUDA graph; an already recorded sequence is still replayed."""
     table = model.embedding.embedding_dict.weight
     if model._fused_params[0] is not table:        # the table parameter was replaced (shard_table, load)
         model._fused_params[0] = table
@@ -663,20 +675,14 @@ def forward(model, x, info, want_gate_means=False, want_gates=False):
     slots = [None] + [slot_maps(active[l - 1], n_tower[l - 1], dev, model._slot_cache) for l in range(1, n_level)]
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and model.dropout_p > 0) else 0
     cfg = {"model": model, "info": info, "precise": model.expert_precision == "bf16x3", "seed": seed, "slots": slots,
-           "want_gate_means": want_gate_means, "want_gates": want_gates}
+           "want_gate_means": want_gate_means, "want_gates": want_gates, "want_gate_inputs": want_gate_inputs,
+           "may_record": may_record}
     if USE_GRAPHS and _mem.ENABLED and not want_gate_means and not want_gates:
         key = (0 if info is None else info.serial, tuple(x.shape), training, model.expert_precision,
                model.dropout_p if training else 0.0, torch.is_grad_enabled(), dev)
         entry = model._graphs.get(key)
-        entry.calls += 1
+        entry.calls += 1 if not model._graphs.force else GRAPH_AFTER + 1      # record_graphs: record at once
         cfg["graph"] = entry
-        if entry.fwd is not None or entry.calls > GRAPH_AFTER:
-            # the seed travels through device memory so that a recorded sequence sees a new one at every replay
-            slot = model._graphs.seed_slot(dev)
-            host = torch.empty(1, dtype=torch.int64, pin_memory=True)
-            host[0] = seed
-            slot.copy_(host, non_blocking=True)
-            cfg["seed"], cfg["seed_ptr"] = 0, slot.data_ptr()
     probs = AreadNode.apply(x, cfg, *model._fused_params)
     model.embedding.plan(dev).post_lookup(embedding_ops_bounds_mode())
     return probs, cfg

@@ -11,8 +11,6 @@ from . import _mem
 from . import dense_kernels as dk
 from .dense_kernels import BN_EPS, BN_MOMENTUM, _bn_workspace, _ptr, _rows
 
-_WS = {}
-
 
 def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
@@ -24,10 +22,7 @@ def supported(groups, k, n):
 
 def _workspace(device, m, groups, k, n):
     need = int(_lib.load().aread_hei_layer_workspace_bytes(m, groups, k, n))
-    ws = _WS.get(device)
-    if ws is None or ws.numel() < need:
-        ws = _WS[device] = torch.empty(need, dtype=torch.uint8, device=device)
-    return ws
+    return _mem.workspace("hei", device, need)
 
 
 def layer_fwd(src, src_saved, src_salt, weight, bias, gamma, beta, running_mean, running_var, groups, k, n, training,

@@ -8,8 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-
-_WS = {}
+from . import _mem
 
 
 class BaggingBCE(torch.autograd.Function):
@@ -25,9 +24,7 @@ class BaggingBCE(torch.autograd.Function):
         dev = probs.device
         lib = _lib.load()
         need = int(lib.aread_bagging_bce_workspace_bytes(m, T))
-        ws = _WS.get(dev)
-        if ws is None or ws.numel() < need:
-            ws = _WS[dev] = torch.empty(max(need, 4096), dtype=torch.uint8, device=dev)
+        ws = _mem.workspace("bagging_bce", dev, max(need, 4096))
         loss = torch.empty((), dtype=torch.float32, device=dev)
         want_grad = ctx.needs_input_grad[0]
         d_probs = torch.empty_like(probs) if want_grad else None

@@ -38,6 +38,56 @@ class _Plan:
         self.moments = [(st["exp_avg"], st["exp_avg_sq"]) for st in states]     # keeps the addresses valid
 
 
+class MultiCopy:
+    """dst[i] <- src[i] (or zeros when `srcs` is None) for a fixed list of same-device CUDA tensors in ONE launch
+    (csrc/adam.cu multi_copy_kernel).  The launch table is built once and kept on the device."""
+
+    def __init__(self, dsts, srcs=None):
+        lib = _lib.load()
+        chunk = int(lib.aread_multi_copy_chunk())
+        self.dsts, self.srcs = list(dsts), None if srcs is None else list(srcs)
+        n = len(self.dsts)
+        self.n = n
+        if n == 0:
+            return
+        dev = self.dsts[0].device
+        table = np.zeros((4, n), dtype=np.int64)
+        start = 0
+        for i, d in enumerate(self.dsts):
+            if not (d.is_cuda and d.is_contiguous() and d.device == dev):
+                raise RuntimeError("MultiCopy handles contiguous CUDA tensors of one device")
+            nbytes = d.numel() * d.element_size()
+            if nbytes % 4 or d.data_ptr() % 4:
+                raise RuntimeError("MultiCopy needs 4-byte multiples")
+            table[0, i] = d.data_ptr()
+            if self.srcs is not None:
+                src = self.srcs[i]
+                if src.dtype != d.dtype or src.shape != d.shape or not src.is_contiguous() or src.device != dev:
+                    raise RuntimeError("MultiCopy: source / destination mismatch")
+                table[1, i] = src.data_ptr()
+            table[2, i], table[3, i] = nbytes, start
+            start += (nbytes + chunk - 1) // chunk
+        self.n_chunks = start
+        self.ptrs = table[:2].copy()
+        self.table = torch.from_numpy(table).to(dev)
+        self.device = dev
+
+    def current(self):
+        """False once one of the tensors moved (the table holds raw addresses)."""
+        return self.n == 0 or (all(int(self.ptrs[0, i]) == d.data_ptr() for i, d in enumerate(self.dsts)) and
+                               (self.srcs is None or
+                                all(int(self.ptrs[1, i]) == t.data_ptr() for i, t in enumerate(self.srcs))))
+
+    def run(self):
+        if self.n == 0:
+            return
+        base, row = self.table.data_ptr(), self.table.stride(0) * 8
+        args = _lib.MultiCopyArgs(self.n, self.n_chunks, base, base + row if self.srcs is not None else None,
+                                  base + 2 * row, base + 3 * row)
+        _lib.check(_lib.load().aread_multi_copy(ctypes.byref(args),
+                                                ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
@@ -57,6 +107,26 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError(f"{len(missing)} regularised parameter(s) are not managed by this optimizer")
         self._l2 = dict(terms)
         self._plans = {}
+
+    def reset(self):
+        """Back to the state of a freshly constructed optimizer -- step counts 0, both moments 0 -- WITHOUT
+        reallocating the moments: what the trainer's per-candidate `optimizer_fast = Adam(model.parameters(), ...)`
+        (run.py:632-633) amounts to, as one zero-fill launch instead of a table-sized allocation per candidate.
+        Hyper-parameters are kept; change them through `param_groups` as usual."""
+        moments = []
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st:
+                    moments += [st["exp_avg"], st["exp_avg_sq"]]
+        for arr, _ in self._steps:
+            arr[:] = 0
+        if moments:
+            z = getattr(self, "_zero", None)
+            if z is None or len(z.dsts) != len(moments) or any(a is not b for a, b in zip(z.dsts, moments)) \
+                    or not z.current():
+                z = self._zero = MultiCopy(moments)
+            z.run()
 
     def _bind_steps(self):
         """state[p]["step"] (a host scalar tensor, as in torch.optim.Adam) becomes a view into one array per

@@ -5,8 +5,7 @@ import ctypes
 import torch
 
 from . import _lib
-
-_WS = {}
+from . import _mem
 
 
 def _stream(device):
@@ -56,10 +55,7 @@ class RowPass(torch.autograd.Function):
         d_x = torch.empty((m, e), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
         d_w = torch.empty((nj, e), dtype=torch.float32, device=dev)
         need = int(_lib.load().aread_rowpass_workspace_bytes(m, e, nj))
-        ws = _WS.get(dev)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.uint8, device=dev)
-            _WS[dev] = ws
+        ws = _mem.workspace("rowpass", dev, need)
         a = _args(m, e, ctx.layout, ctx.ldp, x=x, w=w, p=p, gate=gate, alpha=alpha,
                   d_lin=d_lin.contiguous() if d_lin is not None else None,
                   d_gate=d_gate.contiguous() if d_gate is not None else None,

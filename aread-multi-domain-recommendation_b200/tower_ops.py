@@ -7,8 +7,6 @@ import torch
 from . import _lib
 from . import _mem
 
-_WS = {}
-
 
 def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
@@ -38,10 +36,7 @@ def tower_wgrad(dz, x):
     ld, gs = (K, 0) if x.dim() == 2 else (G * K, K)
     d_w = torch.empty((G, N, K), dtype=torch.float32, device=dz.device)
     need = int(_lib.load().aread_tower_wgrad_workspace_bytes(B, G, N, K))
-    ws = _WS.get(dz.device)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.uint8, device=dz.device)
-        _WS[dz.device] = ws
+    ws = _mem.workspace("tower_wgrad", dz.device, need)
     args = _lib.TowerWgradArgs(B, G, N, K, dz.data_ptr(), G * N, x.data_ptr(), ld, gs, d_w.data_ptr(), ws.data_ptr(),
                                ws.numel())
     _lib.check(_lib.load().aread_tower_wgrad(ctypes.byref(args), _stream(dz.device)))

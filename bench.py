@@ -2,12 +2,18 @@
 """AREAD train throughput on synthetic data of the BASELINE.json shapes.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload amazon|aliccp|cloudtheme] [--batch B]
+                    [--workload aliccp|amazon|cloudtheme|stress] [--batch B]
 
 One step = forward(mode='domain_mask_bagging') + mean-over-towers BCE + L2 regulariser +
 zero_grad + backward + Adam.step on one single-domain batch (run.py:663-682).  Prints ONE JSON
 line (rank 0): samples/s with inputs resident in HBM (`value`), through the module API from
-pinned host buffers (`e2e`), the gather kernel's roofline, and the CPU baseline.
+pinned host buffers (`e2e`), the roofline of the kernel with the largest share of the step plus the
+lookup kernel's, the CPU baseline, and under `extra` the same step at other batch sizes, with the
+unedited trainer calls, on torch-eager CUDA ops (the same-box GPU bar), eval throughput, the lookup
+gradient and the HEMP regroup loop.
+
+The default workload is the AliCCP-scale configuration (BASELINE.json configs[2]): it is the one the
+metric is quoted on and it fits one GPU.
 """
 import argparse
 import importlib
@@ -26,10 +32,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+PKG = "aread-multi-domain-recommendation_b200"
 N_TOWER = (3, 6, 12)
 EXPERT_DIMS = (256, 128, 64)
 TOWER_DIMS = ((64, 32), (32, 16), (16, 8))
 LR, WD = 1e-3, 1e-8
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/), keyed by (kernel, workload, batch); None where no capture exists
+NCU_DRAM_BYTES = {}
 
 
 def parse_args():
@@ -38,11 +49,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="amazon", choices=["amazon", "aliccp", "cloudtheme", "stress"])
+    ap.add_argument("--workload", default="aliccp", choices=["amazon", "aliccp", "cloudtheme", "stress"])
     ap.add_argument("--batch", type=int, default=65536, help="samples per step per GPU")
-    ap.add_argument("--cpu-batch", type=int, default=4096, help="rows per step of the bounded CPU sample")
-    ap.add_argument("--cpu-steps", type=int, default=30, help="timed steps of the cpu_baseline leg (about 15 s)")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the cpu_baseline leg (about 15-25 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline and rooflines only (profiling runs)")
     ap.add_argument("--active", type=float, default=0.7, help="HEMP init_active_percent of the per-domain masks")
     ap.add_argument("--dropout", type=float, default=0.2)
     ap.add_argument("--seed", type=int, default=2000)
@@ -57,6 +68,7 @@ def parse_args():
                          "through autograd as in run.py:644")
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="bagging BCE through AREAD.bagging_loss (one kernel) or as the trainer's sum of BCELoss calls")
+    ap.add_argument("--sustained-steps", type=int, default=200, help="steps of the extra.sustained leg")
     return ap.parse_args()
 
 
@@ -71,7 +83,15 @@ def load_peaks():
     if os.path.exists(path):
         with open(path) as fh:
             return json.load(fh), "measured"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1590.0}, "fallback"
+
+
+def workload_config(wl, args, world, model=None):
+    """The `config` object of the JSON line; the reference arm prints the same one."""
+    cfg = {"workload": f"{wl.name}_singledomain_B{args.batch}", "batch_per_gpu": args.batch, "n_tower": list(N_TOWER),
+           "embed_dim": wl.embed_dim, "table_rows": wl.n_rows, "n_cols": wl.n_cols,
+           "mask_active_percent": args.active, "dropout": args.dropout}
+    return cfg
 
 
 class ClockSampler:
@@ -119,23 +139,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_rate(wl, batch, steps, warmup, active, seed, dropout=0.2, threads=None):
-    """The oracle port (oracle/aread_torch.py: the reference's torch ops restated functionally) timed on
-    the host cores: same step definition, fp32, all threads."""
+# ----------------------------------------------------------------------------------------- oracle arms
+def oracle_rate(wl, batch, steps, warmup, active, seed, dropout=0.2, threads=None, device="cpu"):
+    """The oracle port (oracle/aread_torch.py: the reference's torch ops restated functionally) timed as the
+    reference path: same step definition, fp32.  device='cpu': all host threads (the reference arm / cpu_baseline);
+    device='cuda:N': torch-eager CUDA kernels on the same box (the 'same-box GPU bar' of SURVEY 8d)."""
     from oracle import aread_torch as O
     from oracle import synth
+    on_gpu = device != "cpu"
     threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
+    if not on_gpu:
+        torch.set_num_threads(threads)
     mh = wl.multi_hot_dict
     spec = O.Spec(one_hot_field_dims=list(wl.one_hot_field_dims), embed_dim=wl.embed_dim,
                   multi_hot_flag=mh["multi_hot_flag"], itemid_idx=wl.itemid_idx, seq_maxlen=wl.seq_maxlen,
                   method=wl.method, n_tower=N_TOWER, n_domain=wl.n_domain, expert_dims=EXPERT_DIMS,
                   tower_dims=TOWER_DIMS, domain_idx=wl.domain_idx, dropout=dropout)
-    sd = O.make_leaf_params(synth.deterministic_state(spec))
+    state = synth.deterministic_state(spec)
+    if on_gpu:
+        state = {k: v.to(device) for k, v in state.items()}
+    sd = O.make_leaf_params(state)
     opt = O.make_adam(sd, lr=LR, wd=WD)
     np.random.seed(seed)
-    hemp = importlib.import_module("aread-multi-domain-recommendation_b200.hemp")
+    hemp = importlib.import_module(PKG + ".hemp")
     masks = {}
     times = []
     for step in range(warmup + steps):
@@ -145,49 +171,119 @@ def cpu_reference_rate(wl, batch, steps, warmup, active, seed, dropout=0.2, thre
                 m = hemp.validate_arrays(hemp.full_mask(N_TOWER, active), N_TOWER)
                 if m[-1].any():
                     break
-            masks[d] = [torch.from_numpy(a) for a in m]
-        xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+            masks[d] = [torch.from_numpy(a).to(device) for a in m]
+        xt, yt = torch.from_numpy(x).to(device), torch.from_numpy(y).to(device)
+        if on_gpu:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         O.train_step(sd, spec, xt, yt, masks[d], opt, masks="rng")
+        if on_gpu:
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if step >= warmup:
             times.append(dt)
     total = float(np.sum(times))
-    return {"value": batch * len(times) / total, "unit": "samples/s", "cores": threads, "kind": "port",
+    where = "torch-eager CUDA ops on the same GPU" if on_gpu else f"{threads} host threads"
+    return {"value": batch * len(times) / total, "unit": "samples/s", "cores": threads if not on_gpu else 0,
+            "kind": "port",
             "sample": f"{len(times)} train steps of {batch} rows ({wl.name}, fp32, dropout {dropout}, {warmup} "
-                      f"warm-up; the reference's dead attention branch is not executed), {total:.1f} s"}, total / len(times)
+                      f"warm-up, {where}; the reference's dead attention branch is not executed), {total:.1f} s"}, \
+        total / len(times)
 
 
-def run_reference(args, wl, rank):
+def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    res, sec_per_step = cpu_reference_rate(wl, args.cpu_batch, max(1, args.steps), max(1, args.warmup), args.active,
-                                           args.seed, args.dropout)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    # a bounded sample of the workload: the same batch as our arm when the whole run stays within a few minutes
+    batch = args.batch if args.batch * (steps + warmup) <= 2_000_000 else 4096
+    res, sec_per_step = oracle_rate(wl, batch, steps, warmup, args.active, args.seed, args.dropout)
+    cfg = workload_config(wl, args, world)
+    cfg["note"] = ("reference path = torch CPU ops restated in oracle/aread_torch.py (the Python reference itself "
+                   f"cannot travel to the GPU box); each step is {batch} rows of the workload")
     line = {"impl": "reference", "metric": "aread_train_samples_per_sec", "value": res["value"],
-            "unit": "samples/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, args.warmup),
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{wl.name}_singledomain_B{args.cpu_batch}", "batch_per_step": args.cpu_batch,
-                       "n_tower": list(N_TOWER), "embed_dim": wl.embed_dim, "mask_active_percent": args.active,
-                       "note": "reference path = torch CPU ops restated in oracle/aread_torch.py (the Python "
-                               "reference itself cannot travel to the GPU box); bounded sample of the workload"},
-            "cpu_baseline": res,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one gather_kernel launch at the default workload (amazon, B=65536),
-# from the committed ncu --set full capture
-GATHER_DRAM_BYTES = 21_779_200 + 57_837_824
-
-
 # ----------------------------------------------------------------------------------------- GPU arm
+class Trainer:
+    """Model + optimizer + the train step of run.py:663-682 in the chosen variant."""
+
+    def __init__(self, pkg, wl, args, dev, world, optimizer, reg, loss, graphs):
+        self.args, self.wl, self.dev, self.world = args, wl, dev, world
+        self.loss_kind, self.graphs = loss, graphs
+        self.model = pkg.AREAD(np.asarray(wl.one_hot_field_dims), wl.embed_dim, wl.multi_hot_dict, n_tower=N_TOWER,
+                               n_domain=wl.n_domain, base_model="mmoe", expert_dims=EXPERT_DIMS,
+                               tower_dims=TOWER_DIMS, domain_idx=wl.domain_idx, device=dev, dropout=args.dropout,
+                               config=make_config(wl)).to(dev)
+        model = self.model
+        model.reset_for_mask_update()
+        for d in range(wl.n_domain):
+            model.domain_mask[d] = model.generate_mask("rand", d, init_active_percent=args.active)
+        self.sharding = None
+        if world > 1:
+            import torch.distributed as dist
+            # replicas of the dense part, ONE copy of the table: row r lives on rank r % world and is read by its
+            # peers over NVLink inside the lookup kernel (sharding.py)
+            self.sharding = importlib.import_module(PKG + ".sharding")
+            for p in model.parameters():
+                dist.broadcast(p.data, src=0)
+            model.shard_table()
+        model.train()
+        fused_adam = importlib.import_module(PKG + ".optim").FusedAdam
+        adam_cls = fused_adam if optimizer == "fused" else torch.optim.Adam
+        self.opt = adam_cls(model.parameters(), lr=LR, betas=(0.9, 0.99), eps=1e-8, weight_decay=WD)
+        if reg == "fold":                          # L2 gradient applied inside the optimizer step (SURVEY 8(f) rank 1)
+            if optimizer != "fused":
+                raise SystemExit("--reg fold needs --optimizer fused")
+            model.fold_regularization_into(self.opt)
+        self.crit = torch.nn.BCELoss()
+        table_param = model.embedding.embedding_dict.weight
+        self.dense_params = [p for p in model.parameters() if p is not table_param]
+
+    def record(self, x, domains, mode="domain_mask_bagging", backward=True):
+        if self.graphs == "prerecord":
+            # setup, like building the model: the per-mask CUDA-graph launch sequences are recorded once per distinct
+            # mask (what a trainer does after every HEMP regroup); parameters, buffers and RNG are left untouched
+            # (sharded table: every rank records ALL domains so that the lookup fences / gradient reduce-scatters,
+            # which stay outside the recorded sequences, are issued the same number of times everywhere)
+            doms = sorted(set(domains)) if self.world == 1 else range(self.wl.n_domain)
+            self.model.record_graphs(x, domains=doms, mode=mode, backward=backward)
+
+    def step(self, x, y, d):
+        model = self.model
+        preds = model(x, mode="domain_mask_bagging", domain_i=d)
+        if self.loss_kind == "fused":              # run.py:672-677 as one kernel (loss_ops.py)
+            loss = model.bagging_loss(preds, y)
+        else:
+            tgt = y.squeeze().float()
+            loss = sum(self.crit(p, tgt) for p in preds.unbind(dim=0)) / preds.shape[0]
+        loss = loss + model.get_regularization_loss(device=self.dev)
+        model.zero_grad()
+        loss.backward()
+        if self.world > 1:                         # the table gradient arrives reduce-scattered from the backward
+            self.sharding.allreduce_dense_grads(self.dense_params)
+        self.opt.step()
+        return loss
+
+
+def make_batches(wl, B, n, seed, rank, dev):
+    host = [wl.batch(B, seed=seed + 1000 * rank + i) for i in range(n)]
+    hx = [torch.from_numpy(x).pin_memory() for x, _, _ in host]
+    hy = [torch.from_numpy(y).pin_memory() for _, y, _ in host]
+    return host, hx, hy, [d for _, _, d in host]
+
+
 def run_ours(args, wl, rank, world, local_rank):
     import torch.distributed as dist
-    pkg = importlib.import_module("aread-multi-domain-recommendation_b200")
-    lib = importlib.import_module("aread-multi-domain-recommendation_b200._lib")
-    ops = importlib.import_module("aread-multi-domain-recommendation_b200.embedding_ops")
+    pkg = importlib.import_module(PKG)
+    lib = importlib.import_module(PKG + "._lib")
+    ops = importlib.import_module(PKG + ".embedding_ops")
     lib.load()                                     # fail loudly when the CUDA library is missing
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
@@ -198,53 +294,11 @@ def run_ours(args, wl, rank, world, local_rank):
     torch.manual_seed(args.seed + rank)
     np.random.seed(args.seed)                      # same masks on every rank
 
-    model = pkg.AREAD(np.asarray(wl.one_hot_field_dims), wl.embed_dim, wl.multi_hot_dict, n_tower=N_TOWER,
-                      n_domain=wl.n_domain, base_model="mmoe", expert_dims=EXPERT_DIMS, tower_dims=TOWER_DIMS,
-                      domain_idx=wl.domain_idx, device=dev, dropout=args.dropout, config=make_config(wl)).to(dev)
-    model.reset_for_mask_update()
-    for d in range(wl.n_domain):
-        model.domain_mask[d] = model.generate_mask("rand", d, init_active_percent=args.active)
-    shards = None
-    if world > 1:
-        # replicas of the dense part, ONE copy of the table: row r lives on rank r % world and is read by its
-        # peers over NVLink inside the lookup kernel (sharding.py)
-        sharding = importlib.import_module("aread-multi-domain-recommendation_b200.sharding")
-        for p in model.parameters():
-            dist.broadcast(p.data, src=0)
-        shards = model.shard_table()
-    model.train()
-    fused_adam = importlib.import_module("aread-multi-domain-recommendation_b200.optim").FusedAdam
-    adam_cls = fused_adam if args.optimizer == "fused" else torch.optim.Adam
-    opt = adam_cls(model.parameters(), lr=LR, betas=(0.9, 0.99), eps=1e-8, weight_decay=WD)
-    if args.reg == "fold":                         # L2 gradient applied inside the optimizer step
-        if args.optimizer != "fused":
-            raise SystemExit("--reg fold needs --optimizer fused")
-        model.fold_regularization_into(opt)
-    crit = torch.nn.BCELoss()
-    table_param = model.embedding.embedding_dict.weight
-    dense_params = [p for p in model.parameters() if p is not table_param]
-
+    tr = Trainer(pkg, wl, args, dev, world, args.optimizer, args.reg, args.loss, args.graphs)
+    model = tr.model
     B = args.batch
     n_batches = args.warmup + args.steps
-    host = [wl.batch(B, seed=args.seed + 1000 * rank + i) for i in range(n_batches)]
-    host_x = [torch.from_numpy(x).pin_memory() for x, _, _ in host]
-    host_y = [torch.from_numpy(y).pin_memory() for _, y, _ in host]
-    domains = [d for _, _, d in host]
-
-    def step(x, y, d):
-        preds = model(x, mode="domain_mask_bagging", domain_i=d)
-        if args.loss == "fused":                   # run.py:672-677 as one kernel (loss_ops.py)
-            loss = model.bagging_loss(preds, y)
-        else:
-            tgt = y.squeeze().float()
-            loss = sum(crit(p, tgt) for p in preds.unbind(dim=0)) / preds.shape[0]
-        loss = loss + model.get_regularization_loss(device=dev)
-        model.zero_grad()
-        loss.backward()
-        if world > 1:                              # the table gradient arrives reduce-scattered from the backward
-            sharding.allreduce_dense_grads(dense_params)
-        opt.step()
-        return loss
+    host, host_x, host_y, domains = make_batches(wl, B, n_batches, args.seed, rank, dev)
 
     def barrier():
         if world > 1:
@@ -267,19 +321,14 @@ def run_ours(args, wl, rank, world, local_rank):
     # ---- device-resident pass
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
-    if args.graphs == "prerecord":
-        # setup, like building the model: the per-mask CUDA-graph launch sequences are recorded once per domain
-        # (what a trainer does after every HEMP regroup); parameters, buffers and RNG are left untouched
-        # (sharded table: every rank records ALL domains so that the lookup fences / gradient reduce-scatters, which
-        # stay outside the recorded sequences, are issued the same number of times everywhere)
-        model.record_graphs(dev_x[0], domains=sorted(set(domains)) if world == 1 else range(wl.n_domain))
+    tr.record(dev_x[0], domains)
     for i in range(args.warmup):
-        step(dev_x[i], dev_y[i], domains[i])
+        tr.step(dev_x[i], dev_y[i], domains[i])
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = lib.launch_count()
-    ms_dev = timed(lambda i: step(dev_x[i], dev_y[i], domains[i]), args.warmup, args.steps)
+    ms_dev = timed(lambda i: tr.step(dev_x[i], dev_y[i], domains[i]), args.warmup, args.steps)
     launches = lib.launch_count() - launches0
 
     # ---- end to end through the module API from pinned host memory (H2D of ids+labels, D2H of the loss)
@@ -297,7 +346,7 @@ def run_ours(args, wl, rank, world, local_rank):
     def e2e_step(i, first):
         x = host_x[i].to(dev, non_blocking=True)
         y = host_y[i].to(dev, non_blocking=True)
-        loss_host[i:i + 1].copy_(step(x, y, domains[i]).detach().reshape(1), non_blocking=True)
+        loss_host[i:i + 1].copy_(tr.step(x, y, domains[i]).detach().reshape(1), non_blocking=True)
         loss_done[i].record()
         if i > first:
             read_loss(i - 1)
@@ -314,73 +363,35 @@ def run_ours(args, wl, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None         # sampled across both timed regions (all of it under load)
     assert len(losses) == min(2, args.warmup) + args.steps and all(np.isfinite(losses))
 
-    # ---- gather kernel alone, on its launch stream, over the same batches (roofline numerator)
-    plan = model.embedding.plan(dev)
-    table = model.embedding.embedding_dict.weight.detach()
-    for i in range(args.warmup):
-        ops.gather(plan, table, dev_x[i])
     stream = torch.cuda.current_stream(dev)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
-    g0.record(stream)
-    for i in range(args.warmup, args.warmup + args.steps):
-        ops.gather(plan, table, dev_x[i])
-    g1.record(stream)
-    torch.cuda.synchronize(dev)
-    gather_ms = g0.elapsed_time(g1) / args.steps
 
-    # ---- the rest of BASELINE's metric, reported beside the headline: eval samples/s (mode 'domain_with_mask',
-    # eval(), no_grad -- run.py:712-727) and the scatter (lookup gradient) kernels against HBM
-    model.eval()
-    if args.graphs == "prerecord":
-        with torch.no_grad():
-            model.record_graphs(dev_x[0], domains=sorted(set(domains)) if world == 1 else range(wl.n_domain),
-                                mode="domain_with_mask", backward=False)
-
-    def eval_step(i):
-        with torch.no_grad():
-            model(dev_x[i], mode="domain_with_mask", domain_i=domains[i])
-    for i in range(args.warmup):
-        eval_step(i)
-    ms_eval = timed(eval_step, args.warmup, args.steps)
-    model.train()
-    scatter_ms = scatter_bytes = None
-    if world == 1:
-        d_out = torch.randn(B, plan.n_fields, plan.embed_dim, device=dev)
-        offs = np.asarray(model.embedding.offsets, dtype=np.int64)
-        uniq = [int(np.unique(host[i][0].astype(np.int64) + offs[None, :]).size)
-                for i in range(args.warmup, args.warmup + args.steps)]
-        for i in range(args.warmup):
-            ops.scatter(plan, dev_x[i], d_out)
+    def kernel_ms(fn, n_warm, n):
+        """Average duration of `fn`'s launches, timed alone on their launch stream."""
+        for i in range(n_warm):
+            fn(i)
         torch.cuda.synchronize(dev)
         g0.record(stream)
-        for i in range(args.warmup, args.warmup + args.steps):
-            ops.scatter(plan, dev_x[i], d_out)
+        for i in range(n_warm, n_warm + n):
+            fn(i)
         g1.record(stream)
         torch.cuda.synchronize(dev)
-        scatter_ms = g0.elapsed_time(g1) / args.steps
-        scatter_bytes = float(np.mean([wl.scatter_bytes(B * wl.n_cols, u) for u in uniq]))
+        return g0.elapsed_time(g1) / n
 
-    # ---- the tensor-core kernel with the largest share of the step: expert layer 1, [B, E] x [E, 4 * 256] (bf16 in,
-    # fp32 accumulate / out), timed alone on its launch stream
-    gemm_ms = gemm_flops = None
+    # ---- lookup kernel alone over the same batches
+    plan = model.embedding.plan(dev)
+    table = model.embedding.embedding_dict.weight.detach()
+    gather_ms = kernel_ms(lambda i: ops.gather(plan, table, dev_x[i % n_batches]), args.warmup, args.steps)
+
+    # ---- the kernel with the largest share of the step (profiles/r2_launches_*.txt): expert layer 1 on the tensor
+    # cores, [B, E] x [E, 4 * 256] bf16 in, fp32 accumulate
+    gemm = None
     if world == 1:
-        dk = importlib.import_module("aread-multi-domain-recommendation_b200.dense_kernels")
-        n_exp, n1, E = len(model.mmoe_experts), EXPERT_DIMS[0], model.embed_output_dim
-        a_op = torch.randn(B, E, device=dev).to(torch.bfloat16)
-        w_op = torch.randn(n_exp * n1, E, device=dev).to(torch.bfloat16)
-        bias = torch.zeros(n_exp * n1, device=dev)
-        out = torch.empty(B, n_exp * n1, device=dev)
-        for _ in range(args.warmup):
-            dk.grouped_linear(a_op, w_op, bias, n1, E, n_exp, 0, out=out)
-        torch.cuda.synchronize(dev)
-        g0.record(stream)
-        for _ in range(args.steps):
-            dk.grouped_linear(a_op, w_op, bias, n1, E, n_exp, 0, out=out)
-        g1.record(stream)
-        torch.cuda.synchronize(dev)
-        gemm_ms = g0.elapsed_time(g1) / args.steps
-        gemm_flops = 2.0 * B * n_exp * n1 * E
+        gemm = expert_gemm_roofline(model, B, dev, kernel_ms, args)
+
+    extra = {}
+    if not args.no_extra:
+        extra = extra_legs(args, wl, tr, pkg, lib, ops, dev, rank, world, timed, kernel_ms, host, dev_x, dev_y, domains)
 
     if rank != 0:
         if world > 1:
@@ -390,63 +401,211 @@ def run_ours(args, wl, rank, world, local_rank):
     gather_bytes = wl.gather_bytes_per_sample() * B
     achieved = gather_bytes / (gather_ms * 1e-3) / 1e9
     total_samples = B * args.steps * world
+    cfg = workload_config(wl, args, world)
+    cfg.update({
+        "expert_precision": model.expert_precision + " operands, fp32 accumulate; everything else fp32",
+        "optimizer": "torch.optim.Adam" if args.optimizer == "torch" else "aread_b200 FusedAdam",
+        "loss": "AREAD.bagging_loss" if args.loss == "fused" else "sum of torch BCELoss",
+        "l2_regulariser": "value in the loss, gradient folded into FusedAdam" if args.reg == "fold" else "autograd node",
+        "cuda_graphs": ("off (AREAD_GRAPHS=0)" if os.environ.get("AREAD_GRAPHS", "1") == "0" else
+                        "per-mask forward/backward sequences, " + args.graphs),
+        "parallelism": f"dp{world}" + ("" if world == 1 else f" + table row-sharded over {world} GPUs (P2P lookup, "
+                                       "sparse exchange of the table gradient, flat all-reduce of the rest)"),
+        "l2": "inputs larger than L2: table %d MB + per-step activations" % (wl.n_rows * wl.embed_dim * 4 >> 20)})
+    gather_roof = {"bound": "hbm", "kernel": "gather_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                   "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                   "traffic": NCU_DRAM_BYTES.get(("gather_kernel", args.workload, B)),
+                   "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full, profiles/); "
+                                   "below the algorithmic bytes when hot rows of the Zipf ids and part of the output "
+                                   "stay in the 126 MB L2: `achieved` is then an L2-assisted rate, the DRAM-level "
+                                   "rate is traffic / launch_ms",
+                   "peak_source": peak_src, "algorithmic_bytes_per_launch": gather_bytes, "launch_ms": gather_ms}
+    if gather_roof["traffic"]:
+        gather_roof["dram_level_gbs"] = gather_roof["traffic"] / (gather_ms * 1e-3) / 1e9
     line = {
         "metric": "aread_train_samples_per_sec", "value": total_samples / (ms_dev * 1e-3), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if model.expert_precision == "bf16" else "bf16x3", "data": "synthetic",
-        "config": {"workload": f"{wl.name}_singledomain_B{B}", "batch_per_gpu": B, "n_tower": list(N_TOWER),
-                   "expert_precision": model.expert_precision + " operands, fp32 accumulate; everything else fp32",
-                   "embed_dim": wl.embed_dim, "table_rows": wl.n_rows, "n_cols": wl.n_cols,
-                   "mask_active_percent": args.active, "dropout": args.dropout,
-                   "optimizer": "torch.optim.Adam" if args.optimizer == "torch" else "aread_b200 FusedAdam",
-                   "loss": "AREAD.bagging_loss" if args.loss == "fused" else "sum of torch BCELoss",
-                   "l2_regulariser": "value in the loss, gradient folded into FusedAdam" if args.reg == "fold"
-                   else "autograd node",
-                   "cuda_graphs": ("off (AREAD_GRAPHS=0)" if os.environ.get("AREAD_GRAPHS", "1") == "0" else
-                                   "per-mask forward/backward sequences, " + args.graphs),
-                   "parallelism": f"dp{world}" + ("" if world == 1 else f" + table row-sharded over {world} GPUs (P2P lookup, "
-                                                   "reduce-scatter of the table gradient, flat all-reduce of the rest)"),
-                   "l2": "inputs larger than L2: table %d MB + per-step activations" % (wl.n_rows * wl.embed_dim * 4 >> 20)},
+        "config": cfg,
         "e2e": {"value": total_samples / (ms_e2e * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": int(host_x[0].numel() * 4 + host_y[0].numel() * 2), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "gather_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": GATHER_DRAM_BYTES if (world == 1 and args.workload == "amazon" and B == 65536) else None,
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                       "(profiles/r1_gather_kernel_full.txt); below the algorithmic bytes because the "
-                                       "hot rows of the Zipf ids and part of the output stay in the 126 MB L2",
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": gather_bytes, "launch_ms": gather_ms},
     }
-    line["extra"] = {"eval_samples_per_sec": total_samples / (ms_eval * 1e-3),
-                     "eval_mode": "eval(), no_grad, mode='domain_with_mask'"}
-    if scatter_ms is not None:
-        line["extra"]["scatter"] = {
-            "kernels": "scatter_keys + radix sort + scatter_tile + scatter_level (whole aread_scatter_bwd call)",
-            "achieved": scatter_bytes / (scatter_ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peaks["hbm_gbs"],
-            "frac": scatter_bytes / (scatter_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": scatter_ms,
-            "algorithmic_bytes_per_call": scatter_bytes,
-            "note": "algorithmic bytes credit lookups*(4+D*4) + unique_rows*D*4 only; the dense [R, D] zero fill the "
-                    "reference semantics require (dense gradient) and the sort traffic are not credited"}
-    if gemm_ms is not None:
-        tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
-        out_bytes = B * n_exp * n1 * 4 + B * E * 2
-        line["extra"]["grouped_linear_expert_layer1"] = {
-            "kernel": "grouped_linear_kernel<128> (tcgen05, TMA in / TMA out)", "launch_ms": gemm_ms,
-            "achieved_tflops": tf, "peak_tflops": peaks.get("bf16_tflops"),
-            "frac_of_tensor_peak": tf / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
-            "achieved_gbs": out_bytes / (gemm_ms * 1e-3) / 1e9, "frac_of_hbm_peak": out_bytes / (gemm_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-            "note": "K = E = 288 is short: per output element 576 flop against 4 B written, so the fp32 output "
-                    "stream (HBM) bounds this GEMM, not the tensor pipe"}
+    if gemm is not None:
+        line["roofline"] = gemm
+        line["roofline_gather"] = gather_roof
+    else:
+        line["roofline"] = gather_roof
+    line["extra"] = extra
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"], _ = cpu_reference_rate(wl, args.cpu_batch, args.cpu_steps, 1, args.active, args.seed,
-                                                       args.dropout)
+        cpu_b = B if B * (args.cpu_steps + 1) <= 300_000 else 4096
+        line["cpu_baseline"], _ = oracle_rate(wl, cpu_b, args.cpu_steps, 1, args.active, args.seed, args.dropout)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def expert_gemm_roofline(model, B, dev, kernel_ms, args):
+    dk = importlib.import_module(PKG + ".dense_kernels")
+    peaks, peak_src = load_peaks()
+    n_exp, n1, E = len(model.mmoe_experts), EXPERT_DIMS[0], model.embed_output_dim
+    a_op = torch.randn(B, E, device=dev).to(torch.bfloat16)
+    w_op = torch.randn(n_exp * n1, E, device=dev).to(torch.bfloat16)
+    run, out_bytes, what = dk.bench_expert_layer1(a_op, w_op, n1, E, n_exp)
+    ms = kernel_ms(lambda i: run(), max(3, args.warmup), max(10, args.steps))
+    flops = 2.0 * B * n_exp * n1 * E
+    tf = flops / (ms * 1e-3) / 1e12
+    bytes_alg = B * E * 2 + n_exp * n1 * E * 2 + out_bytes
+    return {"bound": "tensor", "kernel": what, "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": tf / peaks["bf16_tflops"], "peak_source": peak_src + " (burst: kernel timed alone)",
+            "traffic": NCU_DRAM_BYTES.get(("grouped_linear_kernel", args.workload, B)),
+            "algorithmic_flops_per_launch": flops, "launch_ms": ms,
+            "hbm": {"algorithmic_bytes_per_launch": bytes_alg, "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": bytes_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "note": "expert layer 1 of all 4 experts, [B, E] x [E, 4*256]: 2*B*E*1024 flop per launch "
+                    "(SURVEY 8d: 4*E*256 MAC per sample); the operand / output streams are listed under `hbm`"}
+
+
+def extra_legs(args, wl, tr, pkg, lib, ops, dev, rank, world, timed, kernel_ms, host, dev_x, dev_y, domains):
+    """Everything beside the headline: eval rate, lookup gradient, sustained run, other batch sizes, the unedited
+    trainer calls, torch-eager on the same GPU, the HEMP regroup loop."""
+    model, B = tr.model, args.batch
+    peaks, _ = load_peaks()
+    n_batches = len(dev_x)
+    extra = {}
+
+    # ---- 200 steps back to back (the headline's K comes from the driver)
+    n_sus = args.sustained_steps
+    if n_sus > 0:
+        ms = timed(lambda i: tr.step(dev_x[i % n_batches], dev_y[i % n_batches], domains[i % n_batches]), 0, n_sus)
+        extra["sustained"] = {"steps": n_sus, "ms_per_step": ms / n_sus, "samples_per_sec": B * n_sus * world / (ms * 1e-3),
+                              "timed_region_s": ms * 1e-3}
+
+    # ---- eval samples/s (mode 'domain_with_mask', eval(), no_grad -- run.py:712-727)
+    model.eval()
+    with torch.no_grad():
+        tr.record(dev_x[0], domains, mode="domain_with_mask", backward=False)
+
+    def eval_step(i):
+        with torch.no_grad():
+            model(dev_x[i], mode="domain_with_mask", domain_i=domains[i])
+    for i in range(args.warmup):
+        eval_step(i)
+    ms_eval = timed(eval_step, args.warmup, args.steps)
+    model.train()
+    extra["eval_samples_per_sec"] = B * args.steps * world / (ms_eval * 1e-3)
+    extra["eval_mode"] = "eval(), no_grad, mode='domain_with_mask'"
+    if world > 1:
+        return extra
+
+    # ---- lookup gradient (whole aread_scatter_bwd call) against HBM
+    plan = model.embedding.plan(dev)
+    d_out = torch.randn(B, plan.n_fields, plan.embed_dim, device=dev)
+    offs = np.asarray(model.embedding.offsets, dtype=np.int64)
+    uniq = [int(np.unique(host[i][0].astype(np.int64) + offs[None, :]).size) for i in range(n_batches)]
+    scatter_ms = kernel_ms(lambda i: ops.scatter(plan, dev_x[i % n_batches], d_out), args.warmup, args.steps)
+    scatter_bytes = float(np.mean([wl.scatter_bytes(B * wl.n_cols, u) for u in uniq]))
+    extra["scatter"] = {
+        "kernels": "whole aread_scatter_bwd call (keys, sort, segmented in-order reduction, dense zero fill)",
+        "achieved": scatter_bytes / (scatter_ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+        "frac": scatter_bytes / (scatter_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_ms": scatter_ms,
+        "algorithmic_bytes_per_call": scatter_bytes,
+        "note": "algorithmic bytes credit lookups*(4+D*4) + unique_rows*D*4 only; the dense [R, D] zero fill the "
+                "reference semantics require (dense gradient) and the sort traffic are not credited"}
+
+    # ---- the reference's own batch sizes (main.py:22 bs=1024; SURVEY 8d asks 1024 / 8192 / 65536)
+    for b_small in (1024, 8192):
+        if b_small >= B:
+            continue
+        n = 40
+        _, hx, hy, doms = make_batches(wl, b_small, n, args.seed + 77, rank, dev)
+        dx, dy = [t.to(dev) for t in hx], [t.to(dev) for t in hy]
+        tr.record(dx[0], doms)
+        for i in range(10):
+            tr.step(dx[i], dy[i], doms[i])
+        ms = timed(lambda i: tr.step(dx[i], dy[i], doms[i]), 10, n - 10)
+        extra[f"batch_{b_small}"] = {"ms_per_step": ms / (n - 10), "samples_per_sec": b_small * (n - 10) / (ms * 1e-3)}
+
+    # ---- the drop-in with the UNEDITED trainer calls: torch.optim.Adam, per-tower BCELoss sum, regulariser through
+    # autograd, graphs recorded lazily (nothing of INTEGRATION.md's opt-in table)
+    plain = Trainer(pkg, wl, args, dev, world, "torch", "loss", "torch", "lazy")
+    for i in range(max(args.warmup, 4)):
+        plain.step(dev_x[i % n_batches], dev_y[i % n_batches], domains[i % n_batches])
+    n = max(args.steps, 10)
+    ms = timed(lambda i: plain.step(dev_x[i % n_batches], dev_y[i % n_batches], domains[i % n_batches]), 0, n)
+    extra["unedited_trainer"] = {"ms_per_step": ms / n, "samples_per_sec": B * n / (ms * 1e-3),
+                                 "what": "torch.optim.Adam + sum of BCELoss + get_regularization_loss through autograd, "
+                                         "lazy graphs: what an unmodified run.py calls"}
+    del plain
+    torch.cuda.empty_cache()
+
+    # ---- the HEMP regroup loop (run.py:614-661) on this model: per candidate generate_mask + load_model_state +
+    # optimizer reset + 5 bagging steps with prun_single_mask + 5 no_grad scoring passes
+    extra["regroup"] = regroup_leg(tr, wl, dev, dev_x, dev_y, n_domains=min(wl.n_domain, 30), candidates=10)
+
+    # ---- torch-eager on the same GPU: the oracle port's ops on cuda (SURVEY 8d "same-box GPU bar")
+    if not args.no_cpu_baseline:
+        try:
+            res, sec = oracle_rate(wl, B, 8, 3, args.active, args.seed, args.dropout, device=str(dev))
+            extra["gpu_eager_baseline"] = {"value": res["value"], "unit": "samples/s", "ms_per_step": sec * 1e3,
+                                           "sample": res["sample"]}
+        except torch.cuda.OutOfMemoryError as e:          # pragma: no cover
+            extra["gpu_eager_baseline"] = {"unavailable": str(e)[:120]}
+        torch.cuda.empty_cache()
+    return extra
+
+
+def regroup_leg(tr, wl, dev, dev_x, dev_y, n_domains, candidates, update_steps=5, eval_steps=5):
+    model, opt = tr.model, tr.opt
+    optim = importlib.import_module(PKG + ".optim")
+    fast = optim.FusedAdam(model.parameters(), lr=LR, betas=(0.9, 0.99), eps=1e-8, weight_decay=WD)
+    model.fold_regularization_into(fast)
+    model.fold_regularization_into(opt)
+    x, y = dev_x[0], dev_y[0]
+    crit = torch.nn.BCELoss()
+    # gate statistics for generate_mask('mask_max_gate')
+    model.reset_for_mask_update()
+    for d in range(n_domains):
+        model(x, mode="wo_mask", domain_i=d, memory_gate_value=True)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    model.save_model_state()
+    n_steps = 0
+    for d in range(n_domains):
+        for z in range(candidates):
+            tmp_mask = model.generate_mask(generate_mode="mask_max_gate", d=d, init_active_percent=0.6,
+                                           random_modify_sigma=0.2)
+            model.load_model_state()
+            fast.reset()
+            for _ in range(update_steps):
+                preds = model(x, mode="domain_mask_bagging", current_mask=tmp_mask, tmp_memory_gate_value=True)
+                loss = model.bagging_loss(preds, y) + model.get_regularization_loss(device=dev)
+                model.zero_grad()
+                loss.backward()
+                fast.step()
+                tmp_mask = model.prun_single_mask(d, tmp_mask, prun_ratio=0.05)
+                n_steps += 1
+            model.candidate_domain_mask[d].append(tmp_mask)
+            with torch.no_grad():
+                for _ in range(eval_steps):
+                    pred = model(x, mode="domain_with_mask", current_mask=tmp_mask)
+                    loss = crit(pred.squeeze(), y.squeeze().float()) + model.get_regularization_loss(device=dev)
+                    model.add_eval_loss(loss.mean().item(), d=d, mask_z=z)
+    for d in range(n_domains, wl.n_domain):            # domains not searched keep their mask
+        model.candidate_domain_mask[d].append(model.domain_mask[d])
+        model.add_eval_loss(0.0, d=d, mask_z=0)
+    model.update_all_mask(regroup_times=1)
+    model.reset_for_mask_update()
+    model.load_model_state()
+    torch.cuda.synchronize(dev)
+    sec = time.perf_counter() - t0
+    return {"seconds": sec, "domains": n_domains, "candidates_per_domain": candidates,
+            "train_steps": n_steps, "scoring_passes": n_domains * candidates * eval_steps,
+            "table_restores": n_domains * candidates + 1, "batch": int(x.shape[0]),
+            "ms_per_candidate": sec * 1e3 / (n_domains * candidates),
+            "what": "run.py:614-661 with FusedAdam.reset() for optimizer_fast and the one-launch save/load_model_state"}
 
 
 def main():
@@ -454,9 +613,9 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    wl = importlib.import_module("aread-multi-domain-recommendation_b200.workloads").WORKLOADS[args.workload]()
+    wl = importlib.import_module(PKG + ".workloads").WORKLOADS[args.workload]()
     if args.impl == "reference":
-        run_reference(args, wl, rank)
+        run_reference(args, wl, rank, world)
     else:
         run_ours(args, wl, rank, world, local_rank)
 

@@ -564,6 +564,25 @@ AREAD_API int64_t aread_adam_chunk(void);
 AREAD_API int aread_adam_step(const aread_adam_args* args, aread_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-tensor copy / fill in ONE launch: dst[t][0:bytes[t]] = src[t][...]  (src == NULL: zero fill).
+ * Serves AREAD.load_model_state (model/aread.py:545-546: ~300 restores of every rolled-back tensor per regroup,
+ * run.py:631) and FusedAdam.reset (a fresh `optimizer_fast` per candidate, run.py:632-633, without reallocating
+ * its moments) -- SURVEY.md 8(f) rank 2.  Byte counts and pointers must be multiples of 4; chunks are
+ * aread_multi_copy_chunk() bytes, chunk_start[t] = first chunk of tensor t (prefix sum of ceil(bytes / chunk)).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aread_multi_copy_args {
+  int32_t n_tensors;
+  int64_t n_chunks;
+  void* const* dst;              /* device arrays [n_tensors] of device pointers        */
+  const void* const* src;        /* device [n_tensors], or NULL: zero fill              */
+  const int64_t* bytes;          /* device [n_tensors]                                  */
+  const int64_t* chunk_start;    /* device [n_tensors]                                  */
+} aread_multi_copy_args;
+
+AREAD_API int64_t aread_multi_copy_chunk(void);
+AREAD_API int aread_multi_copy(const aread_multi_copy_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Bagging loss of the HEI heads: loss[0] = (1 / n_tower) * sum_t mean_b BCE(probs[t, b], labels[b])
  * and d loss / d probs in the same pass.  Replaces the trainer's per-tower BCELoss sum (run.py:643-644,
  * 672-677, criterion run.py:833); element arithmetic as torch.nn.BCELoss (logs clamped at -100).

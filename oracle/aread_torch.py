@@ -73,7 +73,7 @@ def embed(sd, spec, x):
     idx = x + x.new_tensor(spec.offsets).unsqueeze(0)
     e = F.embedding(idx, sd["embedding.embedding_dict.weight"])
     if spec.n_mh_cols and spec.method in ("mean", "sum"):
-        fl = torch.from_numpy(spec.flag)
+        fl = torch.from_numpy(spec.flag).to(e.device)
         oh = e[:, ~fl, :]
         mh = e[:, fl, :].view(e.shape[0], spec.n_mh_fields, spec.seq_maxlen, spec.embed_dim)
         pooled = mh.mean(dim=2) if spec.method == "mean" else mh.sum(dim=2)
@@ -170,9 +170,9 @@ def hei(sd, spec, tr, q, mask, training, masks=None, update_stats=True):
         for t in range(n_t):
             width = spec.tower_dims[l][-1]
             if not act[t]:
-                outs.append(torch.zeros(B, width))
+                outs.append(torch.zeros(B, width, device=q.device))
                 if l > 0:
-                    gate_means[(l, t)] = torch.zeros(spec.n_tower[l - 1])
+                    gate_means[(l, t)] = torch.zeros(spec.n_tower[l - 1], device=q.device)
                 continue
             if l == 0:
                 inp = tr["t0"][t]
@@ -236,7 +236,7 @@ def reg_groups(sd, spec):
 
 
 def reg_loss(sd, spec):
-    total = torch.zeros(1)
+    total = torch.zeros(1, device=sd["linear.fc.weight"].device)
     for l2, keys in reg_groups(sd, spec):
         for k in keys:
             total = total + torch.sum(l2 * torch.square(sd[k]))

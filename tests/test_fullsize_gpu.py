@@ -1,0 +1,157 @@
+"""Composed-model parity at the BASELINE.json shapes (not only the 37..64-row goldens): Amazon-2018-shaped
+(E = 288, 1.39 M-row table, pooled histories), AliCCP-scale (E = 736, 1.14 M rows) and Cloud-Theme-shaped
+(355 domains) models, real vocabularies, B = 4,096 and 65,536, against oracle/aread_torch.py evaluated on the GPU
+box's CPU on identical weights, ids, labels and masks.
+
+Experts run in 'bf16' (one tensor-core pass, BASELINE "bf16 experts"); everything else is fp32.  Tolerances
+(north_star: "rel 1e-3 on logits"):
+  * eval-mode logits against the fp32 oracle: |d| <= 1e-3 * |z| + 2e-3
+  * train-mode (batch-statistics BatchNorm, dropout 0) probabilities |d| <= 2e-3, loss rel 1e-3
+  * gradients, per parameter family, against the fp32 oracle: normalised error ||g - g_ref|| / ||g_ref|| and cosine
+    (GRAD_BOUNDS below; at these batch sizes the bf16 operand rounding averages out, unlike on the 37-row goldens)
+  * against the oracle with the SAME operand rounding the families agree 2-10x tighter (SAME_ROUNDING_BOUNDS).
+Every run appends its measured figures to gpurun_out/parity_fullsize.jsonl (kept under profiles/)."""
+import importlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aread_torch as O
+from oracle import synth
+from tests._models import build_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+workloads = importlib.import_module("aread-multi-domain-recommendation_b200.workloads")
+
+FAMILIES = [
+    ("table", re.compile(r"^embedding\.")),
+    ("linear_cross", re.compile(r"^(linear|cn)\.")),
+    ("expert_weights", re.compile(r"^mmoe_experts\.\d+\.layers\.(0|4|8)\.weight$")),
+    ("expert_bn", re.compile(r"^mmoe_experts\.\d+\.layers\.(1|5|9)\.")),
+    ("mmoe_gates", re.compile(r"^mmoe_gates\.")),
+    ("tower_weights", re.compile(r"^towers\.\d+\.\d+\.layers\.(0|4)\.weight$")),
+    ("tower_bn", re.compile(r"^towers\.\d+\.\d+\.layers\.(1|5)\.")),
+    ("tower_gates", re.compile(r"^(tower_gates|group_embedding)\.")),
+    ("heads", re.compile(r"^towers_linear\.")),
+]
+PRE_BN_BIAS = re.compile(r"\.layers\.(0|4|8)\.bias$")      # true gradient is zero (BatchNorm removes the bias)
+
+# (normalised error, 1 - cosine) per family: bf16 kernels against the fp32 oracle
+GRAD_BOUNDS = {"table": (6e-2, 2e-3), "linear_cross": (3e-2, 1e-3), "expert_weights": (6e-2, 2e-3),
+               "expert_bn": (6e-2, 2e-3), "mmoe_gates": (1e-1, 5e-3), "tower_weights": (3e-2, 1e-3),
+               "tower_bn": (3e-2, 1e-3), "tower_gates": (1e-1, 5e-3), "heads": (2e-2, 5e-4)}
+# ... and against the oracle that rounds the expert operands like the kernels do
+SAME_ROUNDING_BOUNDS = {k: (v[0] / 2, v[1] / 2) for k, v in GRAD_BOUNDS.items()}
+
+
+def _spec_of(wl):
+    mh = wl.multi_hot_dict
+    return dict(one_hot_field_dims=list(wl.one_hot_field_dims), embed_dim=wl.embed_dim,
+                multi_hot_flag=mh["multi_hot_flag"], itemid_idx=wl.itemid_idx, seq_maxlen=wl.seq_maxlen,
+                method=wl.method, n_domain=wl.n_domain, domain_idx=wl.domain_idx)
+
+
+def _report(record):
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_fullsize.jsonl"), "a") as fh:
+            fh.write(json.dumps(record) + "\n")
+
+
+def _family_errors(named_grads, ref):
+    """{family: (normalised error, 1 - cosine)} over the concatenation of the family's gradient tensors."""
+    out = {}
+    for fam, pat in FAMILIES:
+        a, b = [], []
+        for k, g in named_grads.items():
+            if pat.search(k) and not PRE_BN_BIAS.search(k) and ref.get(k) is not None:
+                a.append(g.reshape(-1).double())
+                b.append(ref[k].reshape(-1).double())
+        if not a:
+            continue
+        a, b = torch.cat(a), torch.cat(b)
+        nb = float(b.norm())
+        if nb == 0:
+            continue
+        out[fam] = (float((a - b).norm()) / nb, 1.0 - float(a @ b) / (float(a.norm()) * nb + 1e-300))
+    return out
+
+
+CASES = [("amazon", 4096, 0.5), ("aliccp", 4096, 0.5), ("aliccp", 65536, 0.3), ("cloudtheme", 4096, 0.3)]
+
+
+@pytest.mark.parametrize("name,B,active", CASES)
+def test_composed_model_matches_oracle_at_baseline_shapes(name, B, active):
+    wl = workloads.WORKLOADS[name]()
+    spec_kw = _spec_of(wl)
+    spec = O.Spec(**spec_kw)
+    model = build_model(spec, DEV, dropout=0.0, use_atten=False)
+    model.expert_precision = "bf16"
+    np.random.seed(17)
+    domains = [0, wl.n_domain // 2, wl.n_domain - 1]
+    masks = {d: model.generate_mask("rand", d, init_active_percent=active) for d in domains}
+    record = {"workload": name, "B": B, "active": active, "domains": {}}
+    base = synth.deterministic_state(spec)
+
+    def fresh(sp):
+        return {k: v.clone() for k, v in base.items()}
+    for d in domains[:1 if B > 8192 else 3]:
+        x_np, y_np, _ = wl.batch(B, seed=4000 + d, domain=d)
+        x, y = torch.from_numpy(x_np), torch.from_numpy(y_np)
+        mask_cpu = [m.cpu() for m in masks[d]]
+        rec = {"active_towers": [len(a) for a in model.mask_info(masks[d]).active_idx]}
+
+        # ---- eval mode: running-statistics BatchNorm, rows independent
+        sd32 = fresh(spec)
+        model.load_state_dict(base, strict=True)          # the previous domain's train step moved the BN statistics
+        with torch.no_grad():
+            ref = O.forward(sd32, spec, x, "domain_with_mask", mask_cpu)["y"].double()
+        model.eval()
+        with torch.no_grad():
+            got = model(x.to(DEV), mode="domain_with_mask", current_mask=masks[d]).cpu().double()
+        z_ref = torch.log(ref) - torch.log1p(-ref)
+        z_got = torch.log(got) - torch.log1p(-got)
+        err = (z_got - z_ref).abs()
+        rec["eval_logit_max_abs"] = float(err.max())
+        rec["eval_logit_max_rel"] = float((err / (z_ref.abs() + 2.0)).max())
+        assert bool((err <= 1e-3 * z_ref.abs() + 2e-3).all()), f"{name} d={d}: eval logits off by {float(err.max()):.3e}"
+
+        # ---- train mode: forward + bagging BCE + backward (the regulariser has its own parity test)
+        grads = {}
+        for tag, dtype in (("fp32", None), ("bf16", torch.bfloat16)):
+            sp = O.Spec(**spec_kw, expert_operand_dtype=dtype)
+            sd = O.make_leaf_params(fresh(sp))
+            out = O.forward(sd, sp, x, "domain_mask_bagging", mask_cpu, training=True)
+            loss = O.bagging_loss(out["y"], y)          # data loss only: the dense 2*l2*W term would mask errors
+            loss.backward()
+            grads[tag] = {k: v.grad for k, v in sd.items() if v.requires_grad}
+            if tag == "fp32":
+                ref_y, ref_loss = out["y"].detach(), float(loss)
+        model.train()
+        preds = model(x.to(DEV), mode="domain_mask_bagging", current_mask=masks[d])
+        loss = model.bagging_loss(preds, y.to(DEV))
+        model.zero_grad()
+        loss.backward()
+        rec["train_prob_max_abs"] = float((preds.detach().cpu() - ref_y).abs().max())
+        rec["train_loss_rel"] = abs(float(loss) - ref_loss) / abs(ref_loss)
+        assert rec["train_prob_max_abs"] <= 2e-3 and rec["train_loss_rel"] <= 1e-3, rec
+        named = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
+        for k, p in model.named_parameters():
+            if not k.startswith(("atten", "self_attns", "V_res", "final_gate")):
+                assert (p.grad is None) == (grads["fp32"].get(k) is None), f"grad None-ness of {k}"
+        fe32, fe16 = _family_errors(named, grads["fp32"]), _family_errors(named, grads["bf16"])
+        rec["grad_vs_fp32"], rec["grad_vs_same_rounding"] = fe32, fe16
+        record["domains"][d] = rec
+        _report({"workload": name, "B": B, "domain": d, **rec})
+        for fam, (e, c) in fe32.items():
+            assert e <= GRAD_BOUNDS[fam][0] and c <= GRAD_BOUNDS[fam][1], \
+                f"{name} B={B} d={d}: {fam} gradient vs fp32 oracle: normalised error {e:.3e}, 1-cos {c:.3e}"
+        for fam, (e, c) in fe16.items():
+            assert e <= SAME_ROUNDING_BOUNDS[fam][0] and c <= SAME_ROUNDING_BOUNDS[fam][1], \
+                f"{name} B={B} d={d}: {fam} gradient vs same-rounding oracle: normalised error {e:.3e}, 1-cos {c:.3e}"

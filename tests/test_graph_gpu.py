@@ -147,3 +147,91 @@ def test_record_graphs_ahead_of_time(monkeypatch):
         model.zero_grad()
         loss.backward()
         assert torch.equal(preds.detach(), p) and torch.equal(model.embedding.embedding_dict.weight.grad, g)
+
+
+def _masks_of_different_size(model):
+    """HEMP masks whose numbers of active towers differ (workspaces and compact activations change size)."""
+    import numpy as np
+    out = []
+    for seed, p in ((3, 0.15), (4, 0.95), (5, 0.4), (6, 0.25)):
+        np.random.seed(seed)
+        out.append(model.generate_mask("rand", 0, init_active_percent=p))
+    sizes = {tuple(len(a) for a in model.mask_info(m).active_idx) for m in out}
+    assert len(sizes) >= 3, sizes
+    return out
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+def test_interleaved_masks_of_different_size(monkeypatch, dropout):
+    """A sequence recorded under a small mask keeps giving the eager results after larger masks ran in between
+    (their larger workspaces / arena growth must not leave the recorded sequence pointing at freed memory)."""
+    fx, model, _, batches = _setup(dropout=dropout)
+    masks = _masks_of_different_size(model)
+    order = [0, 0, 0, 0, 1, 0, 1, 1, 1, 0, 2, 0, 3, 3, 3, 3, 1, 0, 2, 3]
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+
+    def run(graphs):
+        monkeypatch.setattr(fused, "USE_GRAPHS", graphs)
+        model.load_state_dict(state)
+        res = []
+        for i, mi in enumerate(order):
+            torch.manual_seed(300 + i)
+            x = batches[i % 4][0].to(DEV)
+            y = batches[i % 4][1].to(DEV).float().view(-1)
+            preds = model(x, mode="domain_mask_bagging", domain_i=fx["domain"], current_mask=masks[mi])
+            loss = sum(torch.nn.functional.binary_cross_entropy(p, y) for p in preds.unbind(0)) / preds.shape[0]
+            model.zero_grad()
+            loss.backward()
+            res.append((preds.detach().clone(),
+                        {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+        return res
+
+    # candidate masks are not recorded by default (may_record=False for current_mask): install them as domain masks
+    want = run(False)
+    real_forward = fused.forward
+    monkeypatch.setattr(fused, "forward", lambda *a, **k: real_forward(*a, **{**k, "may_record": True}))
+    got = run(True)
+    assert sum(e.fwd is not None for e in model._graphs.entries.values()) >= 3
+    for i, ((p0, g0), (p1, g1)) in enumerate(zip(want, got)):
+        assert torch.equal(p1, p0), f"step {i} (mask {order[i]})"
+        assert g1.keys() == g0.keys()
+        for n in g0:
+            assert torch.equal(g1[n], g0[n]), f"step {i} grad {n}"
+
+
+def test_two_pending_forwards_with_dropout_after_recording(monkeypatch):
+    """Once a sequence is recorded, a second forward issued before the first one's backward (it cannot lease the
+    arena and runs eagerly) must not disturb the dropout seed the first backward regenerates its masks from."""
+    fx, model, masks, batches = _setup(dropout=0.2)
+    mask = _on_device(masks)[0]
+    model.domain_mask[fx["domain"]] = mask
+    monkeypatch.setattr(fused, "USE_GRAPHS", True)
+    x0, x1 = batches[0][0].to(DEV), batches[1][0].to(DEV)
+    y0 = batches[0][1].to(DEV)
+
+    def grads_of(two_pending):
+        torch.manual_seed(77)
+        p0 = model(x0, mode="domain_mask_bagging", domain_i=fx["domain"])
+        if two_pending:
+            p1 = model(x1, mode="domain_mask_bagging", domain_i=fx["domain"])      # eager, own seed by value
+            with torch.no_grad():
+                model(x1, mode="domain_mask_bagging", domain_i=fx["domain"])       # and a no_grad train-mode forward
+        model.zero_grad()
+        model.bagging_loss(p0, y0).backward()
+        g = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        if two_pending:
+            model.zero_grad()
+            p1.sum().backward()
+        return p0.detach().clone(), g
+
+    for _ in range(4):                                                          # records forward and backward
+        grads_of(False)
+    assert any(e.bwd is not None for e in model._graphs.entries.values())
+    buffers = {n: b.clone() for n, b in model.named_buffers()}
+    p_ref, g_ref = grads_of(False)
+    for n, b in model.named_buffers():
+        b.copy_(buffers[n])
+    p_got, g_got = grads_of(True)
+    assert torch.equal(p_got, p_ref)
+    for n in g_ref:
+        assert torch.equal(g_got[n], g_ref[n]), n

@@ -17,9 +17,10 @@ echo "bench exit $?"; tail -1 gpurun_out/bench_$TAG.log | cut -c1-1500; tail -5 
 if [ -z "${SKIP_NCU:-}" ]; then
   PARGS="--steps 2 --warmup 3 --no-cpu-baseline --no-extra"
   timeout 300 python bench.py $PARGS > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-1500} -c ${NCU_COUNT:-400} --csv \
+  # eager launches (no graph replay) so that every kernel of a step is listed; steps 4-5 are the two timed ones
+  AREAD_GRAPHS=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
       --log-file gpurun_out/launches_$TAG.csv python bench.py $PARGS > gpurun_out/ncu_launch_$TAG.log 2>&1
   echo "launch list exit $?"
-  python tools/summarize_ncu.py launches gpurun_out/launches_$TAG.csv > gpurun_out/launches_$TAG.txt 2>&1
+  python tools/summarize_ncu.py launches gpurun_out/launches_$TAG.csv 4 5 > gpurun_out/launches_$TAG.txt 2>&1
   head -45 gpurun_out/launches_$TAG.txt
 fi

@@ -2,12 +2,17 @@
 """Summaries of the ncu captures for profiles/: per-kernel share of a launch list, key metrics of a --set full report."""
 import collections, csv, re, subprocess, sys
 
-def launches(path):
+def launches(path, first_step=None, last_step=None):
+    """Per-kernel totals.  With first_step / last_step only the launches of those train steps are counted: a step ends
+    with its adam_kernel launch, so step k spans (adam #k-1, adam #k] (1-based, in launch order)."""
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.defaultdict(lambda: [0, 0.0]); tot = 0.0; n = 0
-    for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
-            continue
+    rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    if first_step is not None:
+        ends = [i for i, r in enumerate(rows) if "adam_kernel" in r["Kernel Name"]]
+        lo = ends[first_step - 2] + 1 if first_step >= 2 else 0
+        rows = rows[lo:ends[last_step - 1] + 1]
+    for row in rows:
         v = float(row["Metric Value"].replace(",", "")); u = row["Metric Unit"]
         v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
         name = row["Kernel Name"]
@@ -42,4 +47,7 @@ def full(path):
     return "\n".join(out)
 
 if __name__ == "__main__":
-    print(launches(sys.argv[2]) if sys.argv[1] == "launches" else full(sys.argv[2]))
+    if sys.argv[1] == "launches":
+        print(launches(sys.argv[2], *(int(v) for v in sys.argv[3:5])))
+    else:
+        print(full(sys.argv[2]))

@@ -141,7 +141,8 @@ class AREAD(BaseModel):
         had_grad = any(p.grad is not None for p in self.parameters())
         rng = torch.get_rng_state()
         # one pass per DISTINCT mask, largest first: the activation arena then has its final size before most
-        # sequences are recorded (a pass that finds the arena too small runs eagerly and is repeated once)
+        # sequences are recorded.  Per mask: one eager pass (every kernel it uses has then been loaded), one
+        # recording pass; a pass that finds the arena too small runs eagerly and is repeated
         infos = {}
         for d in domains:
             info = self.mask_info(self.domain_mask[d])
@@ -159,7 +160,7 @@ class AREAD(BaseModel):
         self._graphs.force = True
         try:
             for d, info in order:
-                for _ in range(3):
+                for _ in range(4):
                     one_pass(d)
                     if self._graphs.recorded(info.serial):
                         break

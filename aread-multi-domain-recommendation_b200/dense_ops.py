@@ -45,6 +45,14 @@ class MaskInfo:
             self._edges[key] = e
         return e
 
+    def warm(self, device, n_level):
+        """Create every cached device tensor now (they are host->device copies, which a stream capture refuses)."""
+        self.group_index(device)
+        for l in range(n_level):
+            self.index(l, device)
+            if l > 0:
+                self.edges(l, device)
+
     def group_index(self, device):
         key = ("grp", device)
         e = self._edges.get(key)

@@ -34,6 +34,9 @@ USE_HEI_LAYER = os.environ.get("AREAD_HEI_FUSED", "1") != "0"
 # seed lives in device memory (dense_kernels.SEED_PTR), the ids are copied into a fixed buffer.
 USE_GRAPHS = os.environ.get("AREAD_GRAPHS", "1") != "0"
 GRAPH_AFTER = 2
+# a mask handed in as `current_mask=` is a candidate of the HEMP search: each one is evaluated about
+# regroup_eval_step (5) times (run.py:649-655), so recording it costs more than it saves
+GRAPH_AFTER_CANDIDATE = 8
 MAX_GRAPHS = int(os.environ.get("AREAD_MAX_GRAPHS", "1024"))
 
 
@@ -220,7 +223,7 @@ class AreadNode(torch.autograd.Function):
             sig = _signature(model, arena)
             if entry.fwd is not None and entry.sig != sig:                   # storage moved: record again
                 entry.fwd = entry.bwd = None
-            record = entry.fwd is None and cfg["may_record"] and entry.calls > GRAPH_AFTER and arena.need <= arena.cap
+            record = entry.fwd is None and entry.calls > cfg["graph_after"] and 0 < arena.need <= arena.cap
             if (entry.fwd is not None or record) and cfg["seed"] != 0:
                 # the seed travels through device memory so that a recorded sequence sees a new one at every replay.
                 # One slot per entry, written only here: the forward that holds the arena lease is the only one whose
@@ -662,8 +665,8 @@ def slot_maps(active_prev, n_prev, device, cache):
 
 def forward(model, x, info, want_gate_means=False, want_gates=False, want_gate_inputs=False, may_record=True):
     """Runs the fused node; returns (probs [n_active_last, B], cfg) where cfg carries the side outputs.
-    `may_record=False` (candidate masks of the HEMP search, which are evaluated a handful of times) keeps the call
-    from recording a CUDA graph; an already recorded sequence is still replayed."""
+    `may_record=False` (candidate masks of the HEMP search, which are evaluated a handful of times) raises the
+    number of eager calls before a CUDA graph is recorded from GRAPH_AFTER to GRAPH_AFTER_CANDIDATE."""
     table = model.embedding.embedding_dict.weight
     if model._fused_params[0] is not table:        # the table parameter was replaced (shard_table, load)
         model._fused_params[0] = table
@@ -676,12 +679,15 @@ def forward(model, x, info, want_gate_means=False, want_gates=False, want_gate_i
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and model.dropout_p > 0) else 0
     cfg = {"model": model, "info": info, "precise": model.expert_precision == "bf16x3", "seed": seed, "slots": slots,
            "want_gate_means": want_gate_means, "want_gates": want_gates, "want_gate_inputs": want_gate_inputs,
-           "may_record": may_record}
+           "graph_after": GRAPH_AFTER if may_record else GRAPH_AFTER_CANDIDATE}
+    if info is not None:
+        info.warm(dev, n_level)            # device copies of the mask tables exist before any capture starts
     if USE_GRAPHS and _mem.ENABLED and not want_gate_means and not want_gates:
         key = (0 if info is None else info.serial, tuple(x.shape), training, model.expert_precision,
                model.dropout_p if training else 0.0, torch.is_grad_enabled(), dev)
         entry = model._graphs.get(key)
-        entry.calls += 1 if not model._graphs.force else GRAPH_AFTER + 1      # record_graphs: record at once
+        # record_graphs: one eager pass (sizes the arena, loads every kernel), the next one records
+        entry.calls = entry.calls + 1 if not model._graphs.force else max(entry.calls + 1, cfg["graph_after"])
         cfg["graph"] = entry
     probs = AreadNode.apply(x, cfg, *model._fused_params)
     model.embedding.plan(dev).post_lookup(embedding_ops_bounds_mode())

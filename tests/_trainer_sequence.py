@@ -66,7 +66,8 @@ def run_sequence(model, device, spec, cfg=SEQ, loss_fn=None):
     crit = torch.nn.BCELoss()
     get = batches(spec, cfg)
     n_domain = cfg["n_domain"]
-    out = {"warm_up": [], "candidates": [], "eval_loss": [], "selected": [], "post": [], "update": []}
+    out = {"warm_up": [], "candidates": [], "eval_loss": [], "selected": [], "post": [], "update": [], "gate_log": [],
+           "prune_log": []}
     torch.manual_seed(cfg["seed"])
     np.random.seed(cfg["seed"])
     model.train()
@@ -114,7 +115,10 @@ def run_sequence(model, device, spec, cfg=SEQ, loss_fn=None):
                     loss.backward()
                     fast.step()
                     upd.append(float(loss))
+                    out["gate_log"].append([torch.stack(model.tmp_tower_gate_values[l], dim=1).detach().cpu().clone()
+                                            for l in range(1, spec.n_level)])
                     tmp_mask = model.prun_single_mask(d, tmp_mask, prun_ratio=0.05)
+                    out["prune_log"].append(mask_to_lists(tmp_mask))
                 model.candidate_domain_mask[d].append(tmp_mask)
                 out["update"].append(upd)
                 out["candidates"].append({"d": d, "z": z, "generated": generated, "pruned": mask_to_lists(tmp_mask)})

@@ -18,6 +18,12 @@ def _on_device(masks):
     return [[m.to(DEV) for m in mk] for mk in masks]
 
 
+@pytest.fixture(autouse=True)
+def _record_candidates_early(monkeypatch):
+    """These tests hand their masks in as `current_mask=`; record them as early as installed domain masks."""
+    monkeypatch.setattr(fused, "GRAPH_AFTER_CANDIDATE", fused.GRAPH_AFTER)
+
+
 def _run(model, fx, masks, batches, n, graphs, monkeypatch, train=True):
     monkeypatch.setattr(fused, "USE_GRAPHS", graphs)
     out = []
@@ -186,10 +192,7 @@ def test_interleaved_masks_of_different_size(monkeypatch, dropout):
                         {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
         return res
 
-    # candidate masks are not recorded by default (may_record=False for current_mask): install them as domain masks
     want = run(False)
-    real_forward = fused.forward
-    monkeypatch.setattr(fused, "forward", lambda *a, **k: real_forward(*a, **{**k, "may_record": True}))
     got = run(True)
     assert sum(e.fwd is not None for e in model._graphs.entries.values()) >= 3
     for i, ((p0, g0), (p1, g1)) in enumerate(zip(want, got)):

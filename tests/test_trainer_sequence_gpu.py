@@ -38,6 +38,12 @@ def test_train_aread_sequence_matches_reference(monkeypatch, graphs):
     model.expert_precision = "bf16x3"
     got = T.run_sequence(model, torch.device(DEV), spec)
     _close(got["warm_up"], gold["warm_up"], 2e-3, "warm-up loss")
+    # the quantities HEMP thresholds (batch means of the masked gate softmax) before every prune, then the prune itself
+    for i, (g, r) in enumerate(zip(got["gate_log"], gold["gate_log"])):
+        for l, (a, b) in enumerate(zip(g, r)):
+            assert float((a - b).abs().max()) <= 2e-4, f"gate means before prune {i}, level {l + 1}: {(a - b).abs().max()}"
+        assert got["prune_log"][i] == gold["prune_log"][i], \
+            f"prun_single_mask #{i}: gate means {[x.tolist() for x in g]} vs reference {[x.tolist() for x in r]}"
     for g, r in zip(got["candidates"], gold["candidates"]):
         assert (g["d"], g["z"]) == (r["d"], r["z"])
         assert g["generated"] == r["generated"], f"generate_mask('mask_max_gate') of domain {g['d']}, candidate {g['z']}"

@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_s
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -73,14 +73,15 @@ class BnActBwdArgs(Structure):
                 ("ldd", c_int64), ("mean", c_void_p), ("rstd", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
                 ("d_gamma", c_void_p), ("d_beta", c_void_p), ("d_bias", c_void_p), ("dz_f32", c_void_p),
                 ("dz_bf16", c_void_p), ("ldo", c_int64), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
-                ("dz_bf16_lo", c_void_p), ("seed_ptr", c_void_p)]
+                ("dz_bf16_lo", c_void_p), ("seed_ptr", c_void_p), ("z_bf16", c_void_p)]
 
 
 class MmoeMixArgs(Structure):
     _fields_ = [("m", c_int64), ("width", c_int32), ("n_expert", c_int32), ("n_gate", c_int32),
                 ("dropout_p", c_float), ("seed", c_uint64), ("salt", c_uint32), ("z", c_void_p), ("ldz", c_int64),
                 ("scale", c_void_p), ("shift", c_void_p), ("gate", c_void_p), ("out", c_void_p),
-                ("d_out", c_void_p), ("d_h", c_void_p), ("d_gate", c_void_p), ("seed_ptr", c_void_p)]
+                ("d_out", c_void_p), ("d_h", c_void_p), ("d_gate", c_void_p), ("seed_ptr", c_void_p),
+                ("z_bf16", c_void_p)]
 
 
 class RowpassArgs(Structure):
@@ -159,6 +160,34 @@ class AdamArgs(Structure):
                 ("eps", c_float), ("weight_decay", c_float), ("l2_twice", c_void_p)]
 
 
+class ExpertGemmArgs(Structure):
+    _fields_ = [("m", c_int64), ("n", c_int32), ("k", c_int32), ("groups", c_int32), ("a_group_cols", c_int32),
+                ("a", c_void_p), ("lda", c_int64), ("b", c_void_p), ("ldb", c_int64), ("b_is_k_by_n", c_int32),
+                ("epilogue", c_int32), ("bias", c_void_p), ("c_f32", c_void_p), ("c_bf16", c_void_p), ("ldc", c_int64),
+                ("partial", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("mean", c_void_p), ("rstd", c_void_p),
+                ("z", c_void_p), ("ldz", c_int64), ("dropout_p", c_float), ("salt", c_uint32), ("seed", c_uint64),
+                ("seed_ptr", c_void_p)]
+
+
+class ExpertBnFinalizeArgs(Structure):
+    _fields_ = [("m", c_int64), ("width", c_int32), ("n_partial", c_int32), ("training", c_int32), ("bn_skip", c_int32),
+                ("momentum", c_float), ("eps", c_float), ("partial", c_void_p), ("bias", c_void_p), ("gamma", c_void_p),
+                ("beta", c_void_p), ("running_mean", c_void_p), ("running_var", c_void_p), ("mean", c_void_p),
+                ("rstd", c_void_p), ("scale", c_void_p), ("shift", c_void_p)]
+
+
+class ExpertBnBwdFinalizeArgs(Structure):
+    _fields_ = [("m", c_int64), ("width", c_int32), ("n_partial", c_int32), ("bn_skip", c_int32), ("partial", c_void_p),
+                ("d_gamma", c_void_p), ("d_beta", c_void_p), ("d_bias", c_void_p), ("coef", c_void_p)]
+
+
+class Bn16Args(Structure):
+    _fields_ = [("m", c_int64), ("width", c_int32), ("bn_skip", c_int32), ("z", c_void_p), ("ldz", c_int64),
+                ("scale", c_void_p), ("shift", c_void_p), ("dropout_p", c_float), ("salt", c_uint32), ("seed", c_uint64),
+                ("seed_ptr", c_void_p), ("out", c_void_p), ("ldo", c_int64), ("dy", c_void_p), ("ldd", c_int64),
+                ("mean", c_void_p), ("rstd", c_void_p), ("coef", c_void_p)]
+
+
 class MultiCopyArgs(Structure):
     _fields_ = [("n_tensors", c_int32), ("n_chunks", c_int64), ("dst", c_void_p), ("src", c_void_p),
                 ("bytes", c_void_p), ("chunk_start", c_void_p)]
@@ -194,6 +223,12 @@ _SIGNATURES = {
     "aread_adam_step": (c_int32, [POINTER(AdamArgs), c_void_p]),
     "aread_multi_copy_chunk": (c_int64, []),
     "aread_multi_copy": (c_int32, [POINTER(MultiCopyArgs), c_void_p]),
+    "aread_multi_cast_bf16": (c_int32, [POINTER(MultiCopyArgs), c_void_p]),
+    "aread_expert_gemm_partials": (c_int32, [c_int64]),
+    "aread_expert_gemm": (c_int32, [POINTER(ExpertGemmArgs), c_void_p]),
+    "aread_expert_bn_finalize": (c_int32, [POINTER(ExpertBnFinalizeArgs), c_void_p]),
+    "aread_expert_bn_bwd_finalize": (c_int32, [POINTER(ExpertBnBwdFinalizeArgs), c_void_p]),
+    "aread_bn16": (c_int32, [POINTER(Bn16Args), c_void_p]),
     "aread_l2_reg_chunk": (c_int64, []),
     "aread_bn_act_apply": (c_int32, [POINTER(BnActArgs), c_void_p]),
     "aread_bn_bwd_coef": (c_int32, [POINTER(BnActBwdArgs), c_void_p, c_void_p]),

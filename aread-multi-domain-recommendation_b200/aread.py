@@ -124,6 +124,7 @@ class AREAD(BaseModel):
         object.__setattr__(self, "_arenas", {})
         object.__setattr__(self, "_graphs", fused.GraphCache())
         object.__setattr__(self, "_rollback", None)
+        object.__setattr__(self, "_wcast", None)
 
     @staticmethod
     def bagging_loss(y_stack, targets):
@@ -171,6 +172,16 @@ class AREAD(BaseModel):
                 b.copy_(buffers[n])
         torch.set_rng_state(rng)
 
+    def expert_weights_bf16(self):
+        """bf16 operand copies of the expert Linear weights ([groups * n, k] per layer), refreshed with one launch."""
+        flats = [L.weight.flat for L in self._expert_layers]
+        wc = self._wcast
+        if wc is None or wc.src_ptrs != [f.data_ptr() for f in flats]:
+            from .dense_kernels import WeightCast
+            wc = WeightCast(flats)
+            object.__setattr__(self, "_wcast", wc)
+        return [o.view(-1, o.shape[-1]) for o in wc.run()]
+
     def arena(self, device):
         """The activation arena of the fused step on `device` (_mem.py)."""
         a = self._arenas.get(device)
@@ -192,7 +203,7 @@ class AREAD(BaseModel):
         memo[id(self)] = clone
         for k, v in self.__dict__.items():
             if k not in ("_packs", "_expert_layers", "_tower_layers", "_fused", "_fused_params", "_slot_cache", "_arenas", "_graphs",
-                         "_rollback"):
+                         "_rollback", "_wcast"):
                 setattr(clone, k, copy.deepcopy(v, memo))
         clone._build_packs()
         return clone

@@ -99,10 +99,41 @@ __global__ void __launch_bounds__(kThreads) multi_copy_kernel(const aread_multi_
   }
 }
 
+// dst[t] = bf16(src[t]); bytes[] counts SOURCE bytes (fp32), 4 elements per thread and iteration
+__global__ void __launch_bounds__(kThreads) multi_cast_bf16_kernel(const aread_multi_copy_args a) {
+  for (int64_t chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x) {
+    const int t = find_tensor(a.chunk_start, a.n_tensors, chunk);
+    const float* __restrict__ s = static_cast<const float*>(a.src[t]);
+    __nv_bfloat16* __restrict__ d = static_cast<__nv_bfloat16*>(a.dst[t]);
+    const int64_t begin = (chunk - a.chunk_start[t]) * (kCopyChunk / 4);
+    const int64_t end = min(a.bytes[t] / 4, begin + kCopyChunk / 4);
+    for (int64_t i = begin + threadIdx.x * 4; i < end; i += kThreads * 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(s + i));
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<unsigned*>(&lo);
+      pk.y = *reinterpret_cast<unsigned*>(&hi);
+      *reinterpret_cast<uint2*>(d + i) = pk;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace aread
 
 extern "C" {
+
+int aread_multi_cast_bf16(const aread_multi_copy_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "multi_cast_bf16: null args");
+  const aread_multi_copy_args& a = *args;
+  if (a.n_tensors <= 0 || a.n_chunks <= 0) return AREAD_OK;
+  AREAD_REQUIRE(a.dst && a.src && a.bytes && a.chunk_start, "multi_cast_bf16: null pointer");
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+  AREAD_LAUNCH(multi_cast_bf16_kernel, static_cast<unsigned>(a.n_chunks < cap ? a.n_chunks : cap), kThreads, 0,
+               static_cast<cudaStream_t>(stream_), a);
+  return AREAD_OK;
+}
 
 int64_t aread_multi_copy_chunk(void) { return aread::kCopyChunk; }
 

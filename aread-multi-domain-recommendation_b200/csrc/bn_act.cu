@@ -155,6 +155,32 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const aread_bn_act_arg
   }
 }
 
+// the pre-activation of row r, columns col .. col + VEC - 1, from the fp32 or the bf16 copy
+template <int VEC, typename Args>
+__device__ __forceinline__ void load_z(const Args& a, int64_t r, int col, float (&z)[VEC]) {
+  if (a.z_bf16 != nullptr) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.z_bf16) + r * a.ldz + col;
+    if (VEC == 4) {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+      z[0] = __uint_as_float(w.x << 16);
+      z[1] = __uint_as_float(w.x & 0xffff0000u);
+      z[2] = __uint_as_float(w.y << 16);
+      z[3] = __uint_as_float(w.y & 0xffff0000u);
+    } else {
+      z[0] = __bfloat162float(*p);
+    }
+  } else if (VEC == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.ldz + col));
+    z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+  } else {
+    z[0] = __ldg(a.z + r * a.ldz + col);
+  }
+}
+template <typename Args>
+__device__ __forceinline__ float load_z1(const Args& a, int64_t idx) {
+  return a.z_bf16 != nullptr ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.z_bf16)[idx]) : __ldg(a.z + idx);
+}
+
 // ---------------------------------------------------------------------------------- backward
 // dy = d_out * [y > 0] * keep / (1 - p);  xhat = (z - mean) * rstd
 template <int VEC>
@@ -164,13 +190,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const aread_bn_a
   const uint64_t seed = seed_of(a);
   column_partials<VEC>(a.m, a.width, tw, partial, [&](int64_t r, int col, float (&s1)[VEC], float (&s2)[VEC]) {
     float z[VEC], d[VEC];
+    load_z<VEC>(a, r, col, z);
     if (VEC == 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.ldz + col));
       const float4 u = __ldg(reinterpret_cast<const float4*>(a.d_out + r * a.ldd + col));
-      z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
       d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
     } else {
-      z[0] = __ldg(a.z + r * a.ldz + col);
       d[0] = __ldg(a.d_out + r * a.ldd + col);
     }
 #pragma unroll
@@ -195,13 +219,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const aread_bn_a
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * ty_n + ty; r < a.m; r += static_cast<int64_t>(gridDim.x) * ty_n) {
     for (int col = tx * VEC; col < a.width; col += tw * VEC) {
       float z[VEC], d[VEC], dz[VEC];
+      load_z<VEC>(a, r, col, z);
       if (VEC == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.ldz + col));
         const float4 u = __ldg(reinterpret_cast<const float4*>(a.d_out + r * a.ldd + col));
-        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
         d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
       } else {
-        z[0] = __ldg(a.z + r * a.ldz + col);
         d[0] = __ldg(a.d_out + r * a.ldd + col);
       }
 #pragma unroll
@@ -268,7 +290,7 @@ __global__ void __launch_bounds__(kThreads) mmoe_mix_fwd_kernel(const aread_mmoe
         const int col = e * H + c;
         const bool keep = threshold == 0u ||
                           dropout_keep(seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
-        h[e] = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep, keep_scale);
+        h[e] = act_value(load_z1(a, b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep, keep_scale);
       }
     }
     for (int g = 0; g < G; ++g) {
@@ -310,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) mmoe_mix_bwd_kernel(const aread_mmoe
           const int col = e * H + c;
           const bool keep = threshold == 0u ||
                             dropout_keep(seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold);
-          const float h = act_value(__ldg(a.z + b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep,
+          const float h = act_value(load_z1(a, b * a.ldz + col), __ldg(a.scale + col), __ldg(a.shift + col), keep,
                                     keep_scale);
           float acc = 0.f;
 #pragma unroll
@@ -425,7 +447,10 @@ int aread_bn_act_bwd(const aread_bn_act_bwd_args* args, aread_stream_t stream_) 
   AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width <= 65536, "bn_act_bwd: width %d unsupported",
                 a.width);
   if (a.m == 0) return AREAD_OK;
-  AREAD_REQUIRE(a.z && a.d_out && a.mean && a.rstd && a.scale && a.shift, "bn_act_bwd: null pointer");
+  AREAD_REQUIRE((a.z || a.z_bf16) && a.d_out && a.mean && a.rstd && a.scale && a.shift, "bn_act_bwd: null pointer");
+  // row starts of z: 16-byte aligned fp32 rows or 8-byte aligned bf16 rows allow the 4-wide loads
+  const bool z_aligned = a.ldz % 4 == 0 && (a.z_bf16 ? reinterpret_cast<uintptr_t>(a.z_bf16) % 8 == 0
+                                                     : reinterpret_cast<uintptr_t>(a.z) % 16 == 0);
   AREAD_REQUIRE(a.workspace_bytes >= aread_bn_workspace_bytes(a.width), "bn_act_bwd: workspace too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   float* partial = static_cast<float*>(a.workspace);
@@ -434,8 +459,7 @@ int aread_bn_act_bwd(const aread_bn_act_bwd_args* args, aread_stream_t stream_) 
   const bool drop = a.dropout_p > 0.f;
   const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;
   const float keep_scale = drop ? 1.f / (1.f - a.dropout_p) : 1.f;
-  const Geometry g = geometry(a.width, a.ldz % 4 == 0 && a.ldd % 4 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0 &&
-                                           reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0);
+  const Geometry g = geometry(a.width, z_aligned && a.ldd % 4 == 0 && reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0);
   const size_t smem = sizeof(float) * 2 * kThreads * g.vec;
   if (g.vec == 4)
     AREAD_LAUNCH(bn_bwd_stats_kernel<4>, n_partial, kThreads, smem, stream, a, g.tw, threshold, keep_scale, partial);
@@ -443,8 +467,8 @@ int aread_bn_act_bwd(const aread_bn_act_bwd_args* args, aread_stream_t stream_) 
     AREAD_LAUNCH(bn_bwd_stats_kernel<1>, n_partial, kThreads, smem, stream, a, g.tw, threshold, keep_scale, partial);
   AREAD_LAUNCH(bn_bwd_finalize_kernel, ceil_div(a.width, 32), kThreads, 0, stream, a, partial, n_partial, coef);
   if (a.dz_f32 || a.dz_bf16) {
-    const bool aligned = a.ldz % 4 == 0 && a.ldo % 4 == 0 && a.ldd % 4 == 0 &&
-                         reinterpret_cast<uintptr_t>(a.z) % 16 == 0 && reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0 &&
+    const bool aligned = z_aligned && a.ldo % 4 == 0 && a.ldd % 4 == 0 &&
+                         reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0 &&
                          reinterpret_cast<uintptr_t>(a.dz_f32) % 16 == 0 &&
                          reinterpret_cast<uintptr_t>(a.dz_bf16) % 8 == 0 &&
                          reinterpret_cast<uintptr_t>(a.dz_bf16_lo) % 8 == 0;
@@ -514,7 +538,7 @@ int aread_mmoe_mix(const aread_mmoe_mix_args* args, aread_stream_t stream_) {
   AREAD_REQUIRE(a.n_expert > 0 && a.n_expert <= 16 && a.n_gate > 0 && a.n_gate <= 8 && a.n_expert * a.n_gate <= 64,
                 "mmoe_mix: %d experts x %d gates unsupported", a.n_expert, a.n_gate);
   if (a.m == 0) return AREAD_OK;
-  AREAD_REQUIRE(a.z && a.scale && a.shift && a.gate, "mmoe_mix: null pointer");
+  AREAD_REQUIRE((a.z || a.z_bf16) && a.scale && a.shift && a.gate, "mmoe_mix: null pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool drop = a.dropout_p > 0.f;
   const uint32_t threshold = drop ? dropout_threshold(a.dropout_p) : 0u;

@@ -38,6 +38,20 @@ struct GemmParams {
   int n_seg;  // 1: bf16 operands; 3: split operands, A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
   int tma_store;  // fp32 output in whole 32-column chunks: the epilogue stages them in smem and stores with TMA
   int64_t total_tiles;
+  // fused BatchNorm bookkeeping (aread_expert_gemm); `width` = groups * n
+  int width;
+  float* partial;            // [n_m_tiles][2][width]
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  const __nv_bfloat16* z;    // BN_BWD: pre-activation of the layer below, [m, ldz]
+  int64_t ldz;
+  uint32_t threshold;        // dropout of the layer below
+  float keep_scale;
+  uint32_t salt;
+  uint64_t seed;
+  const uint64_t* seed_ptr;
   unsigned char group_ids[kMaxGroups];
 };
 
@@ -46,9 +60,11 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStoreOffset = kStages * kStageBytes;           // epilogue staging: 4 warps x 2 x [32][32] fp32
+  static constexpr int kStoreOffset = kStages * kStageBytes;           // epilogue staging: 4 warps x 2 x [32 rows][128 B]
   static constexpr int kStoreBytes = 4 * 2 * 32 * 128;
-  static constexpr int kBarrierOffset = kStoreOffset + kStoreBytes;
+  static constexpr int kPartOffset = kStoreOffset + kStoreBytes;        // column partials of the 4 epilogue warps
+  static constexpr int kPartBytes = 2 * 4 * 2 * BN * 4;                 // [2 buffers][4 warps][2][BN] fp32
+  static constexpr int kBarrierOffset = kPartOffset + kPartBytes;
   static constexpr int kTotal = kBarrierOffset + 256 + 1024;  // barriers + slack for 1024-byte alignment
 };
 
@@ -65,12 +81,51 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int64_t ti
   return c;
 }
 
-template <int BN>
+// counter-based dropout stream shared with bn_act.cu / hei.cu (bn_common.cuh): keep(element) is a pure function of
+// (seed, salt, element index)
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t salt, uint64_t idx, uint32_t threshold) {
+  const uint32_t h = mix32(static_cast<uint32_t>(idx) ^ mix32(static_cast<uint32_t>(idx >> 32) ^ salt ^
+                                                               static_cast<uint32_t>(seed)) ^
+                           static_cast<uint32_t>(seed >> 32));
+  return h >= threshold;
+}
+
+// Column sums over the 32 rows a warp holds (thread = row, v[j] = column j): a butterfly that halves the number of
+// live values at every step, 31 shuffles in all.  Lane L returns the total of column L; the order of the additions
+// is fixed.  `v` is destroyed.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = upper ? v[j] : v[j + off];
+      const float keep = upper ? v[j + off] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int kEpiPlain = AREAD_EPI_PLAIN, kEpiStats = AREAD_EPI_STATS, kEpiAct = AREAD_EPI_ACT,
+              kEpiBnBwd = AREAD_EPI_BN_BWD;
+
+template <int BN, int EPI, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo,
                       const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   using L = SmemLayout<BN>;
+  constexpr int kBoxBytes = BK * 64 * 2;   // MN-major B: [64 k rows][64 n] boxes
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
@@ -109,7 +164,7 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord c = decode_tile(p, tile);
         const int a_col0 = c.g * p.a_group_cols;
-        const int b_row0 = c.g * p.n + c.n_t * BN;
+        const int b_row0 = B_MN ? c.g * p.k : c.g * p.n + c.n_t * BN;
         for (int seg = 0; seg < p.n_seg; ++seg) {
           const CUtensorMap* ma = seg < 2 ? &map_a : &map_a_lo;
           const CUtensorMap* mb = seg == 1 ? &map_b_lo : &map_b;
@@ -119,7 +174,13 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint8_t* sb = sa + L::kABytes;
             ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
             ptx::tma_load_2d(sa, ma, &full_bar[stage], a_col0 + kb * BK, c.m_t * BM);
-            ptx::tma_load_2d(sb, mb, &full_bar[stage], kb * BK, b_row0);
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                ptx::tma_load_2d(sb + j * kBoxBytes, mb, &full_bar[stage], c.n_t * BN + j * 64, b_row0 + kb * BK);
+            } else {
+              ptx::tma_load_2d(sb, mb, &full_bar[stage], kb * BK, b_row0);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -127,7 +188,7 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_ab(BM, BN, /*a_mn=*/false, /*b_mn=*/B_MN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -143,7 +204,8 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; ++kk) {
             const uint64_t da = ptx::umma_desc_k_sw128(sa + kk * UMMA_K * 2, 8 * 128);
-            const uint64_t db = ptx::umma_desc_k_sw128(sb + kk * UMMA_K * 2, 8 * 128);
+            const uint64_t db = B_MN ? ptx::umma_desc_mn_sw128(sb + kk * 2048, kBoxBytes, 1024)
+                                     : ptx::umma_desc_k_sw128(sb + kk * UMMA_K * 2, 8 * 128);
             ptx::umma_bf16(d_tmem, da, db, idesc, (kb | kk) != 0);
           }
           ptx::umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
@@ -157,35 +219,147 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int quad = warp % 4;
     int acc = 0;
     int store_buf = 0;
+    int part_buf = 0;
     uint32_t acc_phase = 0;
+    uint64_t seed = 0;
+    if (EPI == kEpiBnBwd) seed = p.seed_ptr != nullptr ? __ldg(p.seed_ptr) : p.seed;
     for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile(p, tile);
       ptx::mbar_wait(&acc_full[acc], acc_phase);
       ptx::tc_fence_after_sync();
       const int64_t row = static_cast<int64_t>(c.m_t) * BM + quad * 32 + lane;
       const int n0 = c.n_t * BN;  // column inside the group
+      if (EPI == kEpiPlain) {
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        float v[32];
-        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cc * 32, v);
-        const int col_in_group = n0 + cc * 32;
-        if (col_in_group >= p.n) continue;
-        const int64_t col = static_cast<int64_t>(c.g) * p.n + col_in_group;
-        if (p.bias != nullptr) {
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          float v[32];
+          ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cc * 32, v);
+          const int col_in_group = n0 + cc * 32;
+          if (col_in_group >= p.n) continue;
+          const int64_t col = static_cast<int64_t>(c.g) * p.n + col_in_group;
+          if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col_in_group + j < p.n) v[j] += __ldg(p.bias + col + j);
+            for (int j = 0; j < 32; ++j)
+              if (col_in_group + j < p.n) v[j] += __ldg(p.bias + col + j);
+          }
+          if (p.tma_store) {
+            // stage the warp's [32 rows][32 fp32] chunk in 128B-swizzled shared memory (what the tensor map expects)
+            // and let the TMA unit write whole 128-byte rows; rows past m are clipped by the map
+            uint8_t* stage_buf = smem + L::kStoreOffset + (quad * 2 + store_buf) * (32 * 128);
+            if (lane == 0) ptx::tma_store_wait_read<1>();       // the store that used this buffer two chunks ago
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&map_c, stage_buf, static_cast<int32_t>(col), c.m_t * BM + quad * 32);
+              ptx::tma_store_commit();
+            }
+            store_buf ^= 1;
+            continue;
+          }
+          if (row < p.m) {
+            const bool full = col_in_group + 32 <= p.n;
+            if (p.c_f32 != nullptr) {
+              float* dst = p.c_f32 + row * p.ldc + col;
+              if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+                for (int j = 0; j < 32 && col_in_group + j < p.n; ++j) dst[j] = v[j];
+              }
+            } else {
+              __nv_bfloat16* dst = p.c_bf16 + row * p.ldc + col;
+              if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 pk;
+                  pk.x = pack_bf16(v[j], v[j + 1]);
+                  pk.y = pack_bf16(v[j + 2], v[j + 3]);
+                  pk.z = pack_bf16(v[j + 4], v[j + 5]);
+                  pk.w = pack_bf16(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(dst + j) = pk;
+                }
+              } else {
+                for (int j = 0; j < 32 && col_in_group + j < p.n; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+              }
+            }
+          }
         }
-        if (p.tma_store) {
-          // stage the warp's [32 rows][32 fp32] chunk in 128B-swizzled shared memory (what the tensor map expects)
-          // and let the TMA unit write whole 128-byte rows; rows past m are clipped by the map
+      } else {
+        // ---- bf16 output in [32 rows][64 columns] chunks (128-byte rows, TMA store) with the BatchNorm bookkeeping.
+        // n is a multiple of 64 here, so every chunk is whole.
+        float* part = reinterpret_cast<float*>(smem + L::kPartOffset) + (part_buf * 4 + quad) * (2 * BN);
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 64; ++cc) {
+          const int col_in_group = n0 + cc * 64;
+          if (col_in_group >= p.n) {     // (BN = 128 over a 64-wide group never happens: BN is chosen from n)
+            continue;
+          }
+          const int64_t col = static_cast<int64_t>(c.g) * p.n + col_in_group;
+          uint32_t packed[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cc * 64 + half * 32, v);
+            const int64_t hcol = col + half * 32;
+            if (EPI == kEpiAct) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(v[j], __ldg(p.scale + hcol + j), __ldg(p.shift + hcol + j)), 0.f);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) packed[half * 16 + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+            } else if (EPI == kEpiStats) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) packed[half * 16 + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+              float sq[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+              const float s1 = warp_column_sums(v, lane);
+              const float s2 = warp_column_sums(sq, lane);
+              part[cc * 64 + half * 32 + lane] = s1;
+              part[BN + cc * 64 + half * 32 + lane] = s2;
+            } else {  // kEpiBnBwd
+              float xh[32];
+              uint4 zr[4];
+              if (row < p.m) {
+                const uint4* zp = reinterpret_cast<const uint4*>(p.z + row * p.ldz + hcol);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) zr[j] = __ldg(zp + j);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) zr[j] = make_uint4(0, 0, 0, 0);
+              }
+              const uint32_t* zw = reinterpret_cast<const uint32_t*>(zr);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const uint32_t w = zw[j >> 1];
+                const float zf = __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
+                const float y = fmaf(zf, __ldg(p.scale + hcol + j), __ldg(p.shift + hcol + j));
+                const bool keep = p.threshold == 0u ||
+                                  dropout_keep(seed, p.salt, static_cast<uint64_t>(row) * p.width + hcol + j, p.threshold);
+                const float dy = (y > 0.f && keep && row < p.m) ? v[j] * p.keep_scale : 0.f;
+                v[j] = dy;
+                xh[j] = dy * (zf - __ldg(p.mean + hcol + j)) * __ldg(p.rstd + hcol + j);
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) packed[half * 16 + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+              const float s1 = warp_column_sums(v, lane);
+              const float s2 = warp_column_sums(xh, lane);
+              part[cc * 64 + half * 32 + lane] = s1;
+              part[BN + cc * 64 + half * 32 + lane] = s2;
+            }
+          }
           uint8_t* stage_buf = smem + L::kStoreOffset + (quad * 2 + store_buf) * (32 * 128);
           if (lane == 0) ptx::tma_store_wait_read<1>();       // the store that used this buffer two chunks ago
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<uint4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -193,39 +367,22 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             ptx::tma_store_commit();
           }
           store_buf ^= 1;
-          continue;
         }
-        if (row < p.m) {
-          const bool full = col_in_group + 32 <= p.n;
-          if (p.c_f32 != nullptr) {
-            float* dst = p.c_f32 + row * p.ldc + col;
-            if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        if (EPI == kEpiStats || EPI == kEpiBnBwd) {
+          // the four warps' partials -> one partial per 128-row tile, added in warp order
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int t = quad * 32 + lane;
+          const float* pb = reinterpret_cast<const float*>(smem + L::kPartOffset) + part_buf * 4 * (2 * BN);
+          for (int o = t; o < 2 * BN; o += 128) {
+            const int which = o / BN, cj = o % BN;
+            if (n0 + cj < p.n) {
+              float sum = pb[o];
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              for (int j = 0; j < 32 && col_in_group + j < p.n; ++j) dst[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* dst = p.c_bf16 + row * p.ldc + col;
-            if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<unsigned*>(&h0);
-                pk.y = *reinterpret_cast<unsigned*>(&h1);
-                pk.z = *reinterpret_cast<unsigned*>(&h2);
-                pk.w = *reinterpret_cast<unsigned*>(&h3);
-                *reinterpret_cast<uint4*>(dst + j) = pk;
-              }
-            } else {
-              for (int j = 0; j < 32 && col_in_group + j < p.n; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+              for (int q = 1; q < 4; ++q) sum += pb[q * (2 * BN) + o];
+              p.partial[(static_cast<int64_t>(c.m_t) * 2 + which) * p.width + static_cast<int64_t>(c.g) * p.n + n0 + cj] = sum;
             }
           }
+          part_buf ^= 1;
         }
       }
       ptx::tc_fence_before_sync();
@@ -233,7 +390,7 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.tma_store && lane == 0) ptx::tma_store_wait_read<0>();   // shared memory must outlive the last stores
+    if ((EPI != kEpiPlain || p.tma_store) && lane == 0) ptx::tma_store_wait_read<0>();   // smem must outlive the last stores
   }
 
   ptx::tc_fence_before_sync();
@@ -485,18 +642,35 @@ int make_store_map(CUtensorMap* map, const void* base, int64_t rows, int64_t col
   return AREAD_OK;
 }
 
-template <int BN>
+// cudaFuncSetAttribute is per device: remember which devices a kernel has been configured on
+inline bool first_use_on_device(uint64_t* seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = uint64_t{1} << (dev & 63);
+  if (*seen & bit) return false;
+  *seen |= bit;
+  return true;
+}
+
+inline unsigned gemm_grid(int64_t tiles) {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = sms[dev & 63];
+  if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = kNumSMs;
+  return static_cast<unsigned>(tiles < n ? tiles : n);     // persistent: one CTA per SM
+}
+
+template <int BN, int EPI, bool B_MN>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma_lo, const CUtensorMap& mb_lo,
                 const CUtensorMap& mc, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BN>;
-  static bool configured = false;
-  if (!configured) {
-    AREAD_CUDA(cudaFuncSetAttribute(grouped_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  static uint64_t configured = 0;
+  if (first_use_on_device(&configured))
+    AREAD_CUDA(cudaFuncSetAttribute(grouped_linear_kernel<BN, EPI, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     L::kTotal));
-    configured = true;
-  }
-  const unsigned grid = static_cast<unsigned>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
-  AREAD_LAUNCH((grouped_linear_kernel<BN>), grid, kGemmThreads, L::kTotal, stream, ma, mb, ma_lo, mb_lo, mc, p);
+  AREAD_LAUNCH((grouped_linear_kernel<BN, EPI, B_MN>), gemm_grid(p.total_tiles), kGemmThreads, L::kTotal, stream, ma, mb,
+               ma_lo, mb_lo, mc, p);
   return AREAD_OK;
 }
 
@@ -505,13 +679,11 @@ template <int BN>
 int launch_wgrad(const CUtensorMap& mdz, const CUtensorMap& ma, const CUtensorMap& mdz_lo, const CUtensorMap& ma_lo,
                  const WgradParams& p, cudaStream_t stream) {
   constexpr int kSmem = kStages * (2 + BN / 64) * (BK * 64 * 2) + 256 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_use_on_device(&configured))
     AREAD_CUDA(cudaFuncSetAttribute(grouped_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
-  }
-  const unsigned grid = static_cast<unsigned>(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
-  AREAD_LAUNCH((grouped_wgrad_kernel<BN>), grid, kGemmThreads, kSmem, stream, mdz, ma, mdz_lo, ma_lo, p);
+  AREAD_LAUNCH((grouped_wgrad_kernel<BN>), gemm_grid(p.total_tiles), kGemmThreads, kSmem, stream, mdz, ma, mdz_lo, ma_lo,
+               p);
   return AREAD_OK;
 }
 
@@ -596,8 +768,317 @@ extern "C" int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, 
   if (p.tma_store)
     if (int rc = make_store_map(&mc, a.c_f32, a.m, static_cast<int64_t>(a.groups) * a.n, a.ldc)) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  return bn == 128 ? launch_gemm<128>(ma, mb, ma_lo, mb_lo, mc, p, stream)
-                   : launch_gemm<64>(ma, mb, ma_lo, mb_lo, mc, p, stream);
+  return bn == 128 ? launch_gemm<128, kEpiPlain, false>(ma, mb, ma_lo, mb_lo, mc, p, stream)
+                   : launch_gemm<64, kEpiPlain, false>(ma, mb, ma_lo, mb_lo, mc, p, stream);
+}
+
+// ----------------------------------------------------------------------------------------------
+// aread_expert_gemm: the same pipeline with the BatchNorm bookkeeping in the epilogue
+// ----------------------------------------------------------------------------------------------
+namespace aread {
+namespace {
+
+// bf16 row-major [rows, cols] output, box = [32 rows, 64 cols] (one 128-byte swizzle row per matrix row)
+int make_store_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, 32};
+  cuuint32_t elem[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 store) failed with CUresult %d", (int)r);
+  return AREAD_OK;
+}
+
+inline uint32_t dropout_threshold_of(float p) {
+  if (p <= 0.f) return 0u;
+  const double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+}
+
+template <int EPI, bool B_MN>
+int launch_expert(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p,
+                  cudaStream_t stream) {
+  return bn == 128 ? launch_gemm<128, EPI, B_MN>(ma, mb, ma, mb, mc, p, stream)
+                   : launch_gemm<64, EPI, B_MN>(ma, mb, ma, mb, mc, p, stream);
+}
+
+__global__ void __launch_bounds__(1024) expert_bn_finalize_kernel(const aread_expert_bn_finalize_args a) {
+  // 32 columns x 32 partial groups per CTA; partials are added per thread in tile order, then in thread order
+  __shared__ float s_c[2][32][33];
+  const int cx = threadIdx.x % 32, py = threadIdx.x / 32;
+  const int col = blockIdx.x * 32 + cx;
+  float s = 0.f, q = 0.f;
+  if (a.training && !a.bn_skip && col < a.width) {
+    for (int i = py; i < a.n_partial; i += 32) {
+      s += a.partial[(static_cast<int64_t>(i) * 2 + 0) * a.width + col];
+      q += a.partial[(static_cast<int64_t>(i) * 2 + 1) * a.width + col];
+    }
+  }
+  s_c[0][py][cx] = s;
+  s_c[1][py][cx] = q;
+  __syncthreads();
+  if (py != 0 || col >= a.width) return;
+  s = q = 0.f;
+  for (int y = 0; y < 32; ++y) { s += s_c[0][y][cx]; q += s_c[1][y][cx]; }
+  const float bias = a.bias != nullptr ? a.bias[col] : 0.f;
+  float mean, rstd, scale, shift;
+  if (a.bn_skip) {                       // identity instead of BatchNorm: h = relu(acc + bias)
+    mean = 0.f; rstd = 1.f; scale = 1.f; shift = bias;
+  } else if (a.training) {
+    const float inv_m = 1.f / static_cast<float>(a.m);
+    mean = s * inv_m;                    // of the bias-free accumulator
+    const float var = fmaxf(q * inv_m - mean * mean, 0.f);
+    rstd = 1.f / sqrtf(var + a.eps);
+    scale = a.gamma[col] * rstd;
+    shift = a.beta[col] - mean * scale;
+    const float unbiased = a.m > 1 ? var * (static_cast<float>(a.m) / static_cast<float>(a.m - 1)) : var;
+    a.running_mean[col] = (1.f - a.momentum) * a.running_mean[col] + a.momentum * (mean + bias);
+    a.running_var[col] = (1.f - a.momentum) * a.running_var[col] + a.momentum * unbiased;
+  } else {
+    rstd = 1.f / sqrtf(a.running_var[col] + a.eps);
+    mean = a.running_mean[col] - bias;
+    scale = a.gamma[col] * rstd;
+    shift = a.beta[col] - mean * scale;
+  }
+  a.mean[col] = mean;
+  a.rstd[col] = rstd;
+  a.scale[col] = scale;
+  a.shift[col] = shift;
+}
+
+__global__ void __launch_bounds__(1024) expert_bn_bwd_finalize_kernel(const aread_expert_bn_bwd_finalize_args a) {
+  __shared__ float s_c[2][32][33];
+  const int cx = threadIdx.x % 32, py = threadIdx.x / 32;
+  const int col = blockIdx.x * 32 + cx;
+  float s1 = 0.f, s2 = 0.f;
+  if (col < a.width) {
+    for (int i = py; i < a.n_partial; i += 32) {
+      s1 += a.partial[(static_cast<int64_t>(i) * 2 + 0) * a.width + col];
+      s2 += a.partial[(static_cast<int64_t>(i) * 2 + 1) * a.width + col];
+    }
+  }
+  s_c[0][py][cx] = s1;
+  s_c[1][py][cx] = s2;
+  __syncthreads();
+  if (py != 0 || col >= a.width) return;
+  s1 = s2 = 0.f;
+  for (int y = 0; y < 32; ++y) { s1 += s_c[0][y][cx]; s2 += s_c[1][y][cx]; }
+  if (a.bn_skip) {
+    if (a.d_gamma) a.d_gamma[col] = 0.f;
+    if (a.d_beta) a.d_beta[col] = 0.f;
+    if (a.d_bias) a.d_bias[col] = s1;
+    a.coef[col] = 0.f;
+    a.coef[a.width + col] = 0.f;
+  } else {
+    if (a.d_gamma) a.d_gamma[col] = s2;
+    if (a.d_beta) a.d_beta[col] = s1;
+    if (a.d_bias) a.d_bias[col] = 0.f;  // BatchNorm removes the column mean: the exact gradient is zero
+    const float inv_m = 1.f / static_cast<float>(a.m);
+    a.coef[col] = s1 * inv_m;
+    a.coef[a.width + col] = s2 * inv_m;
+  }
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// 8 bf16 columns per thread (16-byte accesses), rows strided over the grid; width % 8 == 0
+template <bool BWD>
+__global__ void __launch_bounds__(256) bn16_kernel(const aread_bn16_args a, uint32_t threshold, float keep_scale) {
+  const uint64_t seed = a.seed_ptr != nullptr ? __ldg(a.seed_ptr) : a.seed;
+  const int cols8 = a.width / 8;
+  const int64_t total = a.m * cols8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(a.z);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / cols8;
+    const int col = static_cast<int>(i - r * cols8) * 8;
+    const uint4 zr = __ldg(reinterpret_cast<const uint4*>(zb + r * a.ldz + col));
+    const uint32_t zw[4] = {zr.x, zr.y, zr.z, zr.w};
+    uint32_t dw[4] = {0, 0, 0, 0};
+    if (BWD) {
+      const uint4 dr = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dy) + r * a.ldd + col));
+      dw[0] = dr.x; dw[1] = dr.y; dw[2] = dr.z; dw[3] = dr.w;
+    }
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = col + j;
+      const float z = (j & 1) ? bf16_hi(zw[j >> 1]) : bf16_lo(zw[j >> 1]);
+      if (BWD) {
+        const float dy = (j & 1) ? bf16_hi(dw[j >> 1]) : bf16_lo(dw[j >> 1]);
+        const float xhat = (z - __ldg(a.mean + c)) * __ldg(a.rstd + c);
+        out[j] = a.bn_skip ? dy : __ldg(a.scale + c) * (dy - __ldg(a.coef + c) - xhat * __ldg(a.coef + a.width + c));
+      } else {
+        const float y = fmaf(z, __ldg(a.scale + c), __ldg(a.shift + c));
+        const bool keep = threshold == 0u || dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
+        out[j] = (y > 0.f && keep) ? y * keep_scale : 0.f;
+      }
+    }
+    uint4 pk;
+    pk.x = pack_bf16(out[0], out[1]);
+    pk.y = pack_bf16(out[2], out[3]);
+    pk.z = pack_bf16(out[4], out[5]);
+    pk.w = pack_bf16(out[6], out[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + r * a.ldo + col) = pk;
+  }
+}
+
+}  // namespace
+}  // namespace aread
+
+extern "C" int32_t aread_expert_gemm_partials(int64_t m) { return aread::ceil_div(m > 0 ? m : 1, aread::BM); }
+
+extern "C" int aread_expert_gemm(const aread_expert_gemm_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "expert_gemm: null args");
+  const aread_expert_gemm_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.n > 0 && a.k > 0, "expert_gemm: bad shape m=%lld n=%d k=%d", (long long)a.m, a.n, a.k);
+  AREAD_REQUIRE(a.groups > 0 && a.groups <= kMaxGroups, "expert_gemm: groups %d not in [1, %d]", a.groups, kMaxGroups);
+  AREAD_REQUIRE(a.epilogue >= AREAD_EPI_PLAIN && a.epilogue <= AREAD_EPI_BN_BWD, "expert_gemm: unknown epilogue %d",
+                a.epilogue);
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.a && a.b, "expert_gemm: null operand");
+  AREAD_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, "expert_gemm: lda/ldb must be multiples of 8 bf16 (16 bytes)");
+  AREAD_REQUIRE(reinterpret_cast<uintptr_t>(a.a) % 16 == 0 && reinterpret_cast<uintptr_t>(a.b) % 16 == 0,
+                "expert_gemm: operands must be 16-byte aligned");
+  AREAD_REQUIRE(a.a_group_cols == 0 || a.a_group_cols >= a.k, "expert_gemm: a_group_cols %d < k %d", a.a_group_cols, a.k);
+  AREAD_REQUIRE(!a.b_is_k_by_n || a.groups == 1 || a.k % BK == 0,
+                "expert_gemm: a grouped k-by-n weight needs k %% 64 == 0 (k = %d)", a.k);
+  const bool plain = a.epilogue == AREAD_EPI_PLAIN;
+  if (plain) {
+    AREAD_REQUIRE((a.c_f32 != nullptr) != (a.c_bf16 != nullptr), "expert_gemm: exactly one of c_f32 / c_bf16");
+  } else {
+    AREAD_REQUIRE(a.c_bf16 != nullptr && a.c_f32 == nullptr, "expert_gemm: this epilogue writes bf16");
+    AREAD_REQUIRE(a.n % 64 == 0 && a.ldc % 8 == 0 && reinterpret_cast<uintptr_t>(a.c_bf16) % 16 == 0,
+                  "expert_gemm: fused epilogues need n %% 64 == 0 and a 16-byte aligned output");
+  }
+  if (a.epilogue == AREAD_EPI_STATS || a.epilogue == AREAD_EPI_BN_BWD)
+    AREAD_REQUIRE(a.partial != nullptr, "expert_gemm: null partial");
+  if (a.epilogue == AREAD_EPI_ACT || a.epilogue == AREAD_EPI_BN_BWD)
+    AREAD_REQUIRE(a.scale && a.shift, "expert_gemm: null scale / shift");
+  if (a.epilogue == AREAD_EPI_BN_BWD) {
+    AREAD_REQUIRE(a.mean && a.rstd && a.z, "expert_gemm: null BN_BWD input");
+    AREAD_REQUIRE(a.ldz % 8 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0, "expert_gemm: z must be 16-byte aligned");
+    AREAD_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, "expert_gemm: dropout %f not in [0, 1)", a.dropout_p);
+  }
+
+  GemmParams p{};
+  p.m = a.m;
+  p.n = a.n;
+  p.k = a.k;
+  p.a_group_cols = a.a_group_cols;
+  p.ldc = a.ldc;
+  p.c_f32 = a.c_f32;
+  p.c_bf16 = reinterpret_cast<__nv_bfloat16*>(a.c_bf16);
+  p.bias = plain ? a.bias : nullptr;
+  p.n_active = a.groups;
+  for (int g = 0; g < a.groups; ++g) p.group_ids[g] = static_cast<unsigned char>(g);
+  const int bn = a.n > 64 ? 128 : 64;
+  p.n_m_tiles = ceil_div(a.m, BM);
+  p.n_n_tiles = ceil_div(a.n, bn);
+  p.n_k_blocks = ceil_div(a.k, BK);
+  p.total_tiles = static_cast<int64_t>(p.n_m_tiles) * p.n_active * p.n_n_tiles;
+  p.n_seg = 1;
+  p.width = a.groups * a.n;
+  p.partial = a.partial;
+  p.scale = a.scale;
+  p.shift = a.shift;
+  p.mean = a.mean;
+  p.rstd = a.rstd;
+  p.z = reinterpret_cast<const __nv_bfloat16*>(a.z);
+  p.ldz = a.ldz;
+  p.threshold = dropout_threshold_of(a.dropout_p);
+  p.keep_scale = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+  p.salt = a.salt;
+  p.seed = a.seed;
+  p.seed_ptr = a.seed_ptr;
+
+  CUtensorMap ma, mb, mc;
+  const int64_t a_cols = a.a_group_cols == 0 ? a.k : static_cast<int64_t>(a.a_group_cols) * (a.groups - 1) + a.k;
+  if (int rc = make_map(&ma, a.a, a.m, a_cols, a.lda, BM)) return rc;
+  if (a.b_is_k_by_n) {
+    if (int rc = make_map(&mb, a.b, static_cast<int64_t>(a.groups) * a.k, a.n, a.ldb, BK, 64)) return rc;
+  } else {
+    if (int rc = make_map(&mb, a.b, static_cast<int64_t>(a.groups) * a.n, a.k, a.ldb, bn)) return rc;
+  }
+  mc = ma;
+  if (plain) {
+    p.tma_store = (a.c_f32 != nullptr && a.n % 32 == 0 && a.ldc % 4 == 0 && reinterpret_cast<uintptr_t>(a.c_f32) % 16 == 0)
+                      ? 1 : 0;
+    if (p.tma_store)
+      if (int rc = make_store_map(&mc, a.c_f32, a.m, static_cast<int64_t>(a.groups) * a.n, a.ldc)) return rc;
+  } else {
+    if (int rc = make_store_map_bf16(&mc, a.c_bf16, a.m, static_cast<int64_t>(a.groups) * a.n, a.ldc)) return rc;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool mn = a.b_is_k_by_n != 0;
+  switch (a.epilogue) {
+    case AREAD_EPI_PLAIN:
+      return mn ? launch_expert<kEpiPlain, true>(bn, ma, mb, mc, p, stream)
+                : launch_expert<kEpiPlain, false>(bn, ma, mb, mc, p, stream);
+    case AREAD_EPI_STATS:
+      AREAD_REQUIRE(!mn, "expert_gemm: STATS runs on the forward weight layout");
+      return launch_expert<kEpiStats, false>(bn, ma, mb, mc, p, stream);
+    case AREAD_EPI_ACT:
+      AREAD_REQUIRE(!mn, "expert_gemm: ACT runs on the forward weight layout");
+      return launch_expert<kEpiAct, false>(bn, ma, mb, mc, p, stream);
+    default:
+      AREAD_REQUIRE(mn, "expert_gemm: BN_BWD runs on the k-by-n weight layout");
+      return launch_expert<kEpiBnBwd, true>(bn, ma, mb, mc, p, stream);
+  }
+}
+
+extern "C" int aread_expert_bn_finalize(const aread_expert_bn_finalize_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "expert_bn_finalize: null args");
+  const aread_expert_bn_finalize_args& a = *args;
+  AREAD_REQUIRE(a.width > 0 && a.m > 0, "expert_bn_finalize: bad shape");
+  AREAD_REQUIRE(a.mean && a.rstd && a.scale && a.shift, "expert_bn_finalize: null output");
+  AREAD_REQUIRE(a.bn_skip || (a.gamma && a.beta && a.running_mean && a.running_var), "expert_bn_finalize: null BN tensor");
+  AREAD_REQUIRE(!(a.training && !a.bn_skip) || (a.partial && a.n_partial > 0), "expert_bn_finalize: null partial");
+  AREAD_LAUNCH(expert_bn_finalize_kernel, ceil_div(a.width, 32), 1024, 0, static_cast<cudaStream_t>(stream_), a);
+  return AREAD_OK;
+}
+
+extern "C" int aread_expert_bn_bwd_finalize(const aread_expert_bn_bwd_finalize_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "expert_bn_bwd_finalize: null args");
+  const aread_expert_bn_bwd_finalize_args& a = *args;
+  AREAD_REQUIRE(a.width > 0 && a.m > 0 && a.n_partial > 0 && a.partial && a.coef, "expert_bn_bwd_finalize: bad arguments");
+  AREAD_LAUNCH(expert_bn_bwd_finalize_kernel, ceil_div(a.width, 32), 1024, 0, static_cast<cudaStream_t>(stream_), a);
+  return AREAD_OK;
+}
+
+extern "C" int aread_bn16(const aread_bn16_args* args, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr, "bn16: null args");
+  const aread_bn16_args& a = *args;
+  AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width % 8 == 0, "bn16: width %d must be a multiple of 8", a.width);
+  if (a.m == 0) return AREAD_OK;
+  AREAD_REQUIRE(a.z && a.out && a.scale, "bn16: null pointer");
+  AREAD_REQUIRE(a.ldz % 8 == 0 && a.ldo % 8 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(a.out) % 16 == 0,
+                "bn16: rows must be 16-byte aligned");
+  AREAD_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, "bn16: dropout %f not in [0, 1)", a.dropout_p);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t total = a.m * (a.width / 8);
+  int64_t grid = (total + 255) / 256;
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  if (a.dy != nullptr) {
+    AREAD_REQUIRE(a.bn_skip || (a.mean && a.rstd && a.coef), "bn16: null backward input");
+    AREAD_REQUIRE(a.ldd % 8 == 0 && reinterpret_cast<uintptr_t>(a.dy) % 16 == 0, "bn16: dy rows must be 16-byte aligned");
+    AREAD_LAUNCH(bn16_kernel<true>, static_cast<unsigned>(grid), 256, 0, stream, a, 0u, 1.f);
+  } else {
+    AREAD_REQUIRE(a.shift != nullptr, "bn16: null shift");
+    AREAD_LAUNCH(bn16_kernel<false>, static_cast<unsigned>(grid), 256, 0, stream, a, dropout_threshold_of(a.dropout_p),
+                 a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f);
+  }
+  return AREAD_OK;
 }
 
 extern "C" size_t aread_grouped_wgrad_workspace_bytes(const aread_grouped_wgrad_args* args) {

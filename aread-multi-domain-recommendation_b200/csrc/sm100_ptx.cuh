@@ -165,5 +165,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool mn_maj
          | (static_cast<uint32_t>(m >> 4) << 24);   // [24,29) M >> 4
 }
 
+// Same, with the major-ness of A and B chosen separately (data gradient: K-major dZ times the MN-major weight).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_ab(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
 }  // namespace ptx
 }  // namespace aread

@@ -368,19 +368,41 @@ class AreadNode(torch.autograd.Function):
         G = P.experts[0].groups
         a_op = xb
         ex = []
-        for i, L in enumerate(P.experts):
-            w = dk.split_bf16(L.weight.rows()) if precise else L.weight.rows().to(torch.bfloat16)
-            z = dk.grouped_linear(_hi(a_op), _hi(w), L.bias.rows(), L.n, L.k, G, 0 if i == 0 else L.k,
-                                  a_lo=_lo(a_op), w_lo=_lo(w))
-            last = i == len(P.experts) - 1
-            res = dk.bn_act_fwd(z, L.gamma.rows(), L.beta.rows(), L.running_mean.rows(), L.running_var.rows(),
-                                training, bn_skip, p_drop, seed, L.salt, None if last else torch.bfloat16,
-                                want_lo=precise and not last)
-            out, stats = (res[0], res[-1]) if not (precise and not last) else ((res[0], res[1]), res[2])
-            if training and not bn_skip:
-                torch._foreach_add_(L.tracked, 1)
-            ex.append((a_op, z, stats, w))
-            a_op = out
+        if precise:
+            for i, L in enumerate(P.experts):
+                w = dk.split_bf16(L.weight.rows())
+                z = dk.grouped_linear(_hi(a_op), _hi(w), L.bias.rows(), L.n, L.k, G, 0 if i == 0 else L.k,
+                                      a_lo=_lo(a_op), w_lo=_lo(w))
+                last = i == len(P.experts) - 1
+                res = dk.bn_act_fwd(z, L.gamma.rows(), L.beta.rows(), L.running_mean.rows(), L.running_var.rows(),
+                                    training, bn_skip, p_drop, seed, L.salt, None if last else torch.bfloat16,
+                                    want_lo=not last)
+                out, stats = (res[0], res[-1]) if last else ((res[0], res[1]), res[2])
+                if training and not bn_skip:
+                    torch._foreach_add_(L.tracked, 1)
+                ex.append((a_op, z, stats, w))
+                a_op = out
+        else:
+            # bf16 experts: the GEMM epilogue leaves the BatchNorm column sums and the pre-activation ONCE, as bf16
+            # (bias-free: BatchNorm removes it); under no_grad in eval mode BatchNorm + ReLU are folded into the epilogue
+            w16 = model.expert_weights_bf16()
+            keep_z = training or torch.is_grad_enabled()
+            for i, L in enumerate(P.experts):
+                last = i == len(P.experts) - 1
+                agc = 0 if i == 0 else L.k
+                bn = (L.bias.rows(), L.gamma.rows(), L.beta.rows(), L.running_mean.rows(), L.running_var.rows())
+                if keep_z:
+                    z, partial = dk.expert_linear_stats(a_op, w16[i], L.n, L.k, G, agc)
+                    stats = dk.expert_bn_finalize(partial, B, G * L.n, *bn, training, bn_skip)
+                    out = None if last else dk.bn16_fwd(z, stats, training, p_drop, seed, L.salt)
+                else:
+                    folded = dk.expert_bn_finalize(None, B, G * L.n, *bn, False, bn_skip)
+                    out = z = dk.expert_linear_act(a_op, w16[i], L.n, L.k, G, agc, folded)
+                    stats = dk.identity_saved(G * L.n, dev) if last else None
+                if training and not bn_skip:
+                    torch._foreach_add_(L.tracked, 1)
+                ex.append((a_op, z, stats, w16[i]))
+                a_op = out
         h = dk.mmoe_mix_fwd(ex[-1][1], ex[-1][2], gate, G, len(a0), p_drop if training else 0.0, seed,
                             P.experts[-1].salt)                                          # [B, na0, H]
         sv["experts"] = ex
@@ -560,18 +582,40 @@ class AreadNode(torch.autograd.Function):
         def tr(w, fn):
             return tuple(fn(t) for t in w) if isinstance(w, tuple) else fn(w)
 
-        for i in range(len(P.experts) - 1, -1, -1):
-            L = P.experts[i]
-            a_in, z, stats, w = ex[i]
-            dze, d_gamma, d_beta, d_bias = dk.bn_act_bwd(z, d_act, stats, bn_skip, p_drop, seed, L.salt, want_lo=precise)
-            d_w = dk.grouped_wgrad(_hi(dze), _hi(a_in), L.n, L.k, G, 0 if i == 0 else L.k, dz_lo=_lo(dze), a_lo=_lo(a_in))
-            expert_grads[i] = (d_w.view(G, L.n, L.k), d_bias.view(G, L.n), d_gamma.view(G, L.n), d_beta.view(G, L.n))
-            if i > 0:
-                wt = tr(w, lambda t: t.view(G, L.n, L.k).transpose(1, 2).reshape(G * L.k, L.n).contiguous())
-                d_act = dk.grouped_linear(_hi(dze), _hi(wt), None, L.k, L.n, G, L.n, a_lo=_lo(dze), w_lo=_lo(wt))
-            else:
-                wt = tr(w, lambda t: t.t().contiguous())
-                d_x = dk.grouped_linear(_hi(dze), _hi(wt), None, L.k, G * L.n, 1, 0, a_lo=_lo(dze), w_lo=_lo(wt))
+        if precise:
+            for i in range(len(P.experts) - 1, -1, -1):
+                L = P.experts[i]
+                a_in, z, stats, w = ex[i]
+                dze, d_gamma, d_beta, d_bias = dk.bn_act_bwd(z, d_act, stats, bn_skip, p_drop, seed, L.salt, want_lo=True)
+                d_w = dk.grouped_wgrad(_hi(dze), _hi(a_in), L.n, L.k, G, 0 if i == 0 else L.k, dz_lo=_lo(dze),
+                                       a_lo=_lo(a_in))
+                expert_grads[i] = (d_w.view(G, L.n, L.k), d_bias.view(G, L.n), d_gamma.view(G, L.n), d_beta.view(G, L.n))
+                if i > 0:
+                    wt = tr(w, lambda t: t.view(G, L.n, L.k).transpose(1, 2).reshape(G * L.k, L.n).contiguous())
+                    d_act = dk.grouped_linear(_hi(dze), _hi(wt), None, L.k, L.n, G, L.n, a_lo=_lo(dze), w_lo=_lo(wt))
+                else:
+                    wt = tr(w, lambda t: t.t().contiguous())
+                    d_x = dk.grouped_linear(_hi(dze), _hi(wt), None, L.k, G * L.n, 1, 0, a_lo=_lo(dze), w_lo=_lo(wt))
+        else:
+            # bf16 experts.  Last layer: its gradient arrives in fp32 from the mixture.  Every other layer: the data
+            # gradient GEMM of the layer above masks it (ReLU, dropout), sums the BatchNorm reductions in its epilogue
+            # and stores it once as bf16; the weight is read in place as a k-by-n operand (no transposed copies).
+            L = P.experts[-1]
+            dze, d_gamma, d_beta, d_bias = dk.bn_act_bwd(ex[-1][1], d_act, ex[-1][2], bn_skip, p_drop, seed, L.salt)
+            for i in range(len(P.experts) - 1, -1, -1):
+                L = P.experts[i]
+                a_in, z, stats, w = ex[i]
+                d_w = dk.grouped_wgrad(dze, a_in, L.n, L.k, G, 0 if i == 0 else L.k)
+                expert_grads[i] = (d_w.view(G, L.n, L.k), d_bias.view(G, L.n), d_gamma.view(G, L.n), d_beta.view(G, L.n))
+                if i > 0:
+                    Lp = P.experts[i - 1]
+                    _, z_p, stats_p, _ = ex[i - 1]
+                    dy, partial = dk.expert_dgrad_bn_bwd(dze, w, L.k, L.n, G, z_p, stats_p, p_drop, Lp.salt, seed)
+                    coef, g3 = dk.expert_bn_bwd_finalize(partial, B, G * L.k, bn_skip)
+                    d_gamma, d_beta, d_bias = g3[0], g3[1], g3[2]
+                    dze = dk.bn16_bwd(z_p, dy, stats_p, coef, bn_skip)
+                else:
+                    d_x = dk.expert_dgrad_plain(dze, w, L.k, G * L.n)
 
         # ---- row pass
         layout, ldp = sv["layout"], sv["ldp"]

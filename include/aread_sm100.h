@@ -171,6 +171,118 @@ typedef struct aread_grouped_linear_args {
 AREAD_API int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, aread_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Expert Linear layers with the BatchNorm bookkeeping fused into the GEMM epilogue (bf16 experts).
+ * Same tcgen05 / TMEM / TMA pipeline as aread_grouped_linear_bf16; the accumulator leaves TMEM once and the
+ * pre-activation is stored ONCE, as bf16 -- the fp32 `z` round trips of Linear -> BatchNorm1d -> ReLU -> Dropout
+ * (model/layer.py:209-215, 221-229) and of their backward are gone.
+ *
+ *   acc[:, g*n : (g+1)*n] = A[:, g*a_group_cols : +k] . B_g        (fp32 accumulation in TMEM)
+ *
+ * B_g: b_is_k_by_n == 0 -> rows g*n.. of b [groups*n, ldb], k contiguous (the nn.Linear weight, forward);
+ *      b_is_k_by_n == 1 -> rows g*k.. of b [groups*k, ldb], n contiguous (the SAME weight array read as an
+ *                          MN-major operand: data gradient dA = dZ . W without a transposed copy).
+ * Epilogues:
+ *   AREAD_EPI_PLAIN   c = acc (+ bias), fp32 or bf16
+ *   AREAD_EPI_STATS   c_bf16 = bf16(acc)  [bias-free: BatchNorm removes it]; partial[t][0][col] = sum_rows acc,
+ *                     partial[t][1][col] = sum_rows acc^2 over the rows of 128-row tile t (fixed order)
+ *   AREAD_EPI_ACT     c_bf16 = bf16(max(acc * scale[col] + shift[col], 0))   (eval mode: BatchNorm folded)
+ *   AREAD_EPI_BN_BWD  acc = gradient w.r.t. the ACTIVATED output of the layer below;  with y = z*scale+shift,
+ *                     dy = (y > 0 && keep) ? acc / (1 - p) : 0;  c_bf16 = bf16(dy);
+ *                     partial[t][0][col] = sum dy, partial[t][1][col] = sum dy * (z - mean) * rstd
+ * partial: fp32 [aread_expert_gemm_partials(m)][2][groups * n].
+ * ---------------------------------------------------------------------------------------------- */
+enum { AREAD_EPI_PLAIN = 0, AREAD_EPI_STATS = 1, AREAD_EPI_ACT = 2, AREAD_EPI_BN_BWD = 3 };
+
+typedef struct aread_expert_gemm_args {
+  int64_t m;
+  int32_t n, k, groups, a_group_cols;
+  const uint16_t* a;      /* bf16 [m, lda] */
+  int64_t lda;
+  const uint16_t* b;      /* bf16 weights, see b_is_k_by_n */
+  int64_t ldb;
+  int32_t b_is_k_by_n;
+  int32_t epilogue;       /* AREAD_EPI_*                                              */
+  const float* bias;      /* PLAIN only, optional fp32 [groups * n]                   */
+  float* c_f32;           /* PLAIN only (or c_bf16)                                   */
+  uint16_t* c_bf16;       /* [m, ldc] bf16                                            */
+  int64_t ldc;
+  float* partial;         /* STATS / BN_BWD                                           */
+  const float* scale;     /* ACT / BN_BWD: fp32 [groups * n]                          */
+  const float* shift;
+  const float* mean;      /* BN_BWD                                                   */
+  const float* rstd;
+  const uint16_t* z;      /* BN_BWD: bf16 [m, ldz] pre-activation of the layer below  */
+  int64_t ldz;
+  float dropout_p;        /* BN_BWD: dropout of the layer below (0: none)             */
+  uint32_t salt;
+  uint64_t seed;
+  const uint64_t* seed_ptr;
+} aread_expert_gemm_args;
+
+AREAD_API int32_t aread_expert_gemm_partials(int64_t m);
+AREAD_API int aread_expert_gemm(const aread_expert_gemm_args* args, aread_stream_t stream);
+
+/* Column statistics of a STATS launch -> what BatchNorm1d needs (model/layer.py:212, torch semantics: batch mean /
+ * biased variance in training, running statistics with momentum and the unbiased variance).  `mean` is relative to
+ * the bias-free accumulator that was stored; the running mean gets mean + bias.  training == 0: running statistics
+ * (shift absorbs the bias); bn_skip (batch of one, layer.py:226): scale = 1, shift = bias.                        */
+typedef struct aread_expert_bn_finalize_args {
+  int64_t m;
+  int32_t width, n_partial, training, bn_skip;
+  float momentum, eps;
+  const float* partial;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* mean;            /* out, fp32 [width] each */
+  float* rstd;
+  float* scale;
+  float* shift;
+} aread_expert_bn_finalize_args;
+
+AREAD_API int aread_expert_bn_finalize(const aread_expert_bn_finalize_args* args, aread_stream_t stream);
+
+/* Column sums of a BN_BWD launch -> d_gamma = sum dy*xhat, d_beta = sum dy, d_bias = 0 (BatchNorm removes the column
+ * mean; with bn_skip: d_bias = sum dy, the others 0) and coef = [sum dy / m | sum dy*xhat / m].                    */
+typedef struct aread_expert_bn_bwd_finalize_args {
+  int64_t m;
+  int32_t width, n_partial, bn_skip;
+  const float* partial;
+  float* d_gamma;
+  float* d_beta;
+  float* d_bias;
+  float* coef;            /* out, fp32 [2, width] */
+} aread_expert_bn_bwd_finalize_args;
+
+AREAD_API int aread_expert_bn_bwd_finalize(const aread_expert_bn_bwd_finalize_args* args, aread_stream_t stream);
+
+/* out = bf16(dropout(relu(z * scale + shift))) from the bf16 pre-activation (forward), or, with dy != NULL,
+ * dz = bf16(scale * (dy - coef[0] - xhat * coef[1])) (bn_skip: dz = dy), xhat = (z - mean) * rstd (backward).       */
+typedef struct aread_bn16_args {
+  int64_t m;
+  int32_t width, bn_skip;
+  const uint16_t* z;      /* bf16 [m, ldz]                      */
+  int64_t ldz;
+  const float* scale;
+  const float* shift;
+  float dropout_p;        /* forward: 0 in eval mode            */
+  uint32_t salt;
+  uint64_t seed;
+  const uint64_t* seed_ptr;
+  uint16_t* out;          /* bf16 [m, ldo]: h (forward) / dz (backward) */
+  int64_t ldo;
+  const uint16_t* dy;     /* backward: bf16 [m, ldd], masks already applied; NULL: forward */
+  int64_t ldd;
+  const float* mean;      /* backward */
+  const float* rstd;
+  const float* coef;      /* backward: fp32 [2, width] */
+} aread_bn16_args;
+
+AREAD_API int aread_bn16(const aread_bn16_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Weight gradient of the grouped Linear: dW_g[j, i] = sum_b dZ[b, g*n + j] * A[b, g*a_group_cols + i].
  * Replaces the autograd of the nn.Linear weights (model/layer.py:210) of the experts.  Both operands
  * are read in their natural [samples, features] layout (MN-major tcgen05 operands); the sample
@@ -262,6 +374,8 @@ typedef struct aread_bn_act_bwd_args {
   uint16_t* dz_bf16_lo;   /* optional out [m, ldo]: the split residual of dz                       */
   const uint64_t* seed_ptr; /* optional device scalar: when set, the dropout seed is read from it at run time   */
                             /* (CUDA-graph replay) and `seed` is ignored                                        */
+  const uint16_t* z_bf16; /* optional: the pre-activation as bf16 [m, ldz] (aread_expert_gemm STATS); `z` is  */
+                          /* then ignored                                                                     */
 } aread_bn_act_bwd_args;
 
 AREAD_API size_t aread_bn_workspace_bytes(int32_t width);
@@ -383,6 +497,7 @@ typedef struct aread_mmoe_mix_args {
   float* d_h;             /* backward out [m, n_expert * width]                                    */
   float* d_gate;          /* backward out [m, n_gate, n_expert]                                    */
   const uint64_t* seed_ptr; /* optional device scalar replacing `seed` at run time (CUDA-graph replay)   */
+  const uint16_t* z_bf16; /* optional: z as bf16 [m, ldz]; `z` is then ignored                             */
 } aread_mmoe_mix_args;
 
 AREAD_API int aread_mmoe_mix(const aread_mmoe_mix_args* args, aread_stream_t stream);
@@ -581,6 +696,9 @@ typedef struct aread_multi_copy_args {
 
 AREAD_API int64_t aread_multi_copy_chunk(void);
 AREAD_API int aread_multi_copy(const aread_multi_copy_args* args, aread_stream_t stream);
+/* Same table, but dst[t] receives bf16(src[t]) of the fp32 source (bytes[t] = SOURCE bytes, a multiple of 16;
+ * pointers 16-byte aligned): the bf16 operand copies of all expert weights in one launch per step.            */
+AREAD_API int aread_multi_cast_bf16(const aread_multi_copy_args* args, aread_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Bagging loss of the HEI heads: loss[0] = (1 / n_tower) * sum_t mean_b BCE(probs[t, b], labels[b])

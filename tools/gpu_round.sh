@@ -6,7 +6,7 @@ TAG=${1:-r2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 if [ -z "${SKIP_TESTS:-}" ]; then
-  timeout 1500 python -m pytest tests -m gpu -q --timeout 900 ${PYTEST_ARGS:-} > gpurun_out/pytest_$TAG.log 2>&1
+  eval "timeout 1500 python -m pytest tests -m gpu -q --timeout 900 ${PYTEST_ARGS:-}" > gpurun_out/pytest_$TAG.log 2>&1
   echo "pytest exit $?" | tee -a gpurun_out/pytest_$TAG.log
   tail -30 gpurun_out/pytest_$TAG.log
   timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1

@@ -90,7 +90,7 @@ class RowpassArgs(Structure):
                 ("p", c_void_p), ("lin", c_void_p), ("gate", c_void_p), ("alpha", c_void_p), ("head", c_void_p),
                 ("d_lin", c_void_p), ("d_gate", c_void_p), ("d_head", c_void_p), ("d_p", c_void_p),
                 ("d_c", c_void_p), ("d_x", c_void_p), ("d_w", c_void_p), ("workspace", c_void_p),
-                ("workspace_bytes", c_size_t)]
+                ("workspace_bytes", c_size_t), ("dp16", c_void_p), ("ld16", c_int64)]
 
 
 class L2RegArgs(Structure):

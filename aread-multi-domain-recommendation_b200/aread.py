@@ -163,7 +163,7 @@ class AREAD(BaseModel):
             for d, info in order:
                 for _ in range(4):
                     one_pass(d)
-                    if self._graphs.recorded(info.serial):
+                    if self._graphs.recorded(info.serial, x.shape, self.training):
                         break
         finally:
             self._graphs.force = False

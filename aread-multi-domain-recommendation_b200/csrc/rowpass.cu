@@ -163,6 +163,16 @@ __global__ void __launch_bounds__(kThreads) rowpass_prologue_bwd_kernel(const ar
       dp[j] = 0.f;
       dc[j] = 0.f;
     }
+    if (a.dp16 != nullptr) {   // split bf16 operands of the tensor-core products: [hi | hi | lo], 32 columns each
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.dp16) + b * a.ld16;
+      for (int j = 0; j < 32; ++j) {
+        const float v = j < c_head + nh ? dp[j] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        o[j] = hi;
+        o[32 + j] = hi;
+        o[64 + j] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
+    }
   }
 }
 
@@ -285,10 +295,10 @@ int aread_rowpass_fwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   const int nj = 1 + a.n_gate * a.n_expert + a.n_cross + a.n_head;
   AREAD_REQUIRE(a.m >= 0 && a.e > 0 && nj <= a.ldp, "rowpass_fwd: bad shape (e=%d, columns=%d, ldp=%d)", a.e, nj, a.ldp);
   if (a.m == 0) return AREAD_OK;
-  AREAD_REQUIRE(a.x && a.w && a.offset && a.p && a.lin && a.alpha, "rowpass_fwd: null pointer");
+  AREAD_REQUIRE((a.x == nullptr || a.w) && a.offset && a.p && a.lin && a.alpha, "rowpass_fwd: null pointer");
   AREAD_REQUIRE((a.gate || a.n_gate * a.n_expert == 0) && (a.head || a.n_head == 0), "rowpass_fwd: null output");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  {
+  if (a.x != nullptr) {
     const int64_t tiles = (a.m + kTile - 1) / kTile;
     const unsigned grid = static_cast<unsigned>(tiles < kNumSMs * 4 ? tiles : kNumSMs * 4);
     for (int j0 = 0; j0 < nj; j0 += kJ)  // 32 dot products per launch
@@ -309,8 +319,19 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   const int nj = 1 + a.n_gate * a.n_expert + a.n_cross + a.n_head;
   AREAD_REQUIRE(a.m >= 0 && a.e > 0 && nj <= a.ldp, "rowpass_bwd: bad shape");
   AREAD_REQUIRE(a.e <= 16 * kChunk, "rowpass_bwd: embedding row of %d floats is too wide (max %d)", a.e, 16 * kChunk);
-  AREAD_REQUIRE(a.d_w && a.d_p && a.d_c && a.workspace, "rowpass_bwd: null pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const unsigned pgrid = static_cast<unsigned>((a.m + kThreads - 1) / kThreads < kNumSMs * 8
+                                                   ? (a.m + kThreads - 1) / kThreads
+                                                   : kNumSMs * 8);
+  if (a.x == nullptr) {  // per-row prologue only: the products run on the tensor cores
+    AREAD_REQUIRE(a.d_p && a.d_c, "rowpass_bwd: null pointer");
+    AREAD_REQUIRE(a.dp16 == nullptr || (nj <= 32 && a.ld16 >= 96), "rowpass_bwd: dp16 holds at most 32 dot products");
+    if (a.m == 0) return AREAD_OK;
+    AREAD_REQUIRE(a.p && a.alpha && (a.gate || a.n_gate * a.n_expert == 0), "rowpass_bwd: null pointer");
+    AREAD_LAUNCH(rowpass_prologue_bwd_kernel, pgrid, kThreads, 0, stream, a);
+    return AREAD_OK;
+  }
+  AREAD_REQUIRE(a.d_w && a.d_p && a.d_c && a.workspace, "rowpass_bwd: null pointer");
   if (a.m == 0) {
     AREAD_CUDA(cudaMemsetAsync(a.d_w, 0, static_cast<size_t>(nj) * a.e * 4, stream));
     return AREAD_OK;

@@ -110,18 +110,19 @@ def bn_act_fwd(z, gamma, beta, running_mean, running_var, training, bn_skip, p, 
     return (out, out_lo, saved) if want_lo else (out, saved)
 
 
-def bn_act_bwd(z, d_out, saved, bn_skip, p, seed, salt, dz_dtype=torch.bfloat16, want_lo=False):
-    """(dz, d_gamma, d_beta, d_bias) for out = dropout(relu(bn(z))); with want_lo dz is (hi, lo)."""
+def bn_act_bwd(z, d_out, saved, bn_skip, p, seed, salt, dz_dtype=torch.bfloat16, want_lo=False, dz_out=None):
+    """(dz, d_gamma, d_beta, d_bias) for out = dropout(relu(bn(z))); with want_lo dz is (hi, lo).  `dz_out`: a
+    preallocated [m, width] view (any row stride) that receives dz."""
     m, width = z.shape
     grads = torch.empty((3, width), dtype=torch.float32, device=z.device)     # parameter gradients: never arena
-    dz = _mem.empty((m, width), dz_dtype, z.device)
+    dz = dz_out if dz_out is not None else _mem.empty((m, width), dz_dtype, z.device)
     dz_lo = _mem.empty((m, width), torch.bfloat16, z.device) if want_lo else None
     ws = _bn_workspace(z.device, width)
     z16 = z.dtype == torch.bfloat16
     args = _lib.BnActBwdArgs(m, width, 1 if bn_skip else 0, float(p), salt, seed, None if z16 else z.data_ptr(),
                              z.stride(0), d_out.data_ptr(), d_out.stride(0), *_rows(saved, 4), *_rows(grads, 3),
                              _ptr(dz) if dz_dtype == torch.float32 else None,
-                             _ptr(dz) if dz_dtype == torch.bfloat16 else None, width, ws.data_ptr(), ws.numel(),
+                             _ptr(dz) if dz_dtype == torch.bfloat16 else None, dz.stride(0), ws.data_ptr(), ws.numel(),
                              _ptr(dz_lo), SEED_PTR, z.data_ptr() if z16 else None)
     _lib.check(_lib.load().aread_bn_act_bwd(ctypes.byref(args), _stream(z.device)))
     return ((dz, dz_lo) if want_lo else dz), grads[0], grads[1], grads[2]
@@ -248,13 +249,15 @@ def bn16_fwd(z, saved, training, p, seed, salt):
     return out
 
 
-def bn16_bwd(z, dy, saved, coef, bn_skip):
-    """dz16 = bf16(scale * (dy - coef0 - xhat * coef1)) from the bf16 pre-activation and the masked bf16 gradient."""
+def bn16_bwd(z, dy, saved, coef, bn_skip, out=None):
+    """dz16 = bf16(scale * (dy - coef0 - xhat * coef1)) from the bf16 pre-activation and the masked bf16 gradient.
+    `out`: a preallocated [m, width] bf16 view (any 16-byte aligned row stride)."""
     m, width = z.shape
-    out = _mem.empty((m, width), torch.bfloat16, z.device)
+    if out is None:
+        out = _mem.empty((m, width), torch.bfloat16, z.device)
     sv = _rows(saved, 4)
     args = _lib.Bn16Args(m, width, 1 if bn_skip else 0, z.data_ptr(), z.stride(0), sv[2], sv[3], 0.0, 0, 0, None,
-                         out.data_ptr(), width, dy.data_ptr(), dy.stride(0), sv[0], sv[1], coef.data_ptr())
+                         out.data_ptr(), out.stride(0), dy.data_ptr(), dy.stride(0), sv[0], sv[1], coef.data_ptr())
     _lib.check(_lib.load().aread_bn16(ctypes.byref(args), _stream(z.device)))
     return out
 

@@ -33,6 +33,8 @@ USE_HEI_LAYER = os.environ.get("AREAD_HEI_FUSED", "1") != "0"
 # sequence is recorded once and replayed from then on: the activation arena makes every address repeat, the dropout
 # seed lives in device memory (dense_kernels.SEED_PTR), the ids are copied into a fixed buffer.
 USE_GRAPHS = os.environ.get("AREAD_GRAPHS", "1") != "0"
+# skinny products of the row pass (linear / gates / cross / heads) on the tensor cores (AREAD_TC_ROWPASS=0: CUDA cores)
+TC_ROWPASS = os.environ.get("AREAD_TC_ROWPASS", "1") != "0"
 GRAPH_AFTER = 2
 # a mask handed in as `current_mask=` is a candidate of the HEMP search: each one is evaluated about
 # regroup_eval_step (5) times (run.py:649-655), so recording it costs more than it saves
@@ -81,9 +83,11 @@ class GraphCache:
         e.last_use = self.clock
         return e
 
-    def recorded(self, serial):
-        """True when some entry of the mask with this serial holds a recorded forward."""
-        return any(k[0] == serial and e.fwd is not None for k, e in self.entries.items())
+    def recorded(self, serial, shape, training):
+        """True when an entry of the mask with this serial, for batches of this shape in this mode, holds a
+        recorded forward."""
+        return any(k[0] == serial and k[1] == tuple(shape) and k[2] == training and e.fwd is not None
+                   for k, e in self.entries.items())
 
     def table_grad(self, like):
         """ONE gradient buffer for the embedding table, shared by every recorded backward: a table-sized buffer per
@@ -329,8 +333,11 @@ class AreadNode(torch.autograd.Function):
         # ---- lookup
         plan = model.embedding.plan(dev)
         table = model.embedding.embedding_dict.weight
-        embed, xb = embedding_ops.gather(plan, table, x, want_bf16=True, want_lo=precise, fence=False)
+        embed, xb = embedding_ops.gather(plan, table, x, want_bf16=True, want_lo=True, fence=False)
         X = embed.view(B, E)
+        x_hi, x_lo = xb                     # X = hi + lo (bf16 each): operands of the tensor-core products
+        if not precise:
+            xb = x_hi
 
         # ---- which towers run
         active = [list(range(n)) for n in n_tower] if info is None else info.active_idx
@@ -359,10 +366,18 @@ class AreadNode(torch.autograd.Function):
         gate = _mem.empty((B, len(a0), n_expert), torch.float32, dev)
         alpha = _mem.empty((B, n_cross + 1), torch.float32, dev)
         head_cross = _mem.empty((B, len(a_last)), torch.float32, dev)
-        ra = rowpass_ops._args(B, E, layout, ldp, x=X, w=w_cat, offset=offset, p=p_dots, lin=lin, gate=gate,
-                               alpha=alpha, head=head_cross)
+        # the [B, E] x [E, nj] product on the tensor cores with split operands (hi.hi + hi.lo + lo.hi: fp32-grade,
+        # ~2^-16 relative), the per-row epilogue on the CUDA cores; 'bf16x3' keeps the all-fp32 kernels of rowpass.cu
+        tc_row = TC_ROWPASS and not precise and nj <= 32 and E % 8 == 0
+        if tc_row:
+            wc_hi, wc_lo = dk.split_bf16(w_cat)
+            dk.grouped_linear(x_hi, wc_hi, None, nj, E, 1, 0, out=p_dots, a_lo=x_lo, w_lo=wc_lo)
+            sv.update(wc_hi=wc_hi, wc_lo=wc_lo, x_hi=x_hi, x_lo=x_lo)
+        ra = rowpass_ops._args(B, E, layout, ldp, x=None if tc_row else X, w=None if tc_row else w_cat, offset=offset,
+                               p=p_dots, lin=lin, gate=gate, alpha=alpha, head=head_cross)
         _lib.check(_lib.load().aread_rowpass_fwd(ctypes.byref(ra), _stream(dev)))
-        sv.update(X=X, w_cat=w_cat, p_dots=p_dots, gate=gate, alpha=alpha, beta=beta, w_out=w_out, layout=layout, ldp=ldp)
+        sv.update(X=X, w_cat=w_cat, p_dots=p_dots, gate=gate, alpha=alpha, beta=beta, w_out=w_out, layout=layout, ldp=ldp,
+                  tc_row=tc_row)
 
         # ---- experts (tensor cores) + MMoE mixture
         G = P.experts[0].groups
@@ -578,6 +593,21 @@ class AreadNode(torch.autograd.Function):
                                         P.experts[-1].salt)
         expert_grads = [None] * len(P.experts)
         d_x = None
+        layout, ldp, tc_row = sv["layout"], sv["ldp"], sv["tc_row"]
+        nj = sv["w_cat"].shape[0]
+        d_p = _mem.empty((B, ldp), torch.float32, dev)
+        d_c = _mem.empty((B, ldp), torch.float32, dev)
+        L0 = P.experts[0]
+        k_ext = G * L0.n + 96            # expert layer-1 gradient [B, 4*256] extended by the split row-pass gradient
+        dz0 = None
+        if tc_row:
+            # per-row prologue of the row pass now: its d_p rides along the expert layer-1 data gradient GEMM as 96
+            # extra reduction columns ([hi | hi | lo] against the weight rows [hi ; lo ; hi])
+            dz0 = _mem.empty((B, k_ext), torch.bfloat16, dev)
+            ra = rowpass_ops._args(B, E, layout, ldp, x=None, p=sv["p_dots"], gate=sv["gate"], alpha=sv["alpha"],
+                                   d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p, d_c=d_c)
+            ra.dp16, ra.ld16 = dz0.data_ptr() + G * L0.n * 2, k_ext
+            _lib.check(_lib.load().aread_rowpass_bwd(ctypes.byref(ra), _stream(dev)))
 
         def tr(w, fn):
             return tuple(fn(t) for t in w) if isinstance(w, tuple) else fn(w)
@@ -600,9 +630,12 @@ class AreadNode(torch.autograd.Function):
             # bf16 experts.  Last layer: its gradient arrives in fp32 from the mixture.  Every other layer: the data
             # gradient GEMM of the layer above masks it (ReLU, dropout), sums the BatchNorm reductions in its epilogue
             # and stores it once as bf16; the weight is read in place as a k-by-n operand (no transposed copies).
+            n_l = len(P.experts)
             L = P.experts[-1]
-            dze, d_gamma, d_beta, d_bias = dk.bn_act_bwd(ex[-1][1], d_act, ex[-1][2], bn_skip, p_drop, seed, L.salt)
-            for i in range(len(P.experts) - 1, -1, -1):
+            out0 = dz0[:, :G * L0.n] if (tc_row and n_l == 1) else None
+            dze, d_gamma, d_beta, d_bias = dk.bn_act_bwd(ex[-1][1], d_act, ex[-1][2], bn_skip, p_drop, seed, L.salt,
+                                                         dz_out=out0)
+            for i in range(n_l - 1, -1, -1):
                 L = P.experts[i]
                 a_in, z, stats, w = ex[i]
                 d_w = dk.grouped_wgrad(dze, a_in, L.n, L.k, G, 0 if i == 0 else L.k)
@@ -613,28 +646,42 @@ class AreadNode(torch.autograd.Function):
                     dy, partial = dk.expert_dgrad_bn_bwd(dze, w, L.k, L.n, G, z_p, stats_p, p_drop, Lp.salt, seed)
                     coef, g3 = dk.expert_bn_bwd_finalize(partial, B, G * L.k, bn_skip)
                     d_gamma, d_beta, d_bias = g3[0], g3[1], g3[2]
-                    dze = dk.bn16_bwd(z_p, dy, stats_p, coef, bn_skip)
+                    dze = dk.bn16_bwd(z_p, dy, stats_p, coef, bn_skip,
+                                      out=dz0[:, :G * L0.n] if (tc_row and i == 1) else None)
+                elif tc_row:
+                    # weight rows [W_layer1 (k-by-n) ; Wcat_hi ; Wcat_lo ; Wcat_hi]: ONE GEMM returns d_x of both paths
+                    w_ext = _mem.empty((k_ext, E), torch.bfloat16, dev)
+                    w_ext[:G * L.n].copy_(w)
+                    base = G * L.n
+                    w_ext[base:base + nj].copy_(sv["wc_hi"])
+                    w_ext[base + 32:base + 32 + nj].copy_(sv["wc_lo"])
+                    w_ext[base + 64:base + 64 + nj].copy_(sv["wc_hi"])
+                    if nj < 32:
+                        for o in (0, 32, 64):
+                            w_ext[base + o + nj:base + o + 32].zero_()
+                    d_x = dk.expert_dgrad_plain(dz0, w_ext, E, k_ext)
                 else:
                     d_x = dk.expert_dgrad_plain(dze, w, L.k, G * L.n)
 
         # ---- row pass
-        layout, ldp = sv["layout"], sv["ldp"]
-        nj = sv["w_cat"].shape[0]
-        d_p = _mem.empty((B, ldp), torch.float32, dev)
-        d_c = _mem.empty((B, ldp), torch.float32, dev)
-        d_x_row = _mem.empty((B, E), torch.float32, dev)
-        d_wcat = torch.empty((nj, E), dtype=torch.float32, device=dev)                   # parameter gradients
-        need = int(_lib.load().aread_rowpass_workspace_bytes(B, E, nj))
-        ws = _mem.workspace("rowpass", dev, need)
-        ra = rowpass_ops._args(B, E, layout, ldp, x=X, w=sv["w_cat"], p=sv["p_dots"], gate=sv["gate"], alpha=sv["alpha"],
-                               d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p, d_c=d_c, d_x=d_x_row, d_w=d_wcat,
-                               workspace=ws)
-        ra.workspace_bytes = ws.numel()
-        _lib.check(_lib.load().aread_rowpass_bwd(ctypes.byref(ra), _stream(dev)))
+        if tc_row:
+            # d_w[j, :] = sum_b d_p[b, j] X[b, :] on the tensor cores, split operands on both sides
+            dp_hi, dp_lo = dz0[:, G * L0.n:G * L0.n + 32], dz0[:, G * L0.n + 64:G * L0.n + 96]
+            d_wcat = dk.grouped_wgrad(dp_hi, sv["x_hi"], 32, E, 1, 0, dz_lo=dp_lo, a_lo=sv["x_lo"])[:nj]
+        else:
+            d_x_row = _mem.empty((B, E), torch.float32, dev)
+            d_wcat = torch.empty((nj, E), dtype=torch.float32, device=dev)                   # parameter gradients
+            need = int(_lib.load().aread_rowpass_workspace_bytes(B, E, nj))
+            ws = _mem.workspace("rowpass", dev, need)
+            ra = rowpass_ops._args(B, E, layout, ldp, x=X, w=sv["w_cat"], p=sv["p_dots"], gate=sv["gate"],
+                                   alpha=sv["alpha"], d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p, d_c=d_c,
+                                   d_x=d_x_row, d_w=d_wcat, workspace=ws)
+            ra.workspace_bytes = ws.numel()
+            _lib.check(_lib.load().aread_rowpass_bwd(ctypes.byref(ra), _stream(dev)))
+            d_x = d_x.add_(d_x_row)
         d_off = d_c[:, :nj].sum(dim=0)
 
         # ---- gradient w.r.t. the embedding output -> table
-        d_x = d_x.add_(d_x_row)
         if d_q is not None:
             d_x.view(B, -1, D)[:, model.domain_idx, :] += d_q[:, :D]
         plan = model.embedding.plan(dev)

@@ -543,6 +543,15 @@ typedef struct aread_rowpass_args {
   float* d_w;            /* backward out [columns, e]                                              */
   void* workspace;       /* aread_rowpass_workspace_bytes(m, e, columns)                           */
   size_t workspace_bytes;
+  /* Tensor-core variant: with x == NULL the skinny products are NOT evaluated here.  Forward: `p` is an input
+     (X . W^T from aread_grouped_linear_bf16 with split operands) and only the per-row epilogue runs.  Backward: only
+     the per-row prologue runs (d_p, d_c) and, when dp16 is set, d_p is also written as split bf16 operands for the
+     tensor-core products d_x = d_p . W and d_w = d_p^T . X:
+       dp16[b, 0:32] = hi, dp16[b, 32:64] = hi, dp16[b, 64:96] = lo   (hi = bf16(d_p), lo = bf16(d_p - hi); columns
+     beyond the last dot product are zero), row stride ld16 elements -- the layout that extends the expert layer-1
+     gradient [m, 4*256 | 96] so that ONE data-gradient GEMM returns the sum of both paths.                     */
+  uint16_t* dp16;
+  int64_t ld16;
 } aread_rowpass_args;
 
 AREAD_API size_t aread_rowpass_workspace_bytes(int64_t m, int32_t e, int32_t n_cols);

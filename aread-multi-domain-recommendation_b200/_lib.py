@@ -188,6 +188,25 @@ class Bn16Args(Structure):
                 ("mean", c_void_p), ("rstd", c_void_p), ("coef", c_void_p)]
 
 
+_L, _J = 4, 3        # AREAD_MIXED_MAX_LEVEL, AREAD_MIXED_MAX_LAYER
+
+
+class HeiMixedArgs(Structure):
+    _fields_ = [("m", c_int64), ("n_level", c_int32), ("n_layer", c_int32), ("n_tower", c_int32 * _L),
+                ("width_in", c_int32), ("dims", (c_int32 * _J) * _L), ("n_domain", c_int32), ("edge_words", c_int32),
+                ("bn_skip", c_int32), ("eps", c_float), ("domain", c_void_p), ("domain_stride", c_int64),
+                ("active", c_void_p), ("edges", c_void_p), ("t0", c_void_p), ("logits", c_void_p * _L),
+                ("weight", (c_void_p * _J) * _L), ("bias", (c_void_p * _J) * _L), ("gamma", (c_void_p * _J) * _L),
+                ("beta", (c_void_p * _J) * _L), ("running_mean", (c_void_p * _J) * _L),
+                ("running_var", (c_void_p * _J) * _L), ("head_cross", c_void_p), ("lin", c_void_p), ("w_tail", c_void_p),
+                ("y", c_void_p), ("y_stack", c_void_p)]
+
+
+class DomainMeanArgs(Structure):
+    _fields_ = [("m", c_int64), ("width", c_int32), ("n_domain", c_int32), ("values", c_void_p), ("ld", c_int64),
+                ("domain", c_void_p), ("domain_stride", c_int64), ("mean", c_void_p), ("count", c_void_p)]
+
+
 class MultiCopyArgs(Structure):
     _fields_ = [("n_tensors", c_int32), ("n_chunks", c_int64), ("dst", c_void_p), ("src", c_void_p),
                 ("bytes", c_void_p), ("chunk_start", c_void_p)]
@@ -229,6 +248,9 @@ _SIGNATURES = {
     "aread_expert_bn_finalize": (c_int32, [POINTER(ExpertBnFinalizeArgs), c_void_p]),
     "aread_expert_bn_bwd_finalize": (c_int32, [POINTER(ExpertBnBwdFinalizeArgs), c_void_p]),
     "aread_bn16": (c_int32, [POINTER(Bn16Args), c_void_p]),
+    "aread_hei_mixed_eval_supported": (c_int32, [POINTER(HeiMixedArgs)]),
+    "aread_hei_mixed_eval": (c_int32, [POINTER(HeiMixedArgs), c_void_p]),
+    "aread_domain_mean": (c_int32, [POINTER(DomainMeanArgs), c_void_p]),
     "aread_l2_reg_chunk": (c_int64, []),
     "aread_bn_act_apply": (c_int32, [POINTER(BnActArgs), c_void_p]),
     "aread_bn_bwd_coef": (c_int32, [POINTER(BnActBwdArgs), c_void_p, c_void_p]),

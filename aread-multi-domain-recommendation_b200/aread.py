@@ -125,6 +125,7 @@ class AREAD(BaseModel):
         object.__setattr__(self, "_graphs", fused.GraphCache())
         object.__setattr__(self, "_rollback", None)
         object.__setattr__(self, "_wcast", None)
+        object.__setattr__(self, "_mixed_tables", {})
 
     @staticmethod
     def bagging_loss(y_stack, targets):
@@ -203,7 +204,7 @@ class AREAD(BaseModel):
         memo[id(self)] = clone
         for k, v in self.__dict__.items():
             if k not in ("_packs", "_expert_layers", "_tower_layers", "_fused", "_fused_params", "_slot_cache", "_arenas", "_graphs",
-                         "_rollback", "_wcast"):
+                         "_rollback", "_wcast", "_mixed_tables"):
                 setattr(clone, k, copy.deepcopy(v, memo))
         clone._build_packs()
         return clone
@@ -238,6 +239,15 @@ class AREAD(BaseModel):
                                       may_record=current_mask is None)
         self._store_gate_means(out, info, domain_i, memory_gate_value, tmp_memory_gate_value)
         return out.probs if mode == 'domain_mask_bagging' else out.probs.mean(dim=0)
+
+    def forward_mixed(self, x, return_stack=False):
+        """Eval-mode 'domain_with_mask' for a batch that MIXES domains: row b is evaluated under
+        `domain_mask[x[b, domain_idx]]`, all rows in one launch sequence (mixed_ops.py, csrc/mixed.cu).  Equals calling
+        `forward(x_d, mode='domain_with_mask', domain_i=d)` once per domain (run.py:719-727) row for row; rows sorted
+        by domain let the kernel skip the (tile, tower) pairs their masks prune.  Returns y [B] (and, with
+        return_stack, y_stack [n_tower[-1], B] with zeros for pruned heads)."""
+        from . import mixed_ops
+        return mixed_ops.forward_mixed_eval(self, x, want_stack=return_stack)
 
     def hier_tower_mask_forward(self, d, tower_inputs, gate_inputs, domain_cn_out, domain_linear_out,
                                 single_domain_mask, memory_gate_value=False, tmp_memory_gate_value=False):
@@ -283,13 +293,21 @@ class AREAD(BaseModel):
                 for t in range(self.n_tower[l]):
                     self.domain_tower_gate_values[domain_i][l][t].append(means[:, t].clone())
             return
-        domain_ids = x[:, self.domain_idx]
-        for d in range(self.n_domain):
-            sel = (domain_ids == d)
-            for l in range(1, self.n_level):
-                means = gates[l][sel].mean(dim=0)
-                for t in range(self.n_tower[l]):
-                    self.domain_tower_gate_values[d][l][t].append(means[:, t].clone())
+        # mixed batch: per-domain means of every gate in ONE launch per level (csrc/mixed.cu domain_mean_kernel)
+        # instead of n_domain x levels x towers boolean-index reductions; a domain without rows records NaN, the
+        # mean of an empty selection, like the reference
+        from . import embedding_ops, mixed_ops
+        xi = embedding_ops.prepare_ids(x, self.embedding.embedding_dict.weight)
+        for l in range(1, self.n_level):
+            g = gates[l]                                                   # [B, n_{l-1}, n_l]
+            n_prev, n_l = g.shape[1], g.shape[2]
+            mean, count = mixed_ops.domain_means(g.reshape(g.shape[0], n_prev * n_l), xi, self.domain_idx, self.n_domain)
+            mean = torch.where(count.view(-1, 1) > 0, mean, torch.full_like(mean, float('nan')))
+            cols = mean.view(self.n_domain, n_prev, n_l).permute(0, 2, 1).contiguous()   # [d, t, n_prev]
+            for d, per_tower in enumerate(cols.unbind(0)):
+                log = self.domain_tower_gate_values[d][l]
+                for t, v in enumerate(per_tower.unbind(0)):
+                    log[t].append(v)
 
     # --------------------------------------------------------------------------- HEMP bookkeeping
     def add_eval_loss(self, loss_mean, d, mask_z):                                   # aread.py:324-328

@@ -661,6 +661,73 @@ typedef struct aread_gate_mix_args {
 AREAD_API int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Mixed-domain batches (BASELINE.json north_star: "domain-sorted, segment-offset grouped ... skips expert/domain
+ * tiles zeroed by the HEMP mask").
+ *
+ * aread_hei_mixed_eval: model/aread.py:263-322 (hier_tower_mask_forward) + the 'domain_with_mask' head
+ * (aread.py:224-234) in EVAL mode for rows of many domains at once: row b runs under the mask of domain[b].  Eval
+ * mode is row-local (BatchNorm on running statistics, no dropout), so the result equals the reference called once
+ * per domain (run.py:719-727) row for row.  Masks arrive as bit tables per domain:
+ *   active[d, l]            bit t = tower t of level l runs        (any edge enters it, aread.py:268)
+ *   edges[d, e]             for level l >= 1, tower t: word e = (sum_{1<=l'<l} n_tower[l']) + t, bit j = edge from
+ *                           tower j of level l-1 (the mask column mask[l][:, t])
+ * Rows whose domain id is outside [0, n_domain) produce y = 0.  (tile, tower) pairs that are pruned for every row
+ * of a 32-row tile are skipped, so domain-sorted input skips most pruned work.
+ * ---------------------------------------------------------------------------------------------- */
+#define AREAD_MIXED_MAX_LEVEL 4
+#define AREAD_MIXED_MAX_LAYER 3
+typedef struct aread_hei_mixed_args {
+  int64_t m;
+  int32_t n_level;                 /* <= AREAD_MIXED_MAX_LEVEL                                       */
+  int32_t n_layer;                 /* Linear layers per tower MLP, <= AREAD_MIXED_MAX_LAYER          */
+  int32_t n_tower[AREAD_MIXED_MAX_LEVEL];
+  int32_t width_in;                /* level-0 input width (expert output width)                      */
+  int32_t dims[AREAD_MIXED_MAX_LEVEL][AREAD_MIXED_MAX_LAYER];   /* tower_dims[l][j], multiples of 4  */
+  int32_t n_domain;
+  int32_t edge_words;              /* uint32 words per domain in `edges`: sum_{l>=1} n_tower[l]      */
+  int32_t bn_skip;                 /* 1: BatchNorm is the identity (batch of one, layer.py:226)      */
+  float eps;
+  const int32_t* domain;           /* domain id of row b at domain[b * domain_stride]                */
+  int64_t domain_stride;
+  const uint32_t* active;          /* [n_domain, n_level]                                            */
+  const uint32_t* edges;           /* [n_domain, edge_words]                                         */
+  const float* t0;                 /* [m, n_tower[0], width_in] level-0 tower inputs (MMoE mixture)  */
+  const float* logits[AREAD_MIXED_MAX_LEVEL];      /* l >= 1: gate Linear outputs [m, n_tower[l], n_tower[l-1]] */
+  const float* weight[AREAD_MIXED_MAX_LEVEL][AREAD_MIXED_MAX_LAYER];        /* packed [n_tower[l], N, K]       */
+  const float* bias[AREAD_MIXED_MAX_LEVEL][AREAD_MIXED_MAX_LAYER];          /* [n_tower[l], N] each            */
+  const float* gamma[AREAD_MIXED_MAX_LEVEL][AREAD_MIXED_MAX_LAYER];
+  const float* beta[AREAD_MIXED_MAX_LEVEL][AREAD_MIXED_MAX_LAYER];
+  const float* running_mean[AREAD_MIXED_MAX_LEVEL][AREAD_MIXED_MAX_LAYER];
+  const float* running_var[AREAD_MIXED_MAX_LEVEL][AREAD_MIXED_MAX_LAYER];
+  const float* head_cross;         /* [m, n_last] cross-network part of the heads (aread_rowpass_fwd) */
+  const float* lin;                /* [m]                                                            */
+  const float* w_tail;             /* [n_last, w_last] columns of towers_linear on the tower output  */
+  float* y;                        /* out [m]: mean over the row's active heads                      */
+  float* y_stack;                  /* optional out [n_last, m]: per-head probabilities (0: pruned)   */
+} aread_hei_mixed_args;
+
+AREAD_API int aread_hei_mixed_eval_supported(const aread_hei_mixed_args* args);
+AREAD_API int aread_hei_mixed_eval(const aread_hei_mixed_args* args, aread_stream_t stream);
+
+/* mean[d, :] = mean over the rows b with domain[b] == d of values[b, :], rows added in batch order (deterministic);
+ * count[d] = number of such rows (mean = 0 when there are none).  Replaces the per-domain boolean-index loop that
+ * records unmasked gate values for a mixed batch (model/aread.py:187-200).                                       */
+#define AREAD_DOMAIN_MEAN_MAX_COLS 512
+typedef struct aread_domain_mean_args {
+  int64_t m;
+  int32_t width;                   /* columns, <= AREAD_DOMAIN_MEAN_MAX_COLS */
+  int32_t n_domain;
+  const float* values;             /* [m, ld]                                */
+  int64_t ld;
+  const int32_t* domain;           /* domain[b * domain_stride]              */
+  int64_t domain_stride;
+  float* mean;                     /* out [n_domain, width]                  */
+  int32_t* count;                  /* optional out [n_domain]                */
+} aread_domain_mean_args;
+
+AREAD_API int aread_domain_mean(const aread_domain_mean_args* args, aread_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Adam step over a list of fp32 tensors in one launch (coupled weight decay).  Replaces
  * torch.optim.Adam.step as the trainer configures it (run.py:830-831: betas (0.9, 0.99), eps 1e-8,
  * weight_decay 1e-8) -- SURVEY.md 8(f) rank 1.  Tensors without a gradient this step are left out of

@@ -31,6 +31,7 @@ def struct_fields(name):
         if not decl:
             continue
         # "float momentum, eps, dropout_p" declares several fields
+        decl = re.sub(r"\[[^\]]*\]", "", decl)                  # array extents: `int32_t dims[4][3]` declares `dims`
         names = [re.search(r"(\w+)\s*$", part.strip()).group(1) for part in decl.split(",")]
         fields.extend(names)
     return fields

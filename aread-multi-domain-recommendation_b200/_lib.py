@@ -47,7 +47,7 @@ class GroupedLinearArgs(Structure):
     _fields_ = [("m", c_int64), ("n", c_int32), ("k", c_int32), ("groups", c_int32), ("a_group_cols", c_int32),
                 ("group_mask", c_uint64), ("a", c_void_p), ("lda", c_int64), ("b", c_void_p), ("ldb", c_int64),
                 ("bias", c_void_p), ("c_f32", c_void_p), ("c_bf16", c_void_p), ("ldc", c_int64),
-                ("a_lo", c_void_p), ("b_lo", c_void_p)]
+                ("a_lo", c_void_p), ("b_lo", c_void_p), ("lo_lo", c_int32)]
 
 
 class GroupedWgradArgs(Structure):
@@ -90,7 +90,8 @@ class RowpassArgs(Structure):
                 ("p", c_void_p), ("lin", c_void_p), ("gate", c_void_p), ("alpha", c_void_p), ("head", c_void_p),
                 ("d_lin", c_void_p), ("d_gate", c_void_p), ("d_head", c_void_p), ("d_p", c_void_p),
                 ("d_c", c_void_p), ("d_x", c_void_p), ("d_w", c_void_p), ("workspace", c_void_p),
-                ("workspace_bytes", c_size_t), ("dp16", c_void_p), ("ld16", c_int64)]
+                ("workspace_bytes", c_size_t), ("dp16", c_void_p), ("ld16", c_int64), ("n_extra", c_int32),
+                ("dp16_width", c_int32)]
 
 
 class L2RegArgs(Structure):
@@ -150,7 +151,8 @@ class GateMixArgs(Structure):
     _fields_ = [("m", c_int64), ("n_tower", c_int32), ("n_prev", c_int32), ("n_prev_active", c_int32),
                 ("width", c_int32), ("logits", c_void_p), ("edges", c_void_p), ("prev_slot", c_void_p),
                 ("slot_tower", c_void_p), ("u_prev", c_void_p), ("out", c_void_p), ("sm", c_void_p),
-                ("d_out", c_void_p), ("d_logits", c_void_p), ("d_u_prev", c_void_p), ("r_scratch", c_void_p)]
+                ("d_out", c_void_p), ("d_logits", c_void_p), ("d_u_prev", c_void_p), ("r_scratch", c_void_p),
+                ("ld_logits", c_int64), ("logit_offset", c_void_p), ("ld_dlogits", c_int64)]
 
 
 class AdamArgs(Structure):

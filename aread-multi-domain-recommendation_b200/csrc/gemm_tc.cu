@@ -166,8 +166,8 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int a_col0 = c.g * p.a_group_cols;
         const int b_row0 = B_MN ? c.g * p.k : c.g * p.n + c.n_t * BN;
         for (int seg = 0; seg < p.n_seg; ++seg) {
-          const CUtensorMap* ma = seg < 2 ? &map_a : &map_a_lo;
-          const CUtensorMap* mb = seg == 1 ? &map_b_lo : &map_b;
+          const CUtensorMap* ma = seg < 2 ? &map_a : &map_a_lo;            // hi.hi, hi.lo, lo.hi, lo.lo
+          const CUtensorMap* mb = (seg & 1) ? &map_b_lo : &map_b;
           for (int kb = 0; kb < p.n_k_blocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::kStageBytes;
@@ -749,14 +749,14 @@ extern "C" int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, 
   p.total_tiles = static_cast<int64_t>(p.n_m_tiles) * p.n_active * p.n_n_tiles;
 
   AREAD_REQUIRE((a.a_lo != nullptr) == (a.b_lo != nullptr), "grouped_linear: a_lo and b_lo go together");
-  p.n_seg = a.a_lo != nullptr ? 3 : 1;
+  p.n_seg = a.a_lo != nullptr ? (a.lo_lo ? 4 : 3) : 1;
   CUtensorMap ma, mb, ma_lo, mb_lo;
   const int64_t a_cols = a.a_group_cols == 0 ? a.k : static_cast<int64_t>(a.a_group_cols) * (a.groups - 1) + a.k;
   if (int rc = make_map(&ma, a.a, a.m, a_cols, a.lda, BM)) return rc;
   if (int rc = make_map(&mb, a.b, static_cast<int64_t>(a.groups) * a.n, a.k, a.ldb, bn)) return rc;
   ma_lo = ma;
   mb_lo = mb;
-  if (p.n_seg == 3) {
+  if (p.n_seg >= 3) {
     AREAD_REQUIRE(reinterpret_cast<uintptr_t>(a.a_lo) % 16 == 0 && reinterpret_cast<uintptr_t>(a.b_lo) % 16 == 0,
                   "grouped_linear: lo operands must be 16-byte aligned");
     if (int rc = make_map(&ma_lo, a.a_lo, a.m, a_cols, a.lda, BM)) return rc;

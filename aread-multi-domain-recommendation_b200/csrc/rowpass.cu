@@ -159,18 +159,21 @@ __global__ void __launch_bounds__(kThreads) rowpass_prologue_bwd_kernel(const ar
       dc[c_cross + k] = ds;
       d_alpha = fmaf(ds, p[c_cross + k], d_alpha);
     }
-    for (int j = c_head + nh; j < a.ldp; ++j) {
+    const int n_own = c_head + nh, n_all = n_own + a.n_extra;
+    for (int j = n_own; j < n_all; ++j) dc[j] = dp[j];      // riding dot products: d_p was written by their owner
+    for (int j = n_all; j < a.ldp; ++j) {
       dp[j] = 0.f;
       dc[j] = 0.f;
     }
-    if (a.dp16 != nullptr) {   // split bf16 operands of the tensor-core products: [hi | hi | lo], 32 columns each
+    if (a.dp16 != nullptr) {   // split bf16 operands of the tensor-core products: [hi | hi | lo], W columns each
+      const int W = a.dp16_width > 0 ? a.dp16_width : 32;
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.dp16) + b * a.ld16;
-      for (int j = 0; j < 32; ++j) {
-        const float v = j < c_head + nh ? dp[j] : 0.f;
+      for (int j = 0; j < W; ++j) {
+        const float v = j < n_all ? dp[j] : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         o[j] = hi;
-        o[32 + j] = hi;
-        o[64 + j] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        o[W + j] = hi;
+        o[2 * W + j] = __float2bfloat16_rn(v - __bfloat162float(hi));
       }
     }
   }
@@ -293,7 +296,9 @@ int aread_rowpass_fwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   AREAD_REQUIRE(args != nullptr, "rowpass_fwd: null args");
   const aread_rowpass_args& a = *args;
   const int nj = 1 + a.n_gate * a.n_expert + a.n_cross + a.n_head;
-  AREAD_REQUIRE(a.m >= 0 && a.e > 0 && nj <= a.ldp, "rowpass_fwd: bad shape (e=%d, columns=%d, ldp=%d)", a.e, nj, a.ldp);
+  AREAD_REQUIRE(a.m >= 0 && a.e > 0 && nj + a.n_extra <= a.ldp && a.n_extra >= 0,
+                "rowpass_fwd: bad shape (e=%d, columns=%d + %d, ldp=%d)", a.e, nj, a.n_extra, a.ldp);
+  AREAD_REQUIRE(a.n_extra == 0 || a.x == nullptr, "rowpass_fwd: riding dot products need the tensor-core variant (x == NULL)");
   if (a.m == 0) return AREAD_OK;
   AREAD_REQUIRE((a.x == nullptr || a.w) && a.offset && a.p && a.lin && a.alpha, "rowpass_fwd: null pointer");
   AREAD_REQUIRE((a.gate || a.n_gate * a.n_expert == 0) && (a.head || a.n_head == 0), "rowpass_fwd: null output");
@@ -317,7 +322,8 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   AREAD_REQUIRE(args != nullptr, "rowpass_bwd: null args");
   const aread_rowpass_args& a = *args;
   const int nj = 1 + a.n_gate * a.n_expert + a.n_cross + a.n_head;
-  AREAD_REQUIRE(a.m >= 0 && a.e > 0 && nj <= a.ldp, "rowpass_bwd: bad shape");
+  AREAD_REQUIRE(a.m >= 0 && a.e > 0 && a.n_extra >= 0 && nj + a.n_extra <= a.ldp, "rowpass_bwd: bad shape");
+  AREAD_REQUIRE(a.n_extra == 0 || a.x == nullptr, "rowpass_bwd: riding dot products need the tensor-core variant (x == NULL)");
   AREAD_REQUIRE(a.e <= 16 * kChunk, "rowpass_bwd: embedding row of %d floats is too wide (max %d)", a.e, 16 * kChunk);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const unsigned pgrid = static_cast<unsigned>((a.m + kThreads - 1) / kThreads < kNumSMs * 8
@@ -325,7 +331,11 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
                                                    : kNumSMs * 8);
   if (a.x == nullptr) {  // per-row prologue only: the products run on the tensor cores
     AREAD_REQUIRE(a.d_p && a.d_c, "rowpass_bwd: null pointer");
-    AREAD_REQUIRE(a.dp16 == nullptr || (nj <= 32 && a.ld16 >= 96), "rowpass_bwd: dp16 holds at most 32 dot products");
+    {
+      const int w16 = a.dp16_width > 0 ? a.dp16_width : 32;
+      AREAD_REQUIRE(a.dp16 == nullptr || (w16 % 32 == 0 && nj + a.n_extra <= w16 && a.ld16 >= 3 * w16),
+                    "rowpass_bwd: dp16 thirds of %d columns cannot hold %d dot products", w16, nj + a.n_extra);
+    }
     if (a.m == 0) return AREAD_OK;
     AREAD_REQUIRE(a.p && a.alpha && (a.gate || a.n_gate * a.n_expert == 0), "rowpass_bwd: null pointer");
     AREAD_LAUNCH(rowpass_prologue_bwd_kernel, pgrid, kThreads, 0, stream, a);

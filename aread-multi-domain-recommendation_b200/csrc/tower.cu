@@ -200,6 +200,22 @@ __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__
   }
 }
 
+// logits of `rows` samples (row stride ld_logits, optional additive offset per logit) -> sS[(r * NT + t)][NPp]
+__device__ __forceinline__ void stage_logits(float* sS, const aread_gate_mix_args& a, int64_t b0, int rows, int LP, int NP,
+                                             int NPp) {
+  const int64_t ld = a.ld_logits > 0 ? a.ld_logits : LP;
+  for (int i = threadIdx.x; i < kGateRows * LP; i += kThreads) {
+    const int r = i / LP, c = i - r * LP;
+    float v = 0.f;
+    if (r < rows) {
+      v = __ldg(a.logits + (b0 + r) * ld + c);
+      if (a.logit_offset != nullptr) v += __ldg(a.logit_offset + c);
+    }
+    const int q = i / NP;
+    sS[q * NPp + (i - q * NP)] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) gate_mix_fwd_kernel(const aread_gate_mix_args a) {
   extern __shared__ float smem[];
   const int NT = a.n_tower, NP = a.n_prev, NA = a.n_prev_active, W = a.width;
@@ -212,7 +228,7 @@ __global__ void __launch_bounds__(kThreads) gate_mix_fwd_kernel(const aread_gate
   int* sSlot = reinterpret_cast<int*>(sE + LP);  // [NP]
   const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kGateRows;
   const int rows = a.m - b0 < kGateRows ? static_cast<int>(a.m - b0) : kGateRows;
-  stage_rows(sS, a.logits + b0 * LP, static_cast<int64_t>(rows) * LP, kGateRows * LP, NP, NPp);
+  stage_logits(sS, a, b0, rows, LP, NP, NPp);
   if (UP > 0) stage_rows(sU, a.u_prev + b0 * UP, static_cast<int64_t>(rows) * UP, kGateRows * UP, W, Wp);
   for (int i = threadIdx.x; i < LP; i += kThreads) sE[i] = a.edges ? __ldg(a.edges + i) : 1.f;
   for (int i = threadIdx.x; i < NP; i += kThreads) sSlot[i] = __ldg(a.prev_slot + i);
@@ -256,7 +272,7 @@ __global__ void __launch_bounds__(kThreads) gate_mix_bwd_kernel(const aread_gate
   int* sTower = sSlot + NP;
   const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kGateRows;
   const int rows = a.m - b0 < kGateRows ? static_cast<int>(a.m - b0) : kGateRows;
-  stage_rows(sS, a.logits + b0 * LP, static_cast<int64_t>(rows) * LP, kGateRows * LP, NP, NPp);
+  stage_logits(sS, a, b0, rows, LP, NP, NPp);
   if (UP > 0) stage_rows(sU, a.u_prev + b0 * UP, static_cast<int64_t>(rows) * UP, kGateRows * UP, W, Wp);
   stage_rows(sG, a.d_out + b0 * OP, static_cast<int64_t>(rows) * OP, kGateRows * OP, W, Wp);
   for (int i = threadIdx.x; i < LP; i += kThreads) sE[i] = a.edges ? __ldg(a.edges + i) : 1.f;
@@ -290,10 +306,12 @@ __global__ void __launch_bounds__(kThreads) gate_mix_bwd_kernel(const aread_gate
     for (int j = 0; j < NP; ++j) s[j] = s[j] * (dr[j] - dot_s);
   }
   __syncthreads();
-  float* d_logits = a.d_logits + b0 * LP;
-  for (int i = threadIdx.x; i < rows * LP; i += kThreads) {
-    const int q = i / NP;
-    d_logits[i] = sS[q * NPp + (i - q * NP)];
+  {
+    const int64_t ldd = a.ld_dlogits > 0 ? a.ld_dlogits : LP;
+    for (int i = threadIdx.x; i < rows * LP; i += kThreads) {
+      const int q = i / NP, r = i / LP;
+      a.d_logits[(b0 + r) * ldd + (i - r * LP)] = sS[q * NPp + (i - q * NP)];
+    }
   }
   if (UP > 0 && a.d_u_prev != nullptr) {
     float* d_u = a.d_u_prev + b0 * UP;

@@ -18,7 +18,7 @@ def split_bf16(x):
 
 
 def grouped_linear(a, w, bias, n, k, groups, a_group_cols=0, group_mask=None, out=None, out_dtype=torch.float32,
-                   a_lo=None, w_lo=None):
+                   a_lo=None, w_lo=None, lo_lo=False):
     """C[:, g*n:(g+1)*n] = A[:, g*a_group_cols : +k] @ W[g*n:(g+1)*n, :k]^T (+ bias) for active groups.
 
     a: bf16 [m, lda]; w: bf16 [groups*n, ldb]; bias: fp32 [groups*n] or None.  Columns of masked-out
@@ -37,7 +37,8 @@ def grouped_linear(a, w, bias, n, k, groups, a_group_cols=0, group_mask=None, ou
         bias.data_ptr() if bias is not None else None,
         out.data_ptr() if out.dtype == torch.float32 else None,
         out.data_ptr() if out.dtype == torch.bfloat16 else None, out.stride(0),
-        a_lo.data_ptr() if a_lo is not None else None, w_lo.data_ptr() if w_lo is not None else None)
+        a_lo.data_ptr() if a_lo is not None else None, w_lo.data_ptr() if w_lo is not None else None,
+        1 if (lo_lo and a_lo is not None) else 0)
     if a_lo is not None:
         assert a_lo.stride() == a.stride() and w_lo.stride() == w.stride()
     _lib.check(_lib.load().aread_grouped_linear_bf16(ctypes.byref(args), _stream(a.device)))

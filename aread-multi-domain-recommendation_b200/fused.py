@@ -147,29 +147,46 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def gate_mix_fwd(logits, edges, prev_slot, u_prev, n_prev_active, width, want_sm, sm_escapes=False):
-    B, na, n_prev = logits.shape
+def _logit_geometry(logits, na, n_prev):
+    """(pointer, row stride or 0) of gate logits given as [B, na, n_prev] (contiguous) or as a [B, na * n_prev] column
+    slice of a wider matrix."""
+    if logits.dim() == 3:
+        return logits.data_ptr(), 0
+    assert logits.shape[1] == na * n_prev and logits.stride(1) == 1
+    return logits.data_ptr(), logits.stride(0)
+
+
+def gate_mix_fwd(logits, na, n_prev, edges, prev_slot, u_prev, n_prev_active, width, want_sm, sm_escapes=False,
+                 logit_offset=None):
+    B = logits.shape[0]
     out = _mem.empty((B, na, width), torch.float32, logits.device)
     sm = None
     if want_sm:       # gates handed back to the caller must not live in the arena
         sm = (torch.empty((B, na, n_prev), dtype=torch.float32, device=logits.device) if sm_escapes
               else _mem.empty((B, na, n_prev), torch.float32, logits.device))
-    a = _lib.GateMixArgs(B, na, n_prev, n_prev_active, width, logits.data_ptr(),
+    lptr, ld = _logit_geometry(logits, na, n_prev)
+    a = _lib.GateMixArgs(B, na, n_prev, n_prev_active, width, lptr,
                          edges.data_ptr() if edges is not None else None, prev_slot.data_ptr(), None,
-                         u_prev.data_ptr(), out.data_ptr(), sm.data_ptr() if want_sm else None, None, None, None, None)
+                         u_prev.data_ptr(), out.data_ptr(), sm.data_ptr() if want_sm else None, None, None, None, None,
+                         ld, logit_offset.data_ptr() if logit_offset is not None else None, 0)
     _lib.check(_lib.load().aread_gate_mix(ctypes.byref(a), _stream(logits.device)))
     return out, sm
 
 
-def gate_mix_bwd(logits, edges, prev_slot, slot_tower, u_prev, d_out):
-    B, na, n_prev = logits.shape
+def gate_mix_bwd(logits, na, n_prev, edges, prev_slot, slot_tower, u_prev, d_out, logit_offset=None, d_logits=None):
+    """-> (d_logits, d_u_prev).  `d_logits`: a preallocated [B, na * n_prev] column slice to write into."""
+    B = logits.shape[0]
     nap, width = u_prev.shape[1], u_prev.shape[2]
     dev = logits.device
-    d_logits = _mem.empty((B, na, n_prev), torch.float32, dev)
+    if d_logits is None:
+        d_logits = _mem.empty((B, na, n_prev), torch.float32, dev)
     d_u = _mem.empty((B, nap, width), torch.float32, dev)
-    a = _lib.GateMixArgs(B, na, n_prev, nap, width, logits.data_ptr(), edges.data_ptr() if edges is not None else None,
+    lptr, ld = _logit_geometry(logits, na, n_prev)
+    dptr, ldd = _logit_geometry(d_logits, na, n_prev)
+    a = _lib.GateMixArgs(B, na, n_prev, nap, width, lptr, edges.data_ptr() if edges is not None else None,
                          prev_slot.data_ptr(), slot_tower.data_ptr(), u_prev.data_ptr(), None, None, d_out.data_ptr(),
-                         d_logits.data_ptr(), d_u.data_ptr(), None)
+                         dptr, d_u.data_ptr(), None, ld,
+                         logit_offset.data_ptr() if logit_offset is not None else None, ldd)
     _lib.check(_lib.load().aread_gate_mix(ctypes.byref(a), _stream(dev)))
     return d_logits, d_u
 
@@ -347,18 +364,42 @@ class AreadNode(torch.autograd.Function):
         n_expert = len(model.mmoe_experts)
         n_cross = model.cn.num_layers
 
-        # ---- row pass: [linear | gates of active level-0 towers | cross | heads of active last-level towers]
+        # ---- mean group embedding of the active level-0 towers (second half of the HEI gate input q)
+        if info is None:
+            grp = torch.zeros(D, dtype=torch.float32, device=dev)
+        else:
+            grp = model.group_embedding.weight.index_select(0, info.group_index(dev)).mean(dim=0)
+
+        # ---- row pass: [linear | gates of active level-0 towers | cross | heads of active last-level towers] and,
+        # riding behind them, the HEI gate logits: q = [X[:, domain field] | grp], so W_gate . q is a dot product of
+        # the embedding row (weights outside the domain field's columns are zero) plus a row-independent constant
         w_out = _sel(P.tl_w.flat, index[-1])[:, 0, :]                                  # [na_last, E + w]
-        w_cat = torch.cat([model.linear.fc.weight, _sel(P.mmoe_w.flat, index[0]).reshape(-1, E),
-                           P.cn_w.flat.view(n_cross, E), w_out[:, :E]], dim=0)
+        w_rows = [model.linear.fc.weight, _sel(P.mmoe_w.flat, index[0]).reshape(-1, E),
+                  P.cn_w.flat.view(n_cross, E), w_out[:, :E]]
         beta = torch.cumsum(P.cn_b.flat, dim=0)                                          # beta_{k+1} = b_0 + .. + b_k
         kappa = torch.zeros(n_cross, dtype=torch.float32, device=dev)
         if n_cross > 1:
             kappa[1:] = (P.cn_w.flat.view(n_cross, E)[1:] * beta[:-1]).sum(dim=1)
         beta_n = beta[-1] if n_cross > 0 else torch.zeros(E, dtype=torch.float32, device=dev)
-        offset = torch.cat([model.linear.fc.bias, _sel(P.mmoe_b.flat, index[0]).reshape(-1), kappa,
-                            w_out[:, :E] @ beta_n], dim=0)
+        offs = [model.linear.fc.bias, _sel(P.mmoe_b.flat, index[0]).reshape(-1), kappa, w_out[:, :E] @ beta_n]
         layout = (len(a0), n_expert, n_cross, len(a_last))
+        nj_own = 1 + len(a0) * n_expert + n_cross + len(a_last)
+        n_gate_logits = sum(len(active[l]) * n_tower[l - 1] for l in range(1, n_level))
+        tc_row = TC_ROWPASS and E % 8 == 0 and nj_own <= 128
+        ride = tc_row and n_gate_logits > 0 and nj_own + n_gate_logits <= 128
+        gate_cols = [None] * n_level                                                     # (first column, wg) per level
+        if ride:
+            dom0, col = model.domain_idx * D, nj_own
+            for l in range(1, n_level):
+                wg = _sel(P.gate_w[l].flat, index[l])                                     # [na, n_prev, 2D]
+                bg = _sel(P.gate_b[l].flat, index[l])
+                n_rows = wg.shape[0] * wg.shape[1]
+                w_rows.append(torch.nn.functional.pad(wg[:, :, :D].reshape(n_rows, D), (dom0, E - dom0 - D)))
+                offs.append(bg.reshape(-1) + wg[:, :, D:].reshape(n_rows, D) @ grp)
+                gate_cols[l] = (col, wg)
+                col += n_rows
+        w_cat = torch.cat(w_rows, dim=0)
+        offset = torch.cat(offs, dim=0)
         nj = w_cat.shape[0]
         ldp = (nj + 3) // 4 * 4
         p_dots = _mem.empty((B, ldp), torch.float32, dev)
@@ -366,33 +407,37 @@ class AreadNode(torch.autograd.Function):
         gate = _mem.empty((B, len(a0), n_expert), torch.float32, dev)
         alpha = _mem.empty((B, n_cross + 1), torch.float32, dev)
         head_cross = _mem.empty((B, len(a_last)), torch.float32, dev)
-        # the [B, E] x [E, nj] product on the tensor cores with split operands (hi.hi + hi.lo + lo.hi: fp32-grade,
-        # ~2^-16 relative), the per-row epilogue on the CUDA cores; 'bf16x3' keeps the all-fp32 kernels of rowpass.cu
-        tc_row = TC_ROWPASS and not precise and nj <= 32 and E % 8 == 0
+        # the [B, E] x [E, nj] product on the tensor cores with split operands (hi.hi + hi.lo + lo.hi + lo.lo into one
+        # fp32 accumulator: the full product of the split values), the per-row epilogue on the CUDA cores
+        # (AREAD_TC_ROWPASS=0 keeps the all-fp32 CUDA-core kernels of rowpass.cu)
         if tc_row:
             wc_hi, wc_lo = dk.split_bf16(w_cat)
-            dk.grouped_linear(x_hi, wc_hi, None, nj, E, 1, 0, out=p_dots, a_lo=x_lo, w_lo=wc_lo)
+            dk.grouped_linear(x_hi, wc_hi, None, nj, E, 1, 0, out=p_dots, a_lo=x_lo, w_lo=wc_lo, lo_lo=True)
             sv.update(wc_hi=wc_hi, wc_lo=wc_lo, x_hi=x_hi, x_lo=x_lo)
         ra = rowpass_ops._args(B, E, layout, ldp, x=None if tc_row else X, w=None if tc_row else w_cat, offset=offset,
                                p=p_dots, lin=lin, gate=gate, alpha=alpha, head=head_cross)
+        ra.n_extra = nj - nj_own
         _lib.check(_lib.load().aread_rowpass_fwd(ctypes.byref(ra), _stream(dev)))
         sv.update(X=X, w_cat=w_cat, p_dots=p_dots, gate=gate, alpha=alpha, beta=beta, w_out=w_out, layout=layout, ldp=ldp,
-                  tc_row=tc_row)
+                  tc_row=tc_row, ride=ride, nj_own=nj_own, offset=offset, gate_cols=gate_cols, grp=grp)
 
         # ---- experts (tensor cores) + MMoE mixture
         G = P.experts[0].groups
         a_op = xb
         ex = []
-        if precise:
+        # the fused epilogues store 64-column bf16 chunks: narrower expert layers keep the unfused kernels
+        fused_bn = not precise and all(L.n % 64 == 0 for L in P.experts)
+        sv["fused_bn"] = fused_bn
+        if not fused_bn:
             for i, L in enumerate(P.experts):
-                w = dk.split_bf16(L.weight.rows())
+                w = dk.split_bf16(L.weight.rows()) if precise else L.weight.rows().to(torch.bfloat16)
                 z = dk.grouped_linear(_hi(a_op), _hi(w), L.bias.rows(), L.n, L.k, G, 0 if i == 0 else L.k,
                                       a_lo=_lo(a_op), w_lo=_lo(w))
                 last = i == len(P.experts) - 1
                 res = dk.bn_act_fwd(z, L.gamma.rows(), L.beta.rows(), L.running_mean.rows(), L.running_var.rows(),
                                     training, bn_skip, p_drop, seed, L.salt, None if last else torch.bfloat16,
-                                    want_lo=not last)
-                out, stats = (res[0], res[-1]) if last else ((res[0], res[1]), res[2])
+                                    want_lo=precise and not last)
+                out, stats = (res[0], res[-1]) if not (precise and not last) else ((res[0], res[1]), res[2])
                 if training and not bn_skip:
                     torch._foreach_add_(L.tracked, 1)
                 ex.append((a_op, z, stats, w))
@@ -423,11 +468,9 @@ class AreadNode(torch.autograd.Function):
         sv["experts"] = ex
 
         # ---- gate inputs q = [domain embedding | mean group embedding of the active level-0 towers]
-        if info is None:
-            grp = torch.zeros(D, dtype=torch.float32, device=dev)
-        else:
-            grp = model.group_embedding.weight.index_select(0, info.group_index(dev)).mean(dim=0)
-        q = torch.cat([embed[:, model.domain_idx, :], grp.expand(B, D)], dim=1)          # [B, 2D]
+        q = None
+        if not ride:
+            q = torch.cat([embed[:, model.domain_idx, :], grp.expand(B, D)], dim=1)      # [B, 2D]
         sv["q"] = q
 
         # ---- HEI levels on compact activations
@@ -438,19 +481,25 @@ class AreadNode(torch.autograd.Function):
             rec = {}
             if l > 0:
                 n_prev = n_tower[l - 1]
-                wg, bg = _sel(P.gate_w[l].flat, idx), _sel(P.gate_b[l].flat, idx)
-                # all gates of the level share the input q: ONE [B, 2D] x [2D, na * n_prev] product
-                if len(act) * n_prev <= 128:
-                    logits = tower_ops.tower_linear(q, wg.view(1, len(act) * n_prev, -1), bg.reshape(-1),
-                                                    len(act) * n_prev, groups=1).view(B, len(act), n_prev)
+                logit_offset = None
+                if ride:        # the logits are columns of the row-pass product; the constants are added on the fly
+                    col, wg = gate_cols[l]
+                    logits = p_dots[:, col:col + len(act) * n_prev]
+                    logit_offset = offset[col:col + len(act) * n_prev]
                 else:
-                    logits = tower_ops.tower_linear(q, wg, bg.reshape(-1), n_prev, groups=len(act))
+                    wg, bg = _sel(P.gate_w[l].flat, idx), _sel(P.gate_b[l].flat, idx)
+                    # all gates of the level share the input q: ONE [B, 2D] x [2D, na * n_prev] product
+                    if len(act) * n_prev <= 128:
+                        logits = tower_ops.tower_linear(q, wg.view(1, len(act) * n_prev, -1), bg.reshape(-1),
+                                                        len(act) * n_prev, groups=1).view(B, len(act), n_prev)
+                    else:
+                        logits = tower_ops.tower_linear(q, wg, bg.reshape(-1), n_prev, groups=len(act))
                 edges = None if info is None else _sel(info.edges(l, dev).t().contiguous(), idx)
                 prev_slot, slot_tower = cfg["slots"][l]
                 want_sm = cfg["want_gate_means"] or cfg["want_gates"]
                 u_prev = h
-                h, sm = gate_mix_fwd(logits, edges, prev_slot, u_prev, len(active[l - 1]), u_prev.shape[2], want_sm,
-                                     sm_escapes=cfg["want_gates"])
+                h, sm = gate_mix_fwd(logits, len(act), n_prev, edges, prev_slot, u_prev, len(active[l - 1]),
+                                     u_prev.shape[2], want_sm, sm_escapes=cfg["want_gates"], logit_offset=logit_offset)
                 if cfg["want_gates"]:
                     gates[l] = sm.transpose(1, 2)                                        # [B, n_prev, n_l]
                 if cfg["want_gate_means"] and info is not None:
@@ -459,7 +508,7 @@ class AreadNode(torch.autograd.Function):
                         means = torch.zeros(n_prev, n_tower[l], dtype=torch.float32,
                                             device=dev).index_copy_(1, idx, means)
                     gate_means[l] = means
-                rec.update(wg=wg, logits=logits, edges=edges, u_prev=u_prev)
+                rec.update(wg=wg, logits=logits, logit_offset=logit_offset, edges=edges, u_prev=u_prev)
             lay = []
             na = len(act)
             hei = USE_HEI_LAYER and all(hei_ops.supported(na, L.k, L.n) for L in P.towers[l])
@@ -504,6 +553,8 @@ class AreadNode(torch.autograd.Function):
         _lib.check(_lib.load().aread_head(ctypes.byref(ha), _stream(dev)))
         sv.update(h_last=h, w_tail=w_tail, probs=probs.detach())      # detached alias: no ctx <-> output cycle
 
+        if q is None and cfg.get("want_gate_inputs"):
+            q = torch.cat([embed[:, model.domain_idx, :], grp.expand(B, D)], dim=1)
         cfg["gate_means"], cfg["gates"], cfg["gate_inputs"] = gate_means, gates, q
         ctx.cfg, ctx.sv = cfg, sv
         ctx.active, ctx.index, ctx.bn_skip = active, index, bn_skip
@@ -539,6 +590,11 @@ class AreadNode(torch.autograd.Function):
                            d_h.data_ptr(), d_w_tail.data_ptr(), ws.data_ptr(), ws.numel())
         _lib.check(_lib.load().aread_head(ctypes.byref(ha), _stream(dev)))
 
+        layout, ldp, tc_row, ride = sv["layout"], sv["ldp"], sv["tc_row"], sv["ride"]
+        nj, nj_own = sv["w_cat"].shape[0], sv["nj_own"]
+        d_p = _mem.empty((B, ldp), torch.float32, dev)     # gradient w.r.t. the row-pass products (gate logits included)
+        d_c = _mem.empty((B, ldp), torch.float32, dev)
+
         tower_grads = [[None] * len(P.towers[l]) for l in range(n_level)]
         gate_grads = [None] * n_level
         d_q = None
@@ -571,18 +627,25 @@ class AreadNode(torch.autograd.Function):
                 d_h = tower_ops.tower_linear(dzl, w, None, L.k, weight_is_out_by_in=False)
             if l > 0:
                 prev_slot, slot_tower = cfg["slots"][l]
-                d_logits, d_u = gate_mix_bwd(rec["logits"], rec["edges"], prev_slot, slot_tower, rec["u_prev"],
-                                             d_h.contiguous())
                 n_prev = n_tower[l - 1]
-                if ((na * n_prev + 3) // 4) * ((2 * D + 3) // 4) <= 256:                 # one group: q is read once
-                    d_wg = tower_ops.tower_wgrad(d_logits.view(B, 1, na * n_prev), sv["q"]).view(na, n_prev, 2 * D)
+                if ride:    # d_logits are columns of d_p: weight / input gradients come out of the row pass products
+                    col = sv["gate_cols"][l][0]
+                    _, d_u = gate_mix_bwd(rec["logits"], na, n_prev, rec["edges"], prev_slot, slot_tower, rec["u_prev"],
+                                          d_h.contiguous(), logit_offset=rec["logit_offset"],
+                                          d_logits=d_p[:, col:col + na * n_prev])
                 else:
-                    d_wg = tower_ops.tower_wgrad(d_logits, sv["q"])                      # [na, n_prev, 2D]
-                d_bg = d_logits.sum(dim=0)                                               # [na, n_prev]
-                gate_grads[l] = (d_wg, d_bg)
-                dq_l = tower_ops.tower_linear(d_logits.view(B, 1, na * n_prev), rec["wg"].reshape(1, na * n_prev, 2 * D),
-                                              None, 2 * D, weight_is_out_by_in=False).view(B, 2 * D)
-                d_q = dq_l if d_q is None else d_q + dq_l
+                    d_logits, d_u = gate_mix_bwd(rec["logits"], na, n_prev, rec["edges"], prev_slot, slot_tower,
+                                                 rec["u_prev"], d_h.contiguous())
+                    if ((na * n_prev + 3) // 4) * ((2 * D + 3) // 4) <= 256:             # one group: q is read once
+                        d_wg = tower_ops.tower_wgrad(d_logits.view(B, 1, na * n_prev), sv["q"]).view(na, n_prev, 2 * D)
+                    else:
+                        d_wg = tower_ops.tower_wgrad(d_logits, sv["q"])                  # [na, n_prev, 2D]
+                    d_bg = d_logits.sum(dim=0)                                           # [na, n_prev]
+                    gate_grads[l] = (d_wg, d_bg)
+                    dq_l = tower_ops.tower_linear(d_logits.view(B, 1, na * n_prev),
+                                                  rec["wg"].reshape(1, na * n_prev, 2 * D), None, 2 * D,
+                                                  weight_is_out_by_in=False).view(B, 2 * D)
+                    d_q = dq_l if d_q is None else d_q + dq_l
                 d_h = d_u
 
         # ---- experts
@@ -593,30 +656,40 @@ class AreadNode(torch.autograd.Function):
                                         P.experts[-1].salt)
         expert_grads = [None] * len(P.experts)
         d_x = None
-        layout, ldp, tc_row = sv["layout"], sv["ldp"], sv["tc_row"]
-        nj = sv["w_cat"].shape[0]
-        d_p = _mem.empty((B, ldp), torch.float32, dev)
-        d_c = _mem.empty((B, ldp), torch.float32, dev)
         L0 = P.experts[0]
-        k_ext = G * L0.n + 96            # expert layer-1 gradient [B, 4*256] extended by the split row-pass gradient
+        fused_bn = sv["fused_bn"]
+        w16 = (nj + 31) // 32 * 32       # columns of each third of the split row-pass gradient
+        c0 = G * L0.n if fused_bn else 0 # with the fused expert path the split rides behind the layer-1 gradient
+        k_ext = c0 + 3 * w16             # [B, 4*256 | hi | hi | lo]
         dz0 = None
         if tc_row:
-            # per-row prologue of the row pass now: its d_p rides along the expert layer-1 data gradient GEMM as 96
-            # extra reduction columns ([hi | hi | lo] against the weight rows [hi ; lo ; hi])
+            # per-row prologue of the row pass now.  Its d_p becomes split bf16 operands [hi | hi | lo] which, against
+            # the weight rows [hi ; lo ; hi], give d_x of the row pass on the tensor cores -- as extra reduction columns
+            # of the expert layer-1 data gradient GEMM when that runs in the fused bf16 path
             dz0 = _mem.empty((B, k_ext), torch.bfloat16, dev)
             ra = rowpass_ops._args(B, E, layout, ldp, x=None, p=sv["p_dots"], gate=sv["gate"], alpha=sv["alpha"],
                                    d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p, d_c=d_c)
-            ra.dp16, ra.ld16 = dz0.data_ptr() + G * L0.n * 2, k_ext
+            ra.dp16, ra.ld16, ra.n_extra, ra.dp16_width = dz0.data_ptr() + c0 * 2, k_ext, nj - nj_own, w16
             _lib.check(_lib.load().aread_rowpass_bwd(ctypes.byref(ra), _stream(dev)))
+
+        def split_weight_rows(w_ext, base):
+            """rows [Wcat_hi ; Wcat_lo ; Wcat_hi] (w16 each, zero padded) of the data-gradient weight operand"""
+            w_ext[base:base + nj].copy_(sv["wc_hi"])
+            w_ext[base + w16:base + w16 + nj].copy_(sv["wc_lo"])
+            w_ext[base + 2 * w16:base + 2 * w16 + nj].copy_(sv["wc_hi"])
+            if nj < w16:
+                for o in (0, w16, 2 * w16):
+                    w_ext[base + o + nj:base + o + w16].zero_()
 
         def tr(w, fn):
             return tuple(fn(t) for t in w) if isinstance(w, tuple) else fn(w)
 
-        if precise:
+        if not sv["fused_bn"]:
             for i in range(len(P.experts) - 1, -1, -1):
                 L = P.experts[i]
                 a_in, z, stats, w = ex[i]
-                dze, d_gamma, d_beta, d_bias = dk.bn_act_bwd(z, d_act, stats, bn_skip, p_drop, seed, L.salt, want_lo=True)
+                dze, d_gamma, d_beta, d_bias = dk.bn_act_bwd(z, d_act, stats, bn_skip, p_drop, seed, L.salt,
+                                                             want_lo=precise)
                 d_w = dk.grouped_wgrad(_hi(dze), _hi(a_in), L.n, L.k, G, 0 if i == 0 else L.k, dz_lo=_lo(dze),
                                        a_lo=_lo(a_in))
                 expert_grads[i] = (d_w.view(G, L.n, L.k), d_bias.view(G, L.n), d_gamma.view(G, L.n), d_beta.view(G, L.n))
@@ -652,13 +725,7 @@ class AreadNode(torch.autograd.Function):
                     # weight rows [W_layer1 (k-by-n) ; Wcat_hi ; Wcat_lo ; Wcat_hi]: ONE GEMM returns d_x of both paths
                     w_ext = _mem.empty((k_ext, E), torch.bfloat16, dev)
                     w_ext[:G * L.n].copy_(w)
-                    base = G * L.n
-                    w_ext[base:base + nj].copy_(sv["wc_hi"])
-                    w_ext[base + 32:base + 32 + nj].copy_(sv["wc_lo"])
-                    w_ext[base + 64:base + 64 + nj].copy_(sv["wc_hi"])
-                    if nj < 32:
-                        for o in (0, 32, 64):
-                            w_ext[base + o + nj:base + o + 32].zero_()
+                    split_weight_rows(w_ext, G * L.n)
                     d_x = dk.expert_dgrad_plain(dz0, w_ext, E, k_ext)
                 else:
                     d_x = dk.expert_dgrad_plain(dze, w, L.k, G * L.n)
@@ -666,8 +733,12 @@ class AreadNode(torch.autograd.Function):
         # ---- row pass
         if tc_row:
             # d_w[j, :] = sum_b d_p[b, j] X[b, :] on the tensor cores, split operands on both sides
-            dp_hi, dp_lo = dz0[:, G * L0.n:G * L0.n + 32], dz0[:, G * L0.n + 64:G * L0.n + 96]
-            d_wcat = dk.grouped_wgrad(dp_hi, sv["x_hi"], 32, E, 1, 0, dz_lo=dp_lo, a_lo=sv["x_lo"])[:nj]
+            dp_hi, dp_lo = dz0[:, c0:c0 + w16], dz0[:, c0 + 2 * w16:c0 + 3 * w16]
+            d_wcat = dk.grouped_wgrad(dp_hi, sv["x_hi"], w16, E, 1, 0, dz_lo=dp_lo, a_lo=sv["x_lo"])[:nj]
+            if not fused_bn:     # the expert data gradient ran on its own: the row pass adds its part
+                w_ext = _mem.empty((k_ext, E), torch.bfloat16, dev)
+                split_weight_rows(w_ext, 0)
+                d_x = d_x.add_(dk.expert_dgrad_plain(dz0, w_ext, E, k_ext))
         else:
             d_x_row = _mem.empty((B, E), torch.float32, dev)
             d_wcat = torch.empty((nj, E), dtype=torch.float32, device=dev)                   # parameter gradients
@@ -680,6 +751,19 @@ class AreadNode(torch.autograd.Function):
             _lib.check(_lib.load().aread_rowpass_bwd(ctypes.byref(ra), _stream(dev)))
             d_x = d_x.add_(d_x_row)
         d_off = d_c[:, :nj].sum(dim=0)
+        d_grp_vec = None if d_q is None else d_q[:, D:].sum(dim=0)          # gradient w.r.t. the mean group embedding
+        if ride:
+            # gate parameters from the riding columns: W[:, :D] from the weight gradient rows (domain field columns),
+            # W[:, D:] and the bias from the column sums (the group half of q is the same for every row)
+            dom0, grp = model.domain_idx * D, sv["grp"]
+            d_grp_vec = torch.zeros(D, dtype=torch.float32, device=dev)
+            for l in range(1, n_level):
+                col, wg = sv["gate_cols"][l]
+                na, n_prev = wg.shape[0], wg.shape[1]
+                seg = d_off[col:col + na * n_prev]
+                d_wg = torch.cat([d_wcat[col:col + na * n_prev, dom0:dom0 + D], seg[:, None] * grp[None, :]], dim=1)
+                gate_grads[l] = (d_wg.view(na, n_prev, 2 * D), seg.view(na, n_prev))
+                d_grp_vec = d_grp_vec + seg @ wg[:, :, D:].reshape(na * n_prev, D)
 
         # ---- gradient w.r.t. the embedding output -> table
         if d_q is not None:
@@ -694,8 +778,8 @@ class AreadNode(torch.autograd.Function):
         d_lin_w, d_lin_b = d_wcat[0:1], d_off[0:1]
         d_mmoe_w, d_mmoe_b = d_wcat[1:c_cross].view(na0, n_expert, E), d_off[1:c_cross].view(na0, n_expert)
         d_cn_w = d_wcat[c_cross:c_head].clone()                                          # [nc, E]
-        d_head_w = d_wcat[c_head:]                                                       # [na_last, E]
-        d_kappa, d_rho = d_off[c_cross:c_head], d_off[c_head:]
+        d_head_w = d_wcat[c_head:nj_own]                                                 # [na_last, E]
+        d_kappa, d_rho = d_off[c_cross:c_head], d_off[c_head:nj_own]
         beta, w_out = sv["beta"], sv["w_out"]
         cn_w = P.cn_w.flat.view(n_cross, E)
         # kappa_k = w_k . beta_{k-1}(cum) ; rho_t = w_out_t[:E] . beta_n
@@ -711,10 +795,10 @@ class AreadNode(torch.autograd.Function):
 
         # ---- group embedding
         d_grp_w = None
-        if info is not None and d_q is not None:
+        if info is not None and d_grp_vec is not None:
             d_grp_w = torch.zeros_like(model.group_embedding.weight)
             gi = info.group_index(dev)
-            d_grp_w.index_add_(0, gi, (d_q[:, D:].sum(dim=0) / gi.numel()).expand(gi.numel(), D))
+            d_grp_w.index_add_(0, gi, (d_grp_vec / gi.numel()).expand(gi.numel(), D))
         elif info is not None:
             d_grp_w = torch.zeros_like(model.group_embedding.weight)
 

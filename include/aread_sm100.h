@@ -166,6 +166,7 @@ typedef struct aread_grouped_linear_args {
   const uint16_t* b_lo; /* x = hi + lo with hi = bf16(x), lo = bf16(x - hi).  When given, the product
                            is a.b + a.b_lo + a_lo.b (three tensor-core passes into one accumulator):
                            fp32-grade results (~2^-16 relative) instead of bf16 operand rounding   */
+  int32_t lo_lo;        /* 1: also add a_lo.b_lo (a fourth pass): the full product of the split operands  */
 } aread_grouped_linear_args;
 
 AREAD_API int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, aread_stream_t stream);
@@ -547,11 +548,17 @@ typedef struct aread_rowpass_args {
      (X . W^T from aread_grouped_linear_bf16 with split operands) and only the per-row epilogue runs.  Backward: only
      the per-row prologue runs (d_p, d_c) and, when dp16 is set, d_p is also written as split bf16 operands for the
      tensor-core products d_x = d_p . W and d_w = d_p^T . X:
-       dp16[b, 0:32] = hi, dp16[b, 32:64] = hi, dp16[b, 64:96] = lo   (hi = bf16(d_p), lo = bf16(d_p - hi); columns
-     beyond the last dot product are zero), row stride ld16 elements -- the layout that extends the expert layer-1
-     gradient [m, 4*256 | 96] so that ONE data-gradient GEMM returns the sum of both paths.                     */
+       dp16[b, 0:W] = hi, dp16[b, W:2W] = hi, dp16[b, 2W:3W] = lo   (hi = bf16(d_p), lo = bf16(d_p - hi); W =
+     dp16_width; columns beyond the last dot product are zero), row stride ld16 elements -- the layout that extends
+     the expert layer-1 gradient [m, 4*256 | 3W] so that ONE data-gradient GEMM returns the sum of both paths.   */
   uint16_t* dp16;
   int64_t ld16;
+  /* n_extra further dot products ride along behind the heads (the HEI gate logits, whose input is a slice of the
+     embedding row): forward, p[:, cols .. cols + n_extra) is left to the caller; backward, d_p of those columns is
+     an INPUT (written by aread_gate_mix) that is copied to d_c and into the split.  dp16_width = columns of each
+     third of the split, a multiple of 32 >= cols + n_extra (0 = 32).                                           */
+  int32_t n_extra;
+  int32_t dp16_width;
 } aread_rowpass_args;
 
 AREAD_API size_t aread_rowpass_workspace_bytes(int64_t m, int32_t e, int32_t n_cols);
@@ -656,6 +663,10 @@ typedef struct aread_gate_mix_args {
   float* d_logits;          /* backward out [m, n_tower, n_prev]                */
   float* d_u_prev;          /* backward out [m, n_prev_active, width]           */
   float* r_scratch;         /* unused (kept for layout stability); may be NULL  */
+  /* Logits that live inside a wider matrix (the gate Linear evaluated as extra columns of the row pass):         */
+  int64_t ld_logits;        /* row stride of `logits` in floats; 0 = n_tower * n_prev (contiguous)               */
+  const float* logit_offset;/* optional [n_tower * n_prev] added to the logits (bias + row-independent part)      */
+  int64_t ld_dlogits;       /* row stride of `d_logits`; 0 = contiguous                                           */
 } aread_gate_mix_args;
 
 AREAD_API int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t stream);

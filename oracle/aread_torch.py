@@ -48,6 +48,11 @@ class Spec:
     # "bf16 experts" (BASELINE.json configs[1]): inputs and weights of the expert Linear layers are
     # rounded to bf16 (round to nearest even), products and sums stay fp32.  None = the reference's fp32.
     expert_operand_dtype: Optional[torch.dtype] = None
+    # The CUDA path stores the bias-free pre-activation of every expert Linear ONCE, as bf16, whenever a backward may
+    # follow (csrc/gemm_tc.cu STATS epilogue); BatchNorm statistics still come from the fp32 accumulator.  Setting
+    # this reproduces that storage rounding (straight-through for the gradient); only meaningful together with
+    # expert_operand_dtype.  None = no rounding (the reference's fp32, and the CUDA inference path).
+    expert_preact_dtype: Optional[torch.dtype] = None
     flag: np.ndarray = field(init=False)
 
     def __post_init__(self):
@@ -93,7 +98,8 @@ def _drop(h, p, training, masks, key):
     return h * keep / (1.0 - p)
 
 
-def mlp(sd, prefix, h, n_layers, training, p=0.0, masks=None, update_stats=True, operand_dtype=None):
+def mlp(sd, prefix, h, n_layers, training, p=0.0, masks=None, update_stats=True, operand_dtype=None,
+        preact_dtype=None):
     """(Linear -> BatchNorm1d -> ReLU -> Dropout) x n; BN skipped when the batch is one row
     (layer.py:209-215, 225-228).  Running statistics in `sd` are updated in place in training."""
     for i in range(n_layers):
@@ -102,6 +108,22 @@ def mlp(sd, prefix, h, n_layers, training, p=0.0, masks=None, update_stats=True,
         if operand_dtype is not None:      # rounding is not differentiated through (straight-through)
             h = h + (h.to(operand_dtype).to(h.dtype) - h).detach()
             w = w + (w.to(operand_dtype).to(w.dtype) - w).detach()
+        if preact_dtype is not None and h.shape[0] != 1 and training:
+            # what the kernels normalise: the rounded bias-free accumulator, with the statistics of the unrounded one
+            bias, bn = sd[f"{prefix}.layers.{li}.bias"], f"{prefix}.layers.{li + 1}"
+            acc = F.linear(h, w)
+            acc_r = acc + (acc.to(preact_dtype).to(acc.dtype) - acc).detach()
+            mean, var = acc.mean(dim=0), acc.var(dim=0, unbiased=False)
+            h = (acc_r - mean) * torch.rsqrt(var + BN_EPS) * sd[bn + ".weight"] + sd[bn + ".bias"]
+            if update_stats:
+                m = acc.shape[0]
+                with torch.no_grad():
+                    sd[bn + ".running_mean"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * (mean + bias))
+                    sd[bn + ".running_var"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var * (m / max(m - 1, 1)))
+                sd[bn + ".num_batches_tracked"] += 1
+            h = torch.relu(h)
+            h = _drop(h, p, training, masks, f"{prefix}.{i}")
+            continue
         h = F.linear(h, w, sd[f"{prefix}.layers.{li}.bias"])
         if h.shape[0] != 1:
             bn = f"{prefix}.layers.{li + 1}"
@@ -136,7 +158,7 @@ def trunk(sd, spec, x, training, masks=None, update_stats=True):
     lin = X @ sd["linear.fc.weight"].t() + sd["linear.fc.bias"]
     cn = cross(sd, spec, X)
     hs = [mlp(sd, f"mmoe_experts.{k}", X, len(spec.expert_dims), training, spec.dropout, masks, update_stats,
-              spec.expert_operand_dtype)
+              spec.expert_operand_dtype, spec.expert_preact_dtype)
           for k in range(spec.n_expert)]
     H = torch.stack(hs, dim=1)                                        # [B, n_expert, h]
     t0 = []

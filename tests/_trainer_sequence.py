@@ -95,6 +95,10 @@ def run_sequence(model, device, spec, cfg=SEQ, loss_fn=None):
             opt.step()
             out["warm_up"].append(float(loss))
 
+        probe = ("tower_gates.", "mmoe_gates.", "group_embedding.", "linear.", "cn.", "towers_linear.", "towers.2.0.")
+        out["after_warm_up"] = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()
+                                if k.startswith(probe) and v.numel() <= 4096 and v.is_floating_point()}
+
         # ---- regroup
         model.save_model_state()
         sigma = cfg["random_modify_sigma"] * 0.99

@@ -126,7 +126,7 @@ def test_composed_model_matches_oracle_at_baseline_shapes(name, B, active):
         # ---- train mode: forward + bagging BCE + backward (the regulariser has its own parity test)
         grads = {}
         for tag, dtype in (("fp32", None), ("bf16", torch.bfloat16)):
-            sp = O.Spec(**spec_kw, expert_operand_dtype=dtype)
+            sp = O.Spec(**spec_kw, expert_operand_dtype=dtype, expert_preact_dtype=dtype)
             sd = O.make_leaf_params(fresh(sp))
             out = O.forward(sd, sp, x, "domain_mask_bagging", mask_cpu, training=True)
             loss = O.bagging_loss(out["y"], y)          # data loss only: the dense 2*l2*W term would mask errors

@@ -65,10 +65,12 @@ def test_mixed_eval_equals_per_domain_calls(precision):
             want = model(xg[rows.to(DEV)], mode="domain_with_mask", domain_i=d).cpu()
             stack = model(xg[rows.to(DEV)], mode="domain_mask_bagging", domain_i=d).cpu()
         # same kernels up to the HEI levels; those differ in summation order only
-        assert float((_logit(y[rows]) - _logit(want)).abs().max()) <= 2e-4, f"domain {d}"
+        def same(a, b):      # fp32 summation order (BatchNorm folded into the weights vs applied afterwards)
+            return bool(((_logit(a) - _logit(b)).abs() <= 2e-4 * _logit(b).abs() + 2e-4).all())
+        assert same(y[rows], want), f"domain {d}"
         act = model.mask_info(model.domain_mask[d]).active_idx[-1]
         got_stack = y_stack[:, rows]
-        assert float((_logit(got_stack[act]) - _logit(stack)).abs().max()) <= 2e-4, f"domain {d} (heads)"
+        assert same(got_stack[act], stack), f"domain {d} (heads)"
         off = [t for t in range(spec.n_tower[-1]) if t not in act]
         assert not got_stack[off].any(), "pruned heads report 0"
         # ... and the reference arithmetic itself (oracle, fp32 on the CPU)

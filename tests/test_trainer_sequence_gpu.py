@@ -15,7 +15,7 @@ import torch
 from oracle import aread_torch as O
 from tests import _trainer_sequence as T
 from tests._models import build_model
-from tests._util import load_golden
+from tests._util import assert_after_adam, load_golden
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -38,6 +38,12 @@ def test_train_aread_sequence_matches_reference(monkeypatch, graphs):
     model.expert_precision = "bf16x3"
     got = T.run_sequence(model, torch.device(DEV), spec)
     _close(got["warm_up"], gold["warm_up"], 2e-3, "warm-up loss")
+    # parameters after the warm-up (8 Adam steps): Adam moves every element by about lr per step whatever the size of
+    # its gradient, so agreement is required to a fraction of the distance travelled (tests/_util.assert_after_adam)
+    worst = sorted(((float((got["after_warm_up"][k] - v).abs().max()), k) for k, v in gold["after_warm_up"].items()),
+                   reverse=True)[:5]
+    for k, v in gold["after_warm_up"].items():
+        assert_after_adam(got["after_warm_up"][k], {"full": v}, T.SEQ["warm_up"], T.LR, f"{k} after warm-up (worst: {worst})")
     # the quantities HEMP thresholds (batch means of the masked gate softmax) before every prune, then the prune itself
     for i, (g, r) in enumerate(zip(got["gate_log"], gold["gate_log"])):
         for l, (a, b) in enumerate(zip(g, r)):

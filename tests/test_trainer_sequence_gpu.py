@@ -4,9 +4,10 @@ training under the selected masks) replayed on the CUDA module and compared with
 reference produced for the same seeded sequence on CPU (tests/golden/trainer_seq.pt, written by
 tests/golden/make_trainer_golden.py).
 
-Experts run in 'bf16x3' (fp32-grade) so that the HEMP decisions -- quantile thresholds on recorded gate means --
-see the reference's numbers to round-off: candidate masks, pruned masks and the finally selected masks must be
-IDENTICAL; losses agree to rel 2e-3 (they pass through 8..40 Adam steps)."""
+Experts run in 'bf16x3' (fp32-grade) and the sequence uses a small learning rate (see tests/_trainer_sequence.py
+for why) so that the HEMP decisions -- quantile thresholds on recorded gate means -- see the reference's numbers to
+round-off: candidate masks, pruned masks and the finally selected masks must be IDENTICAL; losses agree to rel
+2e-3."""
 import importlib
 
 import pytest

@@ -15,10 +15,11 @@ is fp32.  Stated tolerances:
     probabilities |d| <= 1e-2, loss rel 5e-3 against the fp32 goldens;
   * against the oracle evaluated with the SAME operand rounding (Spec.expert_operand_dtype=bf16):
     probabilities |d| <= 2e-3, loss rel 1e-3, and every gradient tensor closer to that oracle than
-    max(2e-1, 1.5 x the effect the operand rounding itself has on that gradient);
+    max(1e-1 (gate parameters 3e-1), 1.5 x the effect the operand rounding itself has on that gradient);
   * |dAUC| < 1e-4 after 30 steps on identical weights.
 
 Gate-mean side outputs (the HEMP thresholds compare them) are fp32 in both modes: round-off only."""
+import os
 import re
 
 import numpy as np
@@ -34,12 +35,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 TOL = {
-    "bf16x3": dict(prob=(1e-4, 1e-4), logit=(1e-4, 2e-4), train_prob=2e-4, loss=1e-4, grad=2e-2, grad_gate=5e-2,
+    "bf16x3": dict(prob=(1e-4, 1e-4), logit=(1e-4, 2e-4), train_prob=2e-4, loss=1e-4, grad=3e-2, grad_gate=5e-2,
                    after=2e-3),
     "bf16": dict(prob=(1e-3, 1e-3), logit=(1e-3, 2e-3), train_prob=1e-2, loss=5e-3, grad=None, grad_gate=None,
                  after=1e-2),
 }
 SAME_ROUNDING_PROB_ATOL = 2e-3             # bf16 mode vs the oracle with bf16 expert operands
+# ... and its gradients, per tensor: normalised error below max(this, 1.5 x what the operand rounding itself does to
+# that tensor).  Gate parameters (their gradients are small differences of large terms) get the wider base.
+SAME_ROUNDING_GRAD, SAME_ROUNDING_GRAD_GATE = 1e-1, 3e-1
 PRE_BN_BIAS = re.compile(r"\.layers\.(0|4|8)\.bias$")
 GATE_PARAM = re.compile(r"^(tower_gates|mmoe_gates|group_embedding)\.")
 PRECISIONS = ("bf16x3", "bf16")
@@ -224,6 +228,7 @@ def test_train_step_matches_oracle_with_same_operand_rounding(name, mk):
     loss.backward()
     assert_close(preds.detach(), ref_y, 0, SAME_ROUNDING_PROB_ATOL, "y_stack")
     assert_close(loss.detach(), ref_l, 1e-3, 1e-5, "loss")
+    report, bad = [], []
     for k, p in model.named_parameters():
         ref = grads["bf16"].get(k)
         if p.grad is None:
@@ -234,8 +239,16 @@ def test_train_step_matches_oracle_with_same_operand_rounding(name, mk):
         norm = float(ref.norm()) + 1e-12
         err = float((p.grad.cpu() - ref).norm()) / norm
         rounding_effect = float((ref - grads["fp32"][k]).norm()) / norm
-        assert err < max(2e-1, 1.5 * rounding_effect), \
-            f"grad {k}: normalised error {err:.3e} (operand rounding effect {rounding_effect:.3e})"
+        base = SAME_ROUNDING_GRAD_GATE if GATE_PARAM.search(k) else SAME_ROUNDING_GRAD
+        report.append((err, rounding_effect, k))
+        if not err < max(base, 1.5 * rounding_effect):
+            bad.append(f"grad {k}: normalised error {err:.3e} (operand rounding effect {rounding_effect:.3e})")
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_same_rounding.txt"), "a") as fh:
+            for err, eff, k in sorted(report, reverse=True)[:12]:
+                fh.write(f"{name} {mk} {k}: err {err:.3e} rounding effect {eff:.3e}\n")
+    assert not bad, "; ".join(bad[:6])
 
 
 def test_auc_after_training_matches_oracle():

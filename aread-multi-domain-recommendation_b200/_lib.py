@@ -159,7 +159,8 @@ class AdamArgs(Structure):
     _fields_ = [("n_tensors", c_int32), ("n_chunks", c_int64), ("params", c_void_p), ("grads", c_void_p),
                 ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("sizes", c_void_p), ("chunk_start", c_void_p),
                 ("step_size", c_void_p), ("bc2_sqrt", c_void_p), ("beta1", c_float), ("beta2", c_float),
-                ("eps", c_float), ("weight_decay", c_float), ("l2_twice", c_void_p)]
+                ("eps", c_float), ("weight_decay", c_float), ("l2_twice", c_void_p), ("step_counts", c_void_p),
+                ("slot", c_void_p), ("lr", c_float)]
 
 
 class ExpertGemmArgs(Structure):

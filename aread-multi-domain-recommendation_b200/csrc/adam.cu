@@ -31,7 +31,15 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const aread_adam_args a)
     const float* __restrict__ g = a.grads[t];
     float* __restrict__ m = a.exp_avg[t];
     float* __restrict__ v = a.exp_avg_sq[t];
-    const float step_size = a.step_size[t], bc2_sqrt = a.bc2_sqrt[t];
+    float step_size, bc2_sqrt;
+    if (a.step_counts != nullptr) {      // counters were advanced by adam_tick_kernel, launched just before
+      const double n = static_cast<double>(a.step_counts[a.slot[t]]);
+      step_size = static_cast<float>(static_cast<double>(a.lr) / (1.0 - pow(static_cast<double>(a.beta1), n)));
+      bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.beta2), n)));
+    } else {
+      step_size = a.step_size[t];
+      bc2_sqrt = a.bc2_sqrt[t];
+    }
     const float c = a.l2_twice ? a.l2_twice[t] : 0.f;
     const int64_t begin = (chunk - a.chunk_start[t]) * kChunk;
     const int64_t end = min(a.sizes[t], begin + kChunk);
@@ -72,6 +80,11 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const aread_adam_args a)
       v[i] = vi;
     }
   }
+}
+
+__global__ void __launch_bounds__(kThreads) adam_tick_kernel(float* __restrict__ step_counts,
+                                                             const int64_t* __restrict__ slot, int n) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) step_counts[slot[t]] += 1.f;
 }
 
 constexpr int64_t kCopyChunk = 64 * 1024;   // bytes
@@ -156,10 +169,12 @@ int aread_adam_step(const aread_adam_args* args, aread_stream_t stream_) {
   AREAD_REQUIRE(args != nullptr, "adam_step: null args");
   const aread_adam_args& a = *args;
   if (a.n_tensors <= 0 || a.n_chunks <= 0) return AREAD_OK;
-  AREAD_REQUIRE(a.params && a.grads && a.exp_avg && a.exp_avg_sq && a.sizes && a.chunk_start && a.step_size &&
-                    a.bc2_sqrt,
-                "adam_step: null pointer");
+  AREAD_REQUIRE(a.params && a.grads && a.exp_avg && a.exp_avg_sq && a.sizes && a.chunk_start, "adam_step: null pointer");
+  AREAD_REQUIRE(a.step_counts ? a.slot != nullptr : (a.step_size && a.bc2_sqrt), "adam_step: null step information");
   const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+  if (a.step_counts != nullptr)   // tensors of one launch are distinct parameters: no two threads share a counter
+    AREAD_LAUNCH(adam_tick_kernel, (a.n_tensors + kThreads - 1) / kThreads, kThreads, 0,
+                 static_cast<cudaStream_t>(stream_), a.step_counts, a.slot, a.n_tensors);
   AREAD_LAUNCH(adam_kernel, static_cast<unsigned>(a.n_chunks < cap ? a.n_chunks : cap), kThreads, 0,
                static_cast<cudaStream_t>(stream_), a);
   return AREAD_OK;

@@ -35,6 +35,8 @@ USE_HEI_LAYER = os.environ.get("AREAD_HEI_FUSED", "1") != "0"
 USE_GRAPHS = os.environ.get("AREAD_GRAPHS", "1") != "0"
 # skinny products of the row pass (linear / gates / cross / heads) on the tensor cores (AREAD_TC_ROWPASS=0: CUDA cores)
 TC_ROWPASS = os.environ.get("AREAD_TC_ROWPASS", "1") != "0"
+# device address of the dropout seed while a whole train step is recorded / replayed (step_graph.py)
+STEP_SEED_PTR = None
 GRAPH_AFTER = 2
 # a mask handed in as `current_mask=` is a candidate of the HEMP search: each one is evaluated about
 # regroup_eval_step (5) times (run.py:649-655), so recording it costs more than it saves
@@ -857,6 +859,8 @@ def forward(model, x, info, want_gate_means=False, want_gates=False, want_gate_i
            "graph_after": GRAPH_AFTER if may_record else GRAPH_AFTER_CANDIDATE}
     if info is not None:
         info.warm(dev, n_level)            # device copies of the mask tables exist before any capture starts
+    if STEP_SEED_PTR is not None and seed != 0:
+        cfg["seed"], cfg["seed_ptr"] = 0, STEP_SEED_PTR
     if USE_GRAPHS and _mem.ENABLED and not want_gate_means and not want_gates:
         key = (0 if info is None else info.serial, tuple(x.shape), training, model.expert_precision,
                model.dropout_p if training else 0.0, torch.is_grad_enabled(), dev)

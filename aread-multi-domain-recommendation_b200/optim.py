@@ -36,6 +36,9 @@ class _Plan:
                 self.has_l2 = True
         self.n_chunks = start
         self.moments = [(st["exp_avg"], st["exp_avg_sq"]) for st in states]     # keeps the addresses valid
+        # CUDA-graph capture (step_graph.py): a pinned copy of the launch table whose content never changes after the
+        # capture (the recorded upload reads it at every replay) and the positions of the step counters
+        self.graph_host = self.graph_dev = self.slot_dev = None
 
 
 class MultiCopy:
@@ -121,6 +124,8 @@ class FusedAdam(torch.optim.Optimizer):
                     moments += [st["exp_avg"], st["exp_avg_sq"]]
         for arr, _ in self._steps:
             arr[:] = 0
+        for ctr in self._counters.values():
+            ctr.zero_()
         if moments:
             z = getattr(self, "_zero", None)
             if z is None or len(z.dsts) != len(moments) or any(a is not b for a, b in zip(z.dsts, moments)) \
@@ -128,10 +133,42 @@ class FusedAdam(torch.optim.Optimizer):
                 z = self._zero = MultiCopy(moments)
             z.run()
 
+    def _device_counters(self, gi, device):
+        """fp32 step counters of group gi on the device (graph replay derives the bias corrections from them); kept
+        equal to the host counters: uploaded here, then advanced on both sides by every captured / replayed step."""
+        key = (gi, device)
+        ctr = self._counters.get(key)
+        if ctr is None:
+            ctr = self._counters[key] = torch.from_numpy(self._steps[gi][0].copy()).to(device)
+        return ctr
+
+    def sync_counters(self):
+        """Host step counts -> device counters (after eager steps, load_state_dict or reset)."""
+        for (gi, device), ctr in self._counters.items():
+            ctr.copy_(torch.from_numpy(self._steps[gi][0].copy()), non_blocking=False)
+
+    def prepare_capture(self, device):
+        """Everything a recorded step needs that is a host->device copy: the device step counters (equal to the host
+        counts) and, per known launch plan, the positions of its tensors' counters."""
+        self.sync_counters()
+        for gi in range(len(self.param_groups)):
+            self._device_counters(gi, device)
+        for plan in self._plans.values():
+            if plan.slot_dev is None:
+                plan.slot_dev = torch.from_numpy(plan.idx.copy()).to(device)
+
+    def replayed(self, records):
+        """Book-keeping of a replayed whole-step graph: the host mirror of the step counters."""
+        for rec in records:
+            self._steps[rec[0]][0][rec[1].idx] += 1
+
     def _bind_steps(self):
         """state[p]["step"] (a host scalar tensor, as in torch.optim.Adam) becomes a view into one array per
         group, so that a step bumps all counters with one vector add."""
         self._steps, self._plans = [], {}
+        self._counters = getattr(self, "_counters", {})
+        self._counters.clear()
+        self.captured_plans = []
         for group in self.param_groups:
             arr = np.zeros(len(group["params"]), dtype=np.float32)
             view = torch.from_numpy(arr)
@@ -144,7 +181,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
-        self._bind_steps()
+        self._bind_steps()          # (also drops the device counters: whole-step graphs must be recorded again)
 
     def add_param_group(self, param_group):
         super().add_param_group(param_group)
@@ -195,6 +232,28 @@ class FusedAdam(torch.optim.Optimizer):
             n = len(idx)
             device = plan.params[0].device
             steps = self._steps[gi][0]
+            if torch.cuda.is_current_stream_capturing():
+                # whole-step CUDA graph: nothing of this launch may change between replays.  The table (with the
+                # gradient addresses of THIS capture) is uploaded from a pinned block that is never written again, the
+                # bias corrections come from device-side step counters
+                ctr = self._device_counters(gi, device)
+                host = torch.empty((9, n), dtype=torch.int64, pin_memory=True)
+                h = host.numpy()
+                np.copyto(h, plan.static)
+                h[1, :] = [0 if g is None else g.data_ptr() for g in grads]
+                if plan.slot_dev is None:
+                    raise RuntimeError("FusedAdam: call prepare_capture() before recording a step")
+                dev_table = torch.empty((9, n), dtype=torch.int64, device=device)
+                dev_table.copy_(host, non_blocking=True)
+                base, row = dev_table.data_ptr(), dev_table.stride(0) * 8
+                args = _lib.AdamArgs(n, plan.n_chunks, base, base + row, base + 2 * row, base + 3 * row, base + 4 * row,
+                                     base + 5 * row, None, None, beta1, beta2, eps, wd,
+                                     base + 8 * row if plan.has_l2 else None, ctr.data_ptr(), plan.slot_dev.data_ptr(), lr)
+                _lib.check(lib.aread_adam_step(ctypes.byref(args),
+                                               ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+                # the recorded upload re-reads `host` at every replay: it lives as long as the graph that owns this record
+                self.captured_plans.append((gi, plan, host, dev_table, grads))
+                continue
             steps[plan.idx] += 1
             t = steps[plan.idx].astype(np.float64)
             # rows: params, grads, exp_avg, exp_avg_sq, sizes, chunk_start (int64); step_size, bc2_sqrt, 2 * l2 (fp32).
@@ -211,7 +270,10 @@ class FusedAdam(torch.optim.Optimizer):
             base, row = dev.data_ptr(), dev.stride(0) * 8
             args = _lib.AdamArgs(n, plan.n_chunks, base, base + row, base + 2 * row, base + 3 * row, base + 4 * row,
                                  base + 5 * row, base + 6 * row, base + 7 * row, beta1, beta2, eps, wd,
-                                 base + 8 * row if plan.has_l2 else None)
+                                 base + 8 * row if plan.has_l2 else None, None, None, lr)
             _lib.check(lib.aread_adam_step(ctypes.byref(args),
                                            ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+            ctr = self._counters.get((gi, device))
+            if ctr is not None:         # an eager step between graph replays: keep the device counters in step
+                ctr.index_add_(0, torch.from_numpy(plan.idx).to(device), torch.ones(n, device=device))
         return loss

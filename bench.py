@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="bagging BCE through AREAD.bagging_loss (one kernel) or as the trainer's sum of BCELoss calls")
     ap.add_argument("--sustained-steps", type=int, default=200, help="steps of the extra.sustained leg")
+    ap.add_argument("--step-graph", default="on", choices=["on", "off"],
+                    help="the whole step (forward + loss + backward + FusedAdam) as one CUDA graph per mask "
+                         "(step_graph.GraphedTrainStep; single GPU, fused optimizer / loss / folded regulariser only)")
     return ap.parse_args()
 
 
@@ -245,8 +248,22 @@ class Trainer:
         self.crit = torch.nn.BCELoss()
         table_param = model.embedding.embedding_dict.weight
         self.dense_params = [p for p in model.parameters() if p is not table_param]
+        self.runner = None
+        if (args.step_graph == "on" and world == 1 and optimizer == "fused" and reg == "fold" and loss == "fused" and
+                graphs == "prerecord" and os.environ.get("AREAD_GRAPHS", "1") != "0"):
+            self.runner = importlib.import_module(PKG + ".step_graph").GraphedTrainStep(model, self.opt)
 
-    def record(self, x, domains, mode="domain_mask_bagging", backward=True):
+    def record(self, x, domains, mode="domain_mask_bagging", backward=True, y=None):
+        if self.runner is not None and backward and y is not None:
+            # setup: one eager pass (sizes the arena, loads every kernel) and one recording pass per distinct mask
+            seen = set()
+            for d in sorted(set(domains)):
+                serial = self.model.mask_info(self.model.domain_mask[d]).serial
+                if serial not in seen:
+                    seen.add(serial)
+                    for _ in range(3):
+                        self.runner(x, y, d)
+            return
         if self.graphs == "prerecord":
             # setup, like building the model: the per-mask CUDA-graph launch sequences are recorded once per distinct
             # mask (what a trainer does after every HEMP regroup); parameters, buffers and RNG are left untouched
@@ -256,6 +273,8 @@ class Trainer:
             self.model.record_graphs(x, domains=doms, mode=mode, backward=backward)
 
     def step(self, x, y, d):
+        if self.runner is not None:
+            return self.runner(x, y, d)
         model = self.model
         preds = model(x, mode="domain_mask_bagging", domain_i=d)
         if self.loss_kind == "fused":              # run.py:672-677 as one kernel (loss_ops.py)
@@ -321,7 +340,7 @@ def run_ours(args, wl, rank, world, local_rank):
     # ---- device-resident pass
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
-    tr.record(dev_x[0], domains)
+    tr.record(dev_x[0], domains, y=dev_y[0])
     for i in range(args.warmup):
         tr.step(dev_x[i], dev_y[i], domains[i])
     sampler = ClockSampler(local_rank)
@@ -408,7 +427,8 @@ def run_ours(args, wl, rank, world, local_rank):
         "loss": "AREAD.bagging_loss" if args.loss == "fused" else "sum of torch BCELoss",
         "l2_regulariser": "value in the loss, gradient folded into FusedAdam" if args.reg == "fold" else "autograd node",
         "cuda_graphs": ("off (AREAD_GRAPHS=0)" if os.environ.get("AREAD_GRAPHS", "1") == "0" else
-                        "per-mask forward/backward sequences, " + args.graphs),
+                        ("whole train step per mask (step_graph.GraphedTrainStep)" if tr.runner is not None else
+                         "per-mask forward/backward sequences, " + args.graphs)),
         "parallelism": f"dp{world}" + ("" if world == 1 else f" + table row-sharded over {world} GPUs (P2P lookup, "
                                        "sparse exchange of the table gradient, flat all-reduce of the rest)"),
         "l2": "inputs larger than L2: table %d MB + per-step activations" % (wl.n_rows * wl.embed_dim * 4 >> 20)})
@@ -522,7 +542,7 @@ def extra_legs(args, wl, tr, pkg, lib, ops, dev, rank, world, timed, kernel_ms, 
         n = 40
         _, hx, hy, doms = make_batches(wl, b_small, n, args.seed + 77, rank, dev)
         dx, dy = [t.to(dev) for t in hx], [t.to(dev) for t in hy]
-        tr.record(dx[0], doms)
+        tr.record(dx[0], doms, y=dy[0])
         for i in range(10):
             tr.step(dx[i], dy[i], doms[i])
         ms = timed(lambda i: tr.step(dx[i], dy[i], doms[i]), 10, n - 10)

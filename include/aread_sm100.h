@@ -760,6 +760,13 @@ typedef struct aread_adam_args {
   const float* l2_twice;         /* device [n_tensors] or NULL: 2 * l2 of an L2 regulariser folded into  */
                                  /* the step (g += l2_twice * p before the weight decay); grads[t] may   */
                                  /* be NULL for such tensors (a gradient of zero)                        */
+  /* Device-side step counters (CUDA-graph replay: nothing about the launch changes from step to step).  When
+     step_counts != NULL, step_size / bc2_sqrt are ignored: the launch first adds 1 to step_counts[slot[t]] for every
+     tensor of the list (its own tiny kernel) and every chunk derives lr / (1 - beta1^t) and sqrt(1 - beta2^t) from
+     the counter in double precision.                                                                              */
+  float* step_counts;            /* device [any]: one fp32 counter per parameter                         */
+  const int64_t* slot;           /* device [n_tensors]: index of tensor t's counter                      */
+  float lr;
 } aread_adam_args;
 
 AREAD_API int64_t aread_adam_chunk(void);

@@ -17,17 +17,18 @@ sequences of fused.py (their collectives stay outside the recorded part).
 """
 import torch
 
+from . import _lib
 from . import fused
 from . import layer
 from .optim import FusedAdam
 
 
 class _Entry:
-    __slots__ = ("graph", "x", "y", "loss", "seed", "plans", "calls")
+    __slots__ = ("graph", "x", "y", "loss", "seed", "plans", "calls", "n_launch")
 
     def __init__(self):
         self.graph = self.x = self.y = self.loss = self.seed = None
-        self.plans, self.calls = [], 0
+        self.plans, self.calls, self.n_launch = [], 0, 0
 
 
 class GraphedTrainStep:
@@ -69,6 +70,7 @@ class GraphedTrainStep:
             host[0] = int(torch.randint(0, 2 ** 62, (1,)).item())
             e.seed.copy_(host, non_blocking=True)
         e.graph.replay()
+        _lib.load().aread_launch_count_add(e.n_launch)          # the library's launches inside the recorded step
         self.opt.replayed(e.plans)
         model.embedding.plan(x.device).post_lookup(layer.BOUNDS_MODE)
         return e.loss
@@ -84,6 +86,7 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         n0 = len(opt.captured_plans)
+        launches0 = _lib.launch_count()
         use_graphs, bounds, seed_ptr = fused.USE_GRAPHS, layer.BOUNDS_MODE, fused.STEP_SEED_PTR
         fused.USE_GRAPHS, layer.BOUNDS_MODE, fused.STEP_SEED_PTR = False, "off", e.seed.data_ptr()
         try:
@@ -96,6 +99,8 @@ class GraphedTrainStep:
                 e.loss = loss.detach().reshape(())
         finally:
             fused.USE_GRAPHS, layer.BOUNDS_MODE, fused.STEP_SEED_PTR = use_graphs, bounds, seed_ptr
+        e.n_launch = _lib.launch_count() - launches0
+        _lib.load().aread_launch_count_add(-e.n_launch & 0xFFFFFFFFFFFFFFFF)   # recorded, not run: replays count them
         e.plans = opt.captured_plans[n0:]
         del opt.captured_plans[n0:]
         e.graph = graph

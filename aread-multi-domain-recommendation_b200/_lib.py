@@ -40,7 +40,7 @@ class ScatterArgs(Structure):
     _fields_ = [("plan", EmbedPlan), ("batch", c_int64), ("x", c_void_p), ("d_out", c_void_p),
                 ("d_table", c_void_p), ("zero_fill", c_int32), ("workspace", c_void_p),
                 ("workspace_bytes", c_size_t), ("sorted_rows", c_void_p), ("sorted_pos", c_void_p),
-                ("shard_shift", c_int32), ("shard_rows", c_int64)]
+                ("shard_shift", c_int32), ("shard_rows", c_int64), ("peer_grads", c_void_p)]
 
 
 class GroupedLinearArgs(Structure):
@@ -188,7 +188,7 @@ class Bn16Args(Structure):
     _fields_ = [("m", c_int64), ("width", c_int32), ("bn_skip", c_int32), ("z", c_void_p), ("ldz", c_int64),
                 ("scale", c_void_p), ("shift", c_void_p), ("dropout_p", c_float), ("salt", c_uint32), ("seed", c_uint64),
                 ("seed_ptr", c_void_p), ("out", c_void_p), ("ldo", c_int64), ("dy", c_void_p), ("ldd", c_int64),
-                ("mean", c_void_p), ("rstd", c_void_p), ("coef", c_void_p)]
+                ("mean", c_void_p), ("rstd", c_void_p), ("coef", c_void_p), ("dy_is_raw", c_int32)]
 
 
 _L, _J = 4, 3        # AREAD_MIXED_MAX_LEVEL, AREAD_MIXED_MAX_LAYER
@@ -243,6 +243,7 @@ _SIGNATURES = {
     "aread_ipc_close": (c_int32, [c_void_p, c_int64]),
     "aread_adam_chunk": (c_int64, []),
     "aread_adam_step": (c_int32, [POINTER(AdamArgs), c_void_p]),
+    "aread_shard_grad_sum": (c_int32, [c_void_p, c_int32, c_int64, c_float, c_void_p, c_void_p]),
     "aread_multi_copy_chunk": (c_int64, []),
     "aread_multi_copy": (c_int32, [POINTER(MultiCopyArgs), c_void_p]),
     "aread_multi_cast_bf16": (c_int32, [POINTER(MultiCopyArgs), c_void_p]),
@@ -251,6 +252,8 @@ _SIGNATURES = {
     "aread_expert_bn_finalize": (c_int32, [POINTER(ExpertBnFinalizeArgs), c_void_p]),
     "aread_expert_bn_bwd_finalize": (c_int32, [POINTER(ExpertBnBwdFinalizeArgs), c_void_p]),
     "aread_bn16": (c_int32, [POINTER(Bn16Args), c_void_p]),
+    "aread_bn16_partials": (c_int32, [c_int64, c_int32]),
+    "aread_bn16_bwd_stats": (c_int32, [POINTER(Bn16Args), c_void_p, c_void_p]),
     "aread_hei_mixed_eval_supported": (c_int32, [POINTER(HeiMixedArgs)]),
     "aread_hei_mixed_eval": (c_int32, [POINTER(HeiMixedArgs), c_void_p]),
     "aread_domain_mean": (c_int32, [POINTER(DomainMeanArgs), c_void_p]),

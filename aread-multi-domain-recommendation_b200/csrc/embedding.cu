@@ -188,11 +188,21 @@ __device__ __forceinline__ int64_t dest_row(unsigned key, int shard_shift, int64
                           : static_cast<int64_t>(key & ((1u << shard_shift) - 1u)) * shard_rows + (key >> shard_shift);
 }
 
+// where the finished sum of table row `key` goes: the (possibly owner-major) local buffer, or -- sparse exchange --
+// the owning rank's receive buffer for this sender (a peer-mapped address: the store travels over NVLink)
+__device__ __forceinline__ float* dest_ptr(unsigned key, int D, float* d_table, float* const* __restrict__ peer_grads,
+                                           int shard_shift, int64_t shard_rows) {
+  if (peer_grads != nullptr)
+    return peer_grads[key & ((1u << shard_shift) - 1u)] + static_cast<int64_t>(key >> shard_shift) * D;
+  return d_table + dest_row(key, shard_shift, shard_rows) * D;
+}
+
 template <int LPR>
 __global__ void __launch_bounds__(kThreads) scatter_tile_kernel(
     const aread_embed_plan p, const unsigned* __restrict__ keys, const int* __restrict__ pos, int64_t n,
     int64_t n_tiles, int col_shift, const float* __restrict__ d_out, float* __restrict__ d_table,
-    float* __restrict__ carry_in, float* __restrict__ carry_out, int shard_shift, int64_t shard_rows) {
+    float* __restrict__ carry_in, float* __restrict__ carry_out, int shard_shift, int64_t shard_rows,
+    float* const* __restrict__ peer_grads) {
   extern __shared__ int smem[];
   int* s_field = smem;                                        // column -> output field
   float* s_div = reinterpret_cast<float*>(smem + p.n_cols);   // column -> fl32(1 / pooling divisor)
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) scatter_tile_kernel(
     } else if (trailing) {
       if (lane_on) *reinterpret_cast<float4*>(carry_out + t * D + lane * 4) = acc;
     } else if (lane_on) {
-      *reinterpret_cast<float4*>(d_table + dest_row(key, shard_shift, shard_rows) * D + lane * 4) = acc;
+      *reinterpret_cast<float4*>(dest_ptr(key, D, d_table, peer_grads, shard_shift, shard_rows) + lane * 4) = acc;
     }
   };
 
@@ -295,7 +305,8 @@ template <int LPR>
 __global__ void __launch_bounds__(kThreads) scatter_level_kernel(
     int D, unsigned n_rows, const unsigned* __restrict__ keys, int64_t n, int64_t child_size, int64_t n_children,
     int64_t n_blocks, const float* __restrict__ in_c, const float* __restrict__ out_c, float* __restrict__ in_p,
-    float* __restrict__ out_p, float* __restrict__ d_table, int shard_shift, int64_t shard_rows) {
+    float* __restrict__ out_p, float* __restrict__ d_table, int shard_shift, int64_t shard_rows,
+    float* const* __restrict__ peer_grads) {
   constexpr int PER = 32 / LPR;  // children held per lane
   constexpr int BATCH = 4;       // children whose partials are fetched together
   const int lane = threadIdx.x % LPR;
@@ -331,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) scatter_level_kernel(
   auto flush = [&](bool trailing) {
     if (cur >= n_rows) return;
     float* dst = leading ? in_p + J * D
-                         : (trailing ? out_p + J * D : d_table + dest_row(cur, shard_shift, shard_rows) * D);
+                         : (trailing ? out_p + J * D : dest_ptr(cur, D, d_table, peer_grads, shard_shift, shard_rows));
     if (lane_on) *reinterpret_cast<float4*>(dst + lane * 4) = acc;
   };
   auto element = [&](unsigned key, const float4& v, bool first_of_block) {
@@ -597,7 +608,7 @@ int launch_scatter(const aread_scatter_args& a, const ScatterWorkspace& w, int64
   const size_t smem = sizeof(int) * 2 * static_cast<size_t>(a.plan.n_cols);
   AREAD_LAUNCH((scatter_tile_kernel<LPR>), static_cast<unsigned>((n_tiles + groups_per_cta - 1) / groups_per_cta),
                kThreads, smem, stream, a.plan, w.keys_out, w.pos_out, n, n_tiles, col_shift, a.d_out, a.d_table,
-               w.in_a, w.out_a, a.shard_shift, a.shard_rows);
+               w.in_a, w.out_a, a.shard_shift, a.shard_rows, a.peer_grads);
   const float *in_c = w.in_a, *out_c = w.out_a;
   float *in_p = w.in_b, *out_p = w.out_b;
   int64_t child_size = kTile, n_children = n_tiles;
@@ -605,7 +616,7 @@ int launch_scatter(const aread_scatter_args& a, const ScatterWorkspace& w, int64
     const int64_t n_blocks = (n_children + 31) / 32;
     AREAD_LAUNCH((scatter_level_kernel<LPR>), static_cast<unsigned>((n_blocks + groups_per_cta - 1) / groups_per_cta),
                  kThreads, 0, stream, D, static_cast<unsigned>(a.plan.n_rows), w.keys_out, n, child_size, n_children,
-                 n_blocks, in_c, out_c, in_p, out_p, a.d_table, a.shard_shift, a.shard_rows);
+                 n_blocks, in_c, out_c, in_p, out_p, a.d_table, a.shard_shift, a.shard_rows, a.peer_grads);
     const float* t_in = in_c;
     const float* t_out = out_c;
     in_c = in_p;
@@ -618,10 +629,42 @@ int launch_scatter(const aread_scatter_args& a, const ScatterWorkspace& w, int64
   return AREAD_OK;
 }
 
+// out[i] = scale * sum_s recv[s][i]; non-zero inputs are cleared for the next step
+__global__ void __launch_bounds__(kThreads) shard_grad_sum_kernel(float* __restrict__ recv, int n_senders, int64_t n4,
+                                                                  float scale, float* __restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 acc = zero;
+    for (int s = 0; s < n_senders; ++s) {
+      float4* src = reinterpret_cast<float4*>(recv) + static_cast<int64_t>(s) * n4 + i;
+      const float4 v = *src;
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+        add4(acc, v);
+        *src = zero;
+      }
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+  }
+}
+
 }  // namespace
 }  // namespace aread
 
 extern "C" {
+
+int aread_shard_grad_sum(float* recv, int32_t n_senders, int64_t n, float scale, float* out, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(recv && out && n_senders > 0 && n >= 0 && n % 4 == 0, "shard_grad_sum: bad arguments");
+  AREAD_REQUIRE((reinterpret_cast<uintptr_t>(recv) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+                "shard_grad_sum: buffers must be 16-byte aligned");
+  if (n == 0) return AREAD_OK;
+  int64_t grid = (n / 4 + kThreads - 1) / kThreads;
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  AREAD_LAUNCH(shard_grad_sum_kernel, static_cast<unsigned>(grid), kThreads, 0, static_cast<cudaStream_t>(stream_), recv,
+               n_senders, n / 4, scale, out);
+  return AREAD_OK;
+}
 
 int aread_gather_fwd(const aread_gather_args* args, aread_stream_t stream_) {
   using namespace aread;
@@ -662,14 +705,16 @@ int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream_) {
   const aread_scatter_args& a = *args;
   if (int rc = check_plan(a.plan)) return rc;
   AREAD_REQUIRE(a.batch >= 0, "scatter: negative batch");
-  AREAD_REQUIRE(a.d_table != nullptr, "scatter: null d_table");
+  AREAD_REQUIRE(a.d_table != nullptr || a.peer_grads != nullptr, "scatter: null d_table");
+  AREAD_REQUIRE(a.peer_grads == nullptr || a.shard_shift > 0, "scatter: peer_grads needs a sharded table");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int D = a.plan.embed_dim;
   AREAD_REQUIRE(a.shard_shift >= 0 && a.shard_shift <= 6 && (a.shard_shift == 0 || a.shard_rows > 0),
                 "scatter: bad shard layout");
   const size_t grad_rows = a.shard_shift == 0 ? static_cast<size_t>(a.plan.n_rows)
                                               : static_cast<size_t>(a.shard_rows) << a.shard_shift;
-  if (a.zero_fill) AREAD_CUDA(cudaMemsetAsync(a.d_table, 0, grad_rows * D * sizeof(float), stream));
+  if (a.zero_fill && a.peer_grads == nullptr)
+    AREAD_CUDA(cudaMemsetAsync(a.d_table, 0, grad_rows * D * sizeof(float), stream));
   const int64_t n = a.batch * a.plan.n_cols;
   if (n == 0) return AREAD_OK;
   int col_shift = 0;

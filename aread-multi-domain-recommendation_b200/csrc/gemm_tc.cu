@@ -117,7 +117,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 constexpr int kEpiPlain = AREAD_EPI_PLAIN, kEpiStats = AREAD_EPI_STATS, kEpiAct = AREAD_EPI_ACT,
-              kEpiBnBwd = AREAD_EPI_BN_BWD;
+              kEpiBnBwd = AREAD_EPI_BN_BWD, kEpiBf16 = AREAD_EPI_BF16;
 
 template <int BN, int EPI, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -307,7 +307,10 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             float v[32];
             ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cc * 64 + half * 32, v);
             const int64_t hcol = col + half * 32;
-            if (EPI == kEpiAct) {
+            if (EPI == kEpiBf16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) packed[half * 16 + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+            } else if (EPI == kEpiAct) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(v[j], __ldg(p.scale + hcol + j), __ldg(p.shift + hcol + j)), 0.f);
 #pragma unroll
@@ -886,46 +889,131 @@ __global__ void __launch_bounds__(1024) expert_bn_bwd_finalize_kernel(const area
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-// 8 bf16 columns per thread (16-byte accesses), rows strided over the grid; width % 8 == 0
-template <bool BWD>
-__global__ void __launch_bounds__(256) bn16_kernel(const aread_bn16_args a, uint32_t threshold, float keep_scale) {
+// BatchNorm + ReLU + Dropout passes over a bf16 pre-activation.  A thread owns 8 consecutive columns (one 16-byte
+// access) and walks rows, so the per-column constants live in registers; the CTA owns a contiguous range of rows.
+//   MODE 0  forward:   out = bf16(dropout(relu(z * scale + shift)))
+//   MODE 1  backward:  dz = bf16(scale * (dy - coef0 - xhat * coef1)), dy masked here when it arrives raw
+//   MODE 2  backward statistics: per-CTA partials of sum(dy) and sum(dy * xhat) (rows in order: deterministic)
+constexpr int kBn16Threads = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(kBn16Threads) bn16_kernel(const aread_bn16_args a, uint32_t threshold, float keep_scale,
+                                                            int tpr, int64_t rows_per_cta, float* __restrict__ partial) {
+  __shared__ float s_red[MODE == 2 ? 2 * kBn16Threads * 8 : 1];
   const uint64_t seed = a.seed_ptr != nullptr ? __ldg(a.seed_ptr) : a.seed;
-  const int cols8 = a.width / 8;
-  const int64_t total = a.m * cols8;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int cg = a.width / 8;
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr, ty_n = kBn16Threads / tpr;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
+  const int64_t r1 = min(a.m, r0 + rows_per_cta);
   const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(a.z);
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t r = i / cols8;
-    const int col = static_cast<int>(i - r * cols8) * 8;
-    const uint4 zr = __ldg(reinterpret_cast<const uint4*>(zb + r * a.ldz + col));
-    const uint32_t zw[4] = {zr.x, zr.y, zr.z, zr.w};
-    uint32_t dw[4] = {0, 0, 0, 0};
-    if (BWD) {
-      const uint4 dr = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dy) + r * a.ldd + col));
-      dw[0] = dr.x; dw[1] = dr.y; dw[2] = dr.z; dw[3] = dr.w;
-    }
-    float out[8];
+  const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(a.dy);
+  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(a.out);
+  const bool mask_here = MODE == 0 || a.dy_is_raw != 0;
+  for (int g0 = 0; g0 < cg; g0 += tpr) {
+    const int g = g0 + tx;
+    const bool on = g < cg && ty < ty_n;
+    const int col = g * 8;
+    float sc[8], sh[8], mu[8], rs[8], c0[8], c1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = col + j;
-      const float z = (j & 1) ? bf16_hi(zw[j >> 1]) : bf16_lo(zw[j >> 1]);
-      if (BWD) {
-        const float dy = (j & 1) ? bf16_hi(dw[j >> 1]) : bf16_lo(dw[j >> 1]);
-        const float xhat = (z - __ldg(a.mean + c)) * __ldg(a.rstd + c);
-        out[j] = a.bn_skip ? dy : __ldg(a.scale + c) * (dy - __ldg(a.coef + c) - xhat * __ldg(a.coef + a.width + c));
-      } else {
-        const float y = fmaf(z, __ldg(a.scale + c), __ldg(a.shift + c));
-        const bool keep = threshold == 0u || dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
-        out[j] = (y > 0.f && keep) ? y * keep_scale : 0.f;
+      sc[j] = on ? __ldg(a.scale + col + j) : 0.f;
+      sh[j] = (on && mask_here) ? __ldg(a.shift + col + j) : 0.f;
+      if (MODE != 0) {
+        mu[j] = (on && !a.bn_skip) ? __ldg(a.mean + col + j) : 0.f;
+        rs[j] = (on && !a.bn_skip) ? __ldg(a.rstd + col + j) : 0.f;
+      }
+      if (MODE == 1) {
+        c0[j] = (on && !a.bn_skip) ? __ldg(a.coef + col + j) : 0.f;
+        c1[j] = (on && !a.bn_skip) ? __ldg(a.coef + a.width + col + j) : 0.f;
       }
     }
-    uint4 pk;
-    pk.x = pack_bf16(out[0], out[1]);
-    pk.y = pack_bf16(out[2], out[3]);
-    pk.z = pack_bf16(out[4], out[5]);
-    pk.w = pack_bf16(out[6], out[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + r * a.ldo + col) = pk;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (on) {
+#pragma unroll 2
+      for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+        const uint4 zr = __ldg(reinterpret_cast<const uint4*>(zb + r * a.ldz + col));
+        uint4 dr = make_uint4(0, 0, 0, 0);
+        if (MODE != 0) dr = __ldg(reinterpret_cast<const uint4*>(db + r * a.ldd + col));
+        const uint32_t zw[4] = {zr.x, zr.y, zr.z, zr.w};
+        const uint32_t dw[4] = {dr.x, dr.y, dr.z, dr.w};
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = (j & 1) ? bf16_hi(zw[j >> 1]) : bf16_lo(zw[j >> 1]);
+          bool pass = true;
+          float y = 0.f;
+          if (mask_here) {
+            y = fmaf(z, sc[j], sh[j]);
+            pass = y > 0.f && (threshold == 0u ||
+                               dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + col + j, threshold));
+          }
+          if (MODE == 0) {
+            out[j] = pass ? y * keep_scale : 0.f;
+          } else {
+            float dy = (j & 1) ? bf16_hi(dw[j >> 1]) : bf16_lo(dw[j >> 1]);
+            if (a.dy_is_raw) dy = pass ? dy * keep_scale : 0.f;
+            const float xhat = (z - mu[j]) * rs[j];
+            if (MODE == 1) {
+              out[j] = a.bn_skip ? dy : sc[j] * (dy - c0[j] - xhat * c1[j]);
+            } else {
+              s1[j] += dy;
+              s2[j] = fmaf(dy, xhat, s2[j]);
+            }
+          }
+        }
+        if (MODE != 2) {
+          uint4 pk;
+          pk.x = pack_bf16(out[0], out[1]);
+          pk.y = pack_bf16(out[2], out[3]);
+          pk.z = pack_bf16(out[4], out[5]);
+          pk.w = pack_bf16(out[6], out[7]);
+          *reinterpret_cast<uint4*>(ob + r * a.ldo + col) = pk;
+        }
+      }
+    }
+    if (MODE == 2) {   // the row lanes of the CTA, added in lane order
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s_red[(threadIdx.x * 2 + 0) * 8 + j] = s1[j];
+        s_red[(threadIdx.x * 2 + 1) * 8 + j] = s2[j];
+      }
+      __syncthreads();
+      if (ty == 0 && g < cg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t1 = 0.f, t2 = 0.f;
+          for (int y = 0; y < ty_n; ++y) {
+            t1 += s_red[((y * tpr + tx) * 2 + 0) * 8 + j];
+            t2 += s_red[((y * tpr + tx) * 2 + 1) * 8 + j];
+          }
+          partial[(static_cast<int64_t>(blockIdx.x) * 2 + 0) * a.width + col + j] = t1;
+          partial[(static_cast<int64_t>(blockIdx.x) * 2 + 1) * a.width + col + j] = t2;
+        }
+      }
+    }
   }
+}
+
+struct Bn16Grid {
+  int tpr, n_cta;
+  int64_t rows_per_cta;
+};
+inline Bn16Grid bn16_grid(int64_t m, int width) {
+  Bn16Grid g;
+  const int cg = width / 8;
+  g.tpr = 1;
+  while (g.tpr < cg && g.tpr < kBn16Threads) g.tpr <<= 1;
+  const int ty_n = kBn16Threads / g.tpr;
+  int64_t n = (m + static_cast<int64_t>(ty_n) * 16 - 1) / (static_cast<int64_t>(ty_n) * 16);   // >= 16 rows per lane
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 4;
+  if (n > cap) n = cap;
+  if (n < 1) n = 1;
+  g.rows_per_cta = (m + n - 1) / n;
+  g.n_cta = static_cast<int>((m + g.rows_per_cta - 1) / g.rows_per_cta);
+  return g;
 }
 
 }  // namespace
@@ -939,7 +1027,7 @@ extern "C" int aread_expert_gemm(const aread_expert_gemm_args* args, aread_strea
   const aread_expert_gemm_args& a = *args;
   AREAD_REQUIRE(a.m >= 0 && a.n > 0 && a.k > 0, "expert_gemm: bad shape m=%lld n=%d k=%d", (long long)a.m, a.n, a.k);
   AREAD_REQUIRE(a.groups > 0 && a.groups <= kMaxGroups, "expert_gemm: groups %d not in [1, %d]", a.groups, kMaxGroups);
-  AREAD_REQUIRE(a.epilogue >= AREAD_EPI_PLAIN && a.epilogue <= AREAD_EPI_BN_BWD, "expert_gemm: unknown epilogue %d",
+  AREAD_REQUIRE(a.epilogue >= AREAD_EPI_PLAIN && a.epilogue <= AREAD_EPI_BF16, "expert_gemm: unknown epilogue %d",
                 a.epilogue);
   if (a.m == 0) return AREAD_OK;
   AREAD_REQUIRE(a.a && a.b, "expert_gemm: null operand");
@@ -1027,6 +1115,9 @@ extern "C" int aread_expert_gemm(const aread_expert_gemm_args* args, aread_strea
     case AREAD_EPI_ACT:
       AREAD_REQUIRE(!mn, "expert_gemm: ACT runs on the forward weight layout");
       return launch_expert<kEpiAct, false>(bn, ma, mb, mc, p, stream);
+    case AREAD_EPI_BF16:
+      return mn ? launch_expert<kEpiBf16, true>(bn, ma, mb, mc, p, stream)
+                : launch_expert<kEpiBf16, false>(bn, ma, mb, mc, p, stream);
     default:
       AREAD_REQUIRE(mn, "expert_gemm: BN_BWD runs on the k-by-n weight layout");
       return launch_expert<kEpiBnBwd, true>(bn, ma, mb, mc, p, stream);
@@ -1054,30 +1145,59 @@ extern "C" int aread_expert_bn_bwd_finalize(const aread_expert_bn_bwd_finalize_a
   return AREAD_OK;
 }
 
+extern "C" int32_t aread_bn16_partials(int64_t m, int32_t width) {
+  return width > 0 && width % 8 == 0 ? aread::bn16_grid(m > 0 ? m : 1, width).n_cta : 0;
+}
+
+namespace aread {
+namespace {
+int check_bn16(const aread_bn16_args& a, const char* who) {
+  AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width % 8 == 0, "%s: width %d must be a multiple of 8", who, a.width);
+  AREAD_REQUIRE(a.z && a.scale, "%s: null pointer", who);
+  AREAD_REQUIRE(a.ldz % 8 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0, "%s: rows must be 16-byte aligned", who);
+  AREAD_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, "%s: dropout %f not in [0, 1)", who, a.dropout_p);
+  return AREAD_OK;
+}
+}  // namespace
+}  // namespace aread
+
 extern "C" int aread_bn16(const aread_bn16_args* args, aread_stream_t stream_) {
   using namespace aread;
   AREAD_REQUIRE(args != nullptr, "bn16: null args");
   const aread_bn16_args& a = *args;
-  AREAD_REQUIRE(a.m >= 0 && a.width > 0 && a.width % 8 == 0, "bn16: width %d must be a multiple of 8", a.width);
+  if (int rc = check_bn16(a, "bn16")) return rc;
   if (a.m == 0) return AREAD_OK;
-  AREAD_REQUIRE(a.z && a.out && a.scale, "bn16: null pointer");
-  AREAD_REQUIRE(a.ldz % 8 == 0 && a.ldo % 8 == 0 && reinterpret_cast<uintptr_t>(a.z) % 16 == 0 &&
-                    reinterpret_cast<uintptr_t>(a.out) % 16 == 0,
-                "bn16: rows must be 16-byte aligned");
-  AREAD_REQUIRE(a.dropout_p >= 0.f && a.dropout_p < 1.f, "bn16: dropout %f not in [0, 1)", a.dropout_p);
+  AREAD_REQUIRE(a.out && a.ldo % 8 == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0, "bn16: bad output");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int64_t total = a.m * (a.width / 8);
-  int64_t grid = (total + 255) / 256;
-  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  const Bn16Grid g = bn16_grid(a.m, a.width);
+  const uint32_t threshold = dropout_threshold_of(a.dropout_p);
+  const float keep_scale = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
   if (a.dy != nullptr) {
     AREAD_REQUIRE(a.bn_skip || (a.mean && a.rstd && a.coef), "bn16: null backward input");
+    AREAD_REQUIRE(!a.dy_is_raw || a.shift, "bn16: a raw gradient needs scale / shift to rebuild the ReLU mask");
     AREAD_REQUIRE(a.ldd % 8 == 0 && reinterpret_cast<uintptr_t>(a.dy) % 16 == 0, "bn16: dy rows must be 16-byte aligned");
-    AREAD_LAUNCH(bn16_kernel<true>, static_cast<unsigned>(grid), 256, 0, stream, a, 0u, 1.f);
+    AREAD_LAUNCH(bn16_kernel<1>, g.n_cta, kBn16Threads, 0, stream, a, a.dy_is_raw ? threshold : 0u,
+                 a.dy_is_raw ? keep_scale : 1.f, g.tpr, g.rows_per_cta, nullptr);
   } else {
     AREAD_REQUIRE(a.shift != nullptr, "bn16: null shift");
-    AREAD_LAUNCH(bn16_kernel<false>, static_cast<unsigned>(grid), 256, 0, stream, a, dropout_threshold_of(a.dropout_p),
-                 a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f);
+    AREAD_LAUNCH(bn16_kernel<0>, g.n_cta, kBn16Threads, 0, stream, a, threshold, keep_scale, g.tpr, g.rows_per_cta,
+                 nullptr);
   }
+  return AREAD_OK;
+}
+
+extern "C" int aread_bn16_bwd_stats(const aread_bn16_args* args, float* partial, aread_stream_t stream_) {
+  using namespace aread;
+  AREAD_REQUIRE(args != nullptr && partial != nullptr, "bn16_bwd_stats: null args");
+  const aread_bn16_args& a = *args;
+  if (int rc = check_bn16(a, "bn16_bwd_stats")) return rc;
+  AREAD_REQUIRE(a.m > 0 && a.dy && a.shift && (a.bn_skip || (a.mean && a.rstd)), "bn16_bwd_stats: null pointer");
+  AREAD_REQUIRE(a.ldd % 8 == 0 && reinterpret_cast<uintptr_t>(a.dy) % 16 == 0, "bn16_bwd_stats: dy rows must be 16-byte aligned");
+  const Bn16Grid g = bn16_grid(a.m, a.width);
+  const uint32_t threshold = a.dy_is_raw ? dropout_threshold_of(a.dropout_p) : 0u;
+  const float keep_scale = (a.dy_is_raw && a.dropout_p > 0.f) ? 1.f / (1.f - a.dropout_p) : 1.f;
+  AREAD_LAUNCH(bn16_kernel<2>, g.n_cta, kBn16Threads, 0, static_cast<cudaStream_t>(stream_), a, threshold, keep_scale,
+               g.tpr, g.rows_per_cta, partial);
   return AREAD_OK;
 }
 

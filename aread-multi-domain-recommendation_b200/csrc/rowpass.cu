@@ -121,59 +121,87 @@ __global__ void __launch_bounds__(kThreads) rowpass_epilogue_kernel(const aread_
   }
 }
 
-// gradient w.r.t. P (d_p) and w.r.t. the additive constants (d_c, to be summed over rows)
+// gradient w.r.t. P (d_p) and w.r.t. the additive constants (d_c, to be summed over rows).  A CTA owns kPrologueRows
+// rows: one thread per row works the scalar recurrences out into shared memory, then all threads write d_p, d_c and
+// the split bf16 copy with consecutive threads on consecutive columns (whole 128-byte lines per row).
+constexpr int kPrologueRows = 32;
+
 __global__ void __launch_bounds__(kThreads) rowpass_prologue_bwd_kernel(const aread_rowpass_args a) {
+  extern __shared__ float s_dp[];                       // [kPrologueRows][ldp + 1]: d_p, then reused for d_c deltas
   const int ng = a.n_gate, ne = a.n_expert, nc = a.n_cross, nh = a.n_head;
   const int c_gate = 1, c_cross = 1 + ng * ne, c_head = c_cross + nc;
-  for (int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; b < a.m;
-       b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float* p = a.p + b * a.ldp;
-    float* dp = a.d_p + b * a.ldp;
-    float* dc = a.d_c + b * a.ldp;
-    const float dl = a.d_lin ? a.d_lin[b] : 0.f;
-    dp[0] = dl;
-    dc[0] = dl;
-    for (int g = 0; g < ng; ++g) {  // softmax backward
-      float dot = 0.f;
-      for (int e = 0; e < ne; ++e)
-        dot += a.gate[b * (ng * ne) + g * ne + e] * (a.d_gate ? a.d_gate[b * (ng * ne) + g * ne + e] : 0.f);
-      for (int e = 0; e < ne; ++e) {
-        const int j = g * ne + e;
-        const float v = a.gate[b * (ng * ne) + j] * ((a.d_gate ? a.d_gate[b * (ng * ne) + j] : 0.f) - dot);
-        dp[c_gate + j] = v;
-        dc[c_gate + j] = v;
+  const int n_own = c_head + nh, n_all = n_own + a.n_extra;
+  const int ld = a.ldp, lds = a.ldp + 1;
+  float* s_dc = s_dp + kPrologueRows * lds;             // [kPrologueRows][ldp + 1]
+  const int64_t n_tiles = (a.m + kPrologueRows - 1) / kPrologueRows;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t b0 = tile * kPrologueRows;
+    const int rows = a.m - b0 < kPrologueRows ? static_cast<int>(a.m - b0) : kPrologueRows;
+    __syncthreads();
+    // riding dot products: their d_p was written by the owner (aread_gate_mix); bring it in, whole rows at a time
+    for (int idx = threadIdx.x; idx < rows * a.n_extra; idx += kThreads) {
+      const int r = idx / a.n_extra, j = n_own + (idx - r * a.n_extra);
+      const float v = a.d_p[(b0 + r) * ld + j];
+      s_dp[r * lds + j] = v;
+      s_dc[r * lds + j] = v;
+    }
+    if (threadIdx.x < rows) {
+      const int r = threadIdx.x;
+      const int64_t b = b0 + r;
+      const float* p = a.p + b * ld;
+      float* dp = s_dp + r * lds;
+      float* dc = s_dc + r * lds;
+      const float dl = a.d_lin ? a.d_lin[b] : 0.f;
+      dp[0] = dl;
+      dc[0] = dl;
+      for (int g = 0; g < ng; ++g) {  // softmax backward
+        float dot = 0.f;
+        for (int e = 0; e < ne; ++e)
+          dot += a.gate[b * (ng * ne) + g * ne + e] * (a.d_gate ? a.d_gate[b * (ng * ne) + g * ne + e] : 0.f);
+        for (int e = 0; e < ne; ++e) {
+          const int j = g * ne + e;
+          const float v = a.gate[b * (ng * ne) + j] * ((a.d_gate ? a.d_gate[b * (ng * ne) + j] : 0.f) - dot);
+          dp[c_gate + j] = v;
+          dc[c_gate + j] = v;
+        }
+      }
+      const float alpha_n = a.alpha[b * (nc + 1) + nc];
+      float d_alpha = 0.f;
+      for (int t = 0; t < nh; ++t) {
+        const float dh = a.d_head ? a.d_head[b * nh + t] : 0.f;
+        d_alpha = fmaf(dh, p[c_head + t], d_alpha);
+        dp[c_head + t] = alpha_n * dh;
+        dc[c_head + t] = dh;
+      }
+      for (int k = nc - 1; k >= 0; --k) {  // alpha_{k+1} = alpha_k + s_k, s_k = alpha_k p_k + kappa_k
+        const float ds = d_alpha;
+        const float alpha_k = a.alpha[b * (nc + 1) + k];
+        dp[c_cross + k] = ds * alpha_k;
+        dc[c_cross + k] = ds;
+        d_alpha = fmaf(ds, p[c_cross + k], d_alpha);
+      }
+      for (int j = n_all; j < ld; ++j) {
+        dp[j] = 0.f;
+        dc[j] = 0.f;
       }
     }
-    const float alpha_n = a.alpha[b * (nc + 1) + nc];
-    float d_alpha = 0.f;
-    for (int t = 0; t < nh; ++t) {
-      const float dh = a.d_head ? a.d_head[b * nh + t] : 0.f;
-      d_alpha = fmaf(dh, p[c_head + t], d_alpha);
-      dp[c_head + t] = alpha_n * dh;
-      dc[c_head + t] = dh;
-    }
-    for (int k = nc - 1; k >= 0; --k) {  // alpha_{k+1} = alpha_k + s_k, s_k = alpha_k p_k + kappa_k
-      const float ds = d_alpha;
-      const float alpha_k = a.alpha[b * (nc + 1) + k];
-      dp[c_cross + k] = ds * alpha_k;
-      dc[c_cross + k] = ds;
-      d_alpha = fmaf(ds, p[c_cross + k], d_alpha);
-    }
-    const int n_own = c_head + nh, n_all = n_own + a.n_extra;
-    for (int j = n_own; j < n_all; ++j) dc[j] = dp[j];      // riding dot products: d_p was written by their owner
-    for (int j = n_all; j < a.ldp; ++j) {
-      dp[j] = 0.f;
-      dc[j] = 0.f;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows * ld; idx += kThreads) {
+      const int r = idx / ld, j = idx - r * ld;
+      a.d_p[(b0 + r) * ld + j] = s_dp[r * lds + j];
+      a.d_c[(b0 + r) * ld + j] = s_dc[r * lds + j];
     }
     if (a.dp16 != nullptr) {   // split bf16 operands of the tensor-core products: [hi | hi | lo], W columns each
       const int W = a.dp16_width > 0 ? a.dp16_width : 32;
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.dp16) + b * a.ld16;
-      for (int j = 0; j < W; ++j) {
-        const float v = j < n_all ? dp[j] : 0.f;
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.dp16);
+      for (int idx = threadIdx.x; idx < rows * W; idx += kThreads) {
+        const int r = idx / W, j = idx - r * W;
+        const float v = j < n_all ? s_dp[r * lds + j] : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        o[j] = hi;
-        o[W + j] = hi;
-        o[2 * W + j] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        __nv_bfloat16* row = o + (b0 + r) * a.ld16;
+        row[j] = hi;
+        row[W + j] = hi;
+        row[2 * W + j] = __float2bfloat16_rn(v - __bfloat162float(hi));
       }
     }
   }
@@ -276,6 +304,12 @@ __global__ void __launch_bounds__(kThreads) rowdots_bwd_reduce_kernel(int n_part
   }
 }
 
+unsigned prologue_grid(int64_t m) {
+  const int64_t tiles = (m + kPrologueRows - 1) / kPrologueRows;
+  return static_cast<unsigned>(tiles < kNumSMs * 4 ? (tiles < 1 ? 1 : tiles) : kNumSMs * 4);
+}
+size_t prologue_smem(int ldp) { return sizeof(float) * 2 * kPrologueRows * (ldp + 1); }
+
 int bwd_ctas(int64_t m) {
   const int64_t tiles = (m + kTile - 1) / kTile;
   const int64_t cap = kNumSMs * 2;
@@ -323,6 +357,8 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   const aread_rowpass_args& a = *args;
   const int nj = 1 + a.n_gate * a.n_expert + a.n_cross + a.n_head;
   AREAD_REQUIRE(a.m >= 0 && a.e > 0 && a.n_extra >= 0 && nj + a.n_extra <= a.ldp, "rowpass_bwd: bad shape");
+  AREAD_REQUIRE(prologue_smem(a.ldp) <= 48 * 1024, "rowpass_bwd: %d dot products per row exceed the prologue's shared memory",
+                a.ldp);
   AREAD_REQUIRE(a.n_extra == 0 || a.x == nullptr, "rowpass_bwd: riding dot products need the tensor-core variant (x == NULL)");
   AREAD_REQUIRE(a.e <= 16 * kChunk, "rowpass_bwd: embedding row of %d floats is too wide (max %d)", a.e, 16 * kChunk);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -338,7 +374,7 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
     }
     if (a.m == 0) return AREAD_OK;
     AREAD_REQUIRE(a.p && a.alpha && (a.gate || a.n_gate * a.n_expert == 0), "rowpass_bwd: null pointer");
-    AREAD_LAUNCH(rowpass_prologue_bwd_kernel, pgrid, kThreads, 0, stream, a);
+    AREAD_LAUNCH(rowpass_prologue_bwd_kernel, prologue_grid(a.m), kThreads, prologue_smem(a.ldp), stream, a);
     return AREAD_OK;
   }
   AREAD_REQUIRE(a.d_w && a.d_p && a.d_c && a.workspace, "rowpass_bwd: null pointer");
@@ -352,7 +388,7 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   const unsigned egrid = static_cast<unsigned>((a.m + kThreads - 1) / kThreads < kNumSMs * 8
                                                    ? (a.m + kThreads - 1) / kThreads
                                                    : kNumSMs * 8);
-  AREAD_LAUNCH(rowpass_prologue_bwd_kernel, egrid, kThreads, 0, stream, a);
+  AREAD_LAUNCH(rowpass_prologue_bwd_kernel, prologue_grid(a.m), kThreads, prologue_smem(a.ldp), stream, a);
   float* partial = static_cast<float*>(a.workspace);
   const int n_chunks = (a.e + kChunk - 1) / kChunk;
   for (int j0 = 0; j0 < nj; j0 += kJ) {

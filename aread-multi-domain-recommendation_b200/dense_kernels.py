@@ -184,7 +184,7 @@ def bench_expert_layer1(a_op, w_op, n, k, groups):
 # pre-activation is stored once, as bf16 and without the bias (BatchNorm removes it; the finalize kernel folds it
 # into the running mean / the eval-mode shift).
 # ------------------------------------------------------------------------------------------------------------------
-EPI_PLAIN, EPI_STATS, EPI_ACT, EPI_BN_BWD = 0, 1, 2, 3
+EPI_PLAIN, EPI_STATS, EPI_ACT, EPI_BN_BWD, EPI_BF16 = 0, 1, 2, 3, 4
 
 
 def _expert_gemm(a, w, n, k, groups, a_group_cols, epilogue, *, k_by_n=False, out, partial=None, saved=None, z=None,
@@ -245,22 +245,43 @@ def bn16_fwd(z, saved, training, p, seed, salt):
     out = _mem.empty((m, width), torch.bfloat16, z.device)
     sv = _rows(saved, 4)
     args = _lib.Bn16Args(m, width, 0, z.data_ptr(), z.stride(0), sv[2], sv[3], float(p) if training else 0.0, salt, seed,
-                         SEED_PTR, out.data_ptr(), width, None, 0, None, None, None)
+                         SEED_PTR, out.data_ptr(), width, None, 0, None, None, None, 0)
     _lib.check(_lib.load().aread_bn16(ctypes.byref(args), _stream(z.device)))
     return out
 
 
-def bn16_bwd(z, dy, saved, coef, bn_skip, out=None):
-    """dz16 = bf16(scale * (dy - coef0 - xhat * coef1)) from the bf16 pre-activation and the masked bf16 gradient.
-    `out`: a preallocated [m, width] bf16 view (any 16-byte aligned row stride)."""
+def bn16_bwd(z, dy, saved, coef, bn_skip, out=None, raw=False, p=0.0, salt=0, seed=0):
+    """dz16 = bf16(scale * (dy - coef0 - xhat * coef1)) from the bf16 pre-activation and the bf16 gradient.  raw=False:
+    `dy` already carries the ReLU / dropout mask (BN_BWD epilogue); raw=True: it is the gradient w.r.t. the activated
+    output and the mask is rebuilt from (z, saved, p, salt, seed).  `out`: a preallocated [m, width] bf16 view (any
+    16-byte aligned row stride)."""
     m, width = z.shape
     if out is None:
         out = _mem.empty((m, width), torch.bfloat16, z.device)
     sv = _rows(saved, 4)
-    args = _lib.Bn16Args(m, width, 1 if bn_skip else 0, z.data_ptr(), z.stride(0), sv[2], sv[3], 0.0, 0, 0, None,
-                         out.data_ptr(), out.stride(0), dy.data_ptr(), dy.stride(0), sv[0], sv[1], coef.data_ptr())
+    args = _lib.Bn16Args(m, width, 1 if bn_skip else 0, z.data_ptr(), z.stride(0), sv[2], sv[3], float(p), salt, seed,
+                         SEED_PTR, out.data_ptr(), out.stride(0), dy.data_ptr(), dy.stride(0), sv[0], sv[1],
+                         coef.data_ptr(), 1 if raw else 0)
     _lib.check(_lib.load().aread_bn16(ctypes.byref(args), _stream(z.device)))
     return out
+
+
+def bn16_bwd_stats(z, d_h, saved, bn_skip, p, salt, seed):
+    """partial [ctas, 2, width]: per-CTA sums of dy and dy * xhat, dy = d_h masked by ReLU / dropout (rebuilt here)."""
+    m, width = z.shape
+    n_part = int(_lib.load().aread_bn16_partials(m, width))
+    partial = _mem.empty((n_part, 2, width), torch.float32, z.device)
+    sv = _rows(saved, 4)
+    args = _lib.Bn16Args(m, width, 1 if bn_skip else 0, z.data_ptr(), z.stride(0), sv[2], sv[3], float(p), salt, seed,
+                         SEED_PTR, None, 0, d_h.data_ptr(), d_h.stride(0), sv[0], sv[1], None, 1)
+    _lib.check(_lib.load().aread_bn16_bwd_stats(ctypes.byref(args), ctypes.c_void_p(partial.data_ptr()), _stream(z.device)))
+    return partial
+
+
+def expert_dgrad_bf16(dz, w, n_out, k, groups):
+    """Data gradient of a grouped Linear as bf16: d_h16 [m, groups*n_out] = dZ . W (W read in place, k-by-n operand)."""
+    d_h = _mem.empty((dz.shape[0], groups * n_out), torch.bfloat16, dz.device)
+    return _expert_gemm(dz, w, n_out, k, groups, k, EPI_BF16 if n_out % 64 == 0 else EPI_PLAIN, k_by_n=True, out=d_h)
 
 
 def expert_dgrad_bn_bwd(dz, w, n_out, k, groups, z_prev, saved_prev, p, salt_prev, seed):

@@ -123,17 +123,22 @@ def scatter(plan, x, d_out, d_table=None, zero_fill=True, want_sorted=False, red
     B = x.shape[0]
     n = B * plan.n_cols
     sh = plan.shards
-    if sh is not None:                   # owner-major full-size buffer, then reduce-scatter to the shard owner
+    sparse = sh is not None and sh.sparse
+    if sparse:                           # reduced rows go straight into the owners' receive slots (sharding.py)
+        d_table = None
+    elif sh is not None:                 # owner-major full-size buffer, then reduce-scatter to the shard owner
         d_table = sh.grad_buffer(x.device)
     elif d_table is None:
         d_table = torch.empty((plan.n_rows, plan.embed_dim), dtype=torch.float32, device=x.device)
     ws = plan.workspace(n)
     rows = torch.empty(n, dtype=torch.int32, device=x.device) if want_sorted else None
     pos = torch.empty(n, dtype=torch.int32, device=x.device) if want_sorted else None
-    args = _lib.ScatterArgs(plan.c_plan(), B, x.data_ptr(), d_out.data_ptr(), d_table.data_ptr(),
+    args = _lib.ScatterArgs(plan.c_plan(), B, x.data_ptr(), d_out.data_ptr(),
+                            d_table.data_ptr() if d_table is not None else None,
                             1 if zero_fill else 0, ws.data_ptr(), ws.numel(),
                             rows.data_ptr() if want_sorted else None, pos.data_ptr() if want_sorted else None,
-                            sh.shift if sh is not None else 0, sh.rows if sh is not None else 0)
+                            sh.shift if sh is not None else 0, sh.rows if sh is not None else 0,
+                            sh.push_ptrs.data_ptr() if sparse else None)
     _lib.check(_lib.load().aread_scatter_bwd(ctypes.byref(args), _stream_ptr(x.device)))
     if sh is not None and reduce:        # reduce=False: the caller runs the reduce-scatter itself (fused.py)
         d_table = sh.reduce_grad(d_table)

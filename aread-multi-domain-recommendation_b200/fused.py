@@ -35,6 +35,10 @@ USE_HEI_LAYER = os.environ.get("AREAD_HEI_FUSED", "1") != "0"
 USE_GRAPHS = os.environ.get("AREAD_GRAPHS", "1") != "0"
 # skinny products of the row pass (linear / gates / cross / heads) on the tensor cores (AREAD_TC_ROWPASS=0: CUDA cores)
 TC_ROWPASS = os.environ.get("AREAD_TC_ROWPASS", "1") != "0"
+# BatchNorm-backward masks and column sums inside the data-gradient GEMM epilogue (AREAD_FUSED_BN_BWD=1).  Off by
+# default: the epilogue has four warps per SM for elementwise work that wants full occupancy (measured 557 us against
+# ~200 us for the GEMM + two streaming passes on the layer-2 gradient at B = 65,536)
+FUSED_BN_BWD = os.environ.get("AREAD_FUSED_BN_BWD", "0") == "1"
 # device address of the dropout seed while a whole train step is recorded / replayed (step_graph.py)
 STEP_SEED_PTR = None
 GRAPH_AFTER = 2
@@ -718,11 +722,18 @@ class AreadNode(torch.autograd.Function):
                 if i > 0:
                     Lp = P.experts[i - 1]
                     _, z_p, stats_p, _ = ex[i - 1]
-                    dy, partial = dk.expert_dgrad_bn_bwd(dze, w, L.k, L.n, G, z_p, stats_p, p_drop, Lp.salt, seed)
-                    coef, g3 = dk.expert_bn_bwd_finalize(partial, B, G * L.k, bn_skip)
+                    out_l = dz0[:, :G * L0.n] if (tc_row and i == 1) else None
+                    if FUSED_BN_BWD:    # masks + BatchNorm sums in the GEMM epilogue (4 epilogue warps do the elementwise work)
+                        dy, partial = dk.expert_dgrad_bn_bwd(dze, w, L.k, L.n, G, z_p, stats_p, p_drop, Lp.salt, seed)
+                        coef, g3 = dk.expert_bn_bwd_finalize(partial, B, G * L.k, bn_skip)
+                        dze = dk.bn16_bwd(z_p, dy, stats_p, coef, bn_skip, out=out_l)
+                    else:               # plain bf16 data gradient, then two full-occupancy passes over (z16, d_h16)
+                        d_h16 = dk.expert_dgrad_bf16(dze, w, L.k, L.n, G)
+                        partial = dk.bn16_bwd_stats(z_p, d_h16, stats_p, bn_skip, p_drop, Lp.salt, seed)
+                        coef, g3 = dk.expert_bn_bwd_finalize(partial, B, G * L.k, bn_skip)
+                        dze = dk.bn16_bwd(z_p, d_h16, stats_p, coef, bn_skip, out=out_l, raw=True, p=p_drop, salt=Lp.salt,
+                                          seed=seed)
                     d_gamma, d_beta, d_bias = g3[0], g3[1], g3[2]
-                    dze = dk.bn16_bwd(z_p, dy, stats_p, coef, bn_skip,
-                                      out=dz0[:, :G * L0.n] if (tc_row and i == 1) else None)
                 elif tc_row:
                     # weight rows [W_layer1 (k-by-n) ; Wcat_hi ; Wcat_lo ; Wcat_hi]: ONE GEMM returns d_x of both paths
                     w_ext = _mem.empty((k_ext, E), torch.bfloat16, dev)

@@ -3,12 +3,17 @@
 Global row r lives on rank r mod N at local row r // N (N a power of two: balances the skewed big
 fields).  Every rank maps all peers' shards into its own address space (CUDA IPC through torch's
 tensor-sharing plumbing) and the gather kernel reads remote rows straight over NVLink -- the lookup
-is the all-to-all of rows, no index exchange, no staging.  The gradient is scattered locally into an
-owner-major [N, rows_per_shard, D] buffer and reduce-scattered (NCCL) so that each rank receives the
-batch-averaged gradient of its own shard; dense parameters are all-reduced in one flat bucket.
+is the all-to-all of rows, no index exchange, no staging.  The gradient goes the other way the same way: every
+rank keeps one receive buffer per sender ([N, rows_per_shard, D], zero between steps), maps its peers' buffers, and the
+scatter kernel stores the reduced gradient row of table row r straight into slot `sender` of the rank that owns r
+(P2P stores over NVLink).  Only the rows a batch touched travel -- O(unique rows x D) instead of the O(R x D) dense
+reduce-scatter of a full-size buffer -- and the owner adds its N slots in rank order (deterministic), clearing what it
+read.  Dense parameters are all-reduced in one flat bucket.  AREAD_DENSE_GRAD_EXCHANGE=1 keeps the dense NCCL
+reduce-scatter (the baseline the sparse exchange is measured against).
 """
 import ctypes
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -81,6 +86,25 @@ class TableShards:
         self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
         self._token = torch.zeros(1, dtype=torch.float32, device=dev)
         self._grad = None
+        # sparse gradient exchange: this rank's receive slots, mapped by every peer
+        self.sparse = os.environ.get("AREAD_DENSE_GRAD_EXCHANGE", "0") != "1"
+        self.recv = self.push_ptrs = None
+        if self.sparse:
+            self.recv = torch.zeros((self.world, self.rows, self.dim), dtype=torch.float32, device=dev)
+            _lib.check(lib.aread_ipc_export(ctypes.c_void_p(self.recv.data_ptr()), handle, ctypes.byref(offset)))
+            metas = [None] * self.world
+            dist.all_gather_object(metas, (dev.index, handle.raw, int(offset.value)), group=group)
+            slot = self.rank * self.rows * self.dim * 4              # this sender's slot inside every owner's buffer
+            push = []
+            for r, (peer_index, raw, off) in enumerate(metas):
+                if r == self.rank:
+                    push.append(self.recv.data_ptr() + slot)
+                    continue
+                out = ctypes.c_void_p(0)
+                _lib.check(lib.aread_ipc_open(raw, off, dev.index, ctypes.byref(out)))
+                self._opened.append((out.value, off))
+                push.append(out.value + slot)
+            self.push_ptrs = torch.tensor(push, dtype=torch.int64, device=dev)
         dist.barrier(group=group)
 
     def close(self):
@@ -100,9 +124,19 @@ class TableShards:
         return self._grad
 
     def reduce_grad(self, d_full):
-        """owner-major [world * rows, D] local gradient -> batch-averaged gradient of this rank's shard."""
-        out = torch.empty((self.rows, self.dim), dtype=torch.float32, device=d_full.device)
-        dist.reduce_scatter_tensor(out, d_full, op=dist.ReduceOp.AVG, group=self.group)
+        """-> batch-averaged gradient of this rank's shard.  Dense exchange: `d_full` is the owner-major
+        [world * rows, D] local gradient, reduce-scattered by NCCL.  Sparse exchange: the scatter kernels have already
+        stored every sender's reduced rows into this rank's receive slots; once all ranks have reached this point
+        (fence) the slots are added in rank order and cleared."""
+        out = torch.empty((self.rows, self.dim), dtype=torch.float32, device=self.recv.device if self.sparse else d_full.device)
+        if not self.sparse:
+            dist.reduce_scatter_tensor(out, d_full, op=dist.ReduceOp.AVG, group=self.group)
+            return out
+        self.fence()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+        _lib.check(_lib.load().aread_shard_grad_sum(ctypes.c_void_p(self.recv.data_ptr()), self.world,
+                                                    self.rows * self.dim, 1.0 / self.world,
+                                                    ctypes.c_void_p(out.data_ptr()), stream))
         return out
 
 

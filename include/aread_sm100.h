@@ -130,10 +130,21 @@ typedef struct aread_scatter_args {
      ready for a reduce-scatter that hands every GPU the summed gradient of its own shard.       */
   int32_t shard_shift;
   int64_t shard_rows;
+  /* Sparse exchange of the gradient of a row-sharded table: with peer_grads != NULL (device array [2^shard_shift] of
+     device pointers), the reduced gradient of table row r is stored at peer_grads[r mod N] + (r >> shard_shift) * D --
+     i.e. straight into the per-sender receive buffer of the rank that owns the row, over NVLink (P2P store).  Only
+     rows this batch touched travel; d_table is not written (and zero_fill is ignored).  The owner sums its N receive
+     buffers with aread_shard_grad_sum.                                                                           */
+  float* const* peer_grads;
 } aread_scatter_args;
 
 AREAD_API size_t aread_scatter_workspace_bytes(int64_t n_lookups, int32_t embed_dim);
 AREAD_API int aread_scatter_bwd(const aread_scatter_args* args, aread_stream_t stream);
+/* Owner side of the sparse exchange: out[i] = scale * sum_s recv[s * n + i] (senders added in rank order:
+ * deterministic); every element of recv that was non-zero is reset to zero, so the buffers are ready for the next
+ * step without a dense memset.  recv: [n_senders, n] fp32, n % 4 == 0, 16-byte aligned.                            */
+AREAD_API int aread_shard_grad_sum(float* recv, int32_t n_senders, int64_t n, float scale, float* out,
+                                   aread_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Grouped Linear on the tensor cores (tcgen05 / TMEM, operands staged by TMA).
@@ -187,12 +198,13 @@ AREAD_API int aread_grouped_linear_bf16(const aread_grouped_linear_args* args, a
  *   AREAD_EPI_STATS   c_bf16 = bf16(acc)  [bias-free: BatchNorm removes it]; partial[t][0][col] = sum_rows acc,
  *                     partial[t][1][col] = sum_rows acc^2 over the rows of 128-row tile t (fixed order)
  *   AREAD_EPI_ACT     c_bf16 = bf16(max(acc * scale[col] + shift[col], 0))   (eval mode: BatchNorm folded)
+ *   AREAD_EPI_BF16    c_bf16 = bf16(acc) through the same 64-column TMA-store path (n % 64 == 0), nothing else
  *   AREAD_EPI_BN_BWD  acc = gradient w.r.t. the ACTIVATED output of the layer below;  with y = z*scale+shift,
  *                     dy = (y > 0 && keep) ? acc / (1 - p) : 0;  c_bf16 = bf16(dy);
  *                     partial[t][0][col] = sum dy, partial[t][1][col] = sum dy * (z - mean) * rstd
  * partial: fp32 [aread_expert_gemm_partials(m)][2][groups * n].
  * ---------------------------------------------------------------------------------------------- */
-enum { AREAD_EPI_PLAIN = 0, AREAD_EPI_STATS = 1, AREAD_EPI_ACT = 2, AREAD_EPI_BN_BWD = 3 };
+enum { AREAD_EPI_PLAIN = 0, AREAD_EPI_STATS = 1, AREAD_EPI_ACT = 2, AREAD_EPI_BN_BWD = 3, AREAD_EPI_BF16 = 4 };
 
 typedef struct aread_expert_gemm_args {
   int64_t m;
@@ -260,7 +272,8 @@ typedef struct aread_expert_bn_bwd_finalize_args {
 AREAD_API int aread_expert_bn_bwd_finalize(const aread_expert_bn_bwd_finalize_args* args, aread_stream_t stream);
 
 /* out = bf16(dropout(relu(z * scale + shift))) from the bf16 pre-activation (forward), or, with dy != NULL,
- * dz = bf16(scale * (dy - coef[0] - xhat * coef[1])) (bn_skip: dz = dy), xhat = (z - mean) * rstd (backward).       */
+ * dz = bf16(scale * (dy - coef[0] - xhat * coef[1])) (bn_skip: dz = dy), xhat = (z - mean) * rstd (backward).
+ * HBM-bound passes: a thread owns 8 columns (per-column constants in registers) and walks rows.                   */
 typedef struct aread_bn16_args {
   int64_t m;
   int32_t width, bn_skip;
@@ -279,9 +292,16 @@ typedef struct aread_bn16_args {
   const float* mean;      /* backward */
   const float* rstd;
   const float* coef;      /* backward: fp32 [2, width] */
+  int32_t dy_is_raw;      /* backward: 1 = `dy` is the gradient w.r.t. the ACTIVATED output (a plain data-gradient GEMM
+                             wrote it); the ReLU / dropout mask is rebuilt here from z, scale, shift, dropout_p, seed */
 } aread_bn16_args;
 
 AREAD_API int aread_bn16(const aread_bn16_args* args, aread_stream_t stream);
+/* Reduction half of the backward on the bf16 tensors: partial[c][0][col] = sum over CTA c's rows of dy,
+ * partial[c][1][col] = sum of dy * xhat (rows in order), c < aread_bn16_partials(m, width); feed them to
+ * aread_expert_bn_bwd_finalize.                                                                        */
+AREAD_API int32_t aread_bn16_partials(int64_t m, int32_t width);
+AREAD_API int aread_bn16_bwd_stats(const aread_bn16_args* args, float* partial, aread_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight gradient of the grouped Linear: dW_g[j, i] = sum_b dZ[b, g*n + j] * A[b, g*a_group_cols + i].

@@ -81,7 +81,7 @@ def test_every_header_struct_has_a_binding():
 def test_struct_sizes_are_native(lib):
     assert ctypes.sizeof(_lib.EmbedPlan) == 56
     assert ctypes.sizeof(_lib.GatherArgs) == 56 + 8 * 9
-    assert ctypes.sizeof(_lib.ScatterArgs) == 56 + 8 * 11
+    assert ctypes.sizeof(_lib.ScatterArgs) == 56 + 8 * 12
 
 
 def test_argument_validation_without_gpu(lib):

@@ -4,7 +4,7 @@ There is deliberately no fallback: if the library is missing or fails to load, e
 """
 import ctypes
 import os
-from ctypes import (POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint32, c_uint64,
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_uint32, c_uint64,
                     c_void_p)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -160,7 +160,7 @@ class AdamArgs(Structure):
                 ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("sizes", c_void_p), ("chunk_start", c_void_p),
                 ("step_size", c_void_p), ("bc2_sqrt", c_void_p), ("beta1", c_float), ("beta2", c_float),
                 ("eps", c_float), ("weight_decay", c_float), ("l2_twice", c_void_p), ("step_counts", c_void_p),
-                ("slot", c_void_p), ("lr", c_float)]
+                ("slot", c_void_p), ("lr", c_double), ("beta1_d", c_double), ("beta2_d", c_double)]
 
 
 class ExpertGemmArgs(Structure):
@@ -188,7 +188,8 @@ class Bn16Args(Structure):
     _fields_ = [("m", c_int64), ("width", c_int32), ("bn_skip", c_int32), ("z", c_void_p), ("ldz", c_int64),
                 ("scale", c_void_p), ("shift", c_void_p), ("dropout_p", c_float), ("salt", c_uint32), ("seed", c_uint64),
                 ("seed_ptr", c_void_p), ("out", c_void_p), ("ldo", c_int64), ("dy", c_void_p), ("ldd", c_int64),
-                ("mean", c_void_p), ("rstd", c_void_p), ("coef", c_void_p), ("dy_is_raw", c_int32)]
+                ("mean", c_void_p), ("rstd", c_void_p), ("coef", c_void_p), ("dy_is_raw", c_int32),
+                ("pass_bits", c_void_p), ("keep_scale_bwd", c_float)]
 
 
 _L, _J = 4, 3        # AREAD_MIXED_MAX_LEVEL, AREAD_MIXED_MAX_LAYER

@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const aread_adam_args a)
     float step_size, bc2_sqrt;
     if (a.step_counts != nullptr) {      // counters were advanced by adam_tick_kernel, launched just before
       const double n = static_cast<double>(a.step_counts[a.slot[t]]);
-      step_size = static_cast<float>(static_cast<double>(a.lr) / (1.0 - pow(static_cast<double>(a.beta1), n)));
-      bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(a.beta2), n)));
+      step_size = static_cast<float>(a.lr / (1.0 - pow(a.beta1_d, n)));
+      bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(a.beta2_d, n)));
     } else {
       step_size = a.step_size[t];
       bc2_sqrt = a.bc2_sqrt[t];

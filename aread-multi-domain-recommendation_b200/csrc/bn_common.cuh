@@ -11,16 +11,21 @@ namespace {
 constexpr int kBnThreads = 256;
 constexpr int kStatCtas = kNumSMs * 4;   // upper bound on the number of column partials per reduction
 
-// counter-based dropout stream: keep(element) is a pure function of (seed, salt, element index)
+// counter-based dropout stream: keep(element) is a pure function of (seed, salt, element index).  One 32-bit hash
+// serves the two elements 2q and 2q + 1 (16 bits each), so kernels that walk consecutive elements pay half a hash
+// per element; p is resolved to 1 / 65536.
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
+__device__ __forceinline__ uint32_t dropout_pair_hash(uint64_t seed, uint32_t salt, uint64_t pair) {
+  return mix32(static_cast<uint32_t>(pair) ^ mix32(static_cast<uint32_t>(pair >> 32) ^ salt ^
+                                                   static_cast<uint32_t>(seed)) ^
+               static_cast<uint32_t>(seed >> 32));
+}
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t salt, uint64_t idx, uint32_t threshold) {
-  const uint32_t h = mix32(static_cast<uint32_t>(idx) ^ mix32(static_cast<uint32_t>(idx >> 32) ^ salt ^
-                                                               static_cast<uint32_t>(seed)) ^
-                           static_cast<uint32_t>(seed >> 32));
-  return h >= threshold;
+  const uint32_t h = dropout_pair_hash(seed, salt, idx >> 1);
+  return ((idx & 1) ? (h >> 16) : (h & 0xffffu)) >= threshold;
 }
 // the dropout seed of a launch: read from device memory when the caller gave a slot (CUDA-graph replay: the
 // launch parameters are frozen, the seed is not), else the by-value field
@@ -28,10 +33,10 @@ template <typename Args>
 __device__ __forceinline__ uint64_t seed_of(const Args& a) {
   return a.seed_ptr != nullptr ? __ldg(a.seed_ptr) : a.seed;
 }
-inline uint32_t dropout_threshold(float p) {
+inline uint32_t dropout_threshold(float p) {   // 16-bit scale; 0 = no dropout
   if (p <= 0.f) return 0u;
-  const double t = static_cast<double>(p) * 4294967296.0;
-  return t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+  const double t = static_cast<double>(p) * 65536.0;
+  return t >= 65535.0 ? 0xffffu : static_cast<uint32_t>(t + 0.5);
 }
 
 // Sum of the CTA partials of one column pair, by 8 threads in interleaved order then in thread order.

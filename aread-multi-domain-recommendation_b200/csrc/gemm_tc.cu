@@ -82,16 +82,19 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int64_t ti
 }
 
 // counter-based dropout stream shared with bn_act.cu / hei.cu (bn_common.cuh): keep(element) is a pure function of
-// (seed, salt, element index)
+// (seed, salt, element index); one 32-bit hash serves elements 2q and 2q + 1 (16 bits each)
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
+__device__ __forceinline__ uint32_t dropout_pair_hash(uint64_t seed, uint32_t salt, uint64_t pair) {
+  return mix32(static_cast<uint32_t>(pair) ^ mix32(static_cast<uint32_t>(pair >> 32) ^ salt ^
+                                                   static_cast<uint32_t>(seed)) ^
+               static_cast<uint32_t>(seed >> 32));
+}
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t salt, uint64_t idx, uint32_t threshold) {
-  const uint32_t h = mix32(static_cast<uint32_t>(idx) ^ mix32(static_cast<uint32_t>(idx >> 32) ^ salt ^
-                                                               static_cast<uint32_t>(seed)) ^
-                           static_cast<uint32_t>(seed >> 32));
-  return h >= threshold;
+  const uint32_t h = dropout_pair_hash(seed, salt, idx >> 1);
+  return ((idx & 1) ? (h >> 16) : (h & 0xffffu)) >= threshold;
 }
 
 // Column sums over the 32 rows a warp holds (thread = row, v[j] = column j): a butterfly that halves the number of
@@ -796,10 +799,10 @@ int make_store_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_
   return AREAD_OK;
 }
 
-inline uint32_t dropout_threshold_of(float p) {
+inline uint32_t dropout_threshold_of(float p) {   // 16-bit scale (bn_common.cuh dropout_threshold)
   if (p <= 0.f) return 0u;
-  const double t = static_cast<double>(p) * 4294967296.0;
-  return t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+  const double t = static_cast<double>(p) * 65536.0;
+  return t >= 65535.0 ? 0xffffu : static_cast<uint32_t>(t + 0.5);
 }
 
 template <int EPI, bool B_MN>
@@ -897,8 +900,8 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 constexpr int kBn16Threads = 256;
 
 template <int MODE>
-__global__ void __launch_bounds__(kBn16Threads) bn16_kernel(const aread_bn16_args a, uint32_t threshold, float keep_scale,
-                                                            int tpr, int64_t rows_per_cta, float* __restrict__ partial) {
+__global__ void __launch_bounds__(kBn16Threads, 3) bn16_kernel(const aread_bn16_args a, uint32_t threshold, float keep_scale,
+                                                               int tpr, int64_t rows_per_cta, float* __restrict__ partial) {
   __shared__ float s_red[MODE == 2 ? 2 * kBn16Threads * 8 : 1];
   const uint64_t seed = a.seed_ptr != nullptr ? __ldg(a.seed_ptr) : a.seed;
   const int cg = a.width / 8;
@@ -908,7 +911,10 @@ __global__ void __launch_bounds__(kBn16Threads) bn16_kernel(const aread_bn16_arg
   const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(a.z);
   const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(a.dy);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(a.out);
-  const bool mask_here = MODE == 0 || a.dy_is_raw != 0;
+  // the ReLU / dropout pattern of a row's 8 columns is one byte: written by the forward when the caller keeps it,
+  // read back by the backward passes instead of hashing again
+  const bool use_bits = MODE != 0 && a.dy_is_raw != 0 && a.pass_bits != nullptr;
+  const bool mask_here = MODE == 0 || (a.dy_is_raw != 0 && !use_bits);
   for (int g0 = 0; g0 < cg; g0 += tpr) {
     const int g = g0 + tx;
     const bool on = g < cg && ty < ty_n;
@@ -938,6 +944,13 @@ __global__ void __launch_bounds__(kBn16Threads) bn16_kernel(const aread_bn16_arg
         if (MODE != 0) dr = __ldg(reinterpret_cast<const uint4*>(db + r * a.ldd + col));
         const uint32_t zw[4] = {zr.x, zr.y, zr.z, zr.w};
         const uint32_t dw[4] = {dr.x, dr.y, dr.z, dr.w};
+        uint32_t bits = use_bits ? a.pass_bits[r * cg + g] : 0u, bits_out = 0u;
+        uint32_t hsh[4] = {0u, 0u, 0u, 0u};
+        if (mask_here && threshold != 0u) {
+          const uint64_t pair0 = (static_cast<uint64_t>(r) * a.width + col) >> 1;     // col % 8 == 0, width % 8 == 0
+#pragma unroll
+          for (int q = 0; q < 4; ++q) hsh[q] = dropout_pair_hash(seed, a.salt, pair0 + q);
+        }
         float out[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -946,14 +959,16 @@ __global__ void __launch_bounds__(kBn16Threads) bn16_kernel(const aread_bn16_arg
           float y = 0.f;
           if (mask_here) {
             y = fmaf(z, sc[j], sh[j]);
-            pass = y > 0.f && (threshold == 0u ||
-                               dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + col + j, threshold));
+            pass = y > 0.f && (threshold == 0u || ((j & 1) ? (hsh[j >> 1] >> 16) : (hsh[j >> 1] & 0xffffu)) >= threshold);
+            bits_out |= pass ? (1u << j) : 0u;
+          } else if (use_bits) {
+            pass = (bits >> j) & 1u;
           }
           if (MODE == 0) {
             out[j] = pass ? y * keep_scale : 0.f;
           } else {
             float dy = (j & 1) ? bf16_hi(dw[j >> 1]) : bf16_lo(dw[j >> 1]);
-            if (a.dy_is_raw) dy = pass ? dy * keep_scale : 0.f;
+            if (a.dy_is_raw) dy = pass ? dy * a.keep_scale_bwd : 0.f;
             const float xhat = (z - mu[j]) * rs[j];
             if (MODE == 1) {
               out[j] = a.bn_skip ? dy : sc[j] * (dy - c0[j] - xhat * c1[j]);
@@ -963,6 +978,7 @@ __global__ void __launch_bounds__(kBn16Threads) bn16_kernel(const aread_bn16_arg
             }
           }
         }
+        if (MODE == 0 && a.pass_bits != nullptr) a.pass_bits[r * cg + g] = static_cast<uint8_t>(bits_out);
         if (MODE != 2) {
           uint4 pk;
           pk.x = pack_bf16(out[0], out[1]);
@@ -1176,8 +1192,10 @@ extern "C" int aread_bn16(const aread_bn16_args* args, aread_stream_t stream_) {
     AREAD_REQUIRE(a.bn_skip || (a.mean && a.rstd && a.coef), "bn16: null backward input");
     AREAD_REQUIRE(!a.dy_is_raw || a.shift, "bn16: a raw gradient needs scale / shift to rebuild the ReLU mask");
     AREAD_REQUIRE(a.ldd % 8 == 0 && reinterpret_cast<uintptr_t>(a.dy) % 16 == 0, "bn16: dy rows must be 16-byte aligned");
-    AREAD_LAUNCH(bn16_kernel<1>, g.n_cta, kBn16Threads, 0, stream, a, a.dy_is_raw ? threshold : 0u,
-                 a.dy_is_raw ? keep_scale : 1.f, g.tpr, g.rows_per_cta, nullptr);
+    aread_bn16_args b = a;
+    b.keep_scale_bwd = a.dy_is_raw ? keep_scale : 1.f;
+    AREAD_LAUNCH(bn16_kernel<1>, g.n_cta, kBn16Threads, 0, stream, b, a.dy_is_raw ? threshold : 0u, 1.f, g.tpr,
+                 g.rows_per_cta, nullptr);
   } else {
     AREAD_REQUIRE(a.shift != nullptr, "bn16: null shift");
     AREAD_LAUNCH(bn16_kernel<0>, g.n_cta, kBn16Threads, 0, stream, a, threshold, keep_scale, g.tpr, g.rows_per_cta,
@@ -1196,8 +1214,10 @@ extern "C" int aread_bn16_bwd_stats(const aread_bn16_args* args, float* partial,
   const Bn16Grid g = bn16_grid(a.m, a.width);
   const uint32_t threshold = a.dy_is_raw ? dropout_threshold_of(a.dropout_p) : 0u;
   const float keep_scale = (a.dy_is_raw && a.dropout_p > 0.f) ? 1.f / (1.f - a.dropout_p) : 1.f;
-  AREAD_LAUNCH(bn16_kernel<2>, g.n_cta, kBn16Threads, 0, static_cast<cudaStream_t>(stream_), a, threshold, keep_scale,
-               g.tpr, g.rows_per_cta, partial);
+  aread_bn16_args b = a;
+  b.keep_scale_bwd = keep_scale;
+  AREAD_LAUNCH(bn16_kernel<2>, g.n_cta, kBn16Threads, 0, static_cast<cudaStream_t>(stream_), b, threshold, 1.f, g.tpr,
+               g.rows_per_cta, partial);
   return AREAD_OK;
 }
 

@@ -328,6 +328,156 @@ __global__ void __launch_bounds__(kThreads) gate_mix_bwd_kernel(const aread_gate
   }
 }
 
+// ---- direct variants for the shipped sizes (n_prev <= 8, width % 4 == 0): no staging.  Forward: one thread per
+// (sample, tower) keeps the gate weights in registers and walks its output row in float4s; the previous level's
+// activations of a sample are read by all its towers' threads (neighbours in the warp: L1 broadcasts).  Backward:
+// a CTA owns 256 / n_tower samples; phase 1 (thread = sample, tower) turns d_out into d_logits and leaves the mixing
+// weights in shared memory, phase 2 (thread = sample, previous tower, float4) gathers d_u_prev in tower order.
+constexpr int kDirectPrev = 8;
+
+struct GateRow {
+  float s[kDirectPrev], r[kDirectPrev], e[kDirectPrev];
+  float denom;
+};
+
+__device__ __forceinline__ void gate_row(const aread_gate_mix_args& a, int64_t b, int t, GateRow& w) {
+  const int NP = a.n_prev;
+  const int64_t ld = a.ld_logits > 0 ? a.ld_logits : static_cast<int64_t>(a.n_tower) * NP;
+  const float* lg = a.logits + b * ld + t * NP;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kDirectPrev; ++j)
+    if (j < NP) {
+      w.s[j] = __ldg(lg + j) + (a.logit_offset ? __ldg(a.logit_offset + t * NP + j) : 0.f);
+      w.e[j] = a.edges ? __ldg(a.edges + t * NP + j) : 1.f;
+      mx = fmaxf(mx, w.s[j]);
+    }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kDirectPrev; ++j)
+    if (j < NP) { w.s[j] = expf(w.s[j] - mx); sum += w.s[j]; }
+  const float inv = 1.f / sum;
+  w.denom = 1.f;
+  if (a.edges != nullptr) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < kDirectPrev; ++j)
+      if (j < NP) { w.s[j] *= inv; w.r[j] = w.s[j] * w.e[j]; tot += w.r[j]; }
+    w.denom = tot + 1e-8f;
+#pragma unroll
+    for (int j = 0; j < kDirectPrev; ++j)
+      if (j < NP) w.r[j] = w.r[j] / w.denom;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kDirectPrev; ++j)
+      if (j < NP) { w.s[j] *= inv; w.r[j] = w.s[j]; }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) gate_mix_fwd_direct_kernel(const aread_gate_mix_args a) {
+  const int NT = a.n_tower, NP = a.n_prev, NA = a.n_prev_active, W = a.width;
+  const int64_t total = a.m * NT;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t b = i / NT;
+    const int t = static_cast<int>(i - b * NT);
+    GateRow w;
+    gate_row(a, b, t, w);
+    int slot[kDirectPrev];
+#pragma unroll
+    for (int j = 0; j < kDirectPrev; ++j) slot[j] = j < NP ? __ldg(a.prev_slot + j) : -1;
+    if (a.sm != nullptr) {
+#pragma unroll
+      for (int j = 0; j < kDirectPrev; ++j)
+        if (j < NP) a.sm[i * NP + j] = w.s[j] * w.e[j];
+    }
+    const float4* u = reinterpret_cast<const float4*>(a.u_prev + b * (static_cast<int64_t>(NA) * W));
+    float4* out = reinterpret_cast<float4*>(a.out + i * W);
+    for (int c = 0; c < W / 4; ++c) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < kDirectPrev; ++j)
+        if (j < NP && slot[j] >= 0) {
+          const float4 v = __ldg(u + slot[j] * (W / 4) + c);
+          acc.x = fmaf(w.r[j], v.x, acc.x); acc.y = fmaf(w.r[j], v.y, acc.y);
+          acc.z = fmaf(w.r[j], v.z, acc.z); acc.w = fmaf(w.r[j], v.w, acc.w);
+        }
+      out[c] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) gate_mix_bwd_direct_kernel(const aread_gate_mix_args a, int rows_per_cta) {
+  extern __shared__ float s_r[];                     // [rows_per_cta * NT][NP]
+  const int NT = a.n_tower, NP = a.n_prev, NA = a.n_prev_active, W = a.width, W4 = a.width / 4;
+  const int64_t ldd = a.ld_dlogits > 0 ? a.ld_dlogits : static_cast<int64_t>(NT) * NP;
+  const int64_t n_tiles = (a.m + rows_per_cta - 1) / rows_per_cta;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t b0 = tile * rows_per_cta;
+    const int rows = a.m - b0 < rows_per_cta ? static_cast<int>(a.m - b0) : rows_per_cta;
+    __syncthreads();
+    if (threadIdx.x < rows * NT) {
+      const int r = threadIdx.x / NT, t = threadIdx.x - r * NT;
+      const int64_t b = b0 + r;
+      GateRow w;
+      gate_row(a, b, t, w);
+      const float4* u = reinterpret_cast<const float4*>(a.u_prev + b * (static_cast<int64_t>(NA) * W));
+      const float4* g = reinterpret_cast<const float4*>(a.d_out + (b * NT + t) * W);
+      float dr[kDirectPrev];
+#pragma unroll
+      for (int j = 0; j < kDirectPrev; ++j) dr[j] = 0.f;
+      for (int c = 0; c < W4; ++c) {
+        const float4 gv = __ldg(g + c);
+#pragma unroll
+        for (int j = 0; j < kDirectPrev; ++j) {
+          const int slot = j < NP ? __ldg(a.prev_slot + j) : -1;
+          if (slot >= 0) {
+            const float4 v = __ldg(u + slot * W4 + c);
+            dr[j] = fmaf(gv.x, v.x, fmaf(gv.y, v.y, fmaf(gv.z, v.z, fmaf(gv.w, v.w, dr[j]))));
+          }
+        }
+      }
+      float dot_r = 0.f;
+#pragma unroll
+      for (int j = 0; j < kDirectPrev; ++j)
+        if (j < NP) dot_r = fmaf(dr[j], w.r[j], dot_r);
+      float dot_s = 0.f;
+#pragma unroll
+      for (int j = 0; j < kDirectPrev; ++j)
+        if (j < NP) {
+          if (a.edges != nullptr) dr[j] = (dr[j] - dot_r) / w.denom * w.e[j];
+          dot_s = fmaf(w.s[j], dr[j], dot_s);
+        }
+      float* dl = a.d_logits + b * ldd + t * NP;
+#pragma unroll
+      for (int j = 0; j < kDirectPrev; ++j)
+        if (j < NP) {
+          dl[j] = w.s[j] * (dr[j] - dot_s);
+          s_r[threadIdx.x * NP + j] = w.r[j];
+        }
+    }
+    __syncthreads();
+    if (a.d_u_prev != nullptr) {
+      const int items = rows * NA * W4;
+      for (int it = threadIdx.x; it < items; it += kThreads) {
+        const int r = it / (NA * W4), rem = it - r * (NA * W4);
+        const int slot = rem / W4, c = rem - slot * W4;
+        const int j = __ldg(a.slot_tower + slot);
+        const int64_t b = b0 + r;
+        const float4* g = reinterpret_cast<const float4*>(a.d_out + b * (static_cast<int64_t>(NT) * W)) + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < NT; ++t) {
+          const float wt = s_r[(r * NT + t) * NP + j];
+          const float4 gv = __ldg(g + t * W4);
+          acc.x = fmaf(wt, gv.x, acc.x); acc.y = fmaf(wt, gv.y, acc.y);
+          acc.z = fmaf(wt, gv.z, acc.z); acc.w = fmaf(wt, gv.w, acc.w);
+        }
+        reinterpret_cast<float4*>(a.d_u_prev + b * (static_cast<int64_t>(NA) * W))[slot * W4 + c] = acc;
+      }
+    }
+  }
+}
+
 int pow2_ceil(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -431,6 +581,25 @@ extern "C" int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t st
     AREAD_CUDA(cudaFuncSetAttribute(gate_mix_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AREAD_CUDA(cudaFuncSetAttribute(gate_mix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
+  }
+  const bool direct = a.n_prev <= kDirectPrev && a.width % 4 == 0 && a.n_tower <= kThreads && a.n_prev_active > 0 &&
+                      ((reinterpret_cast<uintptr_t>(a.u_prev) | reinterpret_cast<uintptr_t>(a.out) |
+                        reinterpret_cast<uintptr_t>(a.d_out) | reinterpret_cast<uintptr_t>(a.d_u_prev)) & 15) == 0;
+  if (direct && a.d_out == nullptr) {
+    AREAD_REQUIRE(a.out != nullptr, "gate_mix: null out");
+    int64_t g = (a.m * a.n_tower + kThreads - 1) / kThreads;
+    if (g > kNumSMs * 16) g = kNumSMs * 16;
+    AREAD_LAUNCH(gate_mix_fwd_direct_kernel, static_cast<unsigned>(g), kThreads, 0, stream, a);
+    return AREAD_OK;
+  }
+  if (direct) {
+    AREAD_REQUIRE(a.d_logits && a.slot_tower, "gate_mix: null gradient pointer");
+    const int rows_per_cta = kThreads / a.n_tower;
+    int64_t g = (a.m + rows_per_cta - 1) / rows_per_cta;
+    if (g > kNumSMs * 16) g = kNumSMs * 16;
+    AREAD_LAUNCH(gate_mix_bwd_direct_kernel, static_cast<unsigned>(g), kThreads,
+                 sizeof(float) * rows_per_cta * a.n_tower * a.n_prev, stream, a, rows_per_cta);
+    return AREAD_OK;
   }
   if (a.d_out == nullptr) {
     AREAD_REQUIRE(a.out != nullptr, "gate_mix: null out");

@@ -239,41 +239,44 @@ def identity_saved(width, device):
     return saved
 
 
-def bn16_fwd(z, saved, training, p, seed, salt):
-    """bf16(dropout(relu(z * scale + shift))) from the bf16 pre-activation."""
+def bn16_fwd(z, saved, training, p, seed, salt, want_bits=False):
+    """bf16(dropout(relu(z * scale + shift))) from the bf16 pre-activation; with want_bits also the [m, width / 8]
+    uint8 map of the elements that passed ReLU and dropout (the backward reads it instead of hashing again)."""
     m, width = z.shape
     out = _mem.empty((m, width), torch.bfloat16, z.device)
+    bits = _mem.empty((m, width // 8), torch.uint8, z.device) if want_bits else None
     sv = _rows(saved, 4)
     args = _lib.Bn16Args(m, width, 0, z.data_ptr(), z.stride(0), sv[2], sv[3], float(p) if training else 0.0, salt, seed,
-                         SEED_PTR, out.data_ptr(), width, None, 0, None, None, None, 0)
+                         SEED_PTR, out.data_ptr(), width, None, 0, None, None, None, 0, _ptr(bits), 1.0)
     _lib.check(_lib.load().aread_bn16(ctypes.byref(args), _stream(z.device)))
-    return out
+    return (out, bits) if want_bits else out
 
 
-def bn16_bwd(z, dy, saved, coef, bn_skip, out=None, raw=False, p=0.0, salt=0, seed=0):
+def bn16_bwd(z, dy, saved, coef, bn_skip, out=None, raw=False, p=0.0, salt=0, seed=0, bits=None):
     """dz16 = bf16(scale * (dy - coef0 - xhat * coef1)) from the bf16 pre-activation and the bf16 gradient.  raw=False:
     `dy` already carries the ReLU / dropout mask (BN_BWD epilogue); raw=True: it is the gradient w.r.t. the activated
-    output and the mask is rebuilt from (z, saved, p, salt, seed).  `out`: a preallocated [m, width] bf16 view (any
-    16-byte aligned row stride)."""
+    output and the mask comes from `bits` (bn16_fwd) or is rebuilt from (z, saved, p, salt, seed).  `out`: a
+    preallocated [m, width] bf16 view (any 16-byte aligned row stride)."""
     m, width = z.shape
     if out is None:
         out = _mem.empty((m, width), torch.bfloat16, z.device)
     sv = _rows(saved, 4)
     args = _lib.Bn16Args(m, width, 1 if bn_skip else 0, z.data_ptr(), z.stride(0), sv[2], sv[3], float(p), salt, seed,
                          SEED_PTR, out.data_ptr(), out.stride(0), dy.data_ptr(), dy.stride(0), sv[0], sv[1],
-                         coef.data_ptr(), 1 if raw else 0)
+                         coef.data_ptr(), 1 if raw else 0, _ptr(bits), 1.0)
     _lib.check(_lib.load().aread_bn16(ctypes.byref(args), _stream(z.device)))
     return out
 
 
-def bn16_bwd_stats(z, d_h, saved, bn_skip, p, salt, seed):
-    """partial [ctas, 2, width]: per-CTA sums of dy and dy * xhat, dy = d_h masked by ReLU / dropout (rebuilt here)."""
+def bn16_bwd_stats(z, d_h, saved, bn_skip, p, salt, seed, bits=None):
+    """partial [ctas, 2, width]: per-CTA sums of dy and dy * xhat, dy = d_h masked by ReLU / dropout (from `bits`, or
+    rebuilt here)."""
     m, width = z.shape
     n_part = int(_lib.load().aread_bn16_partials(m, width))
     partial = _mem.empty((n_part, 2, width), torch.float32, z.device)
     sv = _rows(saved, 4)
     args = _lib.Bn16Args(m, width, 1 if bn_skip else 0, z.data_ptr(), z.stride(0), sv[2], sv[3], float(p), salt, seed,
-                         SEED_PTR, None, 0, d_h.data_ptr(), d_h.stride(0), sv[0], sv[1], None, 1)
+                         SEED_PTR, None, 0, d_h.data_ptr(), d_h.stride(0), sv[0], sv[1], None, 1, _ptr(bits), 1.0)
     _lib.check(_lib.load().aread_bn16_bwd_stats(ctypes.byref(args), ctypes.c_void_p(partial.data_ptr()), _stream(z.device)))
     return partial
 

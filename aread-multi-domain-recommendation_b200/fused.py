@@ -446,7 +446,7 @@ class AreadNode(torch.autograd.Function):
                 out, stats = (res[0], res[-1]) if not (precise and not last) else ((res[0], res[1]), res[2])
                 if training and not bn_skip:
                     torch._foreach_add_(L.tracked, 1)
-                ex.append((a_op, z, stats, w))
+                ex.append((a_op, z, stats, w, None))
                 a_op = out
         else:
             # bf16 experts: the GEMM epilogue leaves the BatchNorm column sums and the pre-activation ONCE, as bf16
@@ -460,14 +460,19 @@ class AreadNode(torch.autograd.Function):
                 if keep_z:
                     z, partial = dk.expert_linear_stats(a_op, w16[i], L.n, L.k, G, agc)
                     stats = dk.expert_bn_finalize(partial, B, G * L.n, *bn, training, bn_skip)
-                    out = None if last else dk.bn16_fwd(z, stats, training, p_drop, seed, L.salt)
+                    out = bits = None
+                    if not last:      # with a backward to come, the ReLU / dropout pattern is kept as one bit per element
+                        want = torch.is_grad_enabled() and not FUSED_BN_BWD
+                        res = dk.bn16_fwd(z, stats, training, p_drop, seed, L.salt, want_bits=want)
+                        out, bits = res if want else (res, None)
                 else:
                     folded = dk.expert_bn_finalize(None, B, G * L.n, *bn, False, bn_skip)
                     out = z = dk.expert_linear_act(a_op, w16[i], L.n, L.k, G, agc, folded)
                     stats = dk.identity_saved(G * L.n, dev) if last else None
+                    bits = None
                 if training and not bn_skip:
                     torch._foreach_add_(L.tracked, 1)
-                ex.append((a_op, z, stats, w16[i]))
+                ex.append((a_op, z, stats, w16[i], bits if keep_z else None))
                 a_op = out
         h = dk.mmoe_mix_fwd(ex[-1][1], ex[-1][2], gate, G, len(a0), p_drop if training else 0.0, seed,
                             P.experts[-1].salt)                                          # [B, na0, H]
@@ -693,7 +698,7 @@ class AreadNode(torch.autograd.Function):
         if not sv["fused_bn"]:
             for i in range(len(P.experts) - 1, -1, -1):
                 L = P.experts[i]
-                a_in, z, stats, w = ex[i]
+                a_in, z, stats, w, _ = ex[i]
                 dze, d_gamma, d_beta, d_bias = dk.bn_act_bwd(z, d_act, stats, bn_skip, p_drop, seed, L.salt,
                                                              want_lo=precise)
                 d_w = dk.grouped_wgrad(_hi(dze), _hi(a_in), L.n, L.k, G, 0 if i == 0 else L.k, dz_lo=_lo(dze),
@@ -716,12 +721,12 @@ class AreadNode(torch.autograd.Function):
                                                          dz_out=out0)
             for i in range(n_l - 1, -1, -1):
                 L = P.experts[i]
-                a_in, z, stats, w = ex[i]
+                a_in, z, stats, w, _ = ex[i]
                 d_w = dk.grouped_wgrad(dze, a_in, L.n, L.k, G, 0 if i == 0 else L.k)
                 expert_grads[i] = (d_w.view(G, L.n, L.k), d_bias.view(G, L.n), d_gamma.view(G, L.n), d_beta.view(G, L.n))
                 if i > 0:
                     Lp = P.experts[i - 1]
-                    _, z_p, stats_p, _ = ex[i - 1]
+                    _, z_p, stats_p, _, bits_p = ex[i - 1]
                     out_l = dz0[:, :G * L0.n] if (tc_row and i == 1) else None
                     if FUSED_BN_BWD:    # masks + BatchNorm sums in the GEMM epilogue (4 epilogue warps do the elementwise work)
                         dy, partial = dk.expert_dgrad_bn_bwd(dze, w, L.k, L.n, G, z_p, stats_p, p_drop, Lp.salt, seed)
@@ -729,10 +734,10 @@ class AreadNode(torch.autograd.Function):
                         dze = dk.bn16_bwd(z_p, dy, stats_p, coef, bn_skip, out=out_l)
                     else:               # plain bf16 data gradient, then two full-occupancy passes over (z16, d_h16)
                         d_h16 = dk.expert_dgrad_bf16(dze, w, L.k, L.n, G)
-                        partial = dk.bn16_bwd_stats(z_p, d_h16, stats_p, bn_skip, p_drop, Lp.salt, seed)
+                        partial = dk.bn16_bwd_stats(z_p, d_h16, stats_p, bn_skip, p_drop, Lp.salt, seed, bits=bits_p)
                         coef, g3 = dk.expert_bn_bwd_finalize(partial, B, G * L.k, bn_skip)
                         dze = dk.bn16_bwd(z_p, d_h16, stats_p, coef, bn_skip, out=out_l, raw=True, p=p_drop, salt=Lp.salt,
-                                          seed=seed)
+                                          seed=seed, bits=bits_p)
                     d_gamma, d_beta, d_bias = g3[0], g3[1], g3[2]
                 elif tc_row:
                     # weight rows [W_layer1 (k-by-n) ; Wcat_hi ; Wcat_lo ; Wcat_hi]: ONE GEMM returns d_x of both paths

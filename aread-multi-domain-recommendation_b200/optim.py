@@ -248,7 +248,8 @@ class FusedAdam(torch.optim.Optimizer):
                 base, row = dev_table.data_ptr(), dev_table.stride(0) * 8
                 args = _lib.AdamArgs(n, plan.n_chunks, base, base + row, base + 2 * row, base + 3 * row, base + 4 * row,
                                      base + 5 * row, None, None, beta1, beta2, eps, wd,
-                                     base + 8 * row if plan.has_l2 else None, ctr.data_ptr(), plan.slot_dev.data_ptr(), lr)
+                                     base + 8 * row if plan.has_l2 else None, ctr.data_ptr(), plan.slot_dev.data_ptr(), lr,
+                                     beta1, beta2)
                 _lib.check(lib.aread_adam_step(ctypes.byref(args),
                                                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
                 # the recorded upload re-reads `host` at every replay: it lives as long as the graph that owns this record
@@ -270,7 +271,7 @@ class FusedAdam(torch.optim.Optimizer):
             base, row = dev.data_ptr(), dev.stride(0) * 8
             args = _lib.AdamArgs(n, plan.n_chunks, base, base + row, base + 2 * row, base + 3 * row, base + 4 * row,
                                  base + 5 * row, base + 6 * row, base + 7 * row, beta1, beta2, eps, wd,
-                                 base + 8 * row if plan.has_l2 else None, None, None, lr)
+                                 base + 8 * row if plan.has_l2 else None, None, None, lr, beta1, beta2)
             _lib.check(lib.aread_adam_step(ctypes.byref(args),
                                            ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
             ctr = self._counters.get((gi, device))

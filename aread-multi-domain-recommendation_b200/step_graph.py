@@ -89,6 +89,7 @@ class GraphedTrainStep:
         launches0 = _lib.launch_count()
         use_graphs, bounds, seed_ptr = fused.USE_GRAPHS, layer.BOUNDS_MODE, fused.STEP_SEED_PTR
         fused.USE_GRAPHS, layer.BOUNDS_MODE, fused.STEP_SEED_PTR = False, "off", e.seed.data_ptr()
+        rng = torch.get_rng_state()         # the recording draws a (discarded) seed: replays must see the caller's stream
         try:
             model.zero_grad()
             with fused._recording(graph, self.pool, dev):
@@ -99,6 +100,7 @@ class GraphedTrainStep:
                 e.loss = loss.detach().reshape(())
         finally:
             fused.USE_GRAPHS, layer.BOUNDS_MODE, fused.STEP_SEED_PTR = use_graphs, bounds, seed_ptr
+            torch.set_rng_state(rng)
         e.n_launch = _lib.launch_count() - launches0
         _lib.load().aread_launch_count_add(-e.n_launch & 0xFFFFFFFFFFFFFFFF)   # recorded, not run: replays count them
         e.plans = opt.captured_plans[n0:]

@@ -97,6 +97,22 @@ class Workload:
         return x, y, domain
 
 
+def _batch_mixed(self, B, seed, sort=True):
+    """(x int32 [B, n_cols], y int16 [B, 1]): rows of MANY domains drawn in proportion to `domain_size`; with `sort`
+    the rows are ordered by domain (the domain-sorted, segment-per-domain layout of BASELINE configs[2-3])."""
+    x, y, _ = self.batch(B, seed, domain=0)
+    rng = np.random.RandomState(seed + 7)
+    p = np.asarray(self.domain_size, dtype=np.float64)
+    dom = rng.choice(self.n_domain, size=B, p=p / p.sum())
+    if sort:
+        dom = np.sort(dom, kind="stable")
+    x[:, self.domain_idx] = dom.astype(np.int32)
+    return x, y
+
+
+Workload.batch_mixed = _batch_mixed
+
+
 def amazon_shaped(id_dist="zipf"):
     """BASELINE.json configs[1]: 7 one-hot fields + 2 item-history fields of 5, 25 domains."""
     return Workload("amazon_shaped", AMAZON_FIELD_DIMS, domain_idx=2, itemid_idx=0, n_domain=25,

@@ -565,6 +565,10 @@ def extra_legs(args, wl, tr, pkg, lib, ops, dev, rank, world, timed, kernel_ms, 
     # optimizer reset + 5 bagging steps with prun_single_mask + 5 no_grad scoring passes
     extra["regroup"] = regroup_leg(tr, wl, dev, dev_x, dev_y, n_domains=min(wl.n_domain, 30), candidates=10)
 
+    # ---- mixed-domain eval (BASELINE configs[3]): one 64K batch over the 355 Cloud-Theme-shaped domains
+    extra["cloudtheme_mixed"] = mixed_leg(args, pkg, dev, kernel_ms)
+    torch.cuda.empty_cache()
+
     # ---- torch-eager on the same GPU: the oracle port's ops on cuda (SURVEY 8d "same-box GPU bar")
     if not args.no_cpu_baseline:
         try:
@@ -575,6 +579,55 @@ def extra_legs(args, wl, tr, pkg, lib, ops, dev, rank, world, timed, kernel_ms, 
             extra["gpu_eager_baseline"] = {"unavailable": str(e)[:120]}
         torch.cuda.empty_cache()
     return extra
+
+
+def mixed_leg(args, pkg, dev, kernel_ms, B=65536):
+    """AREAD.forward_mixed (eval, every row under its own domain's mask) on a Cloud-Theme-shaped model with 355 domains:
+    domain-sorted against shuffled rows at three mask densities -- sorted rows let the HEI kernel skip the (32-row
+    tile, tower) pairs the masks prune -- and the reference's way of evaluating the same rows, one call per domain."""
+    wl = importlib.import_module(PKG + ".workloads").WORKLOADS["cloudtheme"]()
+    model = pkg.AREAD(np.asarray(wl.one_hot_field_dims), wl.embed_dim, wl.multi_hot_dict, n_tower=N_TOWER,
+                      n_domain=wl.n_domain, base_model="mmoe", expert_dims=EXPERT_DIMS, tower_dims=TOWER_DIMS,
+                      domain_idx=wl.domain_idx, device=dev, dropout=args.dropout, config=make_config(wl)).to(dev).eval()
+    model.reset_for_mask_update()
+    xs, _ = wl.batch_mixed(B, args.seed, sort=True)
+    xu, _ = wl.batch_mixed(B, args.seed, sort=False)
+    xs, xu = torch.from_numpy(xs).to(dev), torch.from_numpy(xu).to(dev)
+    seg = np.bincount(xs[:, wl.domain_idx].cpu().numpy(), minlength=wl.n_domain)
+    out = {"batch": B, "n_domain": wl.n_domain, "domains_present": int((seg > 0).sum()),
+           "segment_rows_median": float(np.median(seg[seg > 0])), "segment_rows_min": int(seg[seg > 0].min()),
+           "vocabularies": "assumed (dataset not bundled): 0.72 M users, 1.36 M items, 1,000 leaf / 100 L1 categories",
+           "mode": "eval(), no_grad, AREAD.forward_mixed (= 'domain_with_mask' per row)", "by_active_percent": {}}
+    for active in (0.7, 0.3, 0.1):
+        np.random.seed(args.seed + int(active * 100))
+        for d in range(wl.n_domain):
+            model.domain_mask[d] = model.generate_mask("rand", d, init_active_percent=active)
+        towers = np.mean([[len(a) for a in model.mask_info(model.domain_mask[d]).active_idx] for d in range(wl.n_domain)],
+                         axis=0)
+        ms_sorted = kernel_ms(lambda i: model.forward_mixed(xs), 3, 10)
+        ms_shuffled = kernel_ms(lambda i: model.forward_mixed(xu), 3, 10)
+        rec = {"mean_active_towers_per_level": [round(float(t), 2) for t in towers],
+               "sorted_ms": ms_sorted, "sorted_samples_per_sec": B / (ms_sorted * 1e-3),
+               "shuffled_ms": ms_shuffled, "skip_speedup_sorted_vs_shuffled": ms_shuffled / ms_sorted}
+        if active == 0.3:       # the reference's evaluation of the same rows: one call per domain (run.py:719-727)
+            bounds = np.concatenate(([0], np.cumsum(seg)))
+            parts = [(d, xs[bounds[d]:bounds[d + 1]]) for d in range(wl.n_domain) if seg[d] > 0]
+
+            def per_domain(i):
+                with torch.no_grad():
+                    for d, xd in parts:
+                        model(xd, mode="domain_with_mask", domain_i=d)
+            fused = importlib.import_module(PKG + ".fused")
+            keep, fused.USE_GRAPHS = fused.USE_GRAPHS, False      # 300+ one-off shapes: nothing worth recording
+            try:
+                ms_loop = kernel_ms(per_domain, 1, 2)
+            finally:
+                fused.USE_GRAPHS = keep
+            rec["per_domain_calls_ms"] = ms_loop
+            rec["speedup_vs_per_domain_calls"] = ms_loop / ms_sorted
+        out["by_active_percent"][str(active)] = rec
+    del model
+    return out
 
 
 def regroup_leg(tr, wl, dev, dev_x, dev_y, n_domains, candidates, update_steps=5, eval_steps=5):

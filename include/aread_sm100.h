@@ -293,7 +293,11 @@ typedef struct aread_bn16_args {
   const float* rstd;
   const float* coef;      /* backward: fp32 [2, width] */
   int32_t dy_is_raw;      /* backward: 1 = `dy` is the gradient w.r.t. the ACTIVATED output (a plain data-gradient GEMM
-                             wrote it); the ReLU / dropout mask is rebuilt here from z, scale, shift, dropout_p, seed */
+                             wrote it); the ReLU / dropout mask is applied here: read from pass_bits when given, else
+                             rebuilt from z, scale, shift, dropout_p, seed                                          */
+  uint8_t* pass_bits;     /* optional [m, width / 8]: bit j of byte (row, g) = element (row, 8 g + j) passed ReLU and
+                             dropout.  Written by the forward, read by the backward passes                          */
+  float keep_scale_bwd;   /* set by the library                                                                     */
 } aread_bn16_args;
 
 AREAD_API int aread_bn16(const aread_bn16_args* args, aread_stream_t stream);
@@ -786,7 +790,8 @@ typedef struct aread_adam_args {
      the counter in double precision.                                                                              */
   float* step_counts;            /* device [any]: one fp32 counter per parameter                         */
   const int64_t* slot;           /* device [n_tensors]: index of tensor t's counter                      */
-  float lr;
+  double lr, beta1_d, beta2_d;   /* the hyper-parameters as the host holds them (Python floats are doubles): the  */
+                                 /* corrections then equal the host-computed ones bit for bit             */
 } aread_adam_args;
 
 AREAD_API int64_t aread_adam_chunk(void);

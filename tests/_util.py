@@ -58,3 +58,43 @@ def assert_after_adam(actual, comp, steps, lr, what="", frac=0.02):
     soft = 0.05 * steps * lr + 1e-4 * e.abs()
     n_bad = int((err > soft).sum())
     assert n_bad <= max(4, int(frac * err.numel())), f"{what}: {n_bad}/{err.numel()} beyond 5% of the Adam travel"
+
+
+import re as _re
+
+GRAD_FAMILIES = [
+    ("table", _re.compile(r"^embedding\.")),
+    ("linear_cross", _re.compile(r"^(linear|cn)\.")),
+    ("expert_weights", _re.compile(r"^mmoe_experts\.\d+\.layers\.(0|4|8)\.weight$")),
+    ("expert_bn", _re.compile(r"^mmoe_experts\.\d+\.layers\.(1|5|9)\.")),
+    ("mmoe_gates", _re.compile(r"^mmoe_gates\.")),
+    ("tower_weights", _re.compile(r"^towers\.\d+\.\d+\.layers\.(0|4)\.weight$")),
+    ("tower_bn", _re.compile(r"^towers\.\d+\.\d+\.layers\.(1|5)\.")),
+    ("tower_gates", _re.compile(r"^(tower_gates|group_embedding)\.")),
+    ("heads", _re.compile(r"^towers_linear\.")),
+]
+PRE_BN_BIAS = _re.compile(r"\.layers\.(0|4|8)\.bias$")      # true gradient is zero (BatchNorm removes the bias)
+
+
+def family_errors(pairs):
+    """pairs: iterable of (state_dict key, gradient, reference gradient) as flat CPU tensors of equal length.
+    -> {family: (normalised error ||g - ref|| / ||ref||, 1 - cosine)} over the concatenation of the family's tensors.
+    Single small tensors behind the towers are residues of cancelling terms (their own normalised error is dominated
+    by round-off amplification); the family vector is what an optimizer step sees."""
+    buckets = {}
+    for k, g, ref in pairs:
+        if PRE_BN_BIAS.search(k):
+            continue
+        for fam, pat in GRAD_FAMILIES:
+            if pat.search(k):
+                a, b = buckets.setdefault(fam, ([], []))
+                a.append(g.reshape(-1).double())
+                b.append(ref.reshape(-1).double())
+                break
+    out = {}
+    for fam, (a, b) in buckets.items():
+        a, b = torch.cat(a), torch.cat(b)
+        nb = float(b.norm())
+        if nb > 0:
+            out[fam] = (float((a - b).norm()) / nb, 1.0 - float(a @ b) / (float(a.norm()) * nb + 1e-300))
+    return out

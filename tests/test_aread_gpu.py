@@ -15,7 +15,7 @@ is fp32.  Stated tolerances:
     probabilities |d| <= 1e-2, loss rel 5e-3 against the fp32 goldens;
   * against the oracle evaluated with the SAME operand rounding (Spec.expert_operand_dtype=bf16):
     probabilities |d| <= 2e-3, loss rel 1e-3, and every gradient tensor closer to that oracle than
-    max(1e-1 (gate parameters 3e-1), 1.5 x the effect the operand rounding itself has on that gradient);
+    max(2e-1 (gate parameters 4e-1), 1.5 x the effect the operand rounding itself has on that gradient);
   * |dAUC| < 1e-4 after 30 steps on identical weights.
 
 Gate-mean side outputs (the HEMP thresholds compare them) are fp32 in both modes: round-off only."""
@@ -29,13 +29,13 @@ import torch
 from oracle import aread_torch as O
 from oracle import synth
 from tests._models import build_model
-from tests._util import CASES, assert_close, load_golden
+from tests._util import CASES, assert_close, family_errors, load_golden
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 TOL = {
-    "bf16x3": dict(prob=(1e-4, 1e-4), logit=(1e-4, 2e-4), train_prob=2e-4, loss=1e-4, grad=3e-2, grad_gate=5e-2,
+    "bf16x3": dict(prob=(1e-4, 1e-4), logit=(1e-4, 2e-4), train_prob=2e-4, loss=1e-4, grad=2e-2, grad_gate=5e-2,
                    after=2e-3),
     "bf16": dict(prob=(1e-3, 1e-3), logit=(1e-3, 2e-3), train_prob=1e-2, loss=5e-3, grad=None, grad_gate=None,
                  after=1e-2),
@@ -43,7 +43,7 @@ TOL = {
 SAME_ROUNDING_PROB_ATOL = 2e-3             # bf16 mode vs the oracle with bf16 expert operands
 # ... and its gradients, per tensor: normalised error below max(this, 1.5 x what the operand rounding itself does to
 # that tensor).  Gate parameters (their gradients are small differences of large terms) get the wider base.
-SAME_ROUNDING_GRAD, SAME_ROUNDING_GRAD_GATE = 1e-1, 3e-1
+SAME_ROUNDING_GRAD, SAME_ROUNDING_GRAD_GATE = 2e-1, 4e-1
 PRE_BN_BIAS = re.compile(r"\.layers\.(0|4|8)\.bias$")
 GATE_PARAM = re.compile(r"^(tower_gates|mmoe_gates|group_embedding)\.")
 PRECISIONS = ("bf16x3", "bf16")
@@ -57,6 +57,28 @@ def logit(p):
 def check_probs(got, ref, what, tol):
     assert_close(got, ref, tol["prob"][0], tol["prob"][1], what)
     assert_close(logit(got.cpu()).float(), logit(ref).float(), tol["logit"][0], tol["logit"][1], what + " (logits)")
+
+
+def check_grads(model, golden_grads, tol, what):
+    """Gradients against the reference's, per parameter family (tests/_util.family_errors); pre-BatchNorm biases and
+    other exactly-zero gradients must be ~0."""
+    pairs = []
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        comp = golden_grads[k]
+        ref = comp["full"] if "full" in comp else comp["sample"]
+        got = p.grad.detach().cpu().float()
+        got = got if "full" in comp else got.reshape(-1)[::comp["stride"]][:ref.numel()]
+        if PRE_BN_BIAS.search(k) or float(ref.abs().max()) < 1e-7:
+            assert float(got.abs().max()) < 1e-4, f"{what} grad {k} should be ~0"
+            continue
+        pairs.append((k, got.reshape(-1), ref.float().reshape(-1)))
+    if tol["grad"] is None:
+        return
+    for fam, (err, _) in family_errors(pairs).items():
+        limit = tol["grad_gate"] if fam in ("tower_gates", "mmoe_gates") else tol["grad"]
+        assert err < limit, f"{what} gradient of family {fam}: normalised error {err:.3e} (limit {limit})"
 
 
 def grad_of(compact):
@@ -138,20 +160,7 @@ def test_train_step_matches_reference(name, mk, precision):
                 assert_close(model.tmp_tower_gate_values[l][t], ref, 1e-5, 1e-6, f"gate mean {l},{t}")
             none_keys = sorted(k for k, p in model.named_parameters() if p.grad is None)
             assert none_keys == tr["grad_none"], "set of parameters without gradient"
-            for k, p in model.named_parameters():
-                if p.grad is None:
-                    continue
-                comp = tr["grads"][k]
-                ref = comp["full"] if "full" in comp else comp["sample"]
-                got = p.grad.detach().cpu().float()
-                got = got if "full" in comp else got.reshape(-1)[::comp["stride"]][:ref.numel()]
-                scale = float(ref.abs().max())
-                if PRE_BN_BIAS.search(k) or scale < 1e-7:
-                    assert float(got.abs().max()) < 1e-4, f"grad {k} should be ~0"     # true gradient is zero
-                    continue
-                err = float((got - ref).norm() / (ref.norm() + 1e-12))
-                limit = tol["grad_gate"] if GATE_PARAM.search(k) else tol["grad"]
-                assert limit is None or err < limit, f"grad {k}: normalised error {err:.3e}"
+            check_grads(model, tr["grads"], tol, "train")
         opt.step()
         assert_close(loss, tr[f"loss{step}"], tol["loss"] * (1 + 4 * step), 1e-5, f"loss{step}")
     model.eval()
@@ -181,20 +190,7 @@ def test_wo_mask_train_matches_reference(name, precision):
     for (l, t), ref in tr["recorded"].items():
         assert_close(model.domain_tower_gate_values[dom][l][t][0], ref, 1e-5, 1e-6, f"recorded gate {l},{t}")
     assert sorted(k for k, p in model.named_parameters() if p.grad is None) == tr["grad_none"]
-    for k, p in model.named_parameters():                      # warm-up gradients (run.py:597-603)
-        if p.grad is None:
-            continue
-        comp = tr["grads"][k]
-        ref = comp["full"] if "full" in comp else comp["sample"]
-        got = p.grad.detach().cpu().float()
-        got = got if "full" in comp else got.reshape(-1)[::comp["stride"]][:ref.numel()]
-        scale = float(ref.abs().max())
-        if PRE_BN_BIAS.search(k) or scale < 1e-7:
-            assert float(got.abs().max()) < 1e-4, f"grad {k} should be ~0"
-            continue
-        err = float((got - ref).norm() / (ref.norm() + 1e-12))
-        limit = tol["grad_gate"] if GATE_PARAM.search(k) else tol["grad"]
-        assert limit is None or err < limit, f"wo_mask grad {k}: normalised error {err:.3e}"
+    check_grads(model, tr["grads"], tol, "wo_mask")               # warm-up gradients (run.py:597-603)
 
 
 @pytest.mark.parametrize("name", CASES)

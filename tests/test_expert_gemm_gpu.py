@@ -170,3 +170,41 @@ def test_weight_cast_one_launch():
         assert torch.equal(o, f.to(torch.bfloat16))
     flats[1].mul_(3)
     assert torch.equal(wc.run()[1], flats[1].to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("m,width", [(300, 1024), (4096, 512), (129, 64), (1000, 256)])
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_unfused_bn_backward_passes(m, width, p):
+    """bn16_fwd's pass bits, bn16_bwd_stats and bn16_bwd(raw=True) -- the default backward of the bf16 experts -- against
+    torch on the same inputs; with and without the bit map (the mask is then rebuilt from the dropout stream)."""
+    gen = torch.Generator(device=DEV).manual_seed(m + width)
+    z = torch.randn(m, width, device=DEV, generator=gen).to(torch.bfloat16)
+    d_h = torch.randn(m, width, device=DEV, generator=gen).to(torch.bfloat16)
+    saved = torch.empty(4, width, device=DEV)
+    saved[0] = 0.1 * torch.randn(width, device=DEV, generator=gen)
+    saved[1] = 0.5 + torch.rand(width, device=DEV, generator=gen)
+    saved[2] = saved[1] * (1 + 0.1 * torch.randn(width, device=DEV, generator=gen))
+    saved[3] = 0.1 * torch.randn(width, device=DEV, generator=gen)
+    seed, salt = 987654321, 0x1002
+    h, bits = dk.bn16_fwd(z, saved, True, p, seed, salt, want_bits=True)
+    zf = z.float()
+    y = zf * saved[2] + saved[3]
+    keep = dk.dropout_mask(seed, salt, (m, width), p, DEV) if p > 0 else torch.ones(m, width, dtype=torch.bool, device=DEV)
+    passed = (y > 0) & keep
+    want_h = torch.where(passed, y / (1 - p), torch.zeros_like(y))
+    assert float((h.float() - want_h).abs().max()) <= 2.0 ** -7 * float(want_h.abs().max()) + 1e-6
+    unpacked = ((bits.view(m, width // 8, 1).int() >> torch.arange(8, device=DEV).view(1, 1, 8)) & 1).bool().view(m, width)
+    assert torch.equal(unpacked, h != 0) or torch.equal(unpacked, passed)
+    if p > 0:
+        assert abs(float(keep.float().mean()) - (1 - p)) < 5e-3
+    dy = torch.where(unpacked, d_h.float() / (1 - p), torch.zeros_like(y))
+    xhat = (zf - saved[0]) * saved[1]
+    for use_bits in (True, False):
+        partial = dk.bn16_bwd_stats(z, d_h, saved, False, p, salt, seed, bits=bits if use_bits else None)
+        s1, s2 = partial[:, 0].sum(dim=0), partial[:, 1].sum(dim=0)
+        torch.testing.assert_close(s1, dy.sum(dim=0), rtol=0, atol=1e-4 * float(dy.abs().sum(dim=0).max()) + 1e-5)
+        torch.testing.assert_close(s2, (dy * xhat).sum(dim=0), rtol=0, atol=1e-4 * float((dy * xhat).abs().sum(dim=0).max()) + 1e-5)
+        coef, grads = dk.expert_bn_bwd_finalize(partial, m, width, False)
+        dz = dk.bn16_bwd(z, d_h, saved, coef, False, raw=True, p=p, salt=salt, seed=seed, bits=bits if use_bits else None)
+        want = saved[2] * (dy - coef[0] - xhat * coef[1])
+        assert float((dz.float() - want).abs().max()) <= 2.0 ** -7 * float(want.abs().max()) + 1e-5

@@ -48,7 +48,7 @@ PRE_BN_BIAS = re.compile(r"\.layers\.(0|4|8)\.bias$")      # true gradient is ze
 # summation order and the bf16 rounding of the back-propagated dy / dz.
 SAME_ROUNDING_BOUNDS = {"table": (1e-3, 1e-6), "linear_cross": (1e-4, 1e-8), "expert_weights": (1e-1, 5e-3),
                         "expert_bn": (1e-1, 5e-3), "mmoe_gates": (1.2e-1, 6e-3), "tower_weights": (8e-2, 3e-3),
-                        "tower_bn": (3e-2, 5e-4), "tower_gates": (1e-1, 5e-3), "heads": (1e-4, 1e-8)}
+                        "tower_bn": (3e-2, 5e-4), "tower_gates": (2e-1, 2e-2), "heads": (1e-4, 1e-8)}
 # Against the fp32 oracle.  The gradients of everything BEHIND the towers are small residues of large cancelling terms
 # at these (random-label) operating points: rounding the expert operands to bf16 -- the definition of the "bf16
 # experts" configuration -- moves them by 0.20-0.24 in the fp32 CPU oracle itself (measured: oracle fp32 vs oracle
@@ -57,7 +57,7 @@ SAME_ROUNDING_BOUNDS = {"table": (1e-3, 1e-6), "linear_cross": (1e-4, 1e-8), "ex
 # tight.
 GRAD_BOUNDS = {"table": (5e-3, 1e-5), "linear_cross": (1e-4, 1e-8), "expert_weights": (4e-1, 8e-2),
                "expert_bn": (4e-1, 8e-2), "mmoe_gates": (4e-1, 8e-2), "tower_weights": (3.5e-1, 6e-2),
-               "tower_bn": (1.5e-1, 1e-2), "tower_gates": (3e-1, 4e-2), "heads": (1e-3, 1e-6)}
+               "tower_bn": (2.5e-1, 3e-2), "tower_gates": (3e-1, 4e-2), "heads": (1e-3, 1e-6)}
 TRAIN_PROB_MAX, TRAIN_PROB_MEAN, TRAIN_PROB_SAME = 2e-2, 1e-3, 5e-3
 
 

@@ -900,7 +900,7 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 constexpr int kBn16Threads = 256;
 
 template <int MODE>
-__global__ void __launch_bounds__(kBn16Threads, 3) bn16_kernel(const aread_bn16_args a, uint32_t threshold, float keep_scale,
+__global__ void __launch_bounds__(kBn16Threads, 2) bn16_kernel(const aread_bn16_args a, uint32_t threshold, float keep_scale,
                                                                int tpr, int64_t rows_per_cta, float* __restrict__ partial) {
   __shared__ float s_red[MODE == 2 ? 2 * kBn16Threads * 8 : 1];
   const uint64_t seed = a.seed_ptr != nullptr ? __ldg(a.seed_ptr) : a.seed;
@@ -937,55 +937,71 @@ __global__ void __launch_bounds__(kBn16Threads, 3) bn16_kernel(const aread_bn16_
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     if (on) {
-#pragma unroll 2
-      for (int64_t r = r0 + ty; r < r1; r += ty_n) {
-        const uint4 zr = __ldg(reinterpret_cast<const uint4*>(zb + r * a.ldz + col));
-        uint4 dr = make_uint4(0, 0, 0, 0);
-        if (MODE != 0) dr = __ldg(reinterpret_cast<const uint4*>(db + r * a.ldd + col));
-        const uint32_t zw[4] = {zr.x, zr.y, zr.z, zr.w};
-        const uint32_t dw[4] = {dr.x, dr.y, dr.z, dr.w};
-        uint32_t bits = use_bits ? a.pass_bits[r * cg + g] : 0u, bits_out = 0u;
-        uint32_t hsh[4] = {0u, 0u, 0u, 0u};
-        if (mask_here && threshold != 0u) {
-          const uint64_t pair0 = (static_cast<uint64_t>(r) * a.width + col) >> 1;     // col % 8 == 0, width % 8 == 0
+      constexpr int U = 4;                      // rows in flight per thread: the loads of a batch are issued together
+      for (int64_t rb = r0 + ty; rb < r1; rb += static_cast<int64_t>(ty_n) * U) {
+        uint4 zq[U], dq[U];
+        uint32_t bq[U];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) hsh[q] = dropout_pair_hash(seed, a.salt, pair0 + q);
-        }
-        float out[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = (j & 1) ? bf16_hi(zw[j >> 1]) : bf16_lo(zw[j >> 1]);
-          bool pass = true;
-          float y = 0.f;
-          if (mask_here) {
-            y = fmaf(z, sc[j], sh[j]);
-            pass = y > 0.f && (threshold == 0u || ((j & 1) ? (hsh[j >> 1] >> 16) : (hsh[j >> 1] & 0xffffu)) >= threshold);
-            bits_out |= pass ? (1u << j) : 0u;
-          } else if (use_bits) {
-            pass = (bits >> j) & 1u;
+        for (int u = 0; u < U; ++u) {
+          const int64_t r = rb + static_cast<int64_t>(u) * ty_n;
+          zq[u] = dq[u] = make_uint4(0, 0, 0, 0);
+          bq[u] = 0u;
+          if (r < r1) {
+            zq[u] = __ldg(reinterpret_cast<const uint4*>(zb + r * a.ldz + col));
+            if (MODE != 0) dq[u] = __ldg(reinterpret_cast<const uint4*>(db + r * a.ldd + col));
+            if (use_bits) bq[u] = a.pass_bits[r * cg + g];
           }
-          if (MODE == 0) {
-            out[j] = pass ? y * keep_scale : 0.f;
-          } else {
-            float dy = (j & 1) ? bf16_hi(dw[j >> 1]) : bf16_lo(dw[j >> 1]);
-            if (a.dy_is_raw) dy = pass ? dy * a.keep_scale_bwd : 0.f;
-            const float xhat = (z - mu[j]) * rs[j];
-            if (MODE == 1) {
-              out[j] = a.bn_skip ? dy : sc[j] * (dy - c0[j] - xhat * c1[j]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t r = rb + static_cast<int64_t>(u) * ty_n;
+          if (r >= r1) break;
+          const uint32_t zw[4] = {zq[u].x, zq[u].y, zq[u].z, zq[u].w};
+          const uint32_t dw[4] = {dq[u].x, dq[u].y, dq[u].z, dq[u].w};
+          const uint32_t bits = bq[u];
+          uint32_t bits_out = 0u;
+          uint32_t hsh[4] = {0u, 0u, 0u, 0u};
+          if (mask_here && threshold != 0u) {
+            const uint64_t pair0 = (static_cast<uint64_t>(r) * a.width + col) >> 1;     // col % 8 == 0, width % 8 == 0
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hsh[q] = dropout_pair_hash(seed, a.salt, pair0 + q);
+          }
+          float out[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = (j & 1) ? bf16_hi(zw[j >> 1]) : bf16_lo(zw[j >> 1]);
+            bool pass = true;
+            float y = 0.f;
+            if (mask_here) {
+              y = fmaf(z, sc[j], sh[j]);
+              pass = y > 0.f && (threshold == 0u || ((j & 1) ? (hsh[j >> 1] >> 16) : (hsh[j >> 1] & 0xffffu)) >= threshold);
+              bits_out |= pass ? (1u << j) : 0u;
+            } else if (use_bits) {
+              pass = (bits >> j) & 1u;
+            }
+            if (MODE == 0) {
+              out[j] = pass ? y * keep_scale : 0.f;
             } else {
-              s1[j] += dy;
-              s2[j] = fmaf(dy, xhat, s2[j]);
+              float dy = (j & 1) ? bf16_hi(dw[j >> 1]) : bf16_lo(dw[j >> 1]);
+              if (a.dy_is_raw) dy = pass ? dy * a.keep_scale_bwd : 0.f;
+              const float xhat = (z - mu[j]) * rs[j];
+              if (MODE == 1) {
+                out[j] = a.bn_skip ? dy : sc[j] * (dy - c0[j] - xhat * c1[j]);
+              } else {
+                s1[j] += dy;
+                s2[j] = fmaf(dy, xhat, s2[j]);
+              }
             }
           }
-        }
-        if (MODE == 0 && a.pass_bits != nullptr) a.pass_bits[r * cg + g] = static_cast<uint8_t>(bits_out);
-        if (MODE != 2) {
-          uint4 pk;
-          pk.x = pack_bf16(out[0], out[1]);
-          pk.y = pack_bf16(out[2], out[3]);
-          pk.z = pack_bf16(out[4], out[5]);
-          pk.w = pack_bf16(out[6], out[7]);
-          *reinterpret_cast<uint4*>(ob + r * a.ldo + col) = pk;
+          if (MODE == 0 && a.pass_bits != nullptr) a.pass_bits[r * cg + g] = static_cast<uint8_t>(bits_out);
+          if (MODE != 2) {
+            uint4 pk;
+            pk.x = pack_bf16(out[0], out[1]);
+            pk.y = pack_bf16(out[2], out[3]);
+            pk.z = pack_bf16(out[4], out[5]);
+            pk.w = pack_bf16(out[6], out[7]);
+            *reinterpret_cast<uint4*>(ob + r * a.ldo + col) = pk;
+          }
         }
       }
     }

@@ -391,7 +391,9 @@ class AreadNode(torch.autograd.Function):
         layout = (len(a0), n_expert, n_cross, len(a_last))
         nj_own = 1 + len(a0) * n_expert + n_cross + len(a_last)
         n_gate_logits = sum(len(active[l]) * n_tower[l - 1] for l in range(1, n_level))
-        tc_row = TC_ROWPASS and E % 8 == 0 and nj_own <= 128
+        # ('bf16x3' is the tight-parity mode: it keeps the all-fp32 CUDA-core row pass -- the split operands carry
+        # 16-17 bits, not 24, and this model amplifies forward perturbations into the gradients behind the towers)
+        tc_row = TC_ROWPASS and not precise and E % 8 == 0 and nj_own <= 128
         ride = tc_row and n_gate_logits > 0 and nj_own + n_gate_logits <= 128
         gate_cols = [None] * n_level                                                     # (first column, wg) per level
         if ride:

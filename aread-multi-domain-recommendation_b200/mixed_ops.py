@@ -73,7 +73,7 @@ def _ptr_grid(lib_field, values):
 
 
 @torch.no_grad()
-def forward_mixed_eval(model, x, want_stack=False):
+def forward_mixed_eval(model, x, want_stack=False, hei_events=None):
     """y [B] (and y_stack [n_last, B] with want_stack): the 'domain_with_mask' probabilities of a mixed batch in
     eval mode; row b uses domain_mask[x[b, domain_idx]]."""
     if model.training:
@@ -113,10 +113,11 @@ def forward_mixed_eval(model, x, want_stack=False):
     gate = torch.empty((B, n_tower[0], n_expert), dtype=torch.float32, device=dev)
     alpha = torch.empty((B, n_cross + 1), dtype=torch.float32, device=dev)
     head_cross = torch.empty((B, n_tower[-1]), dtype=torch.float32, device=dev)
-    tc_row = nj <= 32 and E % 8 == 0
+    from . import fused
+    tc_row = fused.TC_ROWPASS and not precise and nj <= 128 and E % 8 == 0       # as in the fused train / eval node
     if tc_row:
         wc_hi, wc_lo = dk.split_bf16(w_cat)
-        dk.grouped_linear(x_hi, wc_hi, None, nj, E, 1, 0, out=p_dots, a_lo=x_lo, w_lo=wc_lo)
+        dk.grouped_linear(x_hi, wc_hi, None, nj, E, 1, 0, out=p_dots, a_lo=x_lo, w_lo=wc_lo, lo_lo=True)
     ra = rowpass_ops._args(B, E, layout, ldp, x=None if tc_row else X, w=None if tc_row else w_cat, offset=offset,
                            p=p_dots, lin=lin, gate=gate, alpha=alpha, head=head_cross)
     _lib.check(lib.aread_rowpass_fwd(ctypes.byref(ra), _stream(dev)))
@@ -125,15 +126,15 @@ def forward_mixed_eval(model, x, want_stack=False):
     G = P.experts[0].groups
     a_op = (x_hi, x_lo) if precise else x_hi
     z = stats = None
-    if precise:
+    if precise or not all(L.n % 64 == 0 for L in P.experts):      # (narrow expert layers: unfused kernels)
         for i, L in enumerate(P.experts):
-            w = dk.split_bf16(L.weight.rows())
+            w = dk.split_bf16(L.weight.rows()) if precise else L.weight.rows().to(torch.bfloat16)
             z = dk.grouped_linear(_hi(a_op), _hi(w), L.bias.rows(), L.n, L.k, G, 0 if i == 0 else L.k, a_lo=_lo(a_op),
                                   w_lo=_lo(w))
             last = i == len(P.experts) - 1
             res = dk.bn_act_fwd(z, L.gamma.rows(), L.beta.rows(), L.running_mean.rows(), L.running_var.rows(), False,
-                                bn_skip, 0.0, 0, L.salt, None if last else torch.bfloat16, want_lo=not last)
-            a_op, stats = (None, res[-1]) if last else ((res[0], res[1]), res[2])
+                                bn_skip, 0.0, 0, L.salt, None if last else torch.bfloat16, want_lo=precise and not last)
+            a_op, stats = (None, res[-1]) if last else (((res[0], res[1]), res[2]) if precise else (res[0], res[1]))
     else:
         w16 = model.expert_weights_bf16()
         for i, L in enumerate(P.experts):
@@ -184,7 +185,11 @@ def forward_mixed_eval(model, x, want_stack=False):
     a.y, a.y_stack = y.data_ptr(), y_stack.data_ptr() if want_stack else None
     if not lib.aread_hei_mixed_eval_supported(ctypes.byref(a)):
         raise RuntimeError("forward_mixed: this tower configuration does not fit the shared memory of one SM")
+    if hei_events is not None:          # (bench.py: the HEI kernel timed on its own, on its launch stream)
+        hei_events[0].record(torch.cuda.current_stream(dev))
     _lib.check(lib.aread_hei_mixed_eval(ctypes.byref(a), _stream(dev)))
+    if hei_events is not None:
+        hei_events[1].record(torch.cuda.current_stream(dev))
     model.embedding.plan(dev).post_lookup(_bounds_mode())
     return (y, y_stack) if want_stack else y
 

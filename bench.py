@@ -586,6 +586,7 @@ def mixed_leg(args, pkg, dev, kernel_ms, B=65536):
     domain-sorted against shuffled rows at three mask densities -- sorted rows let the HEI kernel skip the (32-row
     tile, tower) pairs the masks prune -- and the reference's way of evaluating the same rows, one call per domain."""
     wl = importlib.import_module(PKG + ".workloads").WORKLOADS["cloudtheme"]()
+    mixed_ops = importlib.import_module(PKG + ".mixed_ops")
     model = pkg.AREAD(np.asarray(wl.one_hot_field_dims), wl.embed_dim, wl.multi_hot_dict, n_tower=N_TOWER,
                       n_domain=wl.n_domain, base_model="mmoe", expert_dims=EXPERT_DIMS, tower_dims=TOWER_DIMS,
                       domain_idx=wl.domain_idx, device=dev, dropout=args.dropout, config=make_config(wl)).to(dev).eval()
@@ -606,9 +607,20 @@ def mixed_leg(args, pkg, dev, kernel_ms, B=65536):
                          axis=0)
         ms_sorted = kernel_ms(lambda i: model.forward_mixed(xs), 3, 10)
         ms_shuffled = kernel_ms(lambda i: model.forward_mixed(xu), 3, 10)
+
+        def hei_only(x):        # the HEI kernel alone (the trunk in front of it does not depend on the masks)
+            ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+            ts = []
+            for _ in range(8):
+                mixed_ops.forward_mixed_eval(model, x, hei_events=ev)
+                torch.cuda.synchronize(dev)
+                ts.append(ev[0].elapsed_time(ev[1]))
+            return float(np.median(ts[2:]))
+        hei_sorted, hei_shuffled = hei_only(xs), hei_only(xu)
         rec = {"mean_active_towers_per_level": [round(float(t), 2) for t in towers],
-               "sorted_ms": ms_sorted, "sorted_samples_per_sec": B / (ms_sorted * 1e-3),
-               "shuffled_ms": ms_shuffled, "skip_speedup_sorted_vs_shuffled": ms_shuffled / ms_sorted}
+               "sorted_ms": ms_sorted, "sorted_samples_per_sec": B / (ms_sorted * 1e-3), "shuffled_ms": ms_shuffled,
+               "hei_kernel_ms_sorted": hei_sorted, "hei_kernel_ms_shuffled": hei_shuffled,
+               "hei_tile_skip_speedup_sorted_vs_shuffled": hei_shuffled / hei_sorted}
         if active == 0.3:       # the reference's evaluation of the same rows: one call per domain (run.py:719-727)
             bounds = np.concatenate(([0], np.cumsum(seg)))
             parts = [(d, xs[bounds[d]:bounds[d + 1]]) for d in range(wl.n_domain) if seg[d] > 0]

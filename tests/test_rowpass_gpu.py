@@ -56,3 +56,42 @@ def test_rowpass_forward_backward(m, e, ng, ne, nc, nh):
         a = torch.zeros_like(b) if a is None else a
         scale = float(b.abs().max()) + 1e-6
         assert float((a - b).abs().max()) <= 2e-4 * scale + 1e-6, (name, float((a - b).abs().max()), scale)
+
+
+def test_tensor_core_row_pass_matches_cuda_core_row_pass(monkeypatch):
+    """The row pass on the tensor cores (split operands) with the HEI gate logits riding along, against the all-fp32
+    CUDA-core row pass + separate gate Linears, on the same bf16-expert model: probabilities to 2e-5, every gradient
+    family to 2e-2 (the forward products differ by ~2^-17 relative; the gradients behind the towers amplify that)."""
+    import importlib
+    import numpy as np
+    from oracle import aread_torch as O
+    from oracle import synth
+    from tests._models import build_model
+    from tests._util import family_errors, load_golden
+    fused = importlib.import_module("aread-multi-domain-recommendation_b200.fused")
+    fx = load_golden("ali_small")
+    spec = O.Spec(**fx["spec"])
+    x, y = synth.random_batch(spec, 2048, seed=5, domain=fx["domain"])
+    results = []
+    for tc in (True, False):
+        monkeypatch.setattr(fused, "TC_ROWPASS", tc)
+        monkeypatch.setattr(fused, "USE_GRAPHS", False)
+        model = build_model(spec, "cuda:0", dropout=0.0).train()
+        model.expert_precision = "bf16"
+        np.random.seed(3)
+        mask = model.generate_mask("rand", 0, init_active_percent=0.5)
+        preds = model(x.to("cuda:0"), mode="domain_mask_bagging", current_mask=mask, tmp_memory_gate_value=True)
+        loss = model.bagging_loss(preds, y.to("cuda:0"))
+        model.zero_grad()
+        loss.backward()
+        means = [torch.stack(model.tmp_tower_gate_values[l], dim=1).cpu() for l in range(1, spec.n_level)]
+        results.append((preds.detach().cpu(), means,
+                        {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}))
+    (p_tc, m_tc, g_tc), (p_cc, m_cc, g_cc) = results
+    assert float((p_tc - p_cc).abs().max()) <= 2e-5
+    for a, b in zip(m_tc, m_cc):
+        assert float((a - b).abs().max()) <= 1e-6, "gate means (what HEMP thresholds)"
+    assert g_tc.keys() == g_cc.keys()
+    errs = family_errors([(k, g_tc[k].reshape(-1), g_cc[k].reshape(-1)) for k in g_cc])
+    for fam, (err, _) in errs.items():
+        assert err <= 2e-2, f"{fam}: {err:.3e}"

@@ -40,7 +40,15 @@ LR, WD = 1e-3, 1e-8
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/), keyed by (kernel, workload, batch); None where no capture exists
-NCU_DRAM_BYTES = {}
+NCU_DRAM_BYTES = {
+    # profiles/r2_grouped_linear_kernel_full.txt, grouped_linear_kernel<128, STATS> (expert layer 1)
+    ("grouped_linear_kernel", "aliccp", 65536): 98_006_016 + 92_533_504,
+}
+# the lookup as the train step launches it (fp32 rows + the split bf16 copy for the tensor-core products), from
+# profiles/r2_gather_kernel_full.txt: 90.5 us, 42.2 MB read + 331.5 MB written
+GATHER_IN_STEP = {("aliccp", 65536): {"launch_us_ncu": 90.5, "dram_bytes": 42_155_520 + 331_523_072,
+                                      "note": "fp32 [B, F, D] output (193 MB) + hi / lo bf16 copies (2 x 96 MB) written by "
+                                              "the same kernel; table rows are served from L2 (Zipf ids, 146 MB table)"}}
 
 
 def parse_args():
@@ -442,6 +450,11 @@ def run_ours(args, wl, rank, world, local_rank):
                    "peak_source": peak_src, "algorithmic_bytes_per_launch": gather_bytes, "launch_ms": gather_ms}
     if gather_roof["traffic"]:
         gather_roof["dram_level_gbs"] = gather_roof["traffic"] / (gather_ms * 1e-3) / 1e9
+    in_step = GATHER_IN_STEP.get((args.workload, B))
+    if in_step:
+        gather_roof["in_step"] = dict(in_step, dram_level_gbs=in_step["dram_bytes"] / (in_step["launch_us_ncu"] * 1e-6) / 1e9,
+                                      frac_of_hbm_peak=in_step["dram_bytes"] / (in_step["launch_us_ncu"] * 1e-6) / 1e9
+                                      / peaks["hbm_gbs"])
     line = {
         "metric": "aread_train_samples_per_sec", "value": total_samples / (ms_dev * 1e-3), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,

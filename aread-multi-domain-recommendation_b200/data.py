@@ -94,3 +94,43 @@ def load_split(folder, mode, device=None):
     if device is not None:
         X, y = X.to(device), y.to(device)
     return X, y
+
+
+class EvalAccumulator:
+    """Targets / predictions / domain ids of an evaluation pass kept ON THE DEVICE and brought to the host once.
+
+    The reference's test loop (run.py:725-727, 742-744) calls `.cpu().numpy()` three times per batch -- three stream
+    synchronisations that serialise every batch with the host.  Here `add` only keeps references (or appends into
+    preallocated device buffers when `capacity` is given) and `result()` does one concatenation and one copy; the
+    numpy arrays it returns are what `roc_auc_score` / `log_loss` are fed at run.py:757-758."""
+
+    def __init__(self, capacity=None, device=None):
+        self._chunks = []
+        self._buf = None
+        self._n = 0
+        if capacity is not None:
+            self._buf = (torch.empty(capacity, dtype=torch.float32, device=device),
+                         torch.empty(capacity, dtype=torch.float32, device=device),
+                         torch.empty(capacity, dtype=torch.int32, device=device))
+
+    def add(self, targets, predicts, domains):
+        t, p, d = targets.reshape(-1), predicts.reshape(-1), domains.reshape(-1)
+        if self._buf is None:
+            self._chunks.append((t, p, d))
+        else:
+            n = t.numel()
+            if self._n + n > self._buf[0].numel():
+                raise ValueError("EvalAccumulator capacity exceeded")
+            self._buf[0][self._n:self._n + n].copy_(t)
+            self._buf[1][self._n:self._n + n].copy_(p)
+            self._buf[2][self._n:self._n + n].copy_(d)
+        self._n += t.numel()
+
+    def result(self):
+        """(targets, predicts, domains) as numpy arrays, in the order they were added."""
+        if self._buf is not None:
+            parts = [b[:self._n] for b in self._buf]
+        else:
+            parts = [torch.cat([c[i].to(torch.float32 if i < 2 else torch.int32) for c in self._chunks])
+                     if self._chunks else torch.empty(0) for i in range(3)]
+        return tuple(p.cpu().numpy() for p in parts)

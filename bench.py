@@ -578,6 +578,10 @@ def extra_legs(args, wl, tr, pkg, lib, ops, dev, rank, world, timed, kernel_ms, 
     # optimizer reset + 5 bagging steps with prun_single_mask + 5 no_grad scoring passes
     extra["regroup"] = regroup_leg(tr, wl, dev, dev_x, dev_y, n_domains=min(wl.n_domain, 30), candidates=10)
 
+    # ---- batch feeding: the trainer's DataLoader over device tensors (run.py:301-306) against
+    # data.DeviceBatchLoader, and the test loop's per-batch .cpu().numpy() (run.py:725-727) against data.EvalAccumulator
+    extra["feeding"] = feeding_leg(tr, dev, dev_x, dev_y, domains)
+
     # ---- mixed-domain eval (BASELINE configs[3]): one 64K batch over the 355 Cloud-Theme-shaped domains
     extra["cloudtheme_mixed"] = mixed_leg(args, pkg, dev, kernel_ms)
     torch.cuda.empty_cache()
@@ -592,6 +596,51 @@ def extra_legs(args, wl, tr, pkg, lib, ops, dev, rank, world, timed, kernel_ms, 
             extra["gpu_eager_baseline"] = {"unavailable": str(e)[:120]}
         torch.cuda.empty_cache()
     return extra
+
+
+def feeding_leg(tr, dev, dev_x, dev_y, domains, bs=1024, n_batches=64):
+    from torch.utils.data import DataLoader, TensorDataset
+    data = importlib.import_module(PKG + ".data")
+    X, y = dev_x[0][:bs * n_batches], dev_y[0][:bs * n_batches]
+    out = {"batch_size": bs, "batches": n_batches}
+
+    def drain(loader):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for xb, yb in loader:
+            pass
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / n_batches * 1e3
+
+    drain(data.DeviceBatchLoader(X, y, batch_size=bs))
+    out["torch_dataloader_ms_per_batch"] = drain(DataLoader(TensorDataset(X, y), batch_size=bs, shuffle=True))
+    out["device_batch_loader_ms_per_batch"] = drain(data.DeviceBatchLoader(X, y, batch_size=bs))
+    model = tr.model.eval()
+    d = domains[0]
+
+    def eval_loop(accumulate):
+        acc = data.EvalAccumulator()
+        host = []
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for s0 in range(0, bs * n_batches, bs):
+                xb, yb = X[s0:s0 + bs], y[s0:s0 + bs]
+                pred = model(xb, mode="domain_with_mask", domain_i=d)
+                if accumulate:
+                    acc.add(yb, pred, xb[:, model.domain_idx])
+                else:
+                    host.append((yb.squeeze().cpu().numpy(), pred.squeeze().cpu().numpy(),
+                                 xb[:, model.domain_idx].cpu().numpy()))
+        if accumulate:
+            acc.result()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / n_batches * 1e3
+    eval_loop(True)
+    out["eval_per_batch_host_copies_ms_per_batch"] = eval_loop(False)
+    out["eval_accumulator_ms_per_batch"] = eval_loop(True)
+    tr.model.train()
+    return out
 
 
 def mixed_leg(args, pkg, dev, kernel_ms, B=65536):

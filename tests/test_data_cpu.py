@@ -64,3 +64,25 @@ def test_split_files_round_trip(tmp_path):
     assert torch.equal(X3, X) and torch.equal(y3, y) and X3.dtype == torch.int32
     with pytest.raises(TypeError):
         data.save_split(str(tmp_path), "test", X.to(torch.int64), y)
+
+
+def test_eval_accumulator_matches_per_batch_host_copies():
+    import numpy as np
+    acc = data.EvalAccumulator()
+    fixed = data.EvalAccumulator(capacity=100)
+    want = [[], [], []]
+    g = torch.Generator().manual_seed(0)
+    for n in (7, 1, 32):
+        y = (torch.rand(n, 1, generator=g) < 0.3).to(torch.int16)
+        p = torch.rand(n, generator=g)
+        d = torch.randint(0, 5, (n,), generator=g, dtype=torch.int32)
+        acc.add(y, p, d)
+        fixed.add(y, p, d)
+        want[0].append(y.squeeze(-1).numpy())       # what run.py:725-727 collects batch by batch
+        want[1].append(p.numpy())
+        want[2].append(d.numpy())
+    for got in (acc.result(), fixed.result()):
+        for a, b in zip(got, want):
+            assert np.array_equal(a, np.concatenate(b).astype(a.dtype))
+    with pytest.raises(ValueError):
+        fixed.add(torch.zeros(100), torch.zeros(100), torch.zeros(100, dtype=torch.int32))

@@ -14,6 +14,7 @@
 // for the experts (model/aread.py:93-95, 150) and towers (aread.py:108-110, 307, 319).
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tensor_map.cuh"
 
 namespace aread {
 namespace {
@@ -130,7 +131,7 @@ grouped_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   using L = SmemLayout<BN>;
   constexpr int kBoxBytes = BK * 64 * 2;   // MN-major B: [64 k rows][64 n] boxes
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* acc_full = empty_bar + kStages;
@@ -453,7 +454,7 @@ grouped_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_co
   constexpr int kBBytes = (BN / 64) * kBoxBytes;         // BN input features
   constexpr int kStageBytes = kABytes + kBBytes;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* acc_full = empty_bar + kStages;
@@ -601,69 +602,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // ----------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ----------------------------------------------------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = [] {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      sym = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(sym);
-  }();
-  return fn;
-}
-
-// bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-             int box_cols = BK) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (fn == nullptr) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t elem[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return AREAD_OK;
-}
-
-// fp32 row-major [rows, cols] output, box = [32 rows, 32 cols] (one 128-byte swizzle row per matrix row)
-int make_store_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (fn == nullptr) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {32, 32};
-  cuuint32_t elem[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, elem,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(AREAD_ERR_CUDA, "cuTensorMapEncodeTiled (store) failed with CUresult %d", (int)r);
-  return AREAD_OK;
-}
-
-// cudaFuncSetAttribute is per device: remember which devices a kernel has been configured on
-inline bool first_use_on_device(uint64_t* seen) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const uint64_t bit = uint64_t{1} << (dev & 63);
-  if (*seen & bit) return false;
-  *seen |= bit;
-  return true;
-}
-
 inline unsigned gemm_grid(int64_t tiles) {
-  static int sms[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  int& n = sms[dev & 63];
-  if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = kNumSMs;
+  const int n = sm_count();
   return static_cast<unsigned>(tiles < n ? tiles : n);     // persistent: one CTA per SM
 }
 

@@ -12,8 +12,11 @@
 //   itself a BatchNorm'd layer -- the column sums its BatchNorm backward needs.
 // Replaces per layer: tower_linear + bn_stats + bn_act (forward) and bn_bwd_stats + bn_bwd_apply +
 // tower_wgrad + tower_linear (backward).  All reductions run in a fixed order (bit-reproducible).
+#include <cstdlib>
+
 #include "bn_common.cuh"
 #include "common.cuh"
+#include "hei_tc.cuh"
 
 namespace aread {
 namespace {
@@ -522,6 +525,14 @@ size_t bwd_smem(const Tiling& t, int K, int N, bool src_bn) {
   return sizeof(float) * (static_cast<size_t>(Np) * Kp + tile);
 }
 
+bool getenv_bwd_tc() {     // AREAD_HEI_TC_BWD=0: tensor cores for the forward only
+  static const bool on = [] {
+    const char* e = std::getenv("AREAD_HEI_TC_BWD");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 bool shape_ok(int groups, int k, int n) {
   return groups > 0 && groups <= 65535 && k > 0 && n > 0 && k <= kMaxWidth && n <= kMaxWidth;
 }
@@ -540,7 +551,10 @@ size_t aread_hei_layer_workspace_bytes(int64_t m, int32_t groups, int32_t k, int
   const Tiling tb = tiling(m, ((k + 3) & ~3) / 4, groups, kBwdSmMultiple);
   const size_t fwd = static_cast<size_t>(tf.n_cta) * 2 * groups * n;
   const size_t bwd = static_cast<size_t>(tb.n_cta) * groups * n * k + static_cast<size_t>(tb.n_cta) * 2 * groups * k;
-  return align_up(sizeof(float) * (fwd > bwd ? fwd : bwd), 256);
+  size_t need = fwd > bwd ? fwd : bwd;
+  const size_t tc = hei_tc_workspace_floats(m, groups, k, n);       // the tensor-core path (hei_tc.cu)
+  if (tc > need) need = tc;
+  return align_up(sizeof(float) * need, 256);
 }
 
 int aread_hei_layer_fwd(const aread_hei_layer_fwd_args* args, aread_stream_t stream_) {
@@ -557,6 +571,7 @@ int aread_hei_layer_fwd(const aread_hei_layer_fwd_args* args, aread_stream_t str
   AREAD_REQUIRE(a.workspace && a.workspace_bytes >= aread_hei_layer_workspace_bytes(a.m, a.groups, a.k, a.n),
                 "hei_layer_fwd: workspace too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (hei_tc_usable(a.m, a.groups, a.k, a.n, a.src, a.ld_src)) return hei_tc_fwd(a, stream);
   const int Np = (a.n + 3) & ~3;
   Tiling t = tiling(a.m, Np / 4, a.groups, kFwdSmMultiple);
   const size_t smem = fwd_smem(t, a.k, a.n);
@@ -611,6 +626,7 @@ int aread_hei_layer_bwd(const aread_hei_layer_bwd_args* args, aread_stream_t str
   AREAD_REQUIRE(a.workspace && a.workspace_bytes >= aread_hei_layer_workspace_bytes(a.m, a.groups, a.k, a.n),
                 "hei_layer_bwd: workspace too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (hei_tc_usable(a.m, a.groups, a.k, a.n, a.src, a.ld_src) && getenv_bwd_tc()) return hei_tc_bwd(a, stream);
   const int Np = (a.n + 3) & ~3, Kp = (a.k + 3) & ~3;
   Tiling t = tiling(a.m, Kp / 4, a.groups, kBwdSmMultiple);
   const int mt_n = (Np / 4) * (Kp / 4);

@@ -1,6 +1,13 @@
 """Fused HEI tower-layer kernels (C ABI: aread_hei_layer_fwd / _bwd, aread_bn_act_apply, aread_bn_bwd_coef) against
 the same two-layer tower stack written with torch ops and differentiated by autograd (fp32; the dropout masks come
-from the library's own counter stream through aread_dropout_mask).  Tolerance: fp32 summation-order noise."""
+from the library's own counter stream through aread_dropout_mask).  Tolerance: fp32 summation-order noise for the
+CUDA-core kernels (csrc/hei.cu); the tensor-core kernels (csrc/hei_tc.cu, rows >= 512 and block-packable widths)
+split every operand into bf16 hi + lo and drop lo.lo, |dz| <= ~1e-4 at these magnitudes.
+
+ReLU boundary: an element whose BatchNorm output is within the forward tolerance of zero may be rectified
+differently by two correct implementations, and that flips a whole gradient term.  The reference therefore takes
+the on/off decision from the kernel's own pre-activation -- after checking that the two only disagree where the
+reference value is within 1e-3 of zero -- so the gradients are compared under one activation pattern."""
 import importlib
 
 import pytest
@@ -13,15 +20,22 @@ ho = importlib.import_module("aread-multi-domain-recommendation_b200.hei_ops")
 dk = importlib.import_module("aread-multi-domain-recommendation_b200.dense_kernels")
 
 
-def _ref_layer(x, w, b, gamma, beta, mask, p, bn_skip):
-    """x [m, G, K] -> (z [m, G, N], act [m, G, N]) with train-mode BatchNorm over the batch."""
+def _ref_layer(x, w, b, gamma, beta, mask, p, bn_skip, kernel_y=None):
+    """x [m, G, K] -> (z [m, G, N], act [m, G, N]) with train-mode BatchNorm over the batch.  `kernel_y`: the
+    kernel's BatchNorm output, whose sign decides the ReLU (see the module docstring)."""
     z = torch.einsum("bgk,gnk->bgn", x, w) + b
     if bn_skip:
         y = z
     else:
         mean, var = z.mean(dim=0), z.var(dim=0, unbiased=False)
         y = (z - mean) / torch.sqrt(var + 1e-5) * gamma + beta
-    a = torch.relu(y)
+    if kernel_y is None:
+        a = torch.relu(y)
+    else:
+        on = kernel_y > 0
+        differ = on != (y.detach() > 0)
+        assert float(y.detach().abs()[differ].max() if differ.any() else 0.0) < 1e-3, "ReLU decision off the boundary"
+        a = y * on
     if p > 0:
         a = a * mask / (1 - p)
     return z, a
@@ -51,10 +65,6 @@ def test_two_layer_stack_matches_autograd(m, G, dims, p):
     mask1 = dk.dropout_mask(seed, salt1, (m, G, N1), p, DEV).float()
     mask2 = dk.dropout_mask(seed, salt2, (m, G, N2), p, DEV).float()
 
-    z1_ref, a1_ref = _ref_layer(x, w1, b1, g1, be1, mask1, p, bn_skip)
-    z2_ref, u_ref = _ref_layer(a1_ref, w2, b2, g2, be2, mask2, p, bn_skip)
-    (u_ref * d_u).sum().backward()
-
     with torch.no_grad():
         src = x.detach().reshape(m, G * K)
         z1, s1 = ho.layer_fwd(src, None, 0, w1.detach(), b1.detach(), g1.detach().reshape(-1), be1.detach().reshape(-1),
@@ -62,6 +72,15 @@ def test_two_layer_stack_matches_autograd(m, G, dims, p):
         z2, s2 = ho.layer_fwd(z1, s1, salt1, w2.detach(), b2.detach(), g2.detach().reshape(-1),
                               be2.detach().reshape(-1), rm2, rv2, G, N1, N2, True, bn_skip, p, seed)
         u = ho.bn_apply(z2, s2, True, p, seed, salt2)
+        # saved = (mean, rstd, scale, shift); addcmul is the kernels' fused multiply-add
+        y1_k = torch.addcmul(s1[3].expand_as(z1), z1, s1[2].expand_as(z1)).view(m, G, N1)
+        y2_k = torch.addcmul(s2[3].expand_as(z2), z2, s2[2].expand_as(z2)).view(m, G, N2)
+
+    z1_ref, a1_ref = _ref_layer(x, w1, b1, g1, be1, mask1, p, bn_skip, y1_k)
+    z2_ref, u_ref = _ref_layer(a1_ref, w2, b2, g2, be2, mask2, p, bn_skip, y2_k)
+    (u_ref * d_u).sum().backward()
+
+    with torch.no_grad():
         tol = dict(rtol=2e-4, atol=2e-4)
         torch.testing.assert_close(z1.view(m, G, N1), z1_ref, **tol)
         torch.testing.assert_close(z2.view(m, G, N2), z2_ref, **tol)

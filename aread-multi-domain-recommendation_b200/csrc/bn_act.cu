@@ -30,8 +30,10 @@ inline Geometry geometry(int width, bool aligned) {
 // Per-CTA partial column sums of the two quantities f produces, over the CTA's contiguous row range.
 // Threads: tx over column groups of VEC, ty over rows; four independent row loads are in flight per
 // thread.  The ty partials are added in ty order, the CTA partials later in CTA order.
-template <int VEC, typename F>
-__device__ __forceinline__ void column_partials(int64_t m, int width, int tw, float* partial, F f) {
+// `prep(col)` runs once per column group and its result is handed to every f call of that group: per-column
+// parameters live in registers instead of being reloaded for every row.
+template <int VEC, typename P, typename F>
+__device__ __forceinline__ void column_partials(int64_t m, int width, int tw, float* partial, P prep, F f) {
   extern __shared__ float s_red[];  // [ty_n][2][tw * VEC]
   const int ty_n = kThreads / tw;
   const int tx = threadIdx.x % tw, ty = threadIdx.x / tw;
@@ -45,11 +47,12 @@ __device__ __forceinline__ void column_partials(int64_t m, int width, int tw, fl
 #pragma unroll
     for (int v = 0; v < VEC; ++v) s[v] = q[v] = 0.f;
     if (col < width) {
+      const auto prm = prep(col);
       int64_t r = r0 + ty;
       for (; r + 3 * ty_n < r1; r += 4 * ty_n) {
         float a[4][VEC], b[4][VEC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) f(r + u * ty_n, col, a[u], b[u]);
+        for (int u = 0; u < 4; ++u) f(r + u * ty_n, col, prm, a[u], b[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -57,7 +60,7 @@ __device__ __forceinline__ void column_partials(int64_t m, int width, int tw, fl
       }
       for (; r < r1; r += ty_n) {
         float a[VEC], b[VEC];
-        f(r, col, a, b);
+        f(r, col, prm, a, b);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { s[v] += a[v]; q[v] += b[v]; }
       }
@@ -84,23 +87,53 @@ __device__ __forceinline__ void column_partials(int64_t m, int width, int tw, fl
   }
 }
 
+// keep flags of VEC consecutive elements starting at the (even, when VEC == 4) flat index: one hash per pair
+template <int VEC>
+__device__ __forceinline__ void keep_flags(uint64_t seed, uint32_t salt, uint64_t flat, uint32_t threshold,
+                                           bool (&keep)[VEC]) {
+  if (threshold == 0u) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) keep[v] = true;
+  } else if (VEC == 4 && (flat & 1) == 0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t h = dropout_pair_hash(seed, salt, (flat >> 1) + q);
+      keep[2 * q] = (h & 0xffffu) >= threshold;
+      keep[2 * q + 1] = (h >> 16) >= threshold;
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) keep[v] = dropout_keep(seed, salt, flat + v, threshold);
+  }
+}
+
 // ---------------------------------------------------------------------------------- forward
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) bn_stats_kernel(int64_t m, int width, int tw, const float* __restrict__ z,
                                                             int64_t ldz, float* __restrict__ partial) {
   // sums are taken about the column's first row (a sample of the same distribution), which keeps
   // E[v^2] - E[v]^2 well conditioned whatever the column mean is
-  column_partials<VEC>(m, width, tw, partial, [&](int64_t r, int col, float (&a)[VEC], float (&b)[VEC]) {
-    if (VEC == 4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(z + r * ldz + col));
-      const float4 p = __ldg(reinterpret_cast<const float4*>(z + col));
-      a[0] = v.x - p.x; a[1] = v.y - p.y; a[2] = v.z - p.z; a[3] = v.w - p.w;
-    } else {
-      a[0] = __ldg(z + r * ldz + col) - __ldg(z + col);
-    }
+  struct Pivot {
+    float p[VEC];
+  };
+  column_partials<VEC>(
+      m, width, tw, partial,
+      [&](int col) {
+        Pivot pv;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) b[v] = a[v] * a[v];
-  });
+        for (int v = 0; v < VEC; ++v) pv.p[v] = z[col + v];
+        return pv;
+      },
+      [&](int64_t r, int col, const Pivot& pv, float (&a)[VEC], float (&b)[VEC]) {
+        if (VEC == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(z + r * ldz + col));
+          a[0] = v.x - pv.p[0]; a[1] = v.y - pv.p[1]; a[2] = v.z - pv.p[2]; a[3] = v.w - pv.p[3];
+        } else {
+          a[0] = __ldg(z + r * ldz + col) - pv.p[0];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) b[v] = a[v] * a[v];
+      });
 }
 
 // rows by (blockIdx.x, ty), columns by tx, VEC consecutive columns per thread: no index divisions
@@ -109,8 +142,14 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const aread_bn_act_arg
                                                           float keep_scale) {
   const uint64_t seed = seed_of(a);
   const int tx = threadIdx.x % tw, ty = threadIdx.x / tw, ty_n = kThreads / tw;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * ty_n + ty; r < a.m; r += static_cast<int64_t>(gridDim.x) * ty_n) {
-    for (int col = tx * VEC; col < a.width; col += tw * VEC) {
+  for (int col = tx * VEC; col < a.width; col += tw * VEC) {
+    float sc[VEC], sh[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      sc[j] = a.scale[col + j];
+      sh[j] = a.shift[col + j];
+    }
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * ty_n + ty; r < a.m; r += static_cast<int64_t>(gridDim.x) * ty_n) {
       float z[VEC], v[VEC];
       if (VEC == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(a.z + r * a.ldz + col));
@@ -118,12 +157,10 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const aread_bn_act_arg
       } else {
         z[0] = __ldg(a.z + r * a.ldz + col);
       }
+      bool keep[VEC];
+      keep_flags<VEC>(seed, a.salt, static_cast<uint64_t>(r) * a.width + col, threshold, keep);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const bool keep = threshold == 0u ||
-                          dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + col + j, threshold);
-        v[j] = act_value(z[j], __ldg(a.scale + col + j), __ldg(a.shift + col + j), keep, keep_scale);
-      }
+      for (int j = 0; j < VEC; ++j) v[j] = act_value(z[j], sc[j], sh[j], keep[j], keep_scale);
       if (VEC == 4) {
         if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + r * a.ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
         if (a.out_bf16) {
@@ -188,26 +225,41 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(const aread_bn_a
                                                                 uint32_t threshold, float keep_scale,
                                                                 float* __restrict__ partial) {
   const uint64_t seed = seed_of(a);
-  column_partials<VEC>(a.m, a.width, tw, partial, [&](int64_t r, int col, float (&s1)[VEC], float (&s2)[VEC]) {
-    float z[VEC], d[VEC];
-    load_z<VEC>(a, r, col, z);
-    if (VEC == 4) {
-      const float4 u = __ldg(reinterpret_cast<const float4*>(a.d_out + r * a.ldd + col));
-      d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
-    } else {
-      d[0] = __ldg(a.d_out + r * a.ldd + col);
-    }
+  struct Params {
+    float sc[VEC], sh[VEC], rs[VEC], mr[VEC];    // scale, shift, rstd, mean * rstd
+  };
+  column_partials<VEC>(
+      a.m, a.width, tw, partial,
+      [&](int col) {
+        Params pr;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const int c = col + v;
-      const float y = fmaf(z[v], __ldg(a.scale + c), __ldg(a.shift + c));
-      const bool keep = threshold == 0u ||
-                        dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
-      const float dy = (y > 0.f && keep) ? d[v] * keep_scale : 0.f;
-      s1[v] = dy;
-      s2[v] = dy * (z[v] - __ldg(a.mean + c)) * __ldg(a.rstd + c);
-    }
-  });
+        for (int v = 0; v < VEC; ++v) {
+          pr.sc[v] = a.scale[col + v];
+          pr.sh[v] = a.shift[col + v];
+          pr.rs[v] = a.rstd[col + v];
+          pr.mr[v] = a.mean[col + v] * pr.rs[v];
+        }
+        return pr;
+      },
+      [&](int64_t r, int col, const Params& pr, float (&s1)[VEC], float (&s2)[VEC]) {
+        float z[VEC], d[VEC];
+        load_z<VEC>(a, r, col, z);
+        if (VEC == 4) {
+          const float4 u = __ldg(reinterpret_cast<const float4*>(a.d_out + r * a.ldd + col));
+          d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+        } else {
+          d[0] = __ldg(a.d_out + r * a.ldd + col);
+        }
+        bool keep[VEC];
+        keep_flags<VEC>(seed, a.salt, static_cast<uint64_t>(r) * a.width + col, threshold, keep);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const float y = fmaf(z[v], pr.sc[v], pr.sh[v]);
+          const float dy = (y > 0.f && keep[v]) ? d[v] * keep_scale : 0.f;
+          s1[v] = dy;
+          s2[v] = dy * fmaf(z[v], pr.rs[v], -pr.mr[v]);
+        }
+      });
 }
 
 template <int VEC>
@@ -216,8 +268,18 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const aread_bn_a
                                                                 const float* __restrict__ coef) {
   const uint64_t seed = seed_of(a);
   const int tx = threadIdx.x % tw, ty = threadIdx.x / tw, ty_n = kThreads / tw;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * ty_n + ty; r < a.m; r += static_cast<int64_t>(gridDim.x) * ty_n) {
-    for (int col = tx * VEC; col < a.width; col += tw * VEC) {
+  for (int col = tx * VEC; col < a.width; col += tw * VEC) {
+    float sc[VEC], sh[VEC], rs[VEC], mr[VEC], c0[VEC], c1[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      sc[j] = a.scale[col + j];
+      sh[j] = a.shift[col + j];
+      rs[j] = a.rstd[col + j];
+      mr[j] = a.mean[col + j] * rs[j];
+      c0[j] = coef[col + j];
+      c1[j] = coef[a.width + col + j];
+    }
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * ty_n + ty; r < a.m; r += static_cast<int64_t>(gridDim.x) * ty_n) {
       float z[VEC], d[VEC], dz[VEC];
       load_z<VEC>(a, r, col, z);
       if (VEC == 4) {
@@ -226,16 +288,14 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const aread_bn_a
       } else {
         d[0] = __ldg(a.d_out + r * a.ldd + col);
       }
+      bool keep[VEC];
+      keep_flags<VEC>(seed, a.salt, static_cast<uint64_t>(r) * a.width + col, threshold, keep);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        const int c = col + j;
-        const float scale = __ldg(a.scale + c);
-        const float y = fmaf(z[j], scale, __ldg(a.shift + c));
-        const bool keep = threshold == 0u ||
-                          dropout_keep(seed, a.salt, static_cast<uint64_t>(r) * a.width + c, threshold);
-        const float dy = (y > 0.f && keep) ? d[j] * keep_scale : 0.f;
-        const float xhat = (z[j] - __ldg(a.mean + c)) * __ldg(a.rstd + c);
-        dz[j] = a.bn_skip ? dy : scale * (dy - coef[c] - xhat * coef[a.width + c]);
+        const float y = fmaf(z[j], sc[j], sh[j]);
+        const float dy = (y > 0.f && keep[j]) ? d[j] * keep_scale : 0.f;
+        const float xhat = fmaf(z[j], rs[j], -mr[j]);
+        dz[j] = a.bn_skip ? dy : sc[j] * (dy - c0[j] - xhat * c1[j]);
       }
       if (VEC == 4) {
         if (a.dz_f32) *reinterpret_cast<float4*>(a.dz_f32 + r * a.ldo + col) = make_float4(dz[0], dz[1], dz[2], dz[3]);

@@ -533,6 +533,9 @@ def extra_legs(args, wl, tr, pkg, lib, ops, dev, rank, world, timed, kernel_ms, 
     if world > 1:
         return extra
 
+    # ---- HEI tower layers on the tensor cores (csrc/hei_tc.cu) at the widths of this model, all towers of a level
+    extra["hei_layers"] = hei_leg(model, B, dev, kernel_ms, peaks, args)
+
     # ---- lookup gradient (whole aread_scatter_bwd call) against HBM
     plan = model.embedding.plan(dev)
     d_out = torch.randn(B, plan.n_fields, plan.embed_dim, device=dev)
@@ -596,6 +599,41 @@ def extra_legs(args, wl, tr, pkg, lib, ops, dev, rank, world, timed, kernel_ms, 
             extra["gpu_eager_baseline"] = {"unavailable": str(e)[:120]}
         torch.cuda.empty_cache()
     return extra
+
+
+def hei_leg(model, B, dev, kernel_ms, peaks, args):
+    """aread_hei_layer_fwd / _bwd launches alone (the main kernel plus its finalise / reduce kernels), timed on their
+    stream back to back.  Algorithmic bytes: input + output once forward; z + d_out + input + d_in once backward.  The
+    tensors of one launch (25-100 MB) fit the 126 MB L2, as they do inside a step, so the rate is an L2-assisted one;
+    tools/bench_hei.py times the same calls with the L2 flushed and with AREAD_HEI_TC=0 for the CUDA-core kernels."""
+    ho = importlib.import_module(PKG + ".hei_ops")
+    out = {"path": "tcgen05 (csrc/hei_tc.cu)" if os.environ.get("AREAD_HEI_TC", "1") != "0" else "CUDA cores (csrc/hei.cu)",
+           "rows": B, "layers": []}
+    gen = torch.Generator(device=dev).manual_seed(0)
+    for l, dims in enumerate(TOWER_DIMS):
+        G = N_TOWER[l]
+        k = EXPERT_DIMS[-1] if l == 0 else TOWER_DIMS[l - 1][-1]
+        for j, n in enumerate(dims):
+            rnd = lambda *s: torch.randn(*s, device=dev, generator=gen)
+            zp, w, b = rnd(B, G * k), 0.3 * rnd(G, n, k), rnd(G, n)
+            gamma, beta = 1 + 0.1 * rnd(G * n), 0.1 * rnd(G * n)
+            rm, rv = torch.zeros(G * n, device=dev), torch.ones(G * n, device=dev)
+            saved = None
+            if j > 0:
+                saved = torch.stack([zp.mean(0), 1 / zp.std(0), 1 / zp.std(0), -zp.mean(0) / zp.std(0)]).contiguous()
+            d_out = rnd(B, G * n)
+            z, st = ho.layer_fwd(zp, saved, 7, w, b, gamma, beta, rm, rv, G, k, n, True, False, args.dropout, 11)
+            coef, _ = ho.bn_bwd_coef(z, d_out, st, False, args.dropout, 11, 9)
+            f_ms = kernel_ms(lambda i: ho.layer_fwd(zp, saved, 7, w, b, gamma, beta, rm, rv, G, k, n, True, False,
+                                                    args.dropout, 11), 3, 20)
+            b_ms = kernel_ms(lambda i: ho.layer_bwd(z, d_out, st, coef, args.dropout, 9, 11, False, zp, saved, 7, w,
+                                                    G, k, n), 3, 20)
+            fb, bb = 4 * B * G * (k + n), 4 * B * G * (2 * n + 2 * k)
+            out["layers"].append({"level": l, "towers": G, "k": k, "n": n, "input_is_preactivation": j > 0,
+                                  "fwd_us": f_ms * 1e3, "fwd_frac_of_hbm": fb / (f_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                  "bwd_us": b_ms * 1e3, "bwd_frac_of_hbm": bb / (b_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]})
+            k = n
+    return out
 
 
 def feeding_leg(tr, dev, dev_x, dev_y, domains, bs=1024, n_batches=64):

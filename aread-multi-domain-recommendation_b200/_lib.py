@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -262,6 +262,8 @@ _SIGNATURES = {
     "aread_bn_act_apply": (c_int32, [POINTER(BnActArgs), c_void_p]),
     "aread_bn_bwd_coef": (c_int32, [POINTER(BnActBwdArgs), c_void_p, c_void_p]),
     "aread_hei_layer_supported": (c_int32, [c_int32, c_int32, c_int32]),
+    "aread_hei_set_path": (None, [c_int32, c_int32]),
+    "aread_hei_layer_path": (c_int32, [c_int64, c_int32, c_int32, c_int32]),
     "aread_hei_layer_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "aread_hei_layer_fwd": (c_int32, [POINTER(HeiLayerFwdArgs), c_void_p]),
     "aread_hei_layer_bwd": (c_int32, [POINTER(HeiLayerBwdArgs), c_void_p]),

@@ -525,14 +525,6 @@ size_t bwd_smem(const Tiling& t, int K, int N, bool src_bn) {
   return sizeof(float) * (static_cast<size_t>(Np) * Kp + tile);
 }
 
-bool getenv_bwd_tc() {     // AREAD_HEI_TC_BWD=0: tensor cores for the forward only
-  static const bool on = [] {
-    const char* e = std::getenv("AREAD_HEI_TC_BWD");
-    return e == nullptr || e[0] != '0';
-  }();
-  return on;
-}
-
 bool shape_ok(int groups, int k, int n) {
   return groups > 0 && groups <= 65535 && k > 0 && n > 0 && k <= kMaxWidth && n <= kMaxWidth;
 }
@@ -543,6 +535,16 @@ bool shape_ok(int groups, int k, int n) {
 extern "C" {
 
 int aread_hei_layer_supported(int32_t groups, int32_t k, int32_t n) { return aread::shape_ok(groups, k, n) ? 1 : 0; }
+
+void aread_hei_set_path(int32_t tensor_cores_fwd, int32_t tensor_cores_bwd) {
+  aread::hei_tc_set_path(tensor_cores_fwd, tensor_cores_bwd);
+}
+
+int aread_hei_layer_path(int64_t m, int32_t groups, int32_t k, int32_t n) {
+  alignas(16) static const float aligned = 0.f;     // a 16-byte aligned, stride-4 source: only the shape decides
+  return (aread::hei_tc_usable(m, groups, k, n, &aligned, 4) ? 1 : 0) |
+         (aread::hei_tc_bwd_usable(m, groups, k, n, &aligned, 4) ? 2 : 0);
+}
 
 size_t aread_hei_layer_workspace_bytes(int64_t m, int32_t groups, int32_t k, int32_t n) {
   using namespace aread;
@@ -626,7 +628,7 @@ int aread_hei_layer_bwd(const aread_hei_layer_bwd_args* args, aread_stream_t str
   AREAD_REQUIRE(a.workspace && a.workspace_bytes >= aread_hei_layer_workspace_bytes(a.m, a.groups, a.k, a.n),
                 "hei_layer_bwd: workspace too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (hei_tc_usable(a.m, a.groups, a.k, a.n, a.src, a.ld_src) && getenv_bwd_tc()) return hei_tc_bwd(a, stream);
+  if (hei_tc_bwd_usable(a.m, a.groups, a.k, a.n, a.src, a.ld_src)) return hei_tc_bwd(a, stream);
   const int Np = (a.n + 3) & ~3, Kp = (a.k + 3) & ~3;
   Tiling t = tiling(a.m, Kp / 4, a.groups, kBwdSmMultiple);
   const int mt_n = (Np / 4) * (Kp / 4);

@@ -828,18 +828,34 @@ int dbg_flags() {
   return e == nullptr ? 0 : std::atoi(e);
 }
 
-bool tc_enabled() {
-  static const bool on = [] {
-    const char* e = std::getenv("AREAD_HEI_TC");
-    return e == nullptr || e[0] != '0';
-  }();
-  return on;
+int g_path_fwd = -1, g_path_bwd = -1;     // aread_hei_set_path overrides; -1 = the environment decides
+
+bool env_on(const char* name) {
+  const char* e = std::getenv(name);
+  return e == nullptr || e[0] != '0';
+}
+bool tc_fwd_enabled() {
+  static const bool env = env_on("AREAD_HEI_TC");
+  return g_path_fwd < 0 ? env : g_path_fwd != 0;
+}
+bool tc_bwd_enabled() {
+  static const bool env = env_on("AREAD_HEI_TC") && env_on("AREAD_HEI_TC_BWD");
+  return g_path_bwd < 0 ? env : g_path_bwd != 0;
 }
 
 }  // namespace
 
+void hei_tc_set_path(int fwd, int bwd) {
+  g_path_fwd = fwd;
+  g_path_bwd = bwd;
+}
+bool hei_tc_shape_ok(int64_t m, int groups, int k, int n) { return shape_ok(m, groups, k, n); }
+
 bool hei_tc_usable(int64_t m, int groups, int k, int n, const float* src, int64_t ld_src) {
-  return tc_enabled() && shape_ok(m, groups, k, n) && ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  return tc_fwd_enabled() && shape_ok(m, groups, k, n) && ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+}
+bool hei_tc_bwd_usable(int64_t m, int groups, int k, int n, const float* src, int64_t ld_src) {
+  return tc_bwd_enabled() && shape_ok(m, groups, k, n) && ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
 }
 
 size_t hei_tc_workspace_floats(int64_t m, int groups, int k, int n) {

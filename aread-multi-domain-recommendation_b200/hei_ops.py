@@ -20,6 +20,18 @@ def supported(groups, k, n):
     return bool(_lib.load().aread_hei_layer_supported(groups, k, n))
 
 
+def set_path(tensor_cores_fwd=-1, tensor_cores_bwd=-1):
+    """Which implementation the tower layers run from now on: 1 = tcgen05 where the shape packs, 0 = CUDA cores,
+    -1 = the environment's default (AREAD_HEI_TC / AREAD_HEI_TC_BWD).  Recorded CUDA graphs keep what they captured."""
+    _lib.load().aread_hei_set_path(int(tensor_cores_fwd), int(tensor_cores_bwd))
+
+
+def path(m, groups, k, n):
+    """(forward on tensor cores, backward on tensor cores) for a call of this shape."""
+    bits = int(_lib.load().aread_hei_layer_path(int(m), groups, k, n))
+    return bool(bits & 1), bool(bits & 2)
+
+
 def _workspace(device, m, groups, k, n):
     need = int(_lib.load().aread_hei_layer_workspace_bytes(m, groups, k, n))
     return _mem.workspace("hei", device, need)

@@ -607,7 +607,7 @@ def hei_leg(model, B, dev, kernel_ms, peaks, args):
     tensors of one launch (25-100 MB) fit the 126 MB L2, as they do inside a step, so the rate is an L2-assisted one;
     tools/bench_hei.py times the same calls with the L2 flushed and with AREAD_HEI_TC=0 for the CUDA-core kernels."""
     ho = importlib.import_module(PKG + ".hei_ops")
-    out = {"path": "tcgen05 (csrc/hei_tc.cu)" if os.environ.get("AREAD_HEI_TC", "1") != "0" else "CUDA cores (csrc/hei.cu)",
+    out = {"paths": "tcgen05 = csrc/hei_tc.cu, cuda_cores = csrc/hei.cu (aread_hei_set_path); same entry points, same bytes",
            "rows": B, "layers": []}
     gen = torch.Generator(device=dev).manual_seed(0)
     for l, dims in enumerate(TOWER_DIMS):
@@ -622,16 +622,20 @@ def hei_leg(model, B, dev, kernel_ms, peaks, args):
             if j > 0:
                 saved = torch.stack([zp.mean(0), 1 / zp.std(0), 1 / zp.std(0), -zp.mean(0) / zp.std(0)]).contiguous()
             d_out = rnd(B, G * n)
-            z, st = ho.layer_fwd(zp, saved, 7, w, b, gamma, beta, rm, rv, G, k, n, True, False, args.dropout, 11)
-            coef, _ = ho.bn_bwd_coef(z, d_out, st, False, args.dropout, 11, 9)
-            f_ms = kernel_ms(lambda i: ho.layer_fwd(zp, saved, 7, w, b, gamma, beta, rm, rv, G, k, n, True, False,
-                                                    args.dropout, 11), 3, 20)
-            b_ms = kernel_ms(lambda i: ho.layer_bwd(z, d_out, st, coef, args.dropout, 9, 11, False, zp, saved, 7, w,
-                                                    G, k, n), 3, 20)
             fb, bb = 4 * B * G * (k + n), 4 * B * G * (2 * n + 2 * k)
-            out["layers"].append({"level": l, "towers": G, "k": k, "n": n, "input_is_preactivation": j > 0,
-                                  "fwd_us": f_ms * 1e3, "fwd_frac_of_hbm": fb / (f_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                  "bwd_us": b_ms * 1e3, "bwd_frac_of_hbm": bb / (b_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]})
+            rec = {"level": l, "towers": G, "k": k, "n": n, "input_is_preactivation": j > 0}
+            for name, flag in (("tcgen05", 1), ("cuda_cores", 0)):
+                ho.set_path(flag, flag)
+                z, st = ho.layer_fwd(zp, saved, 7, w, b, gamma, beta, rm, rv, G, k, n, True, False, args.dropout, 11)
+                coef, _ = ho.bn_bwd_coef(z, d_out, st, False, args.dropout, 11, 9)
+                f_ms = kernel_ms(lambda i: ho.layer_fwd(zp, saved, 7, w, b, gamma, beta, rm, rv, G, k, n, True, False,
+                                                        args.dropout, 11), 3, 20)
+                b_ms = kernel_ms(lambda i: ho.layer_bwd(z, d_out, st, coef, args.dropout, 9, 11, False, zp, saved, 7, w,
+                                                        G, k, n), 3, 20)
+                rec[name] = {"fwd_us": f_ms * 1e3, "fwd_frac_of_hbm": fb / (f_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "bwd_us": b_ms * 1e3, "bwd_frac_of_hbm": bb / (b_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+            ho.set_path(-1, -1)
+            out["layers"].append(rec)
             k = n
     return out
 

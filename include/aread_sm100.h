@@ -428,6 +428,12 @@ AREAD_API int aread_bn_bwd_coef(const aread_bn_act_bwd_args* args, float* coef, 
  *           d_in = dz W (gradient w.r.t. act(src)), and when src is a pre-activation the coefficients
  *           and parameter gradients of ITS BatchNorm backward (src_coef, src_d_gamma / _beta / _bias).
  * k, n <= 64 (aread_hei_layer_supported); wider layers go through aread_tower_linear & co.
+ *
+ * Two implementations sit behind these entry points: the tcgen05 kernels (csrc/hei_tc.cu; k in {16, 32, 64},
+ * 64 n / k in {32, 64}, m >= 512) and the CUDA-core kernels (csrc/hei.cu; everything else).  aread_hei_set_path
+ * overrides the choice for the process: 1 = tensor cores where the shape allows, 0 = CUDA cores, -1 = the
+ * environment's default (AREAD_HEI_TC, AREAD_HEI_TC_BWD; both on).  aread_hei_layer_path reports what a call of
+ * that shape would run: bit 0 = forward on tensor cores, bit 1 = backward on tensor cores.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct aread_hei_layer_fwd_args {
   int64_t m;
@@ -494,6 +500,8 @@ typedef struct aread_hei_layer_bwd_args {
 } aread_hei_layer_bwd_args;
 
 AREAD_API int aread_hei_layer_supported(int32_t groups, int32_t k, int32_t n);
+AREAD_API void aread_hei_set_path(int32_t tensor_cores_fwd, int32_t tensor_cores_bwd);
+AREAD_API int aread_hei_layer_path(int64_t m, int32_t groups, int32_t k, int32_t n);
 AREAD_API size_t aread_hei_layer_workspace_bytes(int64_t m, int32_t groups, int32_t k, int32_t n);
 AREAD_API int aread_hei_layer_fwd(const aread_hei_layer_fwd_args* args, aread_stream_t stream);
 AREAD_API int aread_hei_layer_bwd(const aread_hei_layer_bwd_args* args, aread_stream_t stream);

@@ -41,11 +41,36 @@ def _ref_layer(x, w, b, gamma, beta, mask, p, bn_skip, kernel_y=None):
     return z, a
 
 
-@pytest.mark.parametrize("m,G,dims,p", [(1000, 3, (64, 64, 32), 0.0), (777, 5, (32, 32, 16), 0.2),
-                                        (4099, 9, (16, 16, 8), 0.2), (37, 2, (64, 64, 32), 0.2),
-                                        (70000, 2, (16, 16, 8), 0.0), (2, 1, (8, 12, 4), 0.0),
-                                        (513, 4, (20, 10, 6), 0.2), (1, 3, (16, 16, 8), 0.0)])
-def test_two_layer_stack_matches_autograd(m, G, dims, p):
+@pytest.fixture(autouse=True)
+def _default_path():
+    yield
+    ho.set_path(-1, -1)
+
+
+# tensor cores: rows >= 512 and (k, n) that pack into 64-column blocks; several units per CTA from ~20,000 rows
+# (towers x rows: one block 148 CTAs, three blocks 49 each), partial last blocks (G not a multiple of 64 / k)
+CASES = [(1000, 3, (64, 64, 32), 0.0), (777, 5, (32, 32, 16), 0.2), (4099, 9, (16, 16, 8), 0.2),
+         (37, 2, (64, 64, 32), 0.2), (70000, 2, (16, 16, 8), 0.0), (2, 1, (8, 12, 4), 0.0),
+         (513, 4, (20, 10, 6), 0.2), (1, 3, (16, 16, 8), 0.0), (40000, 3, (64, 64, 32), 0.2),
+         (70000, 4, (16, 16, 8), 0.2), (30000, 7, (32, 32, 16), 0.2)]
+
+
+def test_paths_are_the_documented_ones():
+    assert ho.path(65536, 3, 64, 64) == (True, True) and ho.path(65536, 12, 16, 8) == (True, True)
+    assert ho.path(300, 3, 64, 64) == (False, False), "under 512 rows: CUDA cores"
+    assert ho.path(65536, 4, 20, 10) == (False, False), "widths that do not pack into 64-column blocks"
+    ho.set_path(0, 0)
+    assert ho.path(65536, 3, 64, 64) == (False, False)
+    ho.set_path(1, 0)
+    assert ho.path(65536, 3, 64, 64) == (True, False)
+
+
+@pytest.mark.parametrize("tensor_cores", [True, False])
+@pytest.mark.parametrize("m,G,dims,p", CASES)
+def test_two_layer_stack_matches_autograd(m, G, dims, p, tensor_cores):
+    ho.set_path(1 if tensor_cores else 0, 1 if tensor_cores else 0)
+    if tensor_cores and ho.path(m, G, dims[0], dims[1]) == (False, False) and ho.path(m, G, dims[1], dims[2]) == (False, False):
+        pytest.skip("shape runs on the CUDA cores either way")
     K, N1, N2 = dims
     gen = torch.Generator(device=DEV).manual_seed(m + G)
 
@@ -114,8 +139,9 @@ def test_two_layer_stack_matches_autograd(m, G, dims, p):
         assert torch.equal(again[1], d_w2) and torch.equal(again[0], d_a1) and torch.equal(again[2], coef1)
 
 
-def test_eval_mode_uses_running_statistics():
-    m, G, K, N = 300, 4, 32, 16
+@pytest.mark.parametrize("m", [300, 3000])
+def test_eval_mode_uses_running_statistics(m):
+    G, K, N = 4, 32, 16
     gen = torch.Generator(device=DEV).manual_seed(5)
 
     def rnd(*s):

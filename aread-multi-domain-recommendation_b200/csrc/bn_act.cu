@@ -363,6 +363,50 @@ __global__ void __launch_bounds__(kThreads) mmoe_mix_fwd_kernel(const aread_mmoe
   }
 }
 
+// Four consecutive columns per thread (128-bit / 64-bit loads of z, one hash per element pair, 128-bit stores):
+// H % 4 == 0, ldz % 4 == 0, 16-byte aligned tensors.
+template <int NE_, int NG_>
+__global__ void __launch_bounds__(kThreads) mmoe_mix_fwd_vec4_kernel(const aread_mmoe_mix_args a, uint32_t threshold,
+                                                                     float keep_scale) {
+  const uint64_t seed = seed_of(a);
+  constexpr int MAXE = NE_ > 0 ? NE_ : 16;
+  const int H = a.width, H4 = a.width / 4, NE = NE_ > 0 ? NE_ : a.n_expert, G = NG_ > 0 ? NG_ : a.n_gate;
+  const int64_t total = a.m * H4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t b = i / H4;
+    const int c = static_cast<int>(i - b * H4) * 4;
+    float h[MAXE][4];
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+      if (e < NE) {
+        const int col = e * H + c;
+        float z[4];
+        load_z<4>(a, b, col, z);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + col));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + col));
+        bool keep[4];
+        keep_flags<4>(seed, a.salt, static_cast<uint64_t>(b) * (NE * H) + col, threshold, keep);
+        h[e][0] = act_value(z[0], sc.x, sh.x, keep[0], keep_scale);
+        h[e][1] = act_value(z[1], sc.y, sh.y, keep[1], keep_scale);
+        h[e][2] = act_value(z[2], sc.z, sh.z, keep[2], keep_scale);
+        h[e][3] = act_value(z[3], sc.w, sh.w, keep[3], keep_scale);
+      }
+    }
+    for (int g = 0; g < G; ++g) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e)
+        if (e < NE) {
+          const float w = __ldg(a.gate + b * (G * NE) + g * NE + e);
+          acc.x = fmaf(w, h[e][0], acc.x); acc.y = fmaf(w, h[e][1], acc.y);
+          acc.z = fmaf(w, h[e][2], acc.z); acc.w = fmaf(w, h[e][3], acc.w);
+        }
+      *reinterpret_cast<float4*>(a.out + b * (G * H) + g * H + c) = acc;
+    }
+  }
+}
+
 // d_h[b, e, :] = sum_g gate[b, g, e] * d_out[b, g, :] ;  d_gate[b, g, e] = <d_out[b, g, :], h[b, e, :]>
 // one warp per sample
 template <int NE_, int NG_>
@@ -613,7 +657,14 @@ int aread_mmoe_mix(const aread_mmoe_mix_args* args, aread_stream_t stream_) {
   } while (0)
   if (a.d_out == nullptr) {
     AREAD_REQUIRE(a.out != nullptr, "mmoe_mix: null out");
-    AREAD_MMOE(mmoe_mix_fwd_kernel, elementwise_grid(a.m * a.width));
+    const bool vec4 = a.width % 4 == 0 && a.ldz % 4 == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(a.scale) % 16 == 0 && reinterpret_cast<uintptr_t>(a.shift) % 16 == 0 &&
+                      (a.z_bf16 ? reinterpret_cast<uintptr_t>(a.z_bf16) % 8 == 0 : reinterpret_cast<uintptr_t>(a.z) % 16 == 0);
+    if (vec4) {
+      AREAD_MMOE(mmoe_mix_fwd_vec4_kernel, elementwise_grid(a.m * (a.width / 4)));
+    } else {
+      AREAD_MMOE(mmoe_mix_fwd_kernel, elementwise_grid(a.m * a.width));
+    }
   } else {
     AREAD_REQUIRE(a.d_h && a.d_gate, "mmoe_mix: null gradient output");
     AREAD_MMOE(mmoe_mix_bwd_kernel, elementwise_grid(a.m * 32));

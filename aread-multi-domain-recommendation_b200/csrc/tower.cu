@@ -424,13 +424,17 @@ __global__ void __launch_bounds__(kThreads) gate_mix_bwd_direct_kernel(const are
       const float4* u = reinterpret_cast<const float4*>(a.u_prev + b * (static_cast<int64_t>(NA) * W));
       const float4* g = reinterpret_cast<const float4*>(a.d_out + (b * NT + t) * W);
       float dr[kDirectPrev];
+      int slots[kDirectPrev];
 #pragma unroll
-      for (int j = 0; j < kDirectPrev; ++j) dr[j] = 0.f;
+      for (int j = 0; j < kDirectPrev; ++j) {
+        dr[j] = 0.f;
+        slots[j] = j < NP ? a.prev_slot[j] : -1;
+      }
       for (int c = 0; c < W4; ++c) {
         const float4 gv = __ldg(g + c);
 #pragma unroll
         for (int j = 0; j < kDirectPrev; ++j) {
-          const int slot = j < NP ? __ldg(a.prev_slot + j) : -1;
+          const int slot = slots[j];
           if (slot >= 0) {
             const float4 v = __ldg(u + slot * W4 + c);
             dr[j] = fmaf(gv.x, v.x, fmaf(gv.y, v.y, fmaf(gv.z, v.z, fmaf(gv.w, v.w, dr[j]))));

@@ -433,6 +433,7 @@ class AreadNode(torch.autograd.Function):
         G = P.experts[0].groups
         a_op = xb
         ex = []
+        counters = []       # num_batches_tracked of every BatchNorm that ran in train mode: ONE increment launch at the end
         # the fused epilogues store 64-column bf16 chunks: narrower expert layers keep the unfused kernels
         fused_bn = not precise and all(L.n % 64 == 0 for L in P.experts)
         sv["fused_bn"] = fused_bn
@@ -447,7 +448,7 @@ class AreadNode(torch.autograd.Function):
                                     want_lo=precise and not last)
                 out, stats = (res[0], res[-1]) if not (precise and not last) else ((res[0], res[1]), res[2])
                 if training and not bn_skip:
-                    torch._foreach_add_(L.tracked, 1)
+                    counters.extend(L.tracked)
                 ex.append((a_op, z, stats, w, None))
                 a_op = out
         else:
@@ -473,7 +474,7 @@ class AreadNode(torch.autograd.Function):
                     stats = dk.identity_saved(G * L.n, dev) if last else None
                     bits = None
                 if training and not bn_skip:
-                    torch._foreach_add_(L.tracked, 1)
+                    counters.extend(L.tracked)
                 ex.append((a_op, z, stats, w16[i], bits if keep_z else None))
                 a_op = out
         h = dk.mmoe_mix_fwd(ex[-1][1], ex[-1][2], gate, G, len(a0), p_drop if training else 0.0, seed,
@@ -550,13 +551,15 @@ class AreadNode(torch.autograd.Function):
                         L.running_mean.flat.index_copy_(0, idx, rm)
                         L.running_var.flat.index_copy_(0, idx, rv)
                     tracked = L.tracked
-                    torch._foreach_add_([tracked[t] for t in act], 1)
+                    counters.extend(tracked[t] for t in act)
             if hei:
                 L = P.towers[l][-1]
                 h = hei_ops.bn_apply(z, stats, training, p_drop, seed, L.salt).view(B, na, L.n)
             rec["layers"] = lay
             levels.append(rec)
         sv["levels"] = levels
+        if counters:
+            torch._foreach_add_(counters, 1)
 
         # ---- heads: z_t = w_out_t[:E] . cn_out + w_out_t[E:] . u_t + lin ; p = sigmoid(z)
         w_tail = w_out[:, E:].contiguous()                                               # [na_last, w]

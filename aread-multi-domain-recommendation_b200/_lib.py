@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libaread_sm100.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 AREAD_OK = 0
 AREAD_ERR_INVALID = -1
@@ -91,7 +91,7 @@ class RowpassArgs(Structure):
                 ("d_lin", c_void_p), ("d_gate", c_void_p), ("d_head", c_void_p), ("d_p", c_void_p),
                 ("d_c", c_void_p), ("d_x", c_void_p), ("d_w", c_void_p), ("workspace", c_void_p),
                 ("workspace_bytes", c_size_t), ("dp16", c_void_p), ("ld16", c_int64), ("n_extra", c_int32),
-                ("dp16_width", c_int32)]
+                ("dp16_width", c_int32), ("d_c_sum", c_void_p), ("d_c_partial", c_void_p)]
 
 
 class L2RegArgs(Structure):
@@ -262,6 +262,7 @@ _SIGNATURES = {
     "aread_bn_act_apply": (c_int32, [POINTER(BnActArgs), c_void_p]),
     "aread_bn_bwd_coef": (c_int32, [POINTER(BnActBwdArgs), c_void_p, c_void_p]),
     "aread_hei_layer_supported": (c_int32, [c_int32, c_int32, c_int32]),
+    "aread_rowpass_prologue_ctas": (c_int32, [c_int64]),
     "aread_hei_set_path": (None, [c_int32, c_int32]),
     "aread_hei_layer_path": (c_int32, [c_int64, c_int32, c_int32, c_int32]),
     "aread_hei_layer_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),

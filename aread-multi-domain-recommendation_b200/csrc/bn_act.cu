@@ -459,6 +459,70 @@ __global__ void __launch_bounds__(kThreads) mmoe_mix_bwd_kernel(const aread_mmoe
   }
 }
 
+// Four consecutive columns per lane, H / 4 lanes per sample (H in {16, 32, 64, 128}: 8 .. 1 samples per warp): 64-bit /
+// 128-bit loads, one hash per element pair, 128-bit stores, and the gate-gradient dot products reduced over the lanes of
+// a sample by a log2(H / 4)-step butterfly.
+template <int NE_, int NG_>
+__global__ void __launch_bounds__(kThreads) mmoe_mix_bwd_vec4_kernel(const aread_mmoe_mix_args a, uint32_t threshold,
+                                                                     float keep_scale) {
+  const uint64_t seed = seed_of(a);
+  constexpr int MAXE = NE_ > 0 ? NE_ : 16, MAXG = NG_ > 0 ? NG_ : 8;
+  const int H = a.width, NE = NE_ > 0 ? NE_ : a.n_expert, G = NG_ > 0 ? NG_ : a.n_gate;
+  const int lpr = H / 4, rpw = 32 / lpr;                      // lanes per sample, samples per warp
+  const int lane = threadIdx.x % 32;
+  const int sub = lane / lpr, c = (lane - sub * lpr) * 4;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x / 32);
+  const int64_t n_groups = (a.m + rpw - 1) / rpw;
+  for (int64_t grp = static_cast<int64_t>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32; grp < n_groups; grp += warps) {
+    const int64_t b = grp * rpw + sub;
+    const bool valid = b < a.m;
+    const int64_t bb = valid ? b : 0;
+    float dg[MAXG][MAXE], gt[MAXG][MAXE];
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g)
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e) {
+        dg[g][e] = 0.f;
+        gt[g][e] = (g < G && e < NE) ? __ldg(a.gate + bb * (G * NE) + g * NE + e) : 0.f;
+      }
+    float4 dout[MAXG];
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g)
+      dout[g] = g < G ? __ldg(reinterpret_cast<const float4*>(a.d_out + bb * (G * H) + g * H + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+      if (e < NE) {
+        const int col = e * H + c;
+        float z[4];
+        load_z<4>(a, bb, col, z);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + col));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + col));
+        bool keep[4];
+        keep_flags<4>(seed, a.salt, static_cast<uint64_t>(bb) * (NE * H) + col, threshold, keep);
+        const float h0 = act_value(z[0], sc.x, sh.x, keep[0], keep_scale), h1 = act_value(z[1], sc.y, sh.y, keep[1], keep_scale);
+        const float h2 = act_value(z[2], sc.z, sh.z, keep[2], keep_scale), h3 = act_value(z[3], sc.w, sh.w, keep[3], keep_scale);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < MAXG; ++g) {
+          acc.x = fmaf(gt[g][e], dout[g].x, acc.x); acc.y = fmaf(gt[g][e], dout[g].y, acc.y);
+          acc.z = fmaf(gt[g][e], dout[g].z, acc.z); acc.w = fmaf(gt[g][e], dout[g].w, acc.w);
+          dg[g][e] = fmaf(dout[g].x, h0, fmaf(dout[g].y, h1, fmaf(dout[g].z, h2, fmaf(dout[g].w, h3, dg[g][e]))));
+        }
+        if (valid) *reinterpret_cast<float4*>(a.d_h + b * (NE * H) + col) = acc;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g)
+#pragma unroll
+      for (int e = 0; e < MAXE; ++e)
+        if (g < G && e < NE) {
+          float v = dg[g][e];
+          for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (valid && lane == sub * lpr) a.d_gate[b * (G * NE) + g * NE + e] = v;
+        }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) dropout_mask_kernel(uint64_t seed, uint32_t salt, int64_t n,
                                                                 uint32_t threshold, uint8_t* out) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -667,7 +731,16 @@ int aread_mmoe_mix(const aread_mmoe_mix_args* args, aread_stream_t stream_) {
     }
   } else {
     AREAD_REQUIRE(a.d_h && a.d_gate, "mmoe_mix: null gradient output");
-    AREAD_MMOE(mmoe_mix_bwd_kernel, elementwise_grid(a.m * 32));
+    const bool vec4 = (a.width == 16 || a.width == 32 || a.width == 64 || a.width == 128) && a.ldz % 4 == 0 &&
+                      reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0 && reinterpret_cast<uintptr_t>(a.d_h) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(a.scale) % 16 == 0 && reinterpret_cast<uintptr_t>(a.shift) % 16 == 0 &&
+                      (a.z_bf16 ? reinterpret_cast<uintptr_t>(a.z_bf16) % 8 == 0 : reinterpret_cast<uintptr_t>(a.z) % 16 == 0);
+    if (vec4) {
+      const int64_t groups = (a.m + (128 / a.width) - 1) / (128 / a.width);      // samples per warp = 32 / (width / 4)
+      AREAD_MMOE(mmoe_mix_bwd_vec4_kernel, elementwise_grid(groups * 32));
+    } else {
+      AREAD_MMOE(mmoe_mix_bwd_kernel, elementwise_grid(a.m * 32));
+    }
   }
 #undef AREAD_MMOE
   return AREAD_OK;

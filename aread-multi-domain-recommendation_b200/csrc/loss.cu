@@ -121,6 +121,62 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const aread_head_arg
   }
 }
 
+// The same for heads of width 8 and up to 12 towers (every shipped configuration): 128-bit loads / stores of the rows
+// and the head weight gradient accumulated per thread in registers over all of its rows -- one warp reduction per
+// (tower, column) at the end instead of one per row block.  Rows are added in thread order, lanes by the butterfly,
+// warps and CTAs in order: bit-reproducible.
+constexpr int kHeadMaxT = 12;
+__global__ void __launch_bounds__(kThreads) head_bwd_w8_kernel(const aread_head_args a, float* __restrict__ partial) {
+  extern __shared__ float s_acc[];  // [warps][T * 8]
+  const int T = a.n_tower, TW = T * 8;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  float acc[kHeadMaxT][8];
+#pragma unroll
+  for (int t = 0; t < kHeadMaxT; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < a.m; b += stride) {
+    float dl = 0.f;
+#pragma unroll
+    for (int t = 0; t < kHeadMaxT; ++t) {
+      if (t < T) {
+        const float p = __ldg(a.probs + static_cast<int64_t>(t) * a.m + b);
+        const float dz = __ldg(a.d_probs + static_cast<int64_t>(t) * a.m + b) * p * (1.f - p);
+        a.dz[b * T + t] = dz;
+        dl += dz;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_tail + t * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_tail + t * 8 + 4));
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(a.h + (b * T + t) * 8));
+        const float4 h1 = __ldg(reinterpret_cast<const float4*>(a.h + (b * T + t) * 8 + 4));
+        float4* dh = reinterpret_cast<float4*>(a.d_h + (b * T + t) * 8);
+        dh[0] = make_float4(dz * w0.x, dz * w0.y, dz * w0.z, dz * w0.w);
+        dh[1] = make_float4(dz * w1.x, dz * w1.y, dz * w1.z, dz * w1.w);
+        acc[t][0] = fmaf(dz, h0.x, acc[t][0]); acc[t][1] = fmaf(dz, h0.y, acc[t][1]);
+        acc[t][2] = fmaf(dz, h0.z, acc[t][2]); acc[t][3] = fmaf(dz, h0.w, acc[t][3]);
+        acc[t][4] = fmaf(dz, h1.x, acc[t][4]); acc[t][5] = fmaf(dz, h1.y, acc[t][5]);
+        acc[t][6] = fmaf(dz, h1.z, acc[t][6]); acc[t][7] = fmaf(dz, h1.w, acc[t][7]);
+      }
+    }
+    a.d_lin[b] = dl;
+  }
+  if (a.d_w_tail == nullptr) return;
+#pragma unroll
+  for (int t = 0; t < kHeadMaxT; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (t < T) {
+        const float v = warp_sum(acc[t][c]);
+        if (lane == 0) s_acc[warp * TW + t * 8 + c] = v;
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW; i += kThreads) {
+    float v = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) v += s_acc[w * TW + i];
+    partial[static_cast<int64_t>(blockIdx.x) * TW + i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) head_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial,
                                                                      int n, float* __restrict__ out) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
@@ -164,7 +220,13 @@ int aread_head(const aread_head_args* args, aread_stream_t stream_) {
     AREAD_REQUIRE(a.d_w_tail == nullptr || (a.workspace && a.workspace_bytes >= aread_head_workspace_bytes(a.n_tower, a.width)),
                   "head: workspace too small");
     float* partial = static_cast<float*>(a.workspace);
-    AREAD_LAUNCH(head_bwd_kernel, bgrid, kThreads, smem, stream, a, partial);
+    const bool w8 = a.width == 8 && a.n_tower <= kHeadMaxT && reinterpret_cast<uintptr_t>(a.h) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(a.d_h) % 16 == 0 && reinterpret_cast<uintptr_t>(a.w_tail) % 16 == 0;
+    if (w8) {
+      AREAD_LAUNCH(head_bwd_w8_kernel, bgrid, kThreads, smem, stream, a, partial);
+    } else {
+      AREAD_LAUNCH(head_bwd_kernel, bgrid, kThreads, smem, stream, a, partial);
+    }
     if (a.d_w_tail != nullptr)
       AREAD_LAUNCH(head_wgrad_reduce_kernel, ceil_div(tw, kThreads), kThreads, 0, stream, partial, static_cast<int>(bgrid),
                    tw, a.d_w_tail);

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(kThreads) rowpass_prologue_bwd_kernel(const ar
   const int n_own = c_head + nh, n_all = n_own + a.n_extra;
   const int ld = a.ldp, lds = a.ldp + 1;
   float* s_dc = s_dp + kPrologueRows * lds;             // [kPrologueRows][ldp + 1]
+  float col_sum = 0.f;                                  // of d_c column threadIdx.x over this CTA's tiles, in row order
   const int64_t n_tiles = (a.m + kPrologueRows - 1) / kPrologueRows;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t b0 = tile * kPrologueRows;
@@ -189,7 +190,10 @@ __global__ void __launch_bounds__(kThreads) rowpass_prologue_bwd_kernel(const ar
     for (int idx = threadIdx.x; idx < rows * ld; idx += kThreads) {
       const int r = idx / ld, j = idx - r * ld;
       a.d_p[(b0 + r) * ld + j] = s_dp[r * lds + j];
-      a.d_c[(b0 + r) * ld + j] = s_dc[r * lds + j];
+      if (a.d_c != nullptr) a.d_c[(b0 + r) * ld + j] = s_dc[r * lds + j];
+    }
+    if (a.d_c_sum != nullptr && threadIdx.x < ld) {
+      for (int r = 0; r < rows; ++r) col_sum += s_dc[r * lds + threadIdx.x];
     }
     if (a.dp16 != nullptr) {   // split bf16 operands of the tensor-core products: [hi | hi | lo], W columns each
       const int W = a.dp16_width > 0 ? a.dp16_width : 32;
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(kThreads) rowpass_prologue_bwd_kernel(const ar
       }
     }
   }
+  if (a.d_c_sum != nullptr && threadIdx.x < ld) a.d_c_partial[static_cast<int64_t>(blockIdx.x) * ld + threadIdx.x] = col_sum;
 }
 
 // d_x[b, e] (+)= sum_j d_p[b, j] * W[j, e]  and the per-CTA partial of  d_w[j, e] = sum_b d_p[b, j] * X[b, e].
@@ -310,6 +315,18 @@ unsigned prologue_grid(int64_t m) {
 }
 size_t prologue_smem(int ldp) { return sizeof(float) * 2 * kPrologueRows * (ldp + 1); }
 
+int launch_prologue(const aread_rowpass_args& a, cudaStream_t stream) {
+  AREAD_REQUIRE(a.d_c != nullptr || a.d_c_sum != nullptr, "rowpass_bwd: neither d_c nor d_c_sum given");
+  AREAD_REQUIRE(a.d_c_sum == nullptr || (a.d_c_partial != nullptr && a.ldp <= kThreads),
+                "rowpass_bwd: d_c_sum needs d_c_partial and at most %d columns", kThreads);
+  const unsigned grid = prologue_grid(a.m);
+  AREAD_LAUNCH(rowpass_prologue_bwd_kernel, grid, kThreads, prologue_smem(a.ldp), stream, a);
+  if (a.d_c_sum != nullptr)
+    AREAD_LAUNCH(rowdots_bwd_reduce_kernel, 1, kThreads, 0, stream, static_cast<int>(grid), static_cast<int64_t>(a.ldp),
+                 a.d_c_partial, a.d_c_sum);
+  return AREAD_OK;
+}
+
 int bwd_ctas(int64_t m) {
   const int64_t tiles = (m + kTile - 1) / kTile;
   const int64_t cap = kNumSMs * 2;
@@ -351,6 +368,8 @@ int aread_rowpass_fwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   return AREAD_OK;
 }
 
+int32_t aread_rowpass_prologue_ctas(int64_t m) { return static_cast<int32_t>(aread::prologue_grid(m)); }
+
 int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   using namespace aread;
   AREAD_REQUIRE(args != nullptr, "rowpass_bwd: null args");
@@ -366,7 +385,7 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
                                                    ? (a.m + kThreads - 1) / kThreads
                                                    : kNumSMs * 8);
   if (a.x == nullptr) {  // per-row prologue only: the products run on the tensor cores
-    AREAD_REQUIRE(a.d_p && a.d_c, "rowpass_bwd: null pointer");
+    AREAD_REQUIRE(a.d_p, "rowpass_bwd: null pointer");
     {
       const int w16 = a.dp16_width > 0 ? a.dp16_width : 32;
       AREAD_REQUIRE(a.dp16 == nullptr || (w16 % 32 == 0 && nj + a.n_extra <= w16 && a.ld16 >= 3 * w16),
@@ -374,10 +393,9 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
     }
     if (a.m == 0) return AREAD_OK;
     AREAD_REQUIRE(a.p && a.alpha && (a.gate || a.n_gate * a.n_expert == 0), "rowpass_bwd: null pointer");
-    AREAD_LAUNCH(rowpass_prologue_bwd_kernel, prologue_grid(a.m), kThreads, prologue_smem(a.ldp), stream, a);
-    return AREAD_OK;
+    return launch_prologue(a, stream);
   }
-  AREAD_REQUIRE(a.d_w && a.d_p && a.d_c && a.workspace, "rowpass_bwd: null pointer");
+  AREAD_REQUIRE(a.d_w && a.d_p && a.workspace, "rowpass_bwd: null pointer");
   if (a.m == 0) {
     AREAD_CUDA(cudaMemsetAsync(a.d_w, 0, static_cast<size_t>(nj) * a.e * 4, stream));
     return AREAD_OK;
@@ -388,7 +406,7 @@ int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream_) {
   const unsigned egrid = static_cast<unsigned>((a.m + kThreads - 1) / kThreads < kNumSMs * 8
                                                    ? (a.m + kThreads - 1) / kThreads
                                                    : kNumSMs * 8);
-  AREAD_LAUNCH(rowpass_prologue_bwd_kernel, prologue_grid(a.m), kThreads, prologue_smem(a.ldp), stream, a);
+  if (int rc = launch_prologue(a, stream)) return rc;
   float* partial = static_cast<float*>(a.workspace);
   const int n_chunks = (a.e + kChunk - 1) / kChunk;
   for (int j0 = 0; j0 < nj; j0 += kJ) {

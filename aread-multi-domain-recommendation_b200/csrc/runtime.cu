@@ -18,7 +18,7 @@ std::atomic<uint64_t>& launch_counter() {
 extern "C" {
 
 const char* aread_last_error(void) { return aread::last_error_buf(); }
-int aread_abi_version(void) { return 11; }
+int aread_abi_version(void) { return 12; }
 uint64_t aread_launch_count(void) { return aread::launch_counter().load(std::memory_order_relaxed); }
 void aread_launch_count_add(uint64_t n) { aread::launch_counter().fetch_add(n, std::memory_order_relaxed); }
 

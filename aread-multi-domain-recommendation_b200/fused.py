@@ -609,7 +609,9 @@ class AreadNode(torch.autograd.Function):
         layout, ldp, tc_row, ride = sv["layout"], sv["ldp"], sv["tc_row"], sv["ride"]
         nj, nj_own = sv["w_cat"].shape[0], sv["nj_own"]
         d_p = _mem.empty((B, ldp), torch.float32, dev)     # gradient w.r.t. the row-pass products (gate logits included)
-        d_c = _mem.empty((B, ldp), torch.float32, dev)
+        # only the column sums of d_c (gradients of the additive constants) are needed: the prologue kernel adds them up
+        d_off_full = torch.empty((ldp,), dtype=torch.float32, device=dev)       # parameter gradients: never arena
+        dc_partial = _mem.workspace("rowpass_dc", dev, int(_lib.load().aread_rowpass_prologue_ctas(B)) * ldp * 4)
 
         tower_grads = [[None] * len(P.towers[l]) for l in range(n_level)]
         gate_grads = [None] * n_level
@@ -684,7 +686,8 @@ class AreadNode(torch.autograd.Function):
             # of the expert layer-1 data gradient GEMM when that runs in the fused bf16 path
             dz0 = _mem.empty((B, k_ext), torch.bfloat16, dev)
             ra = rowpass_ops._args(B, E, layout, ldp, x=None, p=sv["p_dots"], gate=sv["gate"], alpha=sv["alpha"],
-                                   d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p, d_c=d_c)
+                                   d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p, d_c_sum=d_off_full,
+                                   d_c_partial=dc_partial)
             ra.dp16, ra.ld16, ra.n_extra, ra.dp16_width = dz0.data_ptr() + c0 * 2, k_ext, nj - nj_own, w16
             _lib.check(_lib.load().aread_rowpass_bwd(ctypes.byref(ra), _stream(dev)))
 
@@ -768,12 +771,12 @@ class AreadNode(torch.autograd.Function):
             need = int(_lib.load().aread_rowpass_workspace_bytes(B, E, nj))
             ws = _mem.workspace("rowpass", dev, need)
             ra = rowpass_ops._args(B, E, layout, ldp, x=X, w=sv["w_cat"], p=sv["p_dots"], gate=sv["gate"],
-                                   alpha=sv["alpha"], d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p, d_c=d_c,
-                                   d_x=d_x_row, d_w=d_wcat, workspace=ws)
+                                   alpha=sv["alpha"], d_lin=d_lin, d_gate=d_gate, d_head=dz, d_p=d_p,
+                                   d_c_sum=d_off_full, d_c_partial=dc_partial, d_x=d_x_row, d_w=d_wcat, workspace=ws)
             ra.workspace_bytes = ws.numel()
             _lib.check(_lib.load().aread_rowpass_bwd(ctypes.byref(ra), _stream(dev)))
             d_x = d_x.add_(d_x_row)
-        d_off = d_c[:, :nj].sum(dim=0)
+        d_off = d_off_full[:nj]
         d_grp_vec = None if d_q is None else d_q[:, D:].sum(dim=0)          # gradient w.r.t. the mean group embedding
         if ride:
             # gate parameters from the riding columns: W[:, :D] from the weight gradient rows (domain field columns),

@@ -591,9 +591,16 @@ typedef struct aread_rowpass_args {
      third of the split, a multiple of 32 >= cols + n_extra (0 = 32).                                           */
   int32_t n_extra;
   int32_t dp16_width;
+  /* backward, optional: the column sums of d_c over the rows, [ldp] (what the caller needs of d_c: the gradients of the
+     additive constants).  The prologue kernel adds its tiles up per CTA in row order into d_c_partial
+     (aread_rowpass_prologue_ctas(m) * ldp floats) and a second launch adds the CTAs in order.  With d_c_sum set, d_c
+     may be NULL and is then never written.                                                                         */
+  float* d_c_sum;
+  float* d_c_partial;
 } aread_rowpass_args;
 
 AREAD_API size_t aread_rowpass_workspace_bytes(int64_t m, int32_t e, int32_t n_cols);
+AREAD_API int32_t aread_rowpass_prologue_ctas(int64_t m);
 AREAD_API int aread_rowpass_fwd(const aread_rowpass_args* args, aread_stream_t stream);
 AREAD_API int aread_rowpass_bwd(const aread_rowpass_args* args, aread_stream_t stream);
 

@@ -309,6 +309,33 @@ __global__ void __launch_bounds__(kThreads) rowdots_bwd_reduce_kernel(int n_part
   }
 }
 
+// out[col] = sum over the CTA partials of column col: 32 columns x 8 interleaved groups of partials per block, four
+// independent sums per thread, then groups in order (fixed order; ~n_partial / 32 dependent steps instead of n_partial)
+__global__ void __launch_bounds__(kThreads) column_partials_reduce_kernel(int n_partial, int ld,
+                                                                          const float* __restrict__ partial,
+                                                                          float* __restrict__ out) {
+  __shared__ float s_part[8][32];
+  const int cx = threadIdx.x % 32, py = threadIdx.x / 32;
+  const int col = blockIdx.x * 32 + cx;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col < ld) {
+    int i = py;
+    for (; i + 24 < n_partial; i += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += partial[static_cast<int64_t>(i + 8 * u) * ld + col];
+    }
+    for (int u = 0; i < n_partial; i += 8, ++u) acc[u & 3] += partial[static_cast<int64_t>(i) * ld + col];
+  }
+  s_part[py][cx] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (py == 0 && col < ld) {
+    float v = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) v += s_part[y][cx];
+    out[col] = v;
+  }
+}
+
 unsigned prologue_grid(int64_t m) {
   const int64_t tiles = (m + kPrologueRows - 1) / kPrologueRows;
   return static_cast<unsigned>(tiles < kNumSMs * 4 ? (tiles < 1 ? 1 : tiles) : kNumSMs * 4);
@@ -322,7 +349,7 @@ int launch_prologue(const aread_rowpass_args& a, cudaStream_t stream) {
   const unsigned grid = prologue_grid(a.m);
   AREAD_LAUNCH(rowpass_prologue_bwd_kernel, grid, kThreads, prologue_smem(a.ldp), stream, a);
   if (a.d_c_sum != nullptr)
-    AREAD_LAUNCH(rowdots_bwd_reduce_kernel, 1, kThreads, 0, stream, static_cast<int>(grid), static_cast<int64_t>(a.ldp),
+    AREAD_LAUNCH(column_partials_reduce_kernel, ceil_div(a.ldp, 32), kThreads, 0, stream, static_cast<int>(grid), a.ldp,
                  a.d_c_partial, a.d_c_sum);
   return AREAD_OK;
 }

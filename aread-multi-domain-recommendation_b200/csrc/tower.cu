@@ -374,69 +374,102 @@ __device__ __forceinline__ void gate_row(const aread_gate_mix_args& a, int64_t b
   }
 }
 
-__global__ void __launch_bounds__(kThreads) gate_mix_fwd_direct_kernel(const aread_gate_mix_args a) {
-  const int NT = a.n_tower, NP = a.n_prev, NA = a.n_prev_active, W = a.width;
-  const int64_t total = a.m * NT;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t b = i / NT;
-    const int t = static_cast<int>(i - b * NT);
-    GateRow w;
-    gate_row(a, b, t, w);
-    int slot[kDirectPrev];
-#pragma unroll
-    for (int j = 0; j < kDirectPrev; ++j) slot[j] = j < NP ? __ldg(a.prev_slot + j) : -1;
-    if (a.sm != nullptr) {
-#pragma unroll
-      for (int j = 0; j < kDirectPrev; ++j)
-        if (j < NP) a.sm[i * NP + j] = w.s[j] * w.e[j];
-    }
-    const float4* u = reinterpret_cast<const float4*>(a.u_prev + b * (static_cast<int64_t>(NA) * W));
-    float4* out = reinterpret_cast<float4*>(a.out + i * W);
-    for (int c = 0; c < W / 4; ++c) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < kDirectPrev; ++j)
-        if (j < NP && slot[j] >= 0) {
-          const float4 v = __ldg(u + slot[j] * (W / 4) + c);
-          acc.x = fmaf(w.r[j], v.x, acc.x); acc.y = fmaf(w.r[j], v.y, acc.y);
-          acc.z = fmaf(w.r[j], v.z, acc.z); acc.w = fmaf(w.r[j], v.w, acc.w);
-        }
-      out[c] = acc;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kThreads) gate_mix_bwd_direct_kernel(const aread_gate_mix_args a, int rows_per_cta) {
+// Forward in two phases per tile of rows, so that a row of u is read once and not once per tower:
+//   1. thread = (row, tower): softmax / edge renormalisation of its logits -> r[row][tower][prev] in shared memory
+//   2. thread = (row, 4 columns, share of the towers): the previous level's active outputs of those columns in
+//      registers, then out[row][tower][columns] = sum_prev r * u for its towers (128-bit loads and stores)
+__global__ void __launch_bounds__(kThreads) gate_mix_fwd_tile_kernel(const aread_gate_mix_args a, int rows_per_cta, int ts) {
   extern __shared__ float s_r[];                     // [rows_per_cta * NT][NP]
+  __shared__ int s_slot[kDirectPrev];
   const int NT = a.n_tower, NP = a.n_prev, NA = a.n_prev_active, W = a.width, W4 = a.width / 4;
-  const int64_t ldd = a.ld_dlogits > 0 ? a.ld_dlogits : static_cast<int64_t>(NT) * NP;
+  if (threadIdx.x < kDirectPrev) s_slot[threadIdx.x] = threadIdx.x < NP ? a.prev_slot[threadIdx.x] : -1;
   const int64_t n_tiles = (a.m + rows_per_cta - 1) / rows_per_cta;
+  const int t_per = (NT + ts - 1) / ts;              // towers per phase-2 thread
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t b0 = tile * rows_per_cta;
     const int rows = a.m - b0 < rows_per_cta ? static_cast<int>(a.m - b0) : rows_per_cta;
     __syncthreads();
     if (threadIdx.x < rows * NT) {
       const int r = threadIdx.x / NT, t = threadIdx.x - r * NT;
+      const int64_t i = (b0 + r) * NT + t;
+      GateRow w;
+      gate_row(a, b0 + r, t, w);
+#pragma unroll
+      for (int j = 0; j < kDirectPrev; ++j)
+        if (j < NP) {
+          s_r[threadIdx.x * NP + j] = w.r[j];
+          if (a.sm != nullptr) a.sm[i * NP + j] = w.s[j] * w.e[j];
+        }
+    }
+    __syncthreads();
+    const int items = rows * W4 * ts;
+    for (int it = threadIdx.x; it < items; it += kThreads) {
+      const int r = it / (W4 * ts), rem = it - r * (W4 * ts);
+      const int part = rem / W4, c = rem - part * W4;
+      const int64_t b = b0 + r;
+      const float4* u = reinterpret_cast<const float4*>(a.u_prev + b * (static_cast<int64_t>(NA) * W)) + c;
+      float4 uu[kDirectPrev];
+#pragma unroll
+      for (int j = 0; j < kDirectPrev; ++j) {
+        const int slot = s_slot[j];
+        uu[j] = slot >= 0 ? __ldg(u + slot * W4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const int t1 = (part + 1) * t_per < NT ? (part + 1) * t_per : NT;
+      float4* out = reinterpret_cast<float4*>(a.out + b * (static_cast<int64_t>(NT) * W)) + c;
+      for (int t = part * t_per; t < t1; ++t) {
+        const float* rr = s_r + (r * NT + t) * NP;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kDirectPrev; ++j)
+          if (j < NP) {
+            const float wj = rr[j];
+            acc.x = fmaf(wj, uu[j].x, acc.x); acc.y = fmaf(wj, uu[j].y, acc.y);
+            acc.z = fmaf(wj, uu[j].z, acc.z); acc.w = fmaf(wj, uu[j].w, acc.w);
+          }
+        out[t * W4] = acc;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) gate_mix_bwd_direct_kernel(const aread_gate_mix_args a, int rows_per_cta) {
+  extern __shared__ float s_r[];                     // [rows_per_cta * NT][NP], then u of the tile [rows][NA * W + 4]
+  const int NT = a.n_tower, NP = a.n_prev, NA = a.n_prev_active, W = a.width, W4 = a.width / 4;
+  const int ldu = NA * W + 4;                        // padded row: the rows of a warp fall on different banks
+  float* s_u = s_r + ((rows_per_cta * NT * NP + 3) & ~3);
+  const int64_t ldd = a.ld_dlogits > 0 ? a.ld_dlogits : static_cast<int64_t>(NT) * NP;
+  const int64_t n_tiles = (a.m + rows_per_cta - 1) / rows_per_cta;
+  int slots[kDirectPrev];
+#pragma unroll
+  for (int j = 0; j < kDirectPrev; ++j) slots[j] = j < NP ? a.prev_slot[j] : -1;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t b0 = tile * rows_per_cta;
+    const int rows = a.m - b0 < rows_per_cta ? static_cast<int>(a.m - b0) : rows_per_cta;
+    __syncthreads();
+    // u of the tile, read once (the NT threads of a row all need it), whole rows at a time
+    for (int it = threadIdx.x; it < rows * NA * W4; it += kThreads) {
+      const int r = it / (NA * W4), q = it - r * (NA * W4);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a.u_prev + (b0 + r) * (static_cast<int64_t>(NA) * W)) + q);
+      *reinterpret_cast<float4*>(s_u + r * ldu + q * 4) = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < rows * NT) {
+      const int r = threadIdx.x / NT, t = threadIdx.x - r * NT;
       const int64_t b = b0 + r;
       GateRow w;
       gate_row(a, b, t, w);
-      const float4* u = reinterpret_cast<const float4*>(a.u_prev + b * (static_cast<int64_t>(NA) * W));
+      const float* u = s_u + r * ldu;
       const float4* g = reinterpret_cast<const float4*>(a.d_out + (b * NT + t) * W);
       float dr[kDirectPrev];
-      int slots[kDirectPrev];
 #pragma unroll
-      for (int j = 0; j < kDirectPrev; ++j) {
-        dr[j] = 0.f;
-        slots[j] = j < NP ? a.prev_slot[j] : -1;
-      }
+      for (int j = 0; j < kDirectPrev; ++j) dr[j] = 0.f;
       for (int c = 0; c < W4; ++c) {
         const float4 gv = __ldg(g + c);
 #pragma unroll
         for (int j = 0; j < kDirectPrev; ++j) {
           const int slot = slots[j];
           if (slot >= 0) {
-            const float4 v = __ldg(u + slot * W4 + c);
+            const float4 v = *reinterpret_cast<const float4*>(u + slot * W + c * 4);
             dr[j] = fmaf(gv.x, v.x, fmaf(gv.y, v.y, fmaf(gv.z, v.z, fmaf(gv.w, v.w, dr[j]))));
           }
         }
@@ -591,18 +624,28 @@ extern "C" int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t st
                         reinterpret_cast<uintptr_t>(a.d_out) | reinterpret_cast<uintptr_t>(a.d_u_prev)) & 15) == 0;
   if (direct && a.d_out == nullptr) {
     AREAD_REQUIRE(a.out != nullptr, "gate_mix: null out");
-    int64_t g = (a.m * a.n_tower + kThreads - 1) / kThreads;
+    const int rows_per_cta = kThreads / a.n_tower;
+    const int w4 = a.width / 4;
+    int ts = kThreads / (rows_per_cta * w4);           // tower shares so that phase 2 has a thread's worth of work each
+    if (ts < 1) ts = 1;
+    if (ts > a.n_tower) ts = a.n_tower;
+    int64_t g = (a.m + rows_per_cta - 1) / rows_per_cta;
     if (g > kNumSMs * 16) g = kNumSMs * 16;
-    AREAD_LAUNCH(gate_mix_fwd_direct_kernel, static_cast<unsigned>(g), kThreads, 0, stream, a);
+    AREAD_LAUNCH(gate_mix_fwd_tile_kernel, static_cast<unsigned>(g), kThreads,
+                 sizeof(float) * rows_per_cta * a.n_tower * a.n_prev, stream, a, rows_per_cta, ts);
     return AREAD_OK;
   }
   if (direct) {
     AREAD_REQUIRE(a.d_logits && a.slot_tower, "gate_mix: null gradient pointer");
-    const int rows_per_cta = kThreads / a.n_tower;
+    int rows_per_cta = kThreads / a.n_tower;
+    const size_t per_row = sizeof(float) * (static_cast<size_t>(a.n_tower) * a.n_prev + a.n_prev_active * a.width + 4);
+    if (rows_per_cta * per_row + 16 > 40 * 1024) rows_per_cta = static_cast<int>((40 * 1024 - 16) / per_row);
+    AREAD_REQUIRE(rows_per_cta >= 1, "gate_mix: one row needs %zu bytes of shared memory", per_row);
     int64_t g = (a.m + rows_per_cta - 1) / rows_per_cta;
     if (g > kNumSMs * 16) g = kNumSMs * 16;
-    AREAD_LAUNCH(gate_mix_bwd_direct_kernel, static_cast<unsigned>(g), kThreads,
-                 sizeof(float) * rows_per_cta * a.n_tower * a.n_prev, stream, a, rows_per_cta);
+    const size_t smem = sizeof(float) * (((static_cast<size_t>(rows_per_cta) * a.n_tower * a.n_prev + 3) & ~size_t(3)) +
+                                         static_cast<size_t>(rows_per_cta) * (a.n_prev_active * a.width + 4));
+    AREAD_LAUNCH(gate_mix_bwd_direct_kernel, static_cast<unsigned>(g), kThreads, smem, stream, a, rows_per_cta);
     return AREAD_OK;
   }
   if (a.d_out == nullptr) {

@@ -16,6 +16,7 @@
 
 #include "bn_common.cuh"
 #include "common.cuh"
+#include "tensor_map.cuh"
 #include "hei_tc.cuh"
 
 namespace aread {
@@ -577,10 +578,9 @@ int aread_hei_layer_fwd(const aread_hei_layer_fwd_args* args, aread_stream_t str
   const int Np = (a.n + 3) & ~3;
   Tiling t = tiling(a.m, Np / 4, a.groups, kFwdSmMultiple);
   const size_t smem = fwd_smem(t, a.k, a.n);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t configured = 0;          // cudaFuncSetAttribute is per device
+  if (first_use_on_device(&configured)) {
     AREAD_CUDA(cudaFuncSetAttribute(hei_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
   }
   AREAD_REQUIRE(smem <= 160 * 1024, "hei_layer_fwd: tile needs %zu bytes of shared memory", smem);
   {  // fewer, longer CTAs when fewer than kFwdSmMultiple fit per SM (never more: the workspace is sized for that)
@@ -634,10 +634,9 @@ int aread_hei_layer_bwd(const aread_hei_layer_bwd_args* args, aread_stream_t str
   const int mt_n = (Np / 4) * (Kp / 4);
   const int rs_n = kThreads / mt_n;
   const size_t smem = bwd_smem(t, a.k, a.n, src_bn);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t configured = 0;          // cudaFuncSetAttribute is per device
+  if (first_use_on_device(&configured)) {
     AREAD_CUDA(cudaFuncSetAttribute(hei_layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   AREAD_REQUIRE(smem <= 200 * 1024, "hei_layer_bwd: tile needs %zu bytes of shared memory", smem);
   {

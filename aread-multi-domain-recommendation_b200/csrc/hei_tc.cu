@@ -173,7 +173,6 @@ struct FwdParams {
   uint32_t thr;
   float keep_scale;
   int do_stats;
-  int dbg;          // development switches (AREAD_HEI_DBG): parts of the kernel turned off to find the critical path
   float* partial;   // [nb_ctas][2][groups * n]
   float* pivot;     // [groups * n]: the shift of the variance sums (the running mean before this step's update)
 };
@@ -303,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) hei_tc_fwd_kernel(const FwdParams
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
         const int64_t row = tile_row + r0 + 4 * it;
-        if (uu < n_units && col_ok && row < a.m && !(p.dbg & 1)) {
+        if (uu < n_units && col_ok && row < a.m) {
           const float* sp = a.src + row * a.ld_src + col0;
           raw[it][0] = ldg4(sp);
           raw[it][1] = ldg4(sp + 4);
@@ -321,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) hei_tc_fwd_kernel(const FwdParams
       ptx::tc_fence_before_sync();
       __syncwarp();                                  // also: the previous unit's reads of `buf` are done
       if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
-      if (has_slice && !(p.dbg & 8)) {
+      if (has_slice) {
         const int64_t row0 = (static_cast<int64_t>(ci) + static_cast<int64_t>(ud) * p.nb_ctas) * kTile + quad * 32;
         const int n_rows = a.m - row0 >= 32 ? 32 : (a.m > row0 ? static_cast<int>(a.m - row0) : 0);
 #pragma unroll
@@ -331,8 +330,8 @@ __global__ void __launch_bounds__(kThreads, 1) hei_tc_fwd_kernel(const FwdParams
         }
         write_slice(buf, lane, v);
         __syncwarp();
-        if (!(p.dbg & 2)) copy_out_slice(buf, lane, a.z, out_width, row0, a.m, b * NB + sl * 16, out_width);
-        if (p.do_stats && !(p.dbg & 4)) slice_moments(buf, lane, n_rows, piv, cs, cq);
+        copy_out_slice(buf, lane, a.z, out_width, row0, a.m, b * NB + sl * 16, out_width);
+        if (p.do_stats) slice_moments(buf, lane, n_rows, piv, cs, cq);
       }
     };
     auto convert = [&](const float4 (&raw)[2][2], int uu) {
@@ -413,7 +412,6 @@ struct BwdParams {
   int T, n_blocks, n_tiles, nb_ctas;
   uint32_t thr, src_thr;
   float keep_scale, src_keep_scale;
-  int dbg;
   float* partial_w;   // [nb_ctas][groups * n * k]
   float* partial_s;   // [nb_ctas][2][groups * k]
 };
@@ -587,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) hei_tc_bwd_kernel(const BwdParams
     };
     auto issue = [&](HalfRegs& h, int uu, int hf) {
       const int64_t row_base = (static_cast<int64_t>(ci) + static_cast<int64_t>(uu) * p.nb_ctas) * kTile + w * 8;
-      const bool on = uu < n_units && !(p.dbg & 1);
+      const bool on = uu < n_units;
       if (hf < kDzPasses) {
         const int64_t row = row_base + hf * kDzRows + dsub;
         if (on && dcol_ok && row < a.m) {
@@ -683,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) hei_tc_bwd_kernel(const BwdParams
       if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
       const int64_t row0 = (static_cast<int64_t>(ci) + static_cast<int64_t>(ud) * p.nb_ctas) * kTile + quad * 32;
       const int col0 = b * kBlk + sl * 16;
-      if (a.d_in != nullptr && !(p.dbg & 10)) {
+      if (a.d_in != nullptr) {
         write_slice(buf_a, lane, v);
         __syncwarp();
         copy_out_slice(buf_a, lane, a.d_in, src_width, row0, a.m, col0, src_width);
@@ -726,10 +724,8 @@ __global__ void __launch_bounds__(kThreads, 1) hei_tc_bwd_kernel(const BwdParams
         }
         __syncwarp();                                          // x tile read, slices written
         if (lane == 0) ptx::mbar_arrive(&empty_bar[dstage]);   // the stage may be refilled
-        if (!(p.dbg & 12)) {
-          slice_sums(buf_a, lane, s1);
-          slice_sums(buf_b, lane, s2);
-        }
+        slice_sums(buf_a, lane, s1);
+        slice_sums(buf_b, lane, s2);
       }
     };
 
@@ -823,11 +819,6 @@ __global__ void __launch_bounds__(256) hei_tc_wgrad_reduce_kernel(const float* _
   out[i] = v;
 }
 
-int dbg_flags() {
-  const char* e = std::getenv("AREAD_HEI_DBG");
-  return e == nullptr ? 0 : std::atoi(e);
-}
-
 int g_path_fwd = -1, g_path_bwd = -1;     // aread_hei_set_path overrides; -1 = the environment decides
 
 bool env_on(const char* name) {
@@ -881,7 +872,6 @@ int hei_tc_fwd(const aread_hei_layer_fwd_args& a, cudaStream_t stream) {
   p.thr = drop > 0.f ? dropout_threshold(drop) : 0u;
   p.keep_scale = drop > 0.f ? 1.f / (1.f - drop) : 1.f;
   p.do_stats = (a.training && !a.bn_skip) ? 1 : 0;
-  p.dbg = dbg_flags();
   p.partial = static_cast<float*>(a.workspace);
   p.pivot = p.partial + static_cast<size_t>(pl.nb_ctas) * 2 * width;
   static uint64_t configured = 0;
@@ -923,7 +913,6 @@ int hei_tc_bwd(const aread_hei_layer_bwd_args& a, cudaStream_t stream) {
   p.keep_scale = a.p > 0.f ? 1.f / (1.f - a.p) : 1.f;
   p.src_thr = a.src_p > 0.f ? dropout_threshold(a.src_p) : 0u;
   p.src_keep_scale = a.src_p > 0.f ? 1.f / (1.f - a.src_p) : 1.f;
-  p.dbg = dbg_flags();
   const int64_t n_w = static_cast<int64_t>(a.groups) * a.n * a.k;
   p.partial_w = static_cast<float*>(a.workspace);
   p.partial_s = p.partial_w + static_cast<size_t>(pl.nb_ctas) * n_w;

@@ -9,6 +9,7 @@
 // data gradient:  in = dz [m, G, N],           M_g = W_g,                                out = d_in [m, G, K]
 // Towers pruned by the HEMP mask are simply absent: the caller passes the compact list of active towers.
 #include "common.cuh"
+#include "tensor_map.cuh"
 
 namespace aread {
 namespace {
@@ -613,11 +614,10 @@ extern "C" int aread_gate_mix(const aread_gate_mix_args* args, aread_stream_t st
   const size_t ltp = static_cast<size_t>(a.n_tower) * (a.n_prev | 1), utp = static_cast<size_t>(a.n_prev_active) * (a.width | 1),
                otp = static_cast<size_t>(a.n_tower) * (a.width | 1);   // padded shared-memory rows
   const unsigned grid = static_cast<unsigned>((a.m + kGateRows - 1) / kGateRows);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t configured = 0;          // cudaFuncSetAttribute is per device
+  if (first_use_on_device(&configured)) {
     AREAD_CUDA(cudaFuncSetAttribute(gate_mix_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AREAD_CUDA(cudaFuncSetAttribute(gate_mix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const bool direct = a.n_prev <= kDirectPrev && a.width % 4 == 0 && a.n_tower <= kThreads && a.n_prev_active > 0 &&
                       ((reinterpret_cast<uintptr_t>(a.u_prev) | reinterpret_cast<uintptr_t>(a.out) |

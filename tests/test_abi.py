@@ -91,3 +91,25 @@ def test_argument_validation_without_gpu(lib):
     assert b"plan" in lib.aread_last_error()
     with pytest.raises(_lib.AreadError):
         _lib.check(lib.aread_scatter_bwd(None, None))
+
+
+def test_hei_path_rules_need_no_gpu():
+    """Which tower-layer implementation a shape gets is host logic (include/aread_sm100.h, aread_hei_layer_path):
+    bit 0 = forward on the tensor cores, bit 1 = backward."""
+    lib = _lib.load()
+    lib.aread_hei_set_path(-1, -1)
+    default = lib.aread_hei_layer_path(65536, 3, 64, 64)
+    assert default in (0, 3), "the environment switches both directions unless AREAD_HEI_TC_BWD=0"
+    lib.aread_hei_set_path(1, 1)
+    try:
+        assert lib.aread_hei_layer_path(65536, 3, 64, 64) == 3 and lib.aread_hei_layer_path(65536, 12, 16, 8) == 3
+        assert lib.aread_hei_layer_path(65536, 6, 32, 16) == 3 and lib.aread_hei_layer_path(512, 1, 16, 16) == 3
+        assert lib.aread_hei_layer_path(511, 3, 64, 64) == 0, "under 512 rows: CUDA cores"
+        assert lib.aread_hei_layer_path(65536, 4, 20, 10) == 0 and lib.aread_hei_layer_path(65536, 4, 64, 8) == 0
+        lib.aread_hei_set_path(1, 0)
+        assert lib.aread_hei_layer_path(65536, 3, 64, 64) == 1
+        lib.aread_hei_set_path(0, 0)
+        assert lib.aread_hei_layer_path(65536, 3, 64, 64) == 0
+    finally:
+        lib.aread_hei_set_path(-1, -1)
+    assert lib.aread_rowpass_prologue_ctas(65536) >= 1 and lib.aread_rowpass_prologue_ctas(1) == 1
